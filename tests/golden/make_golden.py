@@ -1,0 +1,200 @@
+"""Generate golden vectors from the REAL reference (/root/reference) -- build container only.
+
+    python tests/golden/make_golden.py
+
+Writes tests/golden/*.npz.  Every file stores the inputs (X, y, theta, ...) and what the
+unmodified reference returned for them, so the GPU box (which has no /root/reference) can
+check both the NumPy oracle and the CUDA path against the reference's own outputs.
+"""
+import os
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "..", ".."))
+from oracle import ref_loader as RL  # noqa: E402
+
+
+def synth(n, d, seed=0):
+    """BASELINE.md section 3 generator."""
+    rng = np.random.default_rng(seed)
+    X = rng.random((n, d))
+    w = rng.normal(size=d)
+    y = np.sin(X @ w) + 0.1 * (X ** 2).sum(1)
+    return X, y, w
+
+
+MODES = [  # (tag, mucm, alt_nugget, fix_nugget)
+    ("mucm_k_fixT", "T", "F", "T"),
+    ("mucm_k_fixF", "T", "F", "F"),
+    ("gp4ml_k_fixT", "F", "F", "T"),
+    ("gp4ml_k_fixF", "F", "F", "F"),
+    ("gp4ml_alt_fixT", "F", "T", "T"),
+    ("gp4ml_alt_fixF", "F", "T", "F"),
+]
+
+
+def build(g, tmp, X, y, mucm, alt, fix, nugget, name):
+    with RL.cwd(tmp), RL.quiet():
+        cfg = RL.write_emulator_files(tmp, X, y, mucm=mucm, fix_nugget=fix, alt_nugget=alt,
+                                      nugget=nugget, name=name)
+        E = g.setup(cfg, datashuffle=False, scaleinputs=True)
+    return E
+
+
+def gen_llh(g, n, d, seed, n_theta, nugget=1e-4, with_r=False):
+    X, y, _ = synth(n, d, seed)
+    out = {"X_raw": X, "y": y, "nugget_belief": nugget}
+    rng = np.random.default_rng(100 + seed)
+    with tempfile.TemporaryDirectory() as tmp:
+        for tag, mucm, alt, fix in MODES:
+            E = build(g, tmp, X, y, mucm, alt, fix, nugget, "m_" + tag)
+            out["X"] = E.training.inputs.copy()          # scaled inputs as the reference holds them
+            out["H"] = E.training.H.copy()
+            r = None
+            if with_r and alt == "T":
+                r = 0.01 + 0.02 * rng.random(n)
+                with RL.quiet():
+                    E.training.set_r(r)
+                out[tag + "_r"] = r
+            p = d + (1 if fix == "F" else 0) + (1 if mucm == "F" else 0)
+            thetas, llhs, grads, sig = [], [], [], []
+            for t in range(n_theta):
+                delta = 0.15 + 0.85 * rng.random(d)
+                hp = list(delta)
+                if fix == "F":
+                    hp.append(10 ** rng.uniform(-4, -2))
+                if mucm == "F":
+                    hp.append(0.3 + 1.2 * rng.random())
+                theta = E.K.transform(np.array(hp))
+                with RL.quiet():
+                    res = (E.opt_T.loglikelihood_mucm if mucm == "T" else E.opt_T.loglikelihood_gp4ml)(theta.copy())
+                assert res is not None
+                thetas.append(theta); llhs.append(res[0]); grads.append(res[1].copy())
+                sig.append(float(E.par.sigma))
+            out[tag + "_theta"] = np.array(thetas)
+            out[tag + "_llh"] = np.array(llhs)
+            out[tag + "_grad"] = np.array(grads)
+            out[tag + "_sigma"] = np.array(sig)
+            assert out[tag + "_theta"].shape[1] == p
+    return out
+
+
+def gen_posterior(g, n, d, seed, m, nugget=1e-4):
+    X, y, _ = synth(n, d, seed)
+    out = {"X_raw": X, "y": y}
+    rng = np.random.default_rng(200 + seed)
+    Xs = rng.random((m, d))
+    out["Xs"] = Xs
+    with tempfile.TemporaryDirectory() as tmp:
+        for tag, mucm, alt, fix in (MODES[0], MODES[2], MODES[4]):
+            E = build(g, tmp, X, y, mucm, alt, fix, nugget, "p_" + tag)
+            out["X"] = E.training.inputs.copy()
+            delta = 0.3 + 0.5 * rng.random(d)
+            sigma = 0.8 + 0.4 * rng.random()
+            E.par.delta = delta.copy(); E.K.d = E.par.delta; E.K.n = E.par.nugget
+            E.par.sigma = sigma
+            with RL.quiet():
+                if alt == "T":
+                    r = 0.01 + 0.02 * rng.random(n)
+                    E.training.set_r(r)
+                    out[tag + "_r"] = r
+                E.training.remake()
+                E.opt_T.optimalbeta()
+                mean, var = g.posterior(E, Xs.copy())
+            out[tag + "_delta"] = delta
+            out[tag + "_sigma"] = sigma
+            out[tag + "_nugget"] = float(E.par.nugget)
+            out[tag + "_beta"] = np.array(E.par.beta)
+            out[tag + "_mean"] = mean
+            out[tag + "_var"] = var
+    return out
+
+
+def gen_toysim(g):
+    """Config 1: examples/toy-sim as shipped, np.random.seed(0)."""
+    import shutil
+    out = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        for f in ("toy-sim_config", "toy-sim_beliefs", "toy-sim_input", "toy-sim_output"):
+            shutil.copy(os.path.join(RL.REF_ROOT, "examples", "toy-sim", f), tmp)
+        with RL.cwd(tmp), RL.quiet():
+            np.random.seed(0)
+            E = g.setup("toy-sim_config")
+            g.train(E)
+            xs = np.array([[0.1, 0.2], [0.5, 0.5], [0.9, 0.3], [0.25, 0.75]])
+            mean, var = g.posterior(E, xs)
+        out.update(delta=np.array(E.par.delta), sigma=float(E.par.sigma), nugget=float(E.par.nugget),
+                   beta=np.array(E.par.beta), X=E.training.inputs, y=E.training.outputs,
+                   xs=xs, mean=mean, var=var)
+    return out
+
+
+def gen_hm(g, h, n, seed):
+    """History matching: two emulators on 3 inputs; nonimp_data-style flat implausibility.
+    Stores means/variances from the reference Posterior and the reference's own
+    keep decision computed with history_match.py:237-250 arithmetic via nonimp_data."""
+    X, y, w = synth(n, 3, seed)
+    rng = np.random.default_rng(300 + seed)
+    y2 = np.cos(X @ rng.normal(size=3))
+    out = {"X_raw": X, "y0": y, "y1": y2}
+    with tempfile.TemporaryDirectory() as tmp, RL.cwd(tmp), RL.quiet():
+        emuls = []
+        for o, yy in enumerate((y, y2)):
+            cfg = RL.write_emulator_files(tmp, X, yy, mucm="F", fix_nugget="T", alt_nugget="F",
+                                          nugget=1e-4, name="hm%d" % o, tries=3)
+            np.random.seed(5 + o)
+            E = g.setup(cfg, datashuffle=False, scaleinputs=True)
+            g.train(E)
+            # rebuild from the updated beliefs (active_index / input_minmax needed by HM)
+            with open("hm%d_config_r" % o, "w") as f:
+                f.write("beliefs hm%d_beliefs-0f\ninputs hm%d_input-o0-0f\noutputs hm%d_output-o0-0f\n" % (o, o, o))
+                f.write("tv_config 10 0 0\ndelta_bounds [ ]\nsigma_bounds [ ]\nnugget_bounds [ ]\ntries 1\nconstraints bounds\n")
+            E2 = g.setup("hm%d_config_r" % o, datashuffle=False, scaleinputs=True)
+            emuls.append(E2)
+            out["delta%d" % o] = np.array(E2.par.delta); out["sigma%d" % o] = float(E2.par.sigma)
+            out["beta%d" % o] = np.array(E2.par.beta); out["nugget%d" % o] = float(E2.par.nugget)
+            out["Xtrain%d" % o] = E2.training.inputs.copy(); out["ytrain%d" % o] = E2.training.outputs.copy()
+        m = 400
+        pts = rng.random((m, 3))
+        np.savetxt("sim_in", pts, fmt="%.17g")
+        np.savetxt("sim_out", np.column_stack([pts[:, 0], pts[:, 1]]), fmt="%.17g")
+        zs = [float(np.median(y)), float(np.median(y2))]
+        ve = [1e-2, 1e-2]
+        cm = 3.0
+        for maxno in (1, 2):
+            cnt = h.nonimp_data(emuls, zs, cm, ve, ["sim_in", "sim_out"], maxno=maxno)
+            kept = np.atleast_2d(np.loadtxt("nonimp_sim_in")) if cnt else np.zeros((0, 3))
+            out["kept_maxno%d" % maxno] = kept
+            out["count_maxno%d" % maxno] = cnt
+        out.update(pts=pts, zs=np.array(zs), var_extra=np.array(ve), cm=cm)
+        # nonimp_data scales the file's inputs with the emulators' input_minmax
+        # (_hmutilfunctions.py:126-139) before predicting; the kept rows are the scaled ones
+        mm = np.array(emuls[0].beliefs.input_minmax)
+        pts_scaled = (pts - mm[:, 0]) / (mm[:, 1] - mm[:, 0])
+        out["pts_scaled"] = pts_scaled
+        means, variances = [], []
+        for E2 in emuls:
+            mu, V = g.posterior(E2, pts_scaled.copy())
+            means.append(mu); variances.append(np.diag(V))
+        out["means"] = np.array(means); out["vars"] = np.array(variances)
+    return out
+
+
+def main():
+    assert RL.available(), "reference not present"
+    g, h, s, gn = RL.load()
+    save = lambda name, d: (np.savez_compressed(os.path.join(HERE, name), **d), print("wrote", name))
+    save("llh_n60_d2.npz", gen_llh(g, 60, 2, 1, 3, nugget=1e-2))
+    save("llh_n200_d4.npz", gen_llh(g, 200, 4, 2, 3, with_r=True))
+    save("llh_n500_d8.npz", gen_llh(g, 500, 8, 3, 2))
+    save("post_n200_d4.npz", gen_posterior(g, 200, 4, 4, 150))
+    save("post_n500_d8.npz", gen_posterior(g, 500, 8, 5, 100))
+    save("toysim.npz", gen_toysim(g))
+    save("hm_n100_d3.npz", gen_hm(g, h, 100, 6))
+
+
+if __name__ == "__main__":
+    main()
