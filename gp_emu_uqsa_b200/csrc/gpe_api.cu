@@ -1,0 +1,382 @@
+// C-ABI + host orchestration of the B200-native GP hot path (see include/gpe_b200.h).
+#include "gpe_handle.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+using namespace gpe;
+
+// ------------------------------------------------------------------------------------- utils
+int gpe_handle::fail(const char* what, cudaError_t e) {
+    char buf[512];
+    snprintf(buf, sizeof buf, "%s: %s", what, cudaGetErrorString(e));
+    err = buf;
+    cudaGetLastError();
+    return -1;
+}
+int gpe_handle::fail_msg(const char* what) {
+    err = what;
+    return -2;
+}
+
+#define CK(call)                                                   \
+    do {                                                           \
+        cudaError_t e__ = (call);                                  \
+        if (e__ != cudaSuccess) return h->fail(#call, e__);        \
+    } while (0)
+
+bool gpe_is_device_ptr(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+template <class T>
+static cudaError_t dev_alloc(T** p, size_t count) {
+    return cudaMalloc((void**)p, std::max<size_t>(count, 1) * sizeof(T));
+}
+template <class T>
+static void dev_free(T*& p) {
+    if (p) cudaFree(p);
+    p = nullptr;
+}
+
+void gpe_handle::free_batch_ws() {
+    dev_free(A); dev_free(S); dev_free(Li); dev_free(Wy); dev_free(Z); dev_free(U); dev_free(GP);
+    dev_free(logdet_part); dev_free(par); dev_free(out); dev_free(winv); dev_free(beta);
+    dev_free(status); dev_free(gpart); dev_free(theta_d); dev_free(llh_d); dev_free(grad_d); dev_free(sig_d);
+    Bcap = 0;
+}
+
+void gpe_handle::free_training() {
+    dev_free(X); dev_free(y); dev_free(H); dev_free(r); dev_free(HY);
+    free_batch_ws();
+    free_fit();
+    n = d = q = npad = nleaf = 0;
+}
+
+// Batch workspace: three padded n x n matrices per item (A -> A^-1, S scratch, L^-1) plus the
+// skinny panels.  180 GB of HBM3e holds the whole 256-guess batch of config 3 (103 GB), but the
+// default cap keeps sub-batches of <= 64 so the factorisation working set stays L2-friendly.
+int gpe_ensure_batch_ws(gpe_handle* h, int B) {
+    if (B <= h->Bcap) return 0;
+    size_t per_item = 3ull * h->npad * h->npad * sizeof(double) + 3ull * h->npad * NR * sizeof(double);
+    size_t free_b = 0, total_b = 0;
+    h->free_batch_ws();
+    CK(cudaMemGetInfo(&free_b, &total_b));
+    int cap_env = 64;
+    if (const char* e = getenv("GPE_BCAP")) cap_env = std::max(1, atoi(e));
+    long long fit = (long long)((double)free_b * 0.8 / (double)per_item);
+    int want = (int)std::max<long long>(1, std::min<long long>({(long long)B, (long long)cap_env, fit}));
+    if (fit < 1) return h->fail_msg("not enough device memory for one n x n factorisation workspace");
+    size_t nn = (size_t)h->npad * h->npad;
+    CK(dev_alloc(&h->A, want * nn));
+    CK(dev_alloc(&h->S, want * nn));
+    CK(dev_alloc(&h->Li, want * nn));
+    CK(cudaMemsetAsync(h->Li, 0, want * nn * sizeof(double), h->st));
+    size_t pn = (size_t)h->npad * NR;
+    CK(dev_alloc(&h->Wy, want * pn));
+    CK(dev_alloc(&h->Z, want * pn));
+    CK(dev_alloc(&h->U, want * pn));
+    int nslab = (h->npad + GRAM_SLAB - 1) / GRAM_SLAB;
+    CK(dev_alloc(&h->GP, (size_t)want * nslab * NR * NR));
+    CK(dev_alloc(&h->logdet_part, (size_t)want * h->nleaf));
+    CK(dev_alloc(&h->par, (size_t)want));
+    CK(dev_alloc(&h->out, (size_t)want));
+    CK(dev_alloc(&h->winv, (size_t)want * h->d));
+    CK(dev_alloc(&h->beta, (size_t)want * NR));
+    CK(dev_alloc(&h->status, (size_t)want));
+    CK(dev_alloc(&h->gpart, (size_t)want * grad_ntiles(h->npad) * grad_nvals(h->d)));
+    CK(dev_alloc(&h->theta_d, (size_t)want * (h->d + 2)));
+    CK(dev_alloc(&h->llh_d, (size_t)want));
+    CK(dev_alloc(&h->grad_d, (size_t)want * (h->d + 2)));
+    CK(dev_alloc(&h->sig_d, (size_t)want));
+    h->Bcap = want;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------- GEMM helper
+static int run_gemm(gpe_handle* h, const double* A, const double* B, double* C, int lda, int ldb, int ldc,
+                    long long sA, long long sB, long long sC, int M, int N, int K, double alpha, int acc,
+                    int kmode, int lower, int batch, int layout, int epi = EPI_STORE) {
+    GemmP p;
+    p.A = A; p.B = B; p.C = C; p.lda = lda; p.ldb = ldb; p.ldc = ldc; p.sA = sA; p.sB = sB; p.sC = sC;
+    p.M = M; p.N = N; p.K = K; p.alpha = alpha; p.accumulate = acc; p.kmode = kmode; p.lower = lower; p.batch = batch;
+    cudaError_t e = launch_gemm(p, layout, epi, h->st);
+    h->launches++;
+    if (e != cudaSuccess) return h->fail("launch_gemm", e);
+    return 0;
+}
+int gpe_run_gemm(gpe_handle* h, const double* A, const double* B, double* C, int lda, int ldb, int ldc,
+                 long long sA, long long sB, long long sC, int M, int N, int K, double alpha, int acc,
+                 int kmode, int lower, int batch, int layout, int epi) {
+    return run_gemm(h, A, B, C, lda, ldb, ldc, sA, sB, sC, M, N, K, alpha, acc, kmode, lower, batch, layout, epi);
+}
+
+// Recursive Cholesky + triangular inverse of the diagonal block [off, off+m) of every item:
+//   F(A11) ; L21 = A21 L11^-T ; A22 -= L21 L21^T ; F(A22) ; Linv21 = -L22^-1 (L21 L11^-1).
+// All four updates are DMMA GEMMs with a triangular operand (zero tiles skipped); only the
+// 128x128 diagonal leaves are factored by a panel kernel.  2n^3/3 flops, 5 launches per node.
+static int potrf_inv_rec(gpe_handle* h, int off, int m, int B) {
+    const int ld = h->npad;
+    const long long sM = (long long)h->npad * h->npad;
+    if (m == NB) {
+        launch_leaf(h->A, h->Li, ld, sM, sM, off, h->logdet_part, h->nleaf, h->status, B, h->st);
+        h->launches++;
+        return 0;
+    }
+    const int nb = m / NB;
+    const int m1 = ((nb + 1) / 2) * NB, m2 = m - m1;
+    int rc;
+    if ((rc = potrf_inv_rec(h, off, m1, B))) return rc;
+    double* A21 = h->A + (size_t)(off + m1) * ld + off;
+    double* A22 = h->A + (size_t)(off + m1) * ld + off + m1;
+    double* S21 = h->S + (size_t)(off + m1) * ld + off;
+    double* Li11 = h->Li + (size_t)off * ld + off;
+    double* Li22 = h->Li + (size_t)(off + m1) * ld + off + m1;
+    double* Li21 = h->Li + (size_t)(off + m1) * ld + off;
+    // L21 = A21 * Linv11^T           (NT, Linv11 lower: k <= j)
+    if ((rc = run_gemm(h, A21, Li11, S21, ld, ld, ld, sM, sM, sM, m2, m1, m1, 1.0, 0, KM_LE_J, 0, B, 0))) return rc;
+    // A22 -= L21 * L21^T             (SYRK, lower tiles)
+    if ((rc = run_gemm(h, S21, S21, A22, ld, ld, ld, sM, sM, sM, m2, m2, m1, -1.0, 1, KM_FULL, 1, B, 0))) return rc;
+    if ((rc = potrf_inv_rec(h, off + m1, m2, B))) return rc;
+    // T = L21 * Linv11               (NN, Linv11 lower: k >= j)  -> dead A21 block
+    if ((rc = run_gemm(h, S21, Li11, A21, ld, ld, ld, sM, sM, sM, m2, m1, m1, 1.0, 0, KM_GE_J, 0, B, 1))) return rc;
+    // Linv21 = -Linv22 * T           (NN, Linv22 lower: k <= i)
+    if ((rc = run_gemm(h, Li22, A21, Li21, ld, ld, ld, sM, sM, sM, m2, m1, m2, -1.0, 0, KM_LE_I, 0, B, 1))) return rc;
+    return 0;
+}
+int gpe_potrf_inv(gpe_handle* h, int B) { return potrf_inv_rec(h, 0, h->npad, B); }
+
+// Everything after the covariance build for B items already described by h->par / h->winv.
+// with_grad = 0 stops after the GLS/likelihood scalars (fit_state path).
+int gpe_factor_and_reduce(gpe_handle* h, int B, int mode, int with_grad, const double* beta_override) {
+    const int np = h->npad, ld = np;
+    const long long sM = (long long)np * np, sP = (long long)np * NR;
+    int rc;
+    cudaMemsetAsync(h->status, 0, sizeof(int) * B, h->st);
+    if ((rc = potrf_inv_rec(h, 0, np, B))) return rc;
+    // Wy = Linv [H | y]
+    if ((rc = run_gemm(h, h->Li, h->HY, h->Wy, ld, NR, NR, sM, 0, sP, np, NR, np, 1.0, 0, KM_LE_I, 0, B, 1))) return rc;
+    launch_gram(h->Wy, np, B, h->GP, h->st);
+    launch_llh_finalize(h->Wy, h->GP, h->logdet_part, h->nleaf, h->n, h->q, np, mode, h->par, h->out, h->beta, h->Z,
+                        h->status, B, beta_override, h->st);
+    h->launches += 2;
+    // U = Linv^T Z = [A^-1 H K^-T | sqrt(f) A^-1 (y - H beta)]
+    if ((rc = run_gemm(h, h->Li, h->Z, h->U, ld, NR, NR, sM, sP, sP, np, NR, np, 1.0, 0, KM_GE_I, 0, B, 2))) return rc;
+    if (!with_grad) return 0;
+    // LAUUM: A^-1 = Linv^T Linv (lower tiles) into the dead A buffer
+    if ((rc = run_gemm(h, h->Li, h->Li, h->A, ld, ld, ld, sM, sM, sM, np, np, np, 1.0, 0, KM_GE_I, 1, B, 2))) return rc;
+    launch_grad_partial(h->X, h->r, h->n, h->d, np, h->winv, h->A, sM, h->U, h->q + 1, h->gpart, B, h->st);
+    h->launches++;
+    return 0;
+}
+
+static void host_item_par(ItemPar& ip, double nugget, int kind, int predict, double s2_for_r, double s2A) {
+    ip.c = kind ? 1.0 : (1.0 - nugget);
+    ip.offs = s2A * ip.c;
+    double diagK = kind ? (predict ? 1.0 + nugget * nugget : 1.0) : (predict ? 1.0 : 1.0 - nugget);
+    ip.diagv = s2A * diagK;
+    ip.radd = kind ? s2A / s2_for_r : 0.0;
+    ip.s2A = s2A; ip.nugget = nugget; ip.sigma = std::sqrt(s2A); ip.pad_ = 0.0;
+}
+
+int gpe_upload_single_par(gpe_handle* h, const double* delta, double nugget, int kind, int predict, double s2_for_r) {
+    ItemPar ip;
+    host_item_par(ip, nugget, kind, predict, s2_for_r, 1.0);
+    std::vector<double> w(h->d);
+    for (int k = 0; k < h->d; k++) w[k] = 1.0 / delta[k];
+    CK(cudaMemcpyAsync(h->par, &ip, sizeof ip, cudaMemcpyHostToDevice, h->st));
+    CK(cudaMemcpyAsync(h->winv, w.data(), sizeof(double) * h->d, cudaMemcpyHostToDevice, h->st));
+    CK(cudaStreamSynchronize(h->st));   // host vectors go out of scope
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------- C-ABI
+extern "C" {
+
+int gpe_version(void) { return 100; }
+
+int gpe_create(int device, gpe_handle** out) {
+    if (!out) return -2;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return -3;   // no CPU fallback
+    if (device < 0 || device >= count) return -2;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return -3;
+    if (prop.major < 10) return -4;                                           // sm_100a only
+    if (cudaSetDevice(device) != cudaSuccess) return -3;
+    gpe_handle* h = new gpe_handle();
+    h->device = device;
+    h->sms = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking) != cudaSuccess) { delete h; return -3; }
+    *out = h;
+    return 0;
+}
+
+int gpe_destroy(gpe_handle* h) {
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->st);
+    h->free_training();
+    cudaStreamDestroy(h->st);
+    delete h;
+    return 0;
+}
+
+const char* gpe_last_error(gpe_handle* h) { return h ? h->err.c_str() : "null handle"; }
+long long gpe_launch_count(gpe_handle* h) { return h ? h->launches : 0; }
+
+int gpe_set_training(gpe_handle* h, const double* X, const double* y, const double* H, const double* r,
+                     int n, int d, int q) {
+    if (!h || !X || !y || !H || n < 1 || d < 1 || q < 1) return h ? h->fail_msg("bad argument") : -2;
+    if (q + 1 > NR) return h->fail_msg("q + 1 exceeds the skinny panel width (32)");
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->st));
+    h->free_training();
+    h->n = n; h->d = d; h->q = q;
+    h->npad = ((n + NB - 1) / NB) * NB;
+    h->nleaf = h->npad / NB;
+    CK(dev_alloc(&h->X, (size_t)n * d));
+    CK(dev_alloc(&h->y, (size_t)n));
+    CK(dev_alloc(&h->H, (size_t)n * q));
+    CK(cudaMemcpyAsync(h->X, X, sizeof(double) * n * d, cudaMemcpyDefault, h->st));
+    CK(cudaMemcpyAsync(h->y, y, sizeof(double) * n, cudaMemcpyDefault, h->st));
+    CK(cudaMemcpyAsync(h->H, H, sizeof(double) * n * q, cudaMemcpyDefault, h->st));
+    if (r) {
+        CK(dev_alloc(&h->r, (size_t)n));
+        CK(cudaMemcpyAsync(h->r, r, sizeof(double) * n, cudaMemcpyDefault, h->st));
+    }
+    CK(dev_alloc(&h->HY, (size_t)h->npad * NR));
+    launch_build_hy(h->H, h->y, n, q, h->npad, h->HY, h->st);
+    h->launches++;
+    CK(cudaStreamSynchronize(h->st));
+    h->has_basis = false;
+    return 0;
+}
+
+int gpe_set_basis(gpe_handle* h, const int* idx, const int* pw, int q) {
+    if (!h || q != h->q) return h ? h->fail_msg("basis size does not match q") : -2;
+    h->basis_idx[0] = -1; h->basis_pow[0] = 0;
+    for (int j = 1; j < q; j++) {
+        if (idx[j - 1] < 0 || idx[j - 1] >= h->d) return h->fail_msg("basis index out of range");
+        h->basis_idx[j] = idx[j - 1];
+        h->basis_pow[j] = pw[j - 1];
+    }
+    h->has_basis = true;
+    return 0;
+}
+
+int gpe_cov_build(gpe_handle* h, const double* delta, double nugget, int kind, int predict, double s2, double* A_out) {
+    if (!h || !h->n || !delta || !A_out) return h ? h->fail_msg("bad argument / no training set") : -2;
+    CK(cudaSetDevice(h->device));
+    int rc;
+    if ((rc = gpe_ensure_batch_ws(h, 1))) return rc;
+    std::vector<double> dl(h->d);
+    CK(cudaMemcpy(dl.data(), delta, sizeof(double) * h->d, cudaMemcpyDefault));
+    if ((rc = gpe_upload_single_par(h, dl.data(), nugget, kind, predict, s2))) return rc;
+    launch_cov_build(h->X, h->r, h->n, h->d, h->npad, h->par, h->winv, h->A, 0, 1, 1, h->st);
+    h->launches++;
+    size_t nn = (size_t)h->n * h->n;
+    double* dst = A_out;
+    bool dev = gpe_is_device_ptr(A_out);
+    if (!dev) dst = h->S;   // stage through scratch
+    launch_unpad_sym(h->A, h->npad, h->n, dst, 0, h->st);
+    h->launches++;
+    if (!dev) CK(cudaMemcpyAsync(A_out, dst, nn * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    return 0;
+}
+
+int gpe_llh_grad_batch(gpe_handle* h, const double* theta, int B, int p, int mode, double fixed_nugget,
+                       double* llh, double* grad, double* sigma_hat, int* status) {
+    if (!h || !h->n || !theta || B < 1 || !llh || !grad) return h ? h->fail_msg("bad argument / no training set") : -2;
+    int p_expect = h->d + ((mode & GPE_MODE_NUGGET_FREE) ? 1 : 0) + ((mode & GPE_MODE_MUCM) ? 0 : 1);
+    if (p != p_expect) return h->fail_msg("p does not match d and mode");
+    CK(cudaSetDevice(h->device));
+    int rc;
+    if ((rc = gpe_ensure_batch_ws(h, B))) return rc;
+    const long long sM = (long long)h->npad * h->npad;
+    for (int b0 = 0; b0 < B; b0 += h->Bcap) {
+        int Bs = std::min(h->Bcap, B - b0);
+        CK(cudaMemcpyAsync(h->theta_d, theta + (size_t)b0 * p, sizeof(double) * Bs * p, cudaMemcpyDefault, h->st));
+        launch_prep_theta(h->theta_d, Bs, p, h->d, mode, fixed_nugget, h->par, h->winv, h->st);
+        launch_cov_build(h->X, h->r, h->n, h->d, h->npad, h->par, h->winv, h->A, sM, Bs, 0, h->st);
+        h->launches += 2;
+        if ((rc = gpe_factor_and_reduce(h, Bs, mode, 1, nullptr))) return rc;
+        launch_grad_finalize(h->gpart, h->n, h->d, h->npad, p, mode, h->par, h->out, h->status, h->llh_d, h->grad_d,
+                             h->sig_d, Bs, h->st);
+        h->launches++;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(llh + b0, h->llh_d, sizeof(double) * Bs, cudaMemcpyDefault, h->st));
+        CK(cudaMemcpyAsync(grad + (size_t)b0 * p, h->grad_d, sizeof(double) * Bs * p, cudaMemcpyDefault, h->st));
+        if (sigma_hat) CK(cudaMemcpyAsync(sigma_hat + b0, h->sig_d, sizeof(double) * Bs, cudaMemcpyDefault, h->st));
+        if (status) CK(cudaMemcpyAsync(status + b0, h->status, sizeof(int) * Bs, cudaMemcpyDefault, h->st));
+    }
+    CK(cudaStreamSynchronize(h->st));
+    return 0;
+}
+
+int gpe_dbg_gemm(gpe_handle* h, const double* A, const double* B, double* C, int lda, int ldb, int ldc,
+                 long long sA, long long sB, long long sC, int M, int N, int K, double alpha, int accumulate,
+                 int kmode, int lower, int batch, int layout) {
+    if (!h) return -2;
+    CK(cudaSetDevice(h->device));
+    int rc = run_gemm(h, A, B, C, lda, ldb, ldc, sA, sB, sC, M, N, K, alpha, accumulate, kmode, lower, batch, layout);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(h->st));
+    return 0;
+}
+
+int gpe_dbg_potrf_inv(gpe_handle* h, const double* A, int n, int batch, double* Linv_out, double* logdet, int* status) {
+    if (!h || !A || n < 1 || batch < 1) return h ? h->fail_msg("bad argument") : -2;
+    CK(cudaSetDevice(h->device));
+    // temporary "training set" of the right size so the workspace exists
+    int npad = ((n + NB - 1) / NB) * NB;
+    if (h->npad != npad || h->n != n) {
+        std::vector<double> z((size_t)n * 2, 0.0);
+        int rc = gpe_set_training(h, z.data(), z.data(), z.data(), nullptr, n, 1, 1);
+        if (rc) return rc;
+    }
+    int rc;
+    if ((rc = gpe_ensure_batch_ws(h, batch))) return rc;
+    if (batch > h->Bcap) return h->fail_msg("debug batch exceeds workspace capacity");
+    const size_t nn = (size_t)npad * npad;
+    // identity-padded copy
+    std::vector<double> host((size_t)batch * nn, 0.0), src((size_t)batch * n * n);
+    CK(cudaMemcpy(src.data(), A, sizeof(double) * src.size(), cudaMemcpyDefault));
+    for (int b = 0; b < batch; b++) {
+        for (int i = 0; i < npad; i++)
+            for (int j = 0; j < npad; j++)
+                host[b * nn + (size_t)i * npad + j] = (i < n && j < n) ? src[((size_t)b * n + i) * n + j] : (i == j ? 1.0 : 0.0);
+    }
+    CK(cudaMemcpyAsync(h->A, host.data(), sizeof(double) * host.size(), cudaMemcpyHostToDevice, h->st));
+    CK(cudaMemsetAsync(h->status, 0, sizeof(int) * batch, h->st));
+    if ((rc = potrf_inv_rec(h, 0, npad, batch))) return rc;
+    CK(cudaStreamSynchronize(h->st));
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(host.data(), h->Li, sizeof(double) * host.size(), cudaMemcpyDeviceToHost));
+    std::vector<double> outv((size_t)batch * n * n), ldp((size_t)batch * h->nleaf);
+    for (int b = 0; b < batch; b++)
+        for (int i = 0; i < n; i++)
+            for (int j = 0; j < n; j++) outv[((size_t)b * n + i) * n + j] = host[b * nn + (size_t)i * npad + j];
+    if (Linv_out) CK(cudaMemcpy(Linv_out, outv.data(), sizeof(double) * outv.size(), cudaMemcpyDefault));
+    CK(cudaMemcpy(ldp.data(), h->logdet_part, sizeof(double) * ldp.size(), cudaMemcpyDeviceToHost));
+    if (logdet) {
+        std::vector<double> ldv(batch, 0.0);
+        for (int b = 0; b < batch; b++)
+            for (int l = 0; l < h->nleaf; l++) ldv[b] += ldp[(size_t)b * h->nleaf + l];
+        CK(cudaMemcpy(logdet, ldv.data(), sizeof(double) * batch, cudaMemcpyDefault));
+    }
+    if (status) CK(cudaMemcpy(status, h->status, sizeof(int) * batch, cudaMemcpyDefault));
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,54 @@
+// gp_emu_uqsa_b200 -- shared device/host helpers (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "gp_emu_uqsa_b200 kernels are written for sm_100a (B200) only"
+#endif
+
+namespace gpe {
+
+constexpr int NB = 128;        // leaf block / padding granule of every n x n matrix
+constexpr int NUM_SMS = 148;   // B200
+
+// ---- cp.async (LDGSTS) 16-byte copies, the staging path for FP64 DMMA tiles -------------
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+// ---- FP64 tensor-pipe MMA: D(8x8) += A(8x4) * B(4x8); SASS: DMMA.8x8x4 ------------------
+// lane l: a = A[l>>2][l&3], b = B[l&3][l>>2], c0,c1 = C[l>>2][2*(l&3)+{0,1}]
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Block-wide sum; result valid in thread 0. `red` must hold >= 32 doubles.
+__device__ __forceinline__ double block_sum(double v, double* red) {
+    v = warp_sum(v);
+    int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+    __syncthreads();
+    if (l == 0) red[w] = v;
+    __syncthreads();
+    double s = 0.0;
+    if (w == 0) {
+        s = (l < nw) ? red[l] : 0.0;
+        s = warp_sum(s);
+    }
+    return s;
+}
+
+}  // namespace gpe

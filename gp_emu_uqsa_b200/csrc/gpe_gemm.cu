@@ -1,0 +1,32 @@
+// Dispatch for the batched DMMA GEMM family (see gpe_gemm.cuh).
+#include "gpe_gemm.cuh"
+
+namespace gpe {
+
+template <bool A_KC, bool B_KC>
+static cudaError_t dispatch_tiles(const GemmP& p, int epi, cudaStream_t st) {
+    if (p.N == 32) {
+        if (epi != EPI_STORE) return cudaErrorInvalidValue;
+        return launch_gemm_cfg<128, 32, 4, 2, A_KC, B_KC, EPI_STORE>(p, st);
+    }
+    long long t128 = (long long)(p.M / 128) * (p.N / 128) * p.batch;
+    if (p.lower) t128 = t128 / 2 + (p.M / 128) * p.batch / 2;
+    bool big = (p.M % 128 == 0) && (p.N % 128 == 0) && (t128 >= 120);
+    if (epi == EPI_SUMSQ) {
+        // column norms are accumulated per 128-row tile: the partial buffer is sized for BM = 128
+        return launch_gemm_cfg<128, 128, 2, 4, A_KC, B_KC, EPI_SUMSQ>(p, st);
+    }
+    if (big) return launch_gemm_cfg<128, 128, 2, 4, A_KC, B_KC, EPI_STORE>(p, st);
+    return launch_gemm_cfg<64, 64, 2, 2, A_KC, B_KC, EPI_STORE>(p, st);
+}
+
+cudaError_t launch_gemm(const GemmP& p, int layout, int epi, cudaStream_t st) {
+    switch (layout) {
+        case 0: return dispatch_tiles<true, true>(p, epi, st);
+        case 1: return dispatch_tiles<true, false>(p, epi, st);
+        case 2: return dispatch_tiles<false, false>(p, epi, st);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+}  // namespace gpe

@@ -1,0 +1,239 @@
+// Batched FP64 GEMM family on the FP64 tensor pipe (DMMA.8x8x4 via mma.sync.m8n8k4.f64).
+//
+// One kernel template serves every dense contraction on the hot path -- the SYRK/TRMM
+// updates of the recursive Cholesky+inverse, LAUUM (A^-1 = L^-T L^-1), the skinny
+// triangular products for the GLS mean, and the prediction product Z = L^-1 C -- by
+//   * choosing how each operand is stored (K-contiguous or M/N-contiguous), which only
+//     changes the shared-memory indexing of the fragment loads (no transposes are made),
+//   * restricting the K range per output tile (triangular operands: zero tiles skipped),
+//   * optionally computing only tiles that touch the lower triangle of C.
+// tcgen05/UMMA has no FP64 kind, so FP64 tiles are fed Ampere-style: cp.async (LDGSTS) 16-byte
+// copies into padded shared memory (row stride == 4 mod 16 doubles => the 8-byte fragment
+// loads of a half-warp hit 16 distinct bank pairs), 4-stage pipeline, one barrier per k-tile.
+// Measured roof (tools/ub_fp64.cu on B200): 37.2 TFLOP/s, DMMA == DFMA peak.
+#pragma once
+#include "gpe_common.cuh"
+
+namespace gpe {
+
+enum KMode : int {
+    KM_FULL = 0,
+    KM_LE_J = 1,  // k <  (tj+1)*BN   (B lower-triangular, stored [n][k])
+    KM_GE_J = 2,  // k >= tj*BN       (B lower-triangular, stored [k][n])
+    KM_LE_I = 3,  // k <  (ti+1)*BM   (A lower-triangular, stored [m][k])
+    KM_GE_I = 4,  // k >= ti*BM       (A lower-triangular, stored [k][m])
+};
+
+enum Epi : int {
+    EPI_STORE = 0,  // C = alpha*acc (+ C)
+    EPI_SUMSQ = 1,  // part[b][ti][col] = sum_rows acc^2   (column norms of Z = L^-1 C)
+};
+
+struct GemmP {
+    const double* A;
+    const double* B;
+    double* C;          // EPI_SUMSQ: partial buffer [batch][tiles_m][N]
+    int lda, ldb, ldc;  // leading dimensions (elements)
+    long long sA, sB, sC;  // batch strides (elements)
+    int M, N, K;
+    double alpha;
+    int accumulate;  // 1: C += alpha*acc
+    int kmode;
+    int lower;  // 1: skip tiles strictly above the diagonal (square C)
+    int batch;
+};
+
+constexpr int GEMM_BK = 16;
+constexpr int GEMM_STAGES = 4;
+
+template <int ROWS, bool KC>
+struct TileShape {
+    static constexpr int LD = KC ? (GEMM_BK + 4) : (ROWS + 4);
+    static constexpr int ELEMS = KC ? ROWS * LD : GEMM_BK * LD;
+};
+
+// Issue the cp.async copies of one operand tile.  KC: g -> element (row0, k0), row stride ld.
+// !KC: g -> element (k0, row0), k stride ld.
+template <int ROWS, bool KC, int NT>
+__device__ __forceinline__ void load_tile(double* s, const double* __restrict__ g, int ld, int tid) {
+    constexpr int LD = TileShape<ROWS, KC>::LD;
+    if (KC) {
+        constexpr int CH = ROWS * (GEMM_BK / 2);
+#pragma unroll
+        for (int c = tid; c < CH; c += NT) {
+            int row = c >> 3, c2 = c & 7;
+            cp_async16(s + row * LD + c2 * 2, g + (size_t)row * ld + c2 * 2);
+        }
+    } else {
+        constexpr int CPR = ROWS / 2;
+        constexpr int CH = GEMM_BK * CPR;
+#pragma unroll
+        for (int c = tid; c < CH; c += NT) {
+            int kr = c / CPR, c2 = c % CPR;
+            cp_async16(s + kr * LD + c2 * 2, g + (size_t)kr * ld + c2 * 2);
+        }
+    }
+}
+
+template <int BM, int BN, int WMW, int WNW, bool A_KC, bool B_KC, int EPI>
+__global__ void __launch_bounds__(WMW* WNW * 32, 1) gemm_dmma_kernel(GemmP p) {
+    constexpr int NT = WMW * WNW * 32;
+    constexpr int WTM = BM / WMW, WTN = BN / WNW;
+    constexpr int FM = WTM / 8, FN = WTN / 8;
+    constexpr int A_EL = TileShape<BM, A_KC>::ELEMS, B_EL = TileShape<BN, B_KC>::ELEMS;
+    constexpr int A_LD = TileShape<BM, A_KC>::LD, B_LD = TileShape<BN, B_KC>::LD;
+    extern __shared__ __align__(16) double smem[];
+
+    const int tj = blockIdx.x, ti = blockIdx.y, b = blockIdx.z;
+    if (p.lower && (ti + 1) * BM <= tj * BN) return;
+    const int m0 = ti * BM, n0 = tj * BN;
+
+    int kbeg = 0, kend = p.K;
+    switch (p.kmode) {
+        case KM_LE_J: kend = min(p.K, (tj + 1) * BN); break;
+        case KM_GE_J: kbeg = min(p.K, tj * BN); break;
+        case KM_LE_I: kend = min(p.K, (ti + 1) * BM); break;
+        case KM_GE_I: kbeg = min(p.K, ti * BM); break;
+        default: break;
+    }
+    const int KT = (kend - kbeg + GEMM_BK - 1) / GEMM_BK;
+
+    const double* Ag = p.A + (size_t)b * p.sA + (A_KC ? ((size_t)m0 * p.lda + kbeg) : ((size_t)kbeg * p.lda + m0));
+    const double* Bg = p.B + (size_t)b * p.sB + (B_KC ? ((size_t)n0 * p.ldb + kbeg) : ((size_t)kbeg * p.ldb + n0));
+    const size_t a_kstep = A_KC ? (size_t)GEMM_BK : (size_t)GEMM_BK * p.lda;
+    const size_t b_kstep = B_KC ? (size_t)GEMM_BK : (size_t)GEMM_BK * p.ldb;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm0 = (warp / WNW) * WTM, wn0 = (warp % WNW) * WTN;
+    const int fr = lane >> 2, fc = lane & 3;
+
+    double acc[FM][FN][2];
+#pragma unroll
+    for (int i = 0; i < FM; i++)
+#pragma unroll
+        for (int j = 0; j < FN; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    double* As = smem;
+    double* Bs = smem + GEMM_STAGES * A_EL;
+
+#pragma unroll
+    for (int s = 0; s < GEMM_STAGES - 1; s++) {
+        if (s < KT) {
+            load_tile<BM, A_KC, NT>(As + s * A_EL, Ag + s * a_kstep, p.lda, tid);
+            load_tile<BN, B_KC, NT>(Bs + s * B_EL, Bg + s * b_kstep, p.ldb, tid);
+        }
+        cp_async_commit();
+    }
+
+    // fragment base offsets inside a stage
+    const int a_off = A_KC ? ((wm0 + fr) * A_LD + fc) : (fc * A_LD + wm0 + fr);
+    const int b_off = B_KC ? ((wn0 + fr) * B_LD + fc) : (fc * B_LD + wn0 + fr);
+    constexpr int a_fstep = A_KC ? 8 * A_LD : 8;      // next 8-row fragment
+    constexpr int b_fstep = B_KC ? 8 * B_LD : 8;
+    constexpr int a_kk = A_KC ? 4 : 4 * A_LD;         // next k4 step
+    constexpr int b_kk = B_KC ? 4 : 4 * B_LD;
+
+    for (int kt = 0; kt < KT; kt++) {
+        cp_async_wait<GEMM_STAGES - 2>();
+        __syncthreads();
+        {
+            int nk = kt + GEMM_STAGES - 1;
+            if (nk < KT) {
+                int s = nk % GEMM_STAGES;
+                load_tile<BM, A_KC, NT>(As + s * A_EL, Ag + nk * a_kstep, p.lda, tid);
+                load_tile<BN, B_KC, NT>(Bs + s * B_EL, Bg + nk * b_kstep, p.ldb, tid);
+            }
+            cp_async_commit();
+        }
+        const double* at = As + (kt % GEMM_STAGES) * A_EL + a_off;
+        const double* bt = Bs + (kt % GEMM_STAGES) * B_EL + b_off;
+#pragma unroll
+        for (int kk = 0; kk < GEMM_BK / 4; kk++) {
+            double af[FM], bf[FN];
+#pragma unroll
+            for (int i = 0; i < FM; i++) af[i] = at[kk * a_kk + i * a_fstep];
+#pragma unroll
+            for (int j = 0; j < FN; j++) bf[j] = bt[kk * b_kk + j * b_fstep];
+#pragma unroll
+            for (int i = 0; i < FM; i++)
+#pragma unroll
+                for (int j = 0; j < FN; j++) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        }
+    }
+    cp_async_wait<0>();
+
+    if (EPI == EPI_STORE) {
+        double* Cg = p.C + (size_t)b * p.sC + (size_t)(m0 + wm0 + fr) * p.ldc + n0 + wn0 + 2 * fc;
+#pragma unroll
+        for (int i = 0; i < FM; i++)
+#pragma unroll
+            for (int j = 0; j < FN; j++) {
+                double2* dst = reinterpret_cast<double2*>(Cg + (size_t)(8 * i) * p.ldc + 8 * j);
+                double2 v;
+                v.x = p.alpha * acc[i][j][0];
+                v.y = p.alpha * acc[i][j][1];
+                if (p.accumulate) {
+                    double2 o = *dst;
+                    v.x += o.x;
+                    v.y += o.y;
+                }
+                *dst = v;
+            }
+    } else {
+        // column sums of squares over this tile's BM rows -> part[b][ti][n0 + col]
+        __syncthreads();                 // all warps are done with the operand stages
+        double* red = smem;              // [WMW][BN]
+#pragma unroll
+        for (int j = 0; j < FN; j++) {
+            double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+            for (int i = 0; i < FM; i++) {
+                s0 = fma(acc[i][j][0], acc[i][j][0], s0);
+                s1 = fma(acc[i][j][1], acc[i][j][1], s1);
+            }
+#pragma unroll
+            for (int o = 4; o < 32; o <<= 1) {
+                s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+                s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+            }
+            if (fr == 0) {
+                red[(warp / WNW) * BN + wn0 + 8 * j + 2 * fc] = s0;
+                red[(warp / WNW) * BN + wn0 + 8 * j + 2 * fc + 1] = s1;
+            }
+        }
+        __syncthreads();
+        for (int c = tid; c < BN; c += NT) {
+            double s = 0.0;
+#pragma unroll
+            for (int w = 0; w < WMW; w++) s += red[w * BN + c];
+            p.C[(size_t)b * p.sC + (size_t)ti * p.ldc + n0 + c] = s;
+        }
+    }
+}
+
+template <int BM, int BN, bool A_KC, bool B_KC>
+constexpr size_t gemm_smem_bytes() {
+    return (size_t)GEMM_STAGES * (TileShape<BM, A_KC>::ELEMS + TileShape<BN, B_KC>::ELEMS) * sizeof(double);
+}
+
+template <int BM, int BN, int WMW, int WNW, bool A_KC, bool B_KC, int EPI>
+inline cudaError_t launch_gemm_cfg(const GemmP& p, cudaStream_t st) {
+    auto kern = gemm_dmma_kernel<BM, BN, WMW, WNW, A_KC, B_KC, EPI>;
+    constexpr size_t smem = gemm_smem_bytes<BM, BN, A_KC, B_KC>();
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    if (p.M % BM || p.N % BN || p.K % GEMM_BK) return cudaErrorInvalidValue;
+    dim3 grid(p.N / BN, p.M / BM, p.batch);
+    kern<<<grid, WMW * WNW * 32, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+// Layout ids: 0 = (A_KC,B_KC) "NT", 1 = (A_KC,!B_KC) "NN", 2 = (!A_KC,!B_KC) "TN".
+// Tile choice: 128x128 when that still fills the machine, else 64x64; N == 32 panels use 128x32.
+cudaError_t launch_gemm(const GemmP& p, int layout, int epi, cudaStream_t st);
+
+}  // namespace gpe

@@ -1,0 +1,59 @@
+// Internal handle layout shared by the C-ABI translation units.
+#pragma once
+#include <string>
+
+#include "gpe_b200.h"
+#include "gpe_gemm.cuh"
+#include "gpe_kernels.cuh"
+
+struct gpe_handle {
+    int device = 0, sms = 0;
+    cudaStream_t st = nullptr;
+    std::string err;
+    long long launches = 0;
+
+    // training set (device)
+    int n = 0, d = 0, q = 0, npad = 0, nleaf = 0;
+    double *X = nullptr, *y = nullptr, *H = nullptr, *r = nullptr, *HY = nullptr;
+    bool has_basis = false;
+    int basis_idx[gpe::NR] = {0}, basis_pow[gpe::NR] = {0};
+
+    // batched likelihood workspace
+    int Bcap = 0;
+    double *A = nullptr, *S = nullptr, *Li = nullptr;        // [Bcap][npad][npad]
+    double *Wy = nullptr, *Z = nullptr, *U = nullptr;        // [Bcap][npad][NR]
+    double *GP = nullptr, *logdet_part = nullptr, *winv = nullptr, *beta = nullptr, *gpart = nullptr;
+    gpe::ItemPar* par = nullptr;
+    gpe::ItemOut* out = nullptr;
+    int* status = nullptr;
+    double *theta_d = nullptr, *llh_d = nullptr, *grad_d = nullptr, *sig_d = nullptr;
+
+    // fit state for prediction (gpe_predict.cu)
+    bool fitted = false;
+    int fit_kind = 0;
+    double fit_nugget = 0, fit_sigma = 1, fit_c = 1, fit_astar = 1;
+    double *fLi = nullptr;       // [npad][npad]  L^-1 of the training matrix
+    double *fE = nullptr;        // [npad][NR]    U = [A^-1 H K^-T | A^-1 (y - H beta)]
+    double *fK = nullptr;        // [NR][NR]      Cholesky factor of Q = H^T A^-1 H (host-filled)
+    double *fbeta = nullptr;     // [NR]
+    double *fwinv = nullptr;     // [d]
+    double *fXs = nullptr;       // [d][npad] scaled training inputs, k-major
+    // prediction chunk workspace
+    long long pchunk = 0;
+    double *pC = nullptr, *pPart = nullptr, *pAux = nullptr, *pX = nullptr, *pH = nullptr, *pMean = nullptr, *pVar = nullptr;
+
+    int fail(const char* what, cudaError_t e);
+    int fail_msg(const char* what);
+    void free_batch_ws();
+    void free_training();
+    void free_fit();
+};
+
+bool gpe_is_device_ptr(const void* p);
+int gpe_ensure_batch_ws(gpe_handle* h, int B);
+int gpe_potrf_inv(gpe_handle* h, int B);
+int gpe_factor_and_reduce(gpe_handle* h, int B, int mode, int with_grad, const double* beta_override);
+int gpe_upload_single_par(gpe_handle* h, const double* delta, double nugget, int kind, int predict, double s2_for_r);
+int gpe_run_gemm(gpe_handle* h, const double* A, const double* B, double* C, int lda, int ldb, int ldc,
+                 long long sA, long long sB, long long sC, int M, int N, int K, double alpha, int acc,
+                 int kmode, int lower, int batch, int layout, int epi);

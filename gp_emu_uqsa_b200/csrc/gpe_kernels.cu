@@ -1,0 +1,635 @@
+// Non-GEMM kernels of the likelihood path.  Reference arithmetic being replaced:
+//   _emulatorkernels.py:39-71 / :112-144 (var, grad_delta_A, grad_nugget_A),
+//   _emulatoroptimise.py:305-378 / :412-493 (loglikelihood_mucm / _gp4ml).
+#include "gpe_kernels.cuh"
+#include "gpe_b200.h"
+
+namespace gpe {
+
+// =========================================================================== prep
+__global__ void prep_theta_kernel(const double* __restrict__ theta, int B, int p, int d, int mode,
+                                  double fixed_nugget, ItemPar* par, double* winv) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const double* t = theta + (size_t)b * p;
+    for (int k = 0; k < d; k++) winv[(size_t)b * d + k] = 1.0 / exp(t[k] / 2.0);
+    int idx = d;
+    double nug = fixed_nugget;
+    if (mode & GPE_MODE_NUGGET_FREE) nug = exp(t[idx++] / 2.0);
+    double sigma = 1.0, s2 = 1.0;
+    if (!(mode & GPE_MODE_MUCM)) {
+        sigma = exp(t[idx] / 2.0);
+        s2 = sigma * sigma;
+    }
+    ItemPar ip;
+    bool alt = mode & GPE_MODE_ALT_NUGGET;
+    ip.c = alt ? 1.0 : (1.0 - nug);
+    ip.offs = s2 * ip.c;
+    ip.diagv = alt ? s2 * (1.0 + nug * nug) : s2;
+    ip.radd = alt ? 1.0 : 0.0;
+    ip.s2A = s2;
+    ip.nugget = nug;
+    ip.sigma = sigma;
+    ip.pad_ = 0.0;
+    par[b] = ip;
+}
+
+void launch_prep_theta(const double* theta, int B, int p, int d, int mode, double fixed_nugget,
+                       ItemPar* par, double* winv, cudaStream_t st) {
+    prep_theta_kernel<<<(B + 127) / 128, 128, 0, st>>>(theta, B, p, d, mode, fixed_nugget, par, winv);
+}
+
+// =========================================================================== K1 covariance build
+// 64x64 tile per CTA, 256 threads, 4x4 entries per thread.  X tiles are pre-scaled by 1/delta and
+// held k-major in shared memory so the row operand is a broadcast and the column operand a
+// conflict-free double2.  Direct differences (no |x|^2+|y|^2-2xy GEMM trick: it would lose
+// cond(A) digits and break the 1e-10 parity target).
+constexpr int CT = 64;
+
+__global__ void __launch_bounds__(256) cov_build_kernel(const double* __restrict__ X, const double* __restrict__ r,
+                                                        int n, int d, int npad, const ItemPar* __restrict__ par,
+                                                        const double* __restrict__ winv, double* __restrict__ A,
+                                                        long long sA, int full) {
+    const int tj = blockIdx.x, ti = blockIdx.y, b = blockIdx.z;
+    if (!full && tj > ti) return;
+    extern __shared__ __align__(16) double sm[];
+    double* Xi = sm;                   // [d][CT]
+    double* Xj = sm + (size_t)d * CT;  // [d][CT+2]
+    const int tid = threadIdx.x;
+    const double* w = winv + (size_t)b * d;
+    for (int e = tid; e < CT * d; e += 256) {
+        int row = e / d, k = e % d;
+        int gi = ti * CT + row, gj = tj * CT + row;
+        Xi[k * CT + row] = (gi < n) ? X[(size_t)gi * d + k] * w[k] : 0.0;
+        Xj[k * (CT + 2) + row] = (gj < n) ? X[(size_t)gj * d + k] * w[k] : 0.0;
+    }
+    __syncthreads();
+    const ItemPar ip = par[b];
+    const int ty = tid >> 4, tx = tid & 15;
+    double D[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int c = 0; c < 4; c++) D[a][c] = 0.0;
+    for (int k = 0; k < d; k++) {
+        double xi[4], xj[4];
+#pragma unroll
+        for (int a = 0; a < 4; a++) xi[a] = Xi[k * CT + ty + 16 * a];
+        double2 v0 = *reinterpret_cast<const double2*>(&Xj[k * (CT + 2) + 2 * tx]);
+        double2 v1 = *reinterpret_cast<const double2*>(&Xj[k * (CT + 2) + 32 + 2 * tx]);
+        xj[0] = v0.x; xj[1] = v0.y; xj[2] = v1.x; xj[3] = v1.y;
+#pragma unroll
+        for (int a = 0; a < 4; a++)
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                double df = xi[a] - xj[c];
+                D[a][c] = fma(df, df, D[a][c]);
+            }
+    }
+    double* Ab = A + (size_t)b * sA;
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+        int gi = ti * CT + ty + 16 * a;
+        double ri = (r != nullptr && gi < n) ? r[gi] : 0.0;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            int gj0 = tj * CT + 32 * h + 2 * tx;
+            double v[2];
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                int gj = gj0 + e;
+                double val;
+                if (gi >= n || gj >= n) val = (gi == gj) ? 1.0 : 0.0;     // identity padding
+                else if (gi == gj) val = ip.diagv + ip.radd * ri;
+                else val = ip.offs * exp(-D[a][2 * h + e]);
+                v[e] = val;
+            }
+            *reinterpret_cast<double2*>(&Ab[(size_t)gi * npad + gj0]) = make_double2(v[0], v[1]);
+        }
+    }
+}
+
+void launch_cov_build(const double* X, const double* r, int n, int d, int npad, const ItemPar* par,
+                      const double* winv, double* A, long long sA, int B, int full, cudaStream_t st) {
+    dim3 grid(npad / CT, npad / CT, B);
+    size_t smem = (size_t)d * (CT + CT + 2) * sizeof(double);
+    cov_build_kernel<<<grid, 256, smem, st>>>(X, r, n, d, npad, par, winv, A, sA, full);
+}
+
+__global__ void unpad_sym_kernel(const double* __restrict__ A, int npad, int n, double* __restrict__ out, int mirror) {
+    size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (idx >= (size_t)n * n) return;
+    int i = idx / n, j = idx % n;
+    int si = i, sj = j;
+    if (mirror && j > i) { si = j; sj = i; }
+    out[idx] = A[(size_t)si * npad + sj];
+}
+
+void launch_unpad_sym(const double* A, int npad, int n, double* out, int mirror, cudaStream_t st) {
+    size_t tot = (size_t)n * n;
+    unpad_sym_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(A, npad, n, out, mirror);
+}
+
+// =========================================================================== K2 leaf
+// One CTA (1024 threads = 128 groups of 8 lanes) factors a 128x128 SPD block held in shared
+// memory and inverts its Cholesky factor.  Left-looking Cholesky: group i owns row i; at column
+// j it forms a_ij - sum_k l_ik l_jk *and* (redundantly) the pivot a_jj - sum_k l_jk^2, so a single
+// barrier per column suffices.  The inverse is a forward substitution per column (group j owns
+// column j of L^-1, stored transposed in the unused upper triangle), which needs no block barrier.
+constexpr int LS = NB + 1;
+
+__global__ void __launch_bounds__(1024, 1) leaf_potrf_trtri_kernel(const double* __restrict__ A, double* __restrict__ Linv,
+                                                                    int ld, long long sA, long long sL, int off,
+                                                                    double* __restrict__ logdet_part, int nleaf,
+                                                                    int* __restrict__ status) {
+    extern __shared__ __align__(16) double S[];  // [NB][LS] + dinv[NB]
+    double* dinv = S + NB * LS;
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const double* Ab = A + (size_t)b * sA + (size_t)off * ld + off;
+    for (int e = tid; e < NB * NB; e += 1024) {
+        int i = e >> 7, j = e & (NB - 1);
+        S[i * LS + j] = (j <= i) ? Ab[(size_t)i * ld + j] : 0.0;
+    }
+    __syncthreads();
+    const int g = tid >> 3, sub = tid & 7;
+    double logsum = 0.0;
+    int bad_at = 0;
+    for (int j = 0; j < NB; j++) {
+        double s = 0.0, pv = 0.0;
+        if (g >= j) {
+            const double* rj = S + j * LS;
+            const double* ri = S + g * LS;
+            for (int k = sub; k < j; k += 8) {
+                double ljk = rj[k];
+                s = fma(ri[k], ljk, s);
+                pv = fma(ljk, ljk, pv);
+            }
+        }
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+            s += __shfl_xor_sync(0xffffffffu, s, o);
+            pv += __shfl_xor_sync(0xffffffffu, pv, o);
+        }
+        if (g >= j) {
+            double piv = S[j * LS + j] - pv;
+            if (!(piv > 0.0)) {  // LAPACK dpotrf: ajj <= 0 or NaN -> info = j+1
+                if (bad_at == 0) bad_at = off + j + 1;
+                piv = 1.0;
+            }
+            double ljj = sqrt(piv);
+            if (g == j) {
+                if (sub == 0) {
+                    dinv[j] = 1.0 / ljj;
+                    logsum += log(ljj);
+                }
+            } else if (sub == 0) {
+                S[g * LS + j] = (S[g * LS + j] - s) / ljj;
+            }
+        }
+        __syncthreads();
+    }
+    // logsum lives in lane sub==0 of each group g (its own diagonal): block-reduce it.
+    {
+        __shared__ double red[32];
+        double v = (sub == 0) ? logsum : 0.0;
+        double tot = block_sum(v, red);
+        if (tid == 0) logdet_part[(size_t)b * nleaf + off / NB] = 2.0 * tot;
+        int bad = bad_at ? bad_at : 0x7fffffff;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) bad = min(bad, __shfl_xor_sync(0xffffffffu, bad, o));
+        if ((tid & 31) == 0 && bad != 0x7fffffff) {
+            int old = atomicCAS(&status[b], 0, bad);
+            while (old != 0 && old > bad) {
+                int prev = atomicCAS(&status[b], old, bad);
+                if (prev == old) break;
+                old = prev;
+            }
+        }
+    }
+    __syncthreads();
+    // ---- inverse: column j of X = L^-1 ; X[i][j] (i > j) stored at S[j][i]
+    {
+        const int j = g;
+        double* xcol = S + j * LS;  // entries k > j
+        const int jw = (tid >> 5) * 4;   // smallest column owned by this warp: keeps the loop warp-uniform
+        for (int i = jw + 1; i < NB; i++) {
+            const double* li = S + i * LS;
+            double s = 0.0;
+            if (i > j) {
+                for (int k = j + sub; k < i; k += 8) {   // k = j term uses the diagonal inverse
+                    double xk = (k == j) ? dinv[j] : xcol[k];
+                    s = fma(li[k], xk, s);
+                }
+            }
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (sub == 0 && i > j) xcol[i] = -s * dinv[i];
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    double* Lb = Linv + (size_t)b * sL + (size_t)off * ld + off;
+    for (int e = tid; e < NB * NB; e += 1024) {
+        int i = e >> 7, j = e & (NB - 1);
+        double v = (j < i) ? S[j * LS + i] : ((j == i) ? dinv[i] : 0.0);
+        Lb[(size_t)i * ld + j] = v;
+    }
+}
+
+void launch_leaf(const double* A, double* Linv, int ld, long long sA, long long sL, int off,
+                 double* logdet_part, int nleaf, int* status, int B, cudaStream_t st) {
+    size_t smem = (size_t)(NB * LS + NB) * sizeof(double);
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(leaf_potrf_trtri_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr = true;
+    }
+    leaf_potrf_trtri_kernel<<<B, 1024, smem, st>>>(A, Linv, ld, sA, sL, off, logdet_part, nleaf, status);
+}
+
+// =========================================================================== K3 pieces
+__global__ void build_hy_kernel(const double* __restrict__ H, const double* __restrict__ y, int n, int q, int npad,
+                                double* __restrict__ HY) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= npad * NR) return;
+    int i = idx / NR, c = idx % NR;
+    double v = 0.0;
+    if (i < n) {
+        if (c < q) v = H[(size_t)i * q + c];
+        else if (c == q) v = y[i];
+    }
+    HY[idx] = v;
+}
+
+void launch_build_hy(const double* H, const double* y, int n, int q, int npad, double* HY, cudaStream_t st) {
+    build_hy_kernel<<<(npad * NR + 255) / 256, 256, 0, st>>>(H, y, n, q, npad, HY);
+}
+
+// Gram partials: GP[b][slab][c1][c2] = sum_{i in slab} Wy[i][c1] Wy[i][c2]
+__global__ void __launch_bounds__(1024) gram_kernel(const double* __restrict__ Wy, int npad, double* __restrict__ GP) {
+    __shared__ double T[64][NR + 1];
+    const int slab = blockIdx.x, b = blockIdx.y, nslab = gridDim.x;
+    const int c1 = threadIdx.x / NR, c2 = threadIdx.x % NR;
+    const double* Wb = Wy + ((size_t)b * npad + (size_t)slab * GRAM_SLAB) * NR;
+    int rows = min(GRAM_SLAB, npad - slab * GRAM_SLAB);
+    double acc = 0.0;
+    for (int r0 = 0; r0 < rows; r0 += 64) {
+        __syncthreads();
+        for (int e = threadIdx.x; e < 64 * NR; e += 1024) {
+            int rr = e / NR, cc = e % NR;
+            T[rr][cc] = (r0 + rr < rows) ? Wb[(size_t)(r0 + rr) * NR + cc] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int rr = 0; rr < 64; rr++) acc = fma(T[rr][c1], T[rr][c2], acc);
+    }
+    GP[((size_t)b * nslab + slab) * NR * NR + threadIdx.x] = acc;
+}
+
+void launch_gram(const double* Wy, int npad, int B, double* GP, cudaStream_t st) {
+    int nslab = (npad + GRAM_SLAB - 1) / GRAM_SLAB;
+    gram_kernel<<<dim3(nslab, B), 1024, 0, st>>>(Wy, npad, GP);
+}
+
+// GLS mean + log-likelihood scalars (one CTA per batch item).
+//   Wy = L^-1 [H | y] = [w | u];  Q = w^T w = K K^T;  beta = Q^-1 w^T u;  z = u - w beta;
+//   quad = |z|^2 = y^T (A^-1 y - A^-1 H beta)      (_emulatoroptimise.py:324-325 / :438)
+//   Z = [ w K^-T | sqrt(f) z ]  so that  U = L^-T Z = [ A^-1 H K^-T | sqrt(f) (alpha - Gm beta) ].
+__global__ void __launch_bounds__(256) llh_finalize_kernel(const double* __restrict__ Wy, const double* __restrict__ GP,
+                                                           const double* __restrict__ logdet_part, int nleaf, int nslab,
+                                                           int n, int q, int npad, int mode, ItemPar* par, ItemOut* out,
+                                                           double* __restrict__ beta_out, double* __restrict__ Z,
+                                                           int* __restrict__ status, const double* __restrict__ beta_override) {
+    __shared__ double G[NR][NR + 1];
+    __shared__ double Kf[NR][NR + 1];
+    __shared__ double beta[NR], tv[NR];
+    __shared__ double red[32];
+    __shared__ double s_quad, s_sqrtf, s_logdetQ;
+    __shared__ int s_badQ;
+    const int b = blockIdx.x, tid = threadIdx.x;
+    for (int e = tid; e < NR * NR; e += 256) {
+        double s = 0.0;
+        for (int sl = 0; sl < nslab; sl++) s += GP[((size_t)b * nslab + sl) * NR * NR + e];
+        G[e / NR][e % NR] = s;
+    }
+    if (tid == 0) s_badQ = 0;
+    __syncthreads();
+    if (tid < 32) {
+        // warp-level Cholesky of Q (q <= 31): lane i owns row i
+        const int i = tid;
+        for (int j = 0; j < q; j++) {
+            double s = 0.0, pv = 0.0;
+            for (int k = 0; k < j; k++) {
+                double kjk = Kf[j][k];
+                if (i < q) s = fma(Kf[i][k], kjk, s);
+                pv = fma(kjk, kjk, pv);
+            }
+            double piv = G[j][j] - pv;
+            if (!(piv > 0.0)) {
+                if (i == 0 && s_badQ == 0) s_badQ = j + 1;
+                piv = 1.0;
+            }
+            double kjj = sqrt(piv);
+            if (i == j) Kf[j][j] = kjj;
+            else if (i > j && i < q) Kf[i][j] = (G[i][j] - s) / kjj;
+            else if (i < j) Kf[i][j] = 0.0;
+            __syncwarp();
+        }
+        if (i == 0) {
+            // K t = w^T u ; K^T beta = t
+            double ld = 0.0;
+            for (int a = 0; a < q; a++) {
+                double s = G[a][q];
+                for (int k = 0; k < a; k++) s -= Kf[a][k] * tv[k];
+                tv[a] = s / Kf[a][a];
+                ld += log(Kf[a][a]);
+            }
+            for (int a = q - 1; a >= 0; a--) {
+                double s = tv[a];
+                for (int k = a + 1; k < q; k++) s -= Kf[k][a] * beta[k];
+                beta[a] = s / Kf[a][a];
+            }
+            s_logdetQ = 2.0 * ld;
+        }
+    }
+    __syncthreads();
+    const double* Wb = Wy + (size_t)b * npad * NR;
+    double* Zb = Z + (size_t)b * npad * NR;
+    // pass 1: z_i and quad
+    double qp = 0.0;
+    for (int i = tid; i < npad; i += 256) {
+        const double* wr = Wb + (size_t)i * NR;
+        double z = wr[q];
+        for (int a = 0; a < q; a++) z = fma(-wr[a], beta[a], z);
+        qp = fma(z, z, qp);
+        Zb[(size_t)i * NR + q] = z;
+    }
+    double quad = block_sum(qp, red);
+    if (tid == 0) {
+        double logdetA = 0.0;
+        for (int l = 0; l < nleaf; l++) logdetA += logdet_part[(size_t)b * nleaf + l];
+        ItemOut o;
+        o.logdetA = logdetA;
+        o.logdetQ = s_logdetQ;
+        o.quad = quad;
+        const double nq = (double)(n - q);
+        if (mode & GPE_MODE_MUCM) {
+            double sig2 = quad / (nq - 2.0);
+            o.sig2 = sig2;
+            o.llh = 0.5 * (nq * log(sig2) + logdetA + s_logdetQ);
+            o.f = nq / (sig2 * (nq - 2.0));
+            o.s2g = sig2;
+            par[b].sigma = sqrt(sig2);
+        } else {
+            o.sig2 = par[b].s2A;
+            o.llh = 0.5 * (quad + logdetA + s_logdetQ + nq * log(2.0 * 3.14159265358979323846));
+            o.f = 1.0;
+            o.s2g = par[b].s2A;
+        }
+        o.pad_ = 0.0;
+        out[b] = o;
+        s_quad = quad;
+        s_sqrtf = sqrt(o.f);
+        for (int a = 0; a < q; a++) beta_out[(size_t)b * NR + a] = beta[a];
+        if (s_badQ && status[b] == 0) status[b] = npad + s_badQ;
+    }
+    __syncthreads();
+    if (beta_override != nullptr) {   // Posterior with a user-supplied beta (before optimalbeta has run)
+        if (tid < q) beta[tid] = beta_override[tid];
+        __syncthreads();
+        for (int i = tid; i < npad; i += 256) {
+            const double* wr = Wb + (size_t)i * NR;
+            double z = wr[q];
+            for (int a = 0; a < q; a++) z = fma(-wr[a], beta[a], z);
+            Zb[(size_t)i * NR + q] = z;
+        }
+    }
+    const double sf = s_sqrtf;
+    // pass 2: Z rows: v K^T = w_i  <=>  K v^T = w_i^T  (forward substitution), and scale z
+    for (int i = tid; i < npad; i += 256) {
+        const double* wr = Wb + (size_t)i * NR;
+        double v[NR];
+#pragma unroll
+        for (int a = 0; a < NR; a++) {
+            if (a < q) {
+                double s = wr[a];
+                for (int k = 0; k < a; k++) s = fma(-Kf[a][k], v[k], s);
+                v[a] = s / Kf[a][a];
+            } else {
+                v[a] = 0.0;
+            }
+        }
+        double* zr = Zb + (size_t)i * NR;
+        double zq = zr[q] * sf;
+#pragma unroll
+        for (int a = 0; a < NR; a++) zr[a] = (a < q) ? v[a] : ((a == q) ? zq : 0.0);
+    }
+}
+
+void launch_llh_finalize(const double* Wy, const double* GP, const double* logdet_part, int nleaf,
+                         int n, int q, int npad, int mode, ItemPar* par, ItemOut* out, double* beta,
+                         double* Z, int* status, int B, const double* beta_override, cudaStream_t st) {
+    int nslab = (npad + GRAM_SLAB - 1) / GRAM_SLAB;
+    llh_finalize_kernel<<<B, 256, 0, st>>>(Wy, GP, logdet_part, nleaf, nslab, n, q, npad, mode, par, out, beta, Z, status,
+                                           beta_override);
+}
+
+// =========================================================================== K1g fused gradient reduction
+// grad_k = 1/2 sum_ij T^k_ij W_ij,  W = A^-1 - U U^T  (_emulatoroptimise.py:345-372,
+// :450-487 collapse to this).  The d gradient matrices T^k are never formed: each 64x64 tile of
+// A^-1 is read once, E_ij = exp(-D_ij) is recomputed from X, and d+3 weighted sums are reduced.
+constexpr int GD = 16;  // dims accumulated per register pass
+
+__global__ void __launch_bounds__(256) grad_partial_kernel(const double* __restrict__ X, const double* __restrict__ r,
+                                                           int n, int d, int npad, const double* __restrict__ winv,
+                                                           const double* __restrict__ Ainv, long long sAinv,
+                                                           const double* __restrict__ U, int nu, double* __restrict__ part) {
+    const int tj = blockIdx.x, ti = blockIdx.y, b = blockIdx.z;
+    if (tj > ti) return;
+    extern __shared__ __align__(16) double sm[];
+    double* Xi = sm;                                // [d][64]
+    double* Xj = Xi + (size_t)d * CT;               // [d][66]
+    double* Ui = Xj + (size_t)d * (CT + 2);         // [nu][64]
+    double* Uj = Ui + (size_t)nu * CT;              // [nu][66]
+    double* red = Uj + (size_t)nu * (CT + 2);       // [8][d+3]
+    const int tid = threadIdx.x;
+    const double* w = winv + (size_t)b * d;
+    for (int e = tid; e < CT * d; e += 256) {
+        int row = e / d, k = e % d;
+        int gi = ti * CT + row, gj = tj * CT + row;
+        Xi[k * CT + row] = (gi < n) ? X[(size_t)gi * d + k] * w[k] : 0.0;
+        Xj[k * (CT + 2) + row] = (gj < n) ? X[(size_t)gj * d + k] * w[k] : 0.0;
+    }
+    const double* Ub = U + (size_t)b * npad * NR;
+    for (int e = tid; e < CT * nu; e += 256) {
+        int row = e / nu, c = e % nu;
+        Ui[c * CT + row] = Ub[(size_t)(ti * CT + row) * NR + c];
+        Uj[c * (CT + 2) + row] = Ub[(size_t)(tj * CT + row) * NR + c];
+    }
+    __syncthreads();
+    const int ty = tid >> 4, tx = tid & 15;
+    const double* Ab = Ainv + (size_t)b * sAinv;
+    const bool diag_tile = (ti == tj);
+    const double wgt = diag_tile ? 1.0 : 2.0;
+    double t[4][4];
+    double sE = 0.0, sD = 0.0, sDr = 0.0;
+    {
+        double D[4][4], dot[4][4];
+#pragma unroll
+        for (int a = 0; a < 4; a++)
+#pragma unroll
+            for (int c = 0; c < 4; c++) D[a][c] = dot[a][c] = 0.0;
+        for (int k = 0; k < d; k++) {
+            double xi[4], xj[4];
+#pragma unroll
+            for (int a = 0; a < 4; a++) xi[a] = Xi[k * CT + ty + 16 * a];
+            double2 v0 = *reinterpret_cast<const double2*>(&Xj[k * (CT + 2) + 2 * tx]);
+            double2 v1 = *reinterpret_cast<const double2*>(&Xj[k * (CT + 2) + 32 + 2 * tx]);
+            xj[0] = v0.x; xj[1] = v0.y; xj[2] = v1.x; xj[3] = v1.y;
+#pragma unroll
+            for (int a = 0; a < 4; a++)
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    double df = xi[a] - xj[c];
+                    D[a][c] = fma(df, df, D[a][c]);
+                }
+        }
+        for (int k = 0; k < nu; k++) {
+            double ui[4], uj[4];
+#pragma unroll
+            for (int a = 0; a < 4; a++) ui[a] = Ui[k * CT + ty + 16 * a];
+            double2 v0 = *reinterpret_cast<const double2*>(&Uj[k * (CT + 2) + 2 * tx]);
+            double2 v1 = *reinterpret_cast<const double2*>(&Uj[k * (CT + 2) + 32 + 2 * tx]);
+            uj[0] = v0.x; uj[1] = v0.y; uj[2] = v1.x; uj[3] = v1.y;
+#pragma unroll
+            for (int a = 0; a < 4; a++)
+#pragma unroll
+                for (int c = 0; c < 4; c++) dot[a][c] = fma(ui[a], uj[c], dot[a][c]);
+        }
+#pragma unroll
+        for (int a = 0; a < 4; a++) {
+            int gi = ti * CT + ty + 16 * a;
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                int gj0 = tj * CT + 32 * h + 2 * tx;
+                double2 av = *reinterpret_cast<const double2*>(&Ab[(size_t)gi * npad + gj0]);
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    int gj = gj0 + e;
+                    double wv = (e ? av.y : av.x) - dot[a][2 * h + e];
+                    double tv = 0.0;
+                    if (gi < n && gj < n) {
+                        if (gi == gj) {
+                            sD += wv;
+                            if (r != nullptr) sDr = fma(wv, r[gi], sDr);
+                        } else {
+                            tv = wgt * wv * exp(-D[a][2 * h + e]);
+                        }
+                    }
+                    t[a][2 * h + e] = tv;
+                    sE += tv;
+                }
+            }
+        }
+    }
+    const int nv = d + 3;
+    const int warp = tid >> 5, lane = tid & 31;
+    double* pout = part + ((size_t)b * gridDim.y * (gridDim.y + 1) / 2 + (size_t)ti * (ti + 1) / 2 + tj) * nv;
+    sE = warp_sum(sE); sD = warp_sum(sD); sDr = warp_sum(sDr);
+    if (lane == 0) { red[warp * nv + d] = sE; red[warp * nv + d + 1] = sD; red[warp * nv + d + 2] = sDr; }
+    for (int k0 = 0; k0 < d; k0 += GD) {
+        double acc[GD];
+#pragma unroll
+        for (int kk = 0; kk < GD; kk++) acc[kk] = 0.0;
+#pragma unroll
+        for (int kk = 0; kk < GD; kk++) {
+            int k = k0 + kk;
+            if (k < d) {
+                double xi[4], xj[4];
+#pragma unroll
+                for (int a = 0; a < 4; a++) xi[a] = Xi[k * CT + ty + 16 * a];
+                double2 v0 = *reinterpret_cast<const double2*>(&Xj[k * (CT + 2) + 2 * tx]);
+                double2 v1 = *reinterpret_cast<const double2*>(&Xj[k * (CT + 2) + 32 + 2 * tx]);
+                xj[0] = v0.x; xj[1] = v0.y; xj[2] = v1.x; xj[3] = v1.y;
+#pragma unroll
+                for (int a = 0; a < 4; a++)
+#pragma unroll
+                    for (int c = 0; c < 4; c++) {
+                        double df = xi[a] - xj[c];
+                        acc[kk] = fma(t[a][c], df * df, acc[kk]);
+                    }
+            }
+        }
+#pragma unroll
+        for (int kk = 0; kk < GD; kk++) {
+            double v = warp_sum(acc[kk]);
+            if (lane == 0 && k0 + kk < d) red[warp * nv + k0 + kk] = v;
+        }
+    }
+    __syncthreads();
+    for (int v = tid; v < nv; v += 256) {
+        double s = 0.0;
+#pragma unroll
+        for (int wv = 0; wv < 8; wv++) s += red[wv * nv + v];
+        pout[v] = s;
+    }
+}
+
+void launch_grad_partial(const double* X, const double* r, int n, int d, int npad, const double* winv,
+                         const double* Ainv, long long sAinv, const double* U, int nu, double* part,
+                         int B, cudaStream_t st) {
+    int nt = npad / CT;
+    size_t smem = ((size_t)(d + nu) * (CT + CT + 2) + 8 * (size_t)(d + 3)) * sizeof(double);
+    static size_t attr_sz = 0;
+    if (smem > 48 * 1024 && smem > attr_sz) {
+        cudaFuncSetAttribute(grad_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_sz = smem;
+    }
+    grad_partial_kernel<<<dim3(nt, nt, B), 256, smem, st>>>(X, r, n, d, npad, winv, Ainv, sAinv, U, nu, part);
+}
+
+// Sum the tile partials in a fixed order and apply the per-parameter prefactors
+// (parameter order [delta.., nugget?, sigma?], _emulatoroptimise.py:94-103).
+__global__ void __launch_bounds__(256) grad_finalize_kernel(const double* __restrict__ part, int ntile, int n, int d, int p,
+                                                            int mode, const ItemPar* __restrict__ par,
+                                                            const ItemOut* __restrict__ out, const int* __restrict__ status,
+                                                            double* __restrict__ llh, double* __restrict__ grad,
+                                                            double* __restrict__ sigma_hat) {
+    extern __shared__ double sums[];  // [d+3]
+    __shared__ double red[32];
+    const int b = blockIdx.x, tid = threadIdx.x, nv = d + 3;
+    const double* pb = part + (size_t)b * ntile * nv;
+    for (int v = 0; v < nv; v++) {
+        double s = 0.0;
+        for (int t = tid; t < ntile; t += 256) s += pb[(size_t)t * nv + v];
+        double tot = block_sum(s, red);
+        if (tid == 0) sums[v] = tot;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const ItemPar ip = par[b];
+        const ItemOut o = out[b];
+        const double sE = sums[d], sD = sums[d + 1], sDr = sums[d + 2];
+        double* g = grad + (size_t)b * p;
+        for (int k = 0; k < d; k++) g[k] = 0.5 * o.s2g * ip.c * sums[k];
+        int idx = d;
+        if (mode & GPE_MODE_NUGGET_FREE) {
+            if (mode & GPE_MODE_ALT_NUGGET) g[idx] = 0.5 * ip.nugget * ip.nugget * o.s2g * sD;
+            else g[idx] = 0.5 * (-0.5 * ip.nugget * o.s2g) * sE;
+            idx++;
+        }
+        if (!(mode & GPE_MODE_MUCM)) g[idx] = 0.5 * (ip.offs * sE + ip.diagv * sD + (ip.radd - 1.0) * sDr);
+        llh[b] = o.llh;
+        sigma_hat[b] = ip.sigma;
+        (void)status;
+    }
+}
+
+void launch_grad_finalize(const double* part, int n, int d, int npad, int p, int mode, const ItemPar* par,
+                          const ItemOut* out, const int* status, double* llh, double* grad,
+                          double* sigma_hat, int B, cudaStream_t st) {
+    grad_finalize_kernel<<<B, 256, (d + 3) * sizeof(double), st>>>(part, grad_ntiles(npad), n, d, p, mode, par, out, status,
+                                                                  llh, grad, sigma_hat);
+}
+
+}  // namespace gpe

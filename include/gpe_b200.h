@@ -1,0 +1,126 @@
+/* gpe_b200.h -- C-ABI of the B200-native dense-GP hot path of GP_emu_UQSA.
+ *
+ * The reference (MathThyMod/GP_emu_UQSA, pure Python) has no FFI: its hot path sits behind
+ * the Python object protocol of _emulatorkernels.py / _emulatoroptimise.py /
+ * _emulatorclasses.py.  Each entry point below names the reference call site(s) it replaces
+ * (file:line relative to gp_emu_uqsa/ in the reference tree); INTEGRATION.md shows the ctypes
+ * binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every data pointer may be HOST or DEVICE memory (the
+ *    library inspects it with cudaPointerGetAttributes and stages host buffers itself);
+ *  - all matrices are row-major float64; all arithmetic is IEEE float64;
+ *  - return 0 on success, negative on CUDA/argument error (text via gpe_last_error);
+ *    a numerically failed item (non positive-definite covariance, the reference's
+ *    LinAlgError -> None path, _emulatoroptimise.py:374-376, :489-491) is reported only
+ *    through status[] (index+1 of the first non-positive pivot), never as an error code;
+ *  - one handle per device per process; a handle is not thread-safe; calls are synchronous
+ *    with respect to the returned host-visible results;
+ *  - there is NO CPU fallback: every entry point fails if no sm_100 device is present.
+ */
+#ifndef GPE_B200_H
+#define GPE_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gpe_handle gpe_handle;
+
+/* mode bits for gpe_llh_grad_batch / gpe_fit_state */
+#define GPE_MODE_MUCM 1        /* beliefs.mucm == 'T'      (loglikelihood_mucm)              */
+#define GPE_MODE_ALT_NUGGET 2  /* beliefs.alt_nugget == 'T' (kernel_alt_nug)                  */
+#define GPE_MODE_NUGGET_FREE 4 /* beliefs.fix_nugget == 'F' (nugget is an optimised parameter) */
+
+int gpe_version(void);
+int gpe_create(int device, gpe_handle** out);
+int gpe_destroy(gpe_handle* h);
+const char* gpe_last_error(gpe_handle* h);
+/* number of kernels this library has launched on the handle since creation */
+long long gpe_launch_count(gpe_handle* h);
+
+/* Training set of one emulator: Data.inputs/outputs/H/r (_emulatorclasses.py:539-584).
+ * X [n,d] scaled inputs, y [n], H [n,q] (Data.make_H :558-566), r [n] or NULL (set_r :577-584). */
+int gpe_set_training(gpe_handle* h, const double* X, const double* y, const double* H,
+                     const double* r, int n, int d, int q);
+
+/* Polynomial mean basis evaluated on device for new points (Basis/make_H,
+ * _emulatorclasses.py:263-299, :558-566): column 0 is 1, column j is x[idx[j-1]]^pow[j-1].
+ * Needed only when prediction points are not accompanied by an explicit H*. */
+int gpe_set_basis(gpe_handle* h, const int* idx, const int* pow, int q);
+
+/* kernel.var / kernel_alt_nug.var + Data.make_A (_emulatorkernels.py:39-50, :112-123;
+ * _emulatorclasses.py:572-575): A_out [n,n] = K(X,X) with the nugget/r diagonal.
+ * kind 0 = kernel, 1 = kernel_alt_nug; predict as in var(); s2 divides r (alt nugget). */
+int gpe_cov_build(gpe_handle* h, const double* delta, double nugget, int kind, int predict,
+                  double s2, double* A_out);
+
+/* kernel.covar (_emulatorkernels.py:75-79, :148-152): C_out [n,m] = K(X, Xs). */
+int gpe_cross_cov(gpe_handle* h, const double* delta, double nugget, int kind,
+                  const double* Xs, int m, double* C_out);
+
+/* Optimize.loglikelihood_mucm / loglikelihood_gp4ml (_emulatoroptimise.py:305-378, :412-493)
+ * for B transformed parameter vectors at once (the multistart batch of Optimize.optimal,
+ * :227-247).  theta [B,p] with p = d (+1 nugget) (+1 sigma), ordered [delta.., nugget?, sigma?].
+ * Outputs: llh [B] (the minimised value), grad [B,p], sigma_hat [B] (mucm: analytic sigma,
+ * :324-327; gp4ml: sigma from theta), status [B]. */
+int gpe_llh_grad_batch(gpe_handle* h, const double* theta, int B, int p, int mode,
+                       double fixed_nugget, double* llh, double* grad, double* sigma_hat,
+                       int* status);
+
+/* Factor once for fixed hyper-parameters and cache the state prediction needs
+ * (Data.remake + Optimize.optimalbeta + Optimize.sigma_analytic_mucm,
+ * _emulatorclasses.py:553-555, _emulatoroptimise.py:382-408, :497-504).
+ * The matrix factored is the one training.remake() leaves: correlation matrix (s2 = 1) plus
+ * un-scaled r for the alt nugget.  beta_in NULL -> beta = optimalbeta(); else used as given.
+ * Outputs (any may be NULL): beta_out [q], sigma_mucm_out (analytic MUCM sigma), status. */
+int gpe_fit_state(gpe_handle* h, const double* delta, double nugget, double sigma, int kind,
+                  const double* beta_in, double* beta_out, double* sigma_mucm_out, int* status);
+
+/* Posterior mean and diagonal variance (Posterior.make_covar/make_mean/make_var,
+ * _emulatorclasses.py:607-631, diagonal as consumed at history_match.py:117-118,
+ * _emulatorplotting.py:51) for m explicit points Xs [m,d]; Hs [m,q] or NULL (device basis).
+ * var may be NULL (mean only). */
+int gpe_predict(gpe_handle* h, const double* Xs, const double* Hs, long long m, double* mean,
+                double* var);
+
+/* Same over a tensor grid generated on device from the flat index (no input read):
+ * point i has coordinate lo[k] + (digit_k(i) + 0.5) * (hi[k]-lo[k]) / levels[k], digit_0 the
+ * slowest.  Evaluates flat indices [start, start+count). */
+int gpe_predict_grid(gpe_handle* h, const int* levels, const double* lo, const double* hi,
+                     long long start, long long count, double* mean, double* var);
+
+/* Full posterior covariance for small m (Posterior.make_var :618-631 as used by
+ * posterior_sample, mahalanobis_distance, noise_fit): V [m,m]; r_new [m] or NULL is the
+ * new points' r (alt nugget prior diagonal). */
+int gpe_predict_fullcov(gpe_handle* h, const double* Xs, const double* Hs, int m,
+                        const double* r_new, double* mean, double* V);
+
+/* History-matching arithmetic (history_match.py:121-136, :237-250, :317-329) on per-emulator
+ * mean/variance arrays mean [n_emul,m], var [n_emul,m] (device or host):
+ * I_o = sqrt((mean_o - z_o)^2 / (var_o + var_extra_o)); Imax [m,maxno] ascending = the maxno
+ * largest over emulators; keep [m] = Imax[r,0] < cm; count_lt [maxno] = #(Imax[r,maxno-1-k] < cm);
+ * if ncell > 0, points are grouped contiguously in cells of m/ncell points and
+ * cell_min [ncell,maxno], cell_count [ncell,maxno] are produced.  Any output may be NULL. */
+int gpe_implausibility(gpe_handle* h, const double* mean, const double* var, int n_emul,
+                       long long m, const double* z, const double* var_extra, double cm,
+                       int maxno, long long ncell, double* Imax, unsigned char* keep,
+                       unsigned long long* count_lt, double* cell_min,
+                       unsigned long long* cell_count);
+
+/* Debug/test entry: one batched DMMA GEMM of the family used by the factorisation
+ * (gpe_gemm.cuh).  layout 0 NT, 1 NN, 2 TN; device pointers only. */
+int gpe_dbg_gemm(gpe_handle* h, const double* A, const double* B, double* C, int lda, int ldb,
+                 int ldc, long long sA, long long sB, long long sC, int M, int N, int K,
+                 double alpha, int accumulate, int kmode, int lower, int batch, int layout);
+
+/* Debug/test entry: Cholesky + triangular inverse of `batch` SPD matrices A [batch,n,n]
+ * (device or host): Linv_out [batch,n,n] lower-triangular L^-1, logdet [batch] = 2*sum(log L_ii),
+ * status [batch]. */
+int gpe_dbg_potrf_inv(gpe_handle* h, const double* A, int n, int batch, double* Linv_out,
+                      double* logdet, int* status);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPE_B200_H */
