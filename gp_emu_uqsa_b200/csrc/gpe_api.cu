@@ -156,7 +156,7 @@ int gpe_potrf_inv(gpe_handle* h, int B) { return potrf_inv_rec(h, 0, h->npad, B)
 
 // Everything after the covariance build for B items already described by h->par / h->winv.
 // with_grad = 0 stops after the GLS/likelihood scalars (fit_state path).
-int gpe_factor_and_reduce(gpe_handle* h, int B, int mode, int with_grad, const double* beta_override) {
+int gpe_factor_and_reduce(gpe_handle* h, int B, int mode, int with_grad, const double* beta_override, double* Kout) {
     const int np = h->npad, ld = np;
     const long long sM = (long long)np * np, sP = (long long)np * NR;
     int rc;
@@ -166,7 +166,7 @@ int gpe_factor_and_reduce(gpe_handle* h, int B, int mode, int with_grad, const d
     if ((rc = run_gemm(h, h->Li, h->HY, h->Wy, ld, NR, NR, sM, 0, sP, np, NR, np, 1.0, 0, KM_LE_I, 0, B, 1))) return rc;
     launch_gram(h->Wy, np, B, h->GP, h->st);
     launch_llh_finalize(h->Wy, h->GP, h->logdet_part, h->nleaf, h->n, h->q, np, mode, h->par, h->out, h->beta, h->Z,
-                        h->status, B, beta_override, h->st);
+                        h->status, B, beta_override, Kout, h->st);
     h->launches += 2;
     // U = Linv^T Z = [A^-1 H K^-T | sqrt(f) A^-1 (y - H beta)]
     if ((rc = run_gemm(h, h->Li, h->Z, h->U, ld, NR, NR, sM, sP, sP, np, NR, np, 1.0, 0, KM_GE_I, 0, B, 2))) return rc;
@@ -310,7 +310,7 @@ int gpe_llh_grad_batch(gpe_handle* h, const double* theta, int B, int p, int mod
         launch_prep_theta(h->theta_d, Bs, p, h->d, mode, fixed_nugget, h->par, h->winv, h->st);
         launch_cov_build(h->X, h->r, h->n, h->d, h->npad, h->par, h->winv, h->A, sM, Bs, 0, h->st);
         h->launches += 2;
-        if ((rc = gpe_factor_and_reduce(h, Bs, mode, 1, nullptr))) return rc;
+        if ((rc = gpe_factor_and_reduce(h, Bs, mode, 1, nullptr, nullptr))) return rc;
         launch_grad_finalize(h->gpart, h->n, h->d, h->npad, p, mode, h->par, h->out, h->status, h->llh_d, h->grad_d,
                              h->sig_d, Bs, h->st);
         h->launches++;

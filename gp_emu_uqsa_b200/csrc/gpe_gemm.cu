@@ -5,6 +5,10 @@ namespace gpe {
 
 template <bool A_KC, bool B_KC>
 static cudaError_t dispatch_tiles(const GemmP& p, int epi, cudaStream_t st) {
+    if (p.M == 32) {   // skinny-M panel product (prediction: [e | Gm K^-T]^T C)
+        if (epi != EPI_STORE || p.N % 128) return cudaErrorInvalidValue;
+        return launch_gemm_cfg<32, 128, 1, 8, A_KC, B_KC, EPI_STORE>(p, st);
+    }
     if (p.N == 32) {
         if (epi != EPI_STORE) return cudaErrorInvalidValue;
         return launch_gemm_cfg<128, 32, 4, 2, A_KC, B_KC, EPI_STORE>(p, st);

@@ -52,7 +52,7 @@ struct gpe_handle {
 bool gpe_is_device_ptr(const void* p);
 int gpe_ensure_batch_ws(gpe_handle* h, int B);
 int gpe_potrf_inv(gpe_handle* h, int B);
-int gpe_factor_and_reduce(gpe_handle* h, int B, int mode, int with_grad, const double* beta_override);
+int gpe_factor_and_reduce(gpe_handle* h, int B, int mode, int with_grad, const double* beta_override, double* Kout);
 int gpe_upload_single_par(gpe_handle* h, const double* delta, double nugget, int kind, int predict, double s2_for_r);
 int gpe_run_gemm(gpe_handle* h, const double* A, const double* B, double* C, int lda, int ldb, int ldc,
                  long long sA, long long sB, long long sC, int M, int N, int K, double alpha, int acc,

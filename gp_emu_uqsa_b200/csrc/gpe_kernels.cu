@@ -299,7 +299,8 @@ __global__ void __launch_bounds__(256) llh_finalize_kernel(const double* __restr
                                                            const double* __restrict__ logdet_part, int nleaf, int nslab,
                                                            int n, int q, int npad, int mode, ItemPar* par, ItemOut* out,
                                                            double* __restrict__ beta_out, double* __restrict__ Z,
-                                                           int* __restrict__ status, const double* __restrict__ beta_override) {
+                                                           int* __restrict__ status, const double* __restrict__ beta_override,
+                                                           double* __restrict__ Kout) {
     __shared__ double G[NR][NR + 1];
     __shared__ double Kf[NR][NR + 1];
     __shared__ double beta[NR], tv[NR];
@@ -391,6 +392,9 @@ __global__ void __launch_bounds__(256) llh_finalize_kernel(const double* __restr
         s_quad = quad;
         s_sqrtf = sqrt(o.f);
         for (int a = 0; a < q; a++) beta_out[(size_t)b * NR + a] = beta[a];
+        if (Kout != nullptr)
+            for (int a = 0; a < q; a++)
+                for (int k = 0; k < q; k++) Kout[((size_t)b * NR + a) * NR + k] = (k <= a) ? Kf[a][k] : 0.0;
         if (s_badQ && status[b] == 0) status[b] = npad + s_badQ;
     }
     __syncthreads();
@@ -428,10 +432,10 @@ __global__ void __launch_bounds__(256) llh_finalize_kernel(const double* __restr
 
 void launch_llh_finalize(const double* Wy, const double* GP, const double* logdet_part, int nleaf,
                          int n, int q, int npad, int mode, ItemPar* par, ItemOut* out, double* beta,
-                         double* Z, int* status, int B, const double* beta_override, cudaStream_t st) {
+                         double* Z, int* status, int B, const double* beta_override, double* Kout, cudaStream_t st) {
     int nslab = (npad + GRAM_SLAB - 1) / GRAM_SLAB;
     llh_finalize_kernel<<<B, 256, 0, st>>>(Wy, GP, logdet_part, nleaf, nslab, n, q, npad, mode, par, out, beta, Z, status,
-                                           beta_override);
+                                           beta_override, Kout);
 }
 
 // =========================================================================== K1g fused gradient reduction

@@ -50,7 +50,7 @@ void launch_gram(const double* Wy, int npad, int B, double* GP, cudaStream_t st)
 // GLS mean, log-likelihood scalars, and the panel Z = [w K^-T | sqrt(f) z].
 void launch_llh_finalize(const double* Wy, const double* GP, const double* logdet_part, int nleaf,
                          int n, int q, int npad, int mode, ItemPar* par, ItemOut* out, double* beta,
-                         double* Z, int* status, int B, const double* beta_override, cudaStream_t st);
+                         double* Z, int* status, int B, const double* beta_override, double* Kout, cudaStream_t st);
 
 // K1g: per-tile partial sums of  W_ij E_ij Delta_k^2, W_ij E_ij, W_ii, W_ii r_i.
 void launch_grad_partial(const double* X, const double* r, int n, int d, int npad, const double* winv,

@@ -1,7 +1,26 @@
-// K4/K5 prediction + implausibility (filled in below).
+// K4 posterior mean / variance over large point sets, K4f full covariance, K5 implausibility.
+// Reference arithmetic replaced: Posterior.make_covar/make_mean/make_var
+// (_emulatorclasses.py:607-631), kernel.covar (_emulatorkernels.py:75-79, :148-152),
+// history_match.py:121-136 / :237-250 / :317-329.
+//
+// Nothing of size m x m or n x m_total is ever materialised: points are processed in chunks;
+// per chunk the cross-covariance tile C [n, mc] is generated on device (optionally straight from
+// a flat grid index), Z = L^-1 C runs on the FP64 tensor pipe with the column norms |L^-1 c_j|^2
+// reduced in the GEMM epilogue, and a skinny product [A^-1 H K^-T | e]^T C gives the mean and the
+// regression-variance term.   v_j = sigma^2 (a*_jj - |L^-1 c_j|^2 + |K^-1 h_j - (Gm K^-T)^T c_j|^2).
 #include "gpe_handle.h"
 
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
 using namespace gpe;
+
+#define CK(call)                                                   \
+    do {                                                           \
+        cudaError_t e__ = (call);                                  \
+        if (e__ != cudaSuccess) return h->fail(#call, e__);        \
+    } while (0)
 
 void gpe_handle::free_fit() {
     auto fr = [](double*& p) { if (p) cudaFree(p); p = nullptr; };
@@ -11,11 +30,559 @@ void gpe_handle::free_fit() {
     fitted = false;
 }
 
-extern "C" {
-int gpe_cross_cov(gpe_handle* h, const double*, double, int, const double*, int, double*) { return h ? h->fail_msg("not implemented") : -2; }
-int gpe_fit_state(gpe_handle* h, const double*, double, double, int, const double*, double*, double*, int*) { return h ? h->fail_msg("not implemented") : -2; }
-int gpe_predict(gpe_handle* h, const double*, const double*, long long, double*, double*) { return h ? h->fail_msg("not implemented") : -2; }
-int gpe_predict_grid(gpe_handle* h, const int*, const double*, const double*, long long, long long, double*, double*) { return h ? h->fail_msg("not implemented") : -2; }
-int gpe_predict_fullcov(gpe_handle* h, const double*, const double*, int, const double*, double*, double*) { return h ? h->fail_msg("not implemented") : -2; }
-int gpe_implausibility(gpe_handle* h, const double*, const double*, int, long long, const double*, const double*, double, int, long long, double*, unsigned char*, unsigned long long*, double*, unsigned long long*) { return h ? h->fail_msg("not implemented") : -2; }
+namespace {
+
+constexpr int MAXD = 64;
+struct GridDesc {
+    int d;
+    int levels[MAXD];
+    double lo[MAXD], step[MAXD];   // coordinate = lo + (digit + 0.5) * step
+};
+struct BasisDesc {
+    int q;
+    int idx[NR], pw[NR];
+};
+
+// scaled training inputs, k-major, zero padded: Xs[k][i] = X[i][k] / delta_k
+__global__ void scale_train_kernel(const double* __restrict__ X, const double* __restrict__ winv, int n, int d, int npad,
+                                   double* __restrict__ Xs) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= d * npad) return;
+    int k = idx / npad, i = idx % npad;
+    Xs[idx] = (i < n) ? X[(size_t)i * d + k] * winv[k] : 0.0;
 }
+
+// materialise a chunk of grid points [mc, d] from the flat index (digit 0 slowest)
+__global__ void grid_points_kernel(GridDesc g, long long start, long long count, int mc, double* __restrict__ P) {
+    long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (j >= mc) return;
+    long long idx = start + (j < count ? j : 0);
+    for (int k = g.d - 1; k >= 0; k--) {
+        long long dig = idx % g.levels[k];
+        idx /= g.levels[k];
+        P[(size_t)j * g.d + k] = g.lo[k] + ((double)dig + 0.5) * g.step[k];
+    }
+}
+
+// K1x: C[k][j] = c * exp(-sum_dim ((x_k - p_j)/delta)^2) for a chunk of mc points.
+// CTA = 64 training rows x 128 points, 256 threads, each thread 8 rows x 4 points.
+__global__ void __launch_bounds__(256) xcov_kernel(const double* __restrict__ Xs /*[d][npad]*/, const double* __restrict__ P /*[mc][d]*/,
+                                                   const double* __restrict__ winv, int n, int d, int npad, int mc, long long count,
+                                                   double cscale, double* __restrict__ Cm, int ldc) {
+    extern __shared__ __align__(16) double sm[];
+    double* Xt = sm;                   // [d][64]
+    double* Pt = sm + (size_t)d * 64;  // [d][128+2]
+    const int tid = threadIdx.x;
+    const int j0 = blockIdx.x * 128, k0 = blockIdx.y * 64;
+    for (int e = tid; e < d * 64; e += 256) {
+        int k = e / 64, rr = e % 64;
+        Xt[k * 64 + rr] = Xs[(size_t)k * npad + k0 + rr];
+    }
+    for (int e = tid; e < d * 128; e += 256) {
+        int jj = e / d, k = e % d;
+        Pt[k * 130 + jj] = P[(size_t)(j0 + jj) * d + k] * winv[k];
+    }
+    __syncthreads();
+    const int ty = tid >> 5, tx = tid & 31;   // rows ty + 8a (a<8); points 2tx+{0,1}, 64+2tx+{0,1}
+    double D[8][4];
+#pragma unroll
+    for (int a = 0; a < 8; a++)
+#pragma unroll
+        for (int c = 0; c < 4; c++) D[a][c] = 0.0;
+    for (int k = 0; k < d; k++) {
+        double xr[8], pj[4];
+#pragma unroll
+        for (int a = 0; a < 8; a++) xr[a] = Xt[k * 64 + ty + 8 * a];
+        double2 v0 = *reinterpret_cast<const double2*>(&Pt[k * 130 + 2 * tx]);
+        double2 v1 = *reinterpret_cast<const double2*>(&Pt[k * 130 + 64 + 2 * tx]);
+        pj[0] = v0.x; pj[1] = v0.y; pj[2] = v1.x; pj[3] = v1.y;
+#pragma unroll
+        for (int a = 0; a < 8; a++)
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                double df = xr[a] - pj[c];
+                D[a][c] = fma(df, df, D[a][c]);
+            }
+    }
+#pragma unroll
+    for (int a = 0; a < 8; a++) {
+        int gk = k0 + ty + 8 * a;
+        bool live = gk < n;
+#pragma unroll
+        for (int hh = 0; hh < 2; hh++) {
+            int gj = j0 + 64 * hh + 2 * tx;
+            double2 v;
+            v.x = (live && gj < count) ? cscale * exp(-D[a][2 * hh]) : 0.0;
+            v.y = (live && gj + 1 < count) ? cscale * exp(-D[a][2 * hh + 1]) : 0.0;
+            *reinterpret_cast<double2*>(&Cm[(size_t)gk * ldc + gj]) = v;
+        }
+    }
+}
+
+// per point: mean, variance from the GEMM outputs
+__global__ void __launch_bounds__(128) predict_finalize_kernel(const double* __restrict__ part, int ntile, const double* __restrict__ aux,
+                                                               int ld, const double* __restrict__ P, const double* __restrict__ Hs,
+                                                               BasisDesc bd, int d, const double* __restrict__ Kf,
+                                                               const double* __restrict__ beta, double sigma2, double astar,
+                                                               long long count, double* __restrict__ mean, double* __restrict__ var) {
+    __shared__ double Ks[NR][NR + 1];
+    __shared__ double bs[NR];
+    const int q = bd.q;
+    for (int e = threadIdx.x; e < NR * NR; e += blockDim.x) Ks[e / NR][e % NR] = Kf[e];
+    if (threadIdx.x < NR) bs[threadIdx.x] = beta[threadIdx.x];
+    __syncthreads();
+    long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (j >= count) return;
+    double hv[NR];
+#pragma unroll
+    for (int a = 0; a < NR; a++) {
+        double v = 0.0;
+        if (a < q) {
+            if (Hs != nullptr) v = Hs[(size_t)j * q + a];
+            else if (a == 0) v = 1.0;
+            else {
+                double x = P[(size_t)j * d + bd.idx[a]];
+                int pw = bd.pw[a];
+                v = (pw == 1) ? x : pow(x, (double)pw);
+            }
+        }
+        hv[a] = v;
+    }
+    double mu = aux[(size_t)q * ld + j];
+#pragma unroll
+    for (int a = 0; a < NR; a++)
+        if (a < q) mu = fma(hv[a], bs[a], mu);
+    mean[j] = mu;
+    if (var == nullptr) return;
+    // g = K^-1 h - aux[0:q]
+    double gn = 0.0;
+    double kv[NR];
+#pragma unroll
+    for (int a = 0; a < NR; a++) {
+        if (a < q) {
+            double s = hv[a];
+            for (int k = 0; k < a; k++) s = fma(-Ks[a][k], kv[k], s);
+            kv[a] = s / Ks[a][a];
+            double g = kv[a] - aux[(size_t)a * ld + j];
+            gn = fma(g, g, gn);
+        } else {
+            kv[a] = 0.0;
+        }
+    }
+    double zn = 0.0;
+    for (int t = 0; t < ntile; t++) zn += part[(size_t)t * ld + j];
+    var[j] = sigma2 * (astar - zn + gn);
+}
+
+// K5: implausibility per point + reductions.  I >= 0, so the IEEE bit pattern orders like the value
+// and min-reductions can use integer atomics (deterministic).
+constexpr int MAXEM = 16;
+struct ImpDesc {
+    int n_emul, maxno;
+    double z[MAXEM], ve[MAXEM];
+    double cm;
+};
+
+__global__ void __launch_bounds__(256) implaus_kernel(const double* __restrict__ mean, const double* __restrict__ var, long long m,
+                                                      ImpDesc ds, long long cell_pts, double* __restrict__ Imax,
+                                                      unsigned char* __restrict__ keep, unsigned long long* __restrict__ count_lt,
+                                                      unsigned long long* __restrict__ cell_min_bits,
+                                                      unsigned long long* __restrict__ cell_count) {
+    long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const bool live = r < m;
+    double top[MAXEM];   // ascending, top[maxno-1] is the largest
+#pragma unroll
+    for (int k = 0; k < MAXEM; k++) top[k] = -1.0;
+    if (live) {
+        for (int o = 0; o < ds.n_emul; o++) {
+            double mu = mean[(size_t)o * m + r], v = var[(size_t)o * m + r];
+            double dz = mu - ds.z[o];
+            double I = sqrt(dz * dz / (v + ds.ve[o]));
+            // keep the maxno largest, ascending (np.sort(np.partition(I, -maxno)[-maxno:]))
+            if (I > top[0]) {
+                top[0] = I;
+#pragma unroll
+                for (int k = 0; k < MAXEM - 1; k++) {
+                    if (k + 1 < ds.maxno && top[k] > top[k + 1]) {
+                        double t = top[k];
+                        top[k] = top[k + 1];
+                        top[k + 1] = t;
+                    }
+                }
+            }
+        }
+    }
+    // outputs
+    for (int k = 0; k < ds.maxno; k++) {
+        double vk = top[k];
+        if (live && Imax != nullptr) Imax[(size_t)r * ds.maxno + k] = vk;
+    }
+    if (live && keep != nullptr) keep[r] = (top[0] < ds.cm) ? 1 : 0;
+    for (int k = 0; k < ds.maxno; k++) {
+        // k-th output statistic refers to the (k+1)-th largest: top[maxno-1-k]
+        double vk = top[ds.maxno - 1 - k];
+        bool lt = live && (vk < ds.cm);
+        unsigned bal = __ballot_sync(0xffffffffu, lt);
+        if ((threadIdx.x & 31) == 0 && bal && count_lt != nullptr) atomicAdd(&count_lt[k], (unsigned long long)__popc(bal));
+        if (cell_pts > 0 && live) {
+            long long cell = r / cell_pts;
+            if (cell_min_bits != nullptr) atomicMin(&cell_min_bits[(size_t)cell * ds.maxno + k], (unsigned long long)__double_as_longlong(vk));
+            if (lt && cell_count != nullptr) atomicAdd(&cell_count[(size_t)cell * ds.maxno + k], 1ull);
+        }
+    }
+}
+
+// full posterior covariance assembly: V = sigma^2 (A* - Z^T Z + G^T G)
+__global__ void fullcov_finalize_kernel(const double* __restrict__ ZtZ, int mp, const double* __restrict__ aux, int ld,
+                                        const double* __restrict__ P, const double* __restrict__ Hs, BasisDesc bd, int d,
+                                        const double* __restrict__ winv, const double* __restrict__ Kf, double sigma2,
+                                        double cscale, double astar, const double* __restrict__ r_new, int m,
+                                        double* __restrict__ Gbuf /*[q][mp]*/, double* __restrict__ V, int phase) {
+    const int q = bd.q;
+    if (phase == 0) {   // G[:, j] = K^-1 h_j - aux[0:q][j]
+        int j = blockIdx.x * blockDim.x + threadIdx.x;
+        if (j >= m) return;
+        double kv[NR];
+        for (int a = 0; a < q; a++) {
+            double hvv;
+            if (Hs != nullptr) hvv = Hs[(size_t)j * q + a];
+            else if (a == 0) hvv = 1.0;
+            else {
+                double x = P[(size_t)j * d + bd.idx[a]];
+                hvv = (bd.pw[a] == 1) ? x : pow(x, (double)bd.pw[a]);
+            }
+            double s = hvv;
+            for (int k = 0; k < a; k++) s = fma(-Kf[a * NR + k], kv[k], s);
+            kv[a] = s / Kf[a * NR + a];
+            Gbuf[(size_t)a * mp + j] = kv[a] - aux[(size_t)a * ld + j];
+        }
+        return;
+    }
+    size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (idx >= (size_t)m * m) return;
+    int i = idx / m, j = idx % m;
+    double D = 0.0;
+    for (int k = 0; k < d; k++) {
+        double df = P[(size_t)i * d + k] * winv[k] - P[(size_t)j * d + k] * winv[k];
+        D = fma(df, df, D);
+    }
+    double prior = (i == j) ? (astar + (r_new ? r_new[i] : 0.0)) : cscale * exp(-D);
+    double gg = 0.0;
+    for (int a = 0; a < q; a++) gg = fma(Gbuf[(size_t)a * mp + i], Gbuf[(size_t)a * mp + j], gg);
+    V[idx] = sigma2 * (prior - ZtZ[(size_t)i * mp + j] + gg);
+}
+
+int ensure_predict_ws(gpe_handle* h, long long mc) {
+    if (mc <= h->pchunk) return 0;
+    auto fr = [](double*& p) { if (p) cudaFree(p); p = nullptr; };
+    fr(h->pC); fr(h->pPart); fr(h->pAux); fr(h->pX); fr(h->pH); fr(h->pMean); fr(h->pVar);
+    h->pchunk = 0;
+    size_t ntile = h->npad / 128;
+    CK(cudaMalloc((void**)&h->pC, (size_t)h->npad * mc * sizeof(double)));
+    CK(cudaMalloc((void**)&h->pPart, ntile * mc * sizeof(double)));
+    CK(cudaMalloc((void**)&h->pAux, (size_t)NR * mc * sizeof(double)));
+    CK(cudaMalloc((void**)&h->pX, (size_t)mc * h->d * sizeof(double)));
+    CK(cudaMalloc((void**)&h->pH, (size_t)mc * NR * sizeof(double)));
+    CK(cudaMalloc((void**)&h->pMean, (size_t)mc * sizeof(double)));
+    CK(cudaMalloc((void**)&h->pVar, (size_t)mc * sizeof(double)));
+    h->pchunk = mc;
+    return 0;
+}
+
+BasisDesc basis_of(gpe_handle* h) {
+    BasisDesc bd;
+    bd.q = h->q;
+    for (int a = 0; a < NR; a++) { bd.idx[a] = h->basis_idx[a] < 0 ? 0 : h->basis_idx[a]; bd.pw[a] = h->basis_pow[a]; }
+    return bd;
+}
+
+long long default_chunk(gpe_handle* h) {
+    long long c = 16384;
+    if (const char* e = getenv("GPE_PRED_CHUNK")) c = std::max(128ll, atoll(e));
+    return (c + 127) / 128 * 128;
+}
+
+// One chunk: points already in P_dev [mc, d] (rows >= count arbitrary but finite).
+int predict_chunk(gpe_handle* h, const double* P_dev, const double* Hs_dev, long long count, int mc, double* mean_dev,
+                  double* var_dev) {
+    const int np = h->npad;
+    size_t smem = (size_t)h->d * (64 + 130) * sizeof(double);
+    xcov_kernel<<<dim3(mc / 128, np / 64), 256, smem, h->st>>>(h->fXs, P_dev, h->fwinv, h->n, h->d, np, mc, count, h->fit_c,
+                                                               h->pC, mc);
+    h->launches++;
+    int rc;
+    // aux = [A^-1 H K^-T | e]^T C     (TN, skinny M = 32)
+    if ((rc = gpe_run_gemm(h, h->fE, h->pC, h->pAux, NR, mc, mc, 0, 0, 0, NR, mc, np, 1.0, 0, KM_FULL, 0, 1, 2, EPI_STORE))) return rc;
+    int ntile = 0;
+    if (var_dev != nullptr) {
+        // column norms of Z = Linv C    (NN, Linv lower: k <= i), reduced in the epilogue
+        if ((rc = gpe_run_gemm(h, h->fLi, h->pC, h->pPart, np, mc, mc, 0, 0, 0, np, mc, np, 1.0, 0, KM_LE_I, 0, 1, 1, EPI_SUMSQ))) return rc;
+        ntile = np / 128;
+    }
+    predict_finalize_kernel<<<(unsigned)((count + 127) / 128), 128, 0, h->st>>>(
+        h->pPart, ntile, h->pAux, mc, P_dev, Hs_dev, basis_of(h), h->d, h->fK, h->fbeta, h->fit_sigma * h->fit_sigma, h->fit_astar,
+        count, mean_dev, var_dev);
+    h->launches++;
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int gpe_fit_state(gpe_handle* h, const double* delta, double nugget, double sigma, int kind, const double* beta_in,
+                  double* beta_out, double* sigma_mucm_out, int* status) {
+    if (!h || !h->n || !delta) return h ? h->fail_msg("bad argument / no training set") : -2;
+    CK(cudaSetDevice(h->device));
+    int rc;
+    if ((rc = gpe_ensure_batch_ws(h, 1))) return rc;
+    const int np = h->npad, q = h->q;
+    std::vector<double> dl(h->d), bin(NR, 0.0);
+    CK(cudaMemcpy(dl.data(), delta, sizeof(double) * h->d, cudaMemcpyDefault));
+    if ((rc = gpe_upload_single_par(h, dl.data(), nugget, kind, 1, 1.0))) return rc;
+    if (!h->fLi) {
+        CK(cudaMalloc((void**)&h->fLi, (size_t)np * np * sizeof(double)));
+        CK(cudaMalloc((void**)&h->fE, (size_t)np * NR * sizeof(double)));
+        CK(cudaMalloc((void**)&h->fK, (size_t)NR * NR * sizeof(double)));
+        CK(cudaMalloc((void**)&h->fbeta, (size_t)NR * sizeof(double)));
+        CK(cudaMalloc((void**)&h->fwinv, (size_t)h->d * sizeof(double)));
+        CK(cudaMalloc((void**)&h->fXs, (size_t)h->d * np * sizeof(double)));
+    }
+    double* bov = nullptr;
+    if (beta_in) {
+        CK(cudaMemcpy(bin.data(), beta_in, sizeof(double) * q, cudaMemcpyDefault));
+        CK(cudaMemcpyAsync(h->fbeta, bin.data(), sizeof(double) * NR, cudaMemcpyHostToDevice, h->st));
+        bov = h->fbeta;
+    }
+    launch_cov_build(h->X, h->r, h->n, h->d, np, h->par, h->winv, h->A, 0, 1, 0, h->st);
+    h->launches++;
+    CK(cudaMemsetAsync(h->fK, 0, sizeof(double) * NR * NR, h->st));
+    if ((rc = gpe_factor_and_reduce(h, 1, 0, 0, bov, h->fK))) return rc;
+    CK(cudaMemcpyAsync(h->fLi, h->Li, (size_t)np * np * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
+    CK(cudaMemcpyAsync(h->fE, h->U, (size_t)np * NR * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
+    CK(cudaMemcpyAsync(h->fwinv, h->winv, (size_t)h->d * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
+    std::vector<double> bopt(NR, 0.0);
+    ItemOut io;
+    int st = 0;
+    CK(cudaMemcpyAsync(bopt.data(), h->beta, sizeof(double) * NR, cudaMemcpyDeviceToHost, h->st));
+    CK(cudaMemcpyAsync(&io, h->out, sizeof io, cudaMemcpyDeviceToHost, h->st));
+    CK(cudaMemcpyAsync(&st, h->status, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+    if (!beta_in) CK(cudaMemcpyAsync(h->fbeta, h->beta, sizeof(double) * NR, cudaMemcpyDeviceToDevice, h->st));
+    scale_train_kernel<<<(h->d * np + 255) / 256, 256, 0, h->st>>>(h->X, h->fwinv, h->n, h->d, np, h->fXs);
+    h->launches++;
+    CK(cudaStreamSynchronize(h->st));
+    CK(cudaGetLastError());
+    h->fit_kind = kind; h->fit_nugget = nugget; h->fit_sigma = sigma;
+    h->fit_c = kind ? 1.0 : (1.0 - nugget);
+    h->fit_astar = kind ? (1.0 + nugget * nugget) : 1.0;
+    h->fitted = (st == 0);
+    if (beta_out) CK(cudaMemcpy(beta_out, bopt.data(), sizeof(double) * q, cudaMemcpyDefault));
+    double sm = std::sqrt(io.quad / ((double)(h->n - q) - 2.0));
+    if (sigma_mucm_out) CK(cudaMemcpy(sigma_mucm_out, &sm, sizeof(double), cudaMemcpyDefault));
+    if (status) CK(cudaMemcpy(status, &st, sizeof(int), cudaMemcpyDefault));
+    return 0;
+}
+
+static int predict_common(gpe_handle* h, const double* Xs, const double* Hs, const GridDesc* grid, long long start,
+                          long long m, double* mean, double* var) {
+    if (!h->fitted) return h->fail_msg("gpe_fit_state has not succeeded on this handle");
+    if (!Hs && !h->has_basis) return h->fail_msg("no H* given and no device basis set (gpe_set_basis)");
+    CK(cudaSetDevice(h->device));
+    long long chunk = std::min<long long>(default_chunk(h), (m + 127) / 128 * 128);
+    int rc;
+    if ((rc = ensure_predict_ws(h, chunk))) return rc;
+    // staging buffers are reused across chunks; every copy/kernel is ordered on h->st
+    const bool x_dev = Xs && gpe_is_device_ptr(Xs), h_dev = Hs && gpe_is_device_ptr(Hs);
+    const bool mean_dev = gpe_is_device_ptr(mean), var_dev = var && gpe_is_device_ptr(var);
+    const int d = h->d, q = h->q;
+    for (long long s = 0; s < m; s += chunk) {
+        long long cnt = std::min(chunk, m - s);
+        int mc = (int)((cnt + 127) / 128 * 128);
+        const double* P = nullptr;
+        if (grid) {
+            grid_points_kernel<<<(mc + 255) / 256, 256, 0, h->st>>>(*grid, start + s, cnt, mc, h->pX);
+            h->launches++;
+            P = h->pX;
+        } else if (x_dev && cnt == mc) {
+            P = Xs + (size_t)s * d;
+        } else {
+            if (cnt < mc) CK(cudaMemsetAsync(h->pX, 0, (size_t)mc * d * sizeof(double), h->st));
+            CK(cudaMemcpyAsync(h->pX, Xs + (size_t)s * d, (size_t)cnt * d * sizeof(double), cudaMemcpyDefault, h->st));
+            P = h->pX;
+        }
+        const double* Hc = nullptr;
+        if (Hs) {
+            if (h_dev) Hc = Hs + (size_t)s * q;
+            else {
+                CK(cudaMemcpyAsync(h->pH, Hs + (size_t)s * q, (size_t)cnt * q * sizeof(double), cudaMemcpyDefault, h->st));
+                Hc = h->pH;
+            }
+        }
+        double* mo = mean_dev ? mean + s : h->pMean;
+        double* vo = var ? (var_dev ? var + s : h->pVar) : nullptr;
+        if ((rc = predict_chunk(h, P, Hc, cnt, mc, mo, vo))) return rc;
+        if (!mean_dev) CK(cudaMemcpyAsync(mean + s, h->pMean, cnt * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+        if (var && !var_dev) CK(cudaMemcpyAsync(var + s, h->pVar, cnt * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    }
+    CK(cudaStreamSynchronize(h->st));
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int gpe_predict(gpe_handle* h, const double* Xs, const double* Hs, long long m, double* mean, double* var) {
+    if (!h || !Xs || !mean || m < 1) return h ? h->fail_msg("bad argument") : -2;
+    return predict_common(h, Xs, Hs, nullptr, 0, m, mean, var);
+}
+
+int gpe_predict_grid(gpe_handle* h, const int* levels, const double* lo, const double* hi, long long start,
+                     long long count, double* mean, double* var) {
+    if (!h || !levels || !lo || !hi || !mean || count < 1) return h ? h->fail_msg("bad argument") : -2;
+    if (h->d > MAXD) return h->fail_msg("grid prediction supports d <= 64");
+    GridDesc g;
+    g.d = h->d;
+    for (int k = 0; k < h->d; k++) {
+        g.levels[k] = levels[k];
+        g.lo[k] = lo[k];
+        g.step[k] = (hi[k] - lo[k]) / (double)levels[k];
+    }
+    return predict_common(h, nullptr, nullptr, &g, start, count, mean, var);
+}
+
+int gpe_cross_cov(gpe_handle* h, const double* delta, double nugget, int kind, const double* Xs, int m, double* C_out) {
+    if (!h || !h->n || !delta || !Xs || !C_out || m < 1) return h ? h->fail_msg("bad argument") : -2;
+    CK(cudaSetDevice(h->device));
+    const int np = h->npad, d = h->d;
+    int mc = (m + 127) / 128 * 128;
+    std::vector<double> w(d), dl(d);
+    CK(cudaMemcpy(dl.data(), delta, sizeof(double) * d, cudaMemcpyDefault));
+    for (int k = 0; k < d; k++) w[k] = 1.0 / dl[k];
+    double *wd = nullptr, *xs = nullptr, *P = nullptr, *Cm = nullptr, *Cd = nullptr;
+    CK(cudaMalloc((void**)&wd, sizeof(double) * d));
+    CK(cudaMalloc((void**)&xs, sizeof(double) * d * np));
+    CK(cudaMalloc((void**)&P, sizeof(double) * (size_t)mc * d));
+    CK(cudaMalloc((void**)&Cm, sizeof(double) * (size_t)np * mc));
+    CK(cudaMemcpyAsync(wd, w.data(), sizeof(double) * d, cudaMemcpyHostToDevice, h->st));
+    CK(cudaMemsetAsync(P, 0, sizeof(double) * (size_t)mc * d, h->st));
+    CK(cudaMemcpyAsync(P, Xs, sizeof(double) * (size_t)m * d, cudaMemcpyDefault, h->st));
+    scale_train_kernel<<<(d * np + 255) / 256, 256, 0, h->st>>>(h->X, wd, h->n, d, np, xs);
+    size_t smem = (size_t)d * (64 + 130) * sizeof(double);
+    xcov_kernel<<<dim3(mc / 128, np / 64), 256, smem, h->st>>>(xs, P, wd, h->n, d, np, mc, m, kind ? 1.0 : 1.0 - nugget, Cm, mc);
+    h->launches += 2;
+    bool dev = gpe_is_device_ptr(C_out);
+    CK(cudaMemcpy2DAsync(C_out, sizeof(double) * m, Cm, sizeof(double) * mc, sizeof(double) * m, h->n,
+                         dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    cudaFree(wd); cudaFree(xs); cudaFree(P); cudaFree(Cm); (void)Cd;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int gpe_predict_fullcov(gpe_handle* h, const double* Xs, const double* Hs, int m, const double* r_new, double* mean,
+                        double* V) {
+    if (!h || !Xs || !mean || !V || m < 1) return h ? h->fail_msg("bad argument") : -2;
+    if (!h->fitted) return h->fail_msg("gpe_fit_state has not succeeded on this handle");
+    if (!Hs && !h->has_basis) return h->fail_msg("no H* given and no device basis set (gpe_set_basis)");
+    CK(cudaSetDevice(h->device));
+    const int np = h->npad, d = h->d, q = h->q;
+    const int mp = (m + 127) / 128 * 128;
+    double *P = nullptr, *Hd = nullptr, *Cm = nullptr, *Zm = nullptr, *ZtZ = nullptr, *aux = nullptr, *G = nullptr, *rn = nullptr,
+           *md = nullptr, *Vd = nullptr;
+    CK(cudaMalloc((void**)&P, sizeof(double) * (size_t)mp * d));
+    CK(cudaMalloc((void**)&Cm, sizeof(double) * (size_t)np * mp));
+    CK(cudaMalloc((void**)&Zm, sizeof(double) * (size_t)np * mp));
+    CK(cudaMalloc((void**)&ZtZ, sizeof(double) * (size_t)mp * mp));
+    CK(cudaMalloc((void**)&aux, sizeof(double) * (size_t)NR * mp));
+    CK(cudaMalloc((void**)&G, sizeof(double) * (size_t)NR * mp));
+    CK(cudaMalloc((void**)&md, sizeof(double) * (size_t)mp));
+    CK(cudaMalloc((void**)&Vd, sizeof(double) * (size_t)m * m));
+    CK(cudaMemsetAsync(P, 0, sizeof(double) * (size_t)mp * d, h->st));
+    CK(cudaMemcpyAsync(P, Xs, sizeof(double) * (size_t)m * d, cudaMemcpyDefault, h->st));
+    if (Hs) {
+        CK(cudaMalloc((void**)&Hd, sizeof(double) * (size_t)m * q));
+        CK(cudaMemcpyAsync(Hd, Hs, sizeof(double) * (size_t)m * q, cudaMemcpyDefault, h->st));
+    }
+    if (r_new) {
+        CK(cudaMalloc((void**)&rn, sizeof(double) * m));
+        CK(cudaMemcpyAsync(rn, r_new, sizeof(double) * m, cudaMemcpyDefault, h->st));
+    }
+    size_t smem = (size_t)d * (64 + 130) * sizeof(double);
+    xcov_kernel<<<dim3(mp / 128, np / 64), 256, smem, h->st>>>(h->fXs, P, h->fwinv, h->n, d, np, mp, m, h->fit_c, Cm, mp);
+    h->launches++;
+    int rc = 0;
+    if (!rc) rc = gpe_run_gemm(h, h->fE, Cm, aux, NR, mp, mp, 0, 0, 0, NR, mp, np, 1.0, 0, KM_FULL, 0, 1, 2, EPI_STORE);
+    if (!rc) rc = gpe_run_gemm(h, h->fLi, Cm, Zm, np, mp, mp, 0, 0, 0, np, mp, np, 1.0, 0, KM_LE_I, 0, 1, 1, EPI_STORE);
+    if (!rc) rc = gpe_run_gemm(h, Zm, Zm, ZtZ, mp, mp, mp, 0, 0, 0, mp, mp, np, 1.0, 0, KM_FULL, 0, 1, 2, EPI_STORE);
+    if (!rc) {
+        BasisDesc bd = basis_of(h);
+        double s2 = h->fit_sigma * h->fit_sigma;
+        // mean via the diagonal finalize (var == nullptr)
+        predict_finalize_kernel<<<(m + 127) / 128, 128, 0, h->st>>>(nullptr, 0, aux, mp, P, Hd, bd, d, h->fK, h->fbeta, s2,
+                                                                     h->fit_astar, m, md, nullptr);
+        fullcov_finalize_kernel<<<(m + 127) / 128, 128, 0, h->st>>>(ZtZ, mp, aux, mp, P, Hd, bd, d, h->fwinv, h->fK, s2, h->fit_c,
+                                                                     h->fit_astar, rn, m, G, Vd, 0);
+        size_t tot = (size_t)m * m;
+        fullcov_finalize_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, h->st>>>(ZtZ, mp, aux, mp, P, Hd, bd, d, h->fwinv, h->fK, s2,
+                                                                                   h->fit_c, h->fit_astar, rn, m, G, Vd, 1);
+        h->launches += 3;
+        cudaMemcpyAsync(mean, md, sizeof(double) * m, cudaMemcpyDefault, h->st);
+        cudaMemcpyAsync(V, Vd, sizeof(double) * (size_t)m * m, cudaMemcpyDefault, h->st);
+    }
+    cudaStreamSynchronize(h->st);
+    cudaFree(P); cudaFree(Hd); cudaFree(Cm); cudaFree(Zm); cudaFree(ZtZ); cudaFree(aux); cudaFree(G); cudaFree(rn);
+    cudaFree(md); cudaFree(Vd);
+    if (rc) return rc;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int gpe_implausibility(gpe_handle* h, const double* mean, const double* var, int n_emul, long long m, const double* z,
+                       const double* var_extra, double cm, int maxno, long long ncell, double* Imax, unsigned char* keep,
+                       unsigned long long* count_lt, double* cell_min, unsigned long long* cell_count) {
+    if (!h || !mean || !var || !z || !var_extra || n_emul < 1 || m < 1) return h ? h->fail_msg("bad argument") : -2;
+    if (n_emul > MAXEM || maxno < 1 || maxno > n_emul) return h->fail_msg("need 1 <= maxno <= n_emul <= 16");
+    if (ncell > 0 && m % ncell) return h->fail_msg("m must be a multiple of ncell");
+    CK(cudaSetDevice(h->device));
+    ImpDesc ds;
+    ds.n_emul = n_emul; ds.maxno = maxno; ds.cm = cm;
+    std::vector<double> zz(n_emul), vv(n_emul);
+    CK(cudaMemcpy(zz.data(), z, sizeof(double) * n_emul, cudaMemcpyDefault));
+    CK(cudaMemcpy(vv.data(), var_extra, sizeof(double) * n_emul, cudaMemcpyDefault));
+    for (int o = 0; o < n_emul; o++) { ds.z[o] = zz[o]; ds.ve[o] = vv[o]; }
+    const bool in_dev = gpe_is_device_ptr(mean);
+    const double *md = mean, *vd = var;
+    double *mtmp = nullptr, *vtmp = nullptr, *Id = nullptr;
+    unsigned char* kd = nullptr;
+    unsigned long long *cnt = nullptr, *cmin = nullptr, *ccnt = nullptr;
+    if (!in_dev) {
+        CK(cudaMalloc((void**)&mtmp, sizeof(double) * (size_t)n_emul * m));
+        CK(cudaMalloc((void**)&vtmp, sizeof(double) * (size_t)n_emul * m));
+        CK(cudaMemcpyAsync(mtmp, mean, sizeof(double) * (size_t)n_emul * m, cudaMemcpyHostToDevice, h->st));
+        CK(cudaMemcpyAsync(vtmp, var, sizeof(double) * (size_t)n_emul * m, cudaMemcpyHostToDevice, h->st));
+        md = mtmp; vd = vtmp;
+    }
+    const bool I_dev = Imax && gpe_is_device_ptr(Imax), k_dev = keep && gpe_is_device_ptr(keep);
+    if (Imax) { if (I_dev) Id = Imax; else CK(cudaMalloc((void**)&Id, sizeof(double) * (size_t)m * maxno)); }
+    if (keep) { if (k_dev) kd = keep; else CK(cudaMalloc((void**)&kd, (size_t)m)); }
+    CK(cudaMalloc((void**)&cnt, sizeof(unsigned long long) * maxno));
+    CK(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long) * maxno, h->st));
+    if (ncell > 0) {
+        CK(cudaMalloc((void**)&cmin, sizeof(unsigned long long) * ncell * maxno));
+        CK(cudaMalloc((void**)&ccnt, sizeof(unsigned long long) * ncell * maxno));
+        CK(cudaMemsetAsync(cmin, 0x7f, sizeof(unsigned long long) * ncell * maxno, h->st));   // large positive double
+        CK(cudaMemsetAsync(ccnt, 0, sizeof(unsigned long long) * ncell * maxno, h->st));
+    }
+    implaus_kernel<<<(unsigned)((m + 255) / 256), 256, 0, h->st>>>(md, vd, m, ds, ncell > 0 ? m / ncell : 0, Id, kd, cnt, cmin, ccnt);
+    h->launches++;
+    if (Imax && !I_dev) CK(cudaMemcpyAsync(Imax, Id, sizeof(double) * (size_t)m * maxno, cudaMemcpyDeviceToHost, h->st));
+    if (keep && !k_dev) CK(cudaMemcpyAsync(keep, kd, (size_t)m, cudaMemcpyDeviceToHost, h->st));
+    if (count_lt) CK(cudaMemcpyAsync(count_lt, cnt, sizeof(unsigned long long) * maxno, cudaMemcpyDefault, h->st));
+    if (ncell > 0 && cell_min) CK(cudaMemcpyAsync(cell_min, cmin, sizeof(double) * ncell * maxno, cudaMemcpyDefault, h->st));
+    if (ncell > 0 && cell_count) CK(cudaMemcpyAsync(cell_count, ccnt, sizeof(unsigned long long) * ncell * maxno, cudaMemcpyDefault, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    cudaFree(mtmp); cudaFree(vtmp); if (!I_dev) cudaFree(Id); if (!k_dev) cudaFree(kd);
+    cudaFree(cnt); cudaFree(cmin); cudaFree(ccnt);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+}  // extern "C"

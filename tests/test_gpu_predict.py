@@ -1,0 +1,137 @@
+"""GPU parity: posterior mean / variance (K4, K4f), cross-covariance (K1x) and implausibility (K5)
+through the C-ABI, against the reference's golden outputs and the oracle."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+from oracle import gp_oracle as O  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def dev():
+    from gp_emu_uqsa_b200 import _lib
+    d = _lib.Device(0)
+    yield d
+    d.close()
+
+
+def _setup(dev, G, tag, kind, d):
+    X, y = G["X"], G["y"]
+    H = O.make_H_linear(X)
+    r = G[tag + "_r"] if tag + "_r" in G.files else None
+    dev.set_training(X, y, H, r)
+    dev.set_basis(list(range(d)), [1] * d)
+    delta, sigma, nugget = G[tag + "_delta"], float(G[tag + "_sigma"]), float(G[tag + "_nugget"])
+    beta, sig_mucm, st = dev.fit_state(delta, nugget, sigma, kind)
+    assert st == 0
+    return X, y, H, r, delta, sigma, nugget, beta
+
+
+@pytest.mark.parametrize("fname,d", [("post_n200_d4.npz", 4), ("post_n500_d8.npz", 8)])
+@pytest.mark.parametrize("tag,kind", [("mucm_k_fixT", 0), ("gp4ml_k_fixT", 0), ("gp4ml_alt_fixT", 1)])
+def test_posterior_vs_reference_golden(dev, golden_dir, fname, d, tag, kind):
+    """north_star tolerance: rel 1e-8 on posterior mean and variance."""
+    G = np.load(os.path.join(golden_dir, fname))
+    X, y, H, r, delta, sigma, nugget, beta = _setup(dev, G, tag, kind, d)
+    assert np.allclose(beta, G[tag + "_beta"], rtol=1e-9, atol=1e-12)     # optimalbeta
+    Xs = G["Xs"]
+    mean, var = dev.predict(Xs)                                            # device basis
+    vref = np.diag(G[tag + "_var"])
+    assert np.allclose(mean, G[tag + "_mean"], rtol=1e-8, atol=1e-10)
+    assert np.allclose(var, vref, rtol=1e-8, atol=1e-8 * np.abs(vref).max())
+    mean2, var2 = dev.predict(Xs, Hs=O.make_H_linear(Xs))                  # explicit H*
+    assert np.allclose(mean2, mean, rtol=1e-13) and np.allclose(var2, var, rtol=1e-12, atol=1e-16)
+    mean3, _ = dev.predict(Xs, want_var=False)
+    assert np.array_equal(mean3, mean)
+    # full covariance (posterior_sample / mahalanobis / noisefit consumers)
+    mu, V = dev.predict_fullcov(Xs)
+    assert np.allclose(mu, G[tag + "_mean"], rtol=1e-8, atol=1e-10)
+    assert np.allclose(V, G[tag + "_var"], rtol=1e-8, atol=1e-8 * np.abs(vref).max())
+    # cross covariance
+    Cm = dev.cross_cov(delta, nugget, kind, Xs)
+    assert np.allclose(Cm, O.cov_covar(X, Xs, delta, nugget, kind), rtol=1e-14, atol=1e-300)
+
+
+def test_mucm_sigma_and_user_beta(dev, golden_dir):
+    G = np.load(os.path.join(golden_dir, "post_n200_d4.npz"))
+    tag = "mucm_k_fixT"
+    X, y = G["X"], G["y"]
+    H = O.make_H_linear(X)
+    dev.set_training(X, y, H)
+    dev.set_basis([0, 1, 2, 3], [1, 1, 1, 1])
+    delta, nugget = G[tag + "_delta"], float(G[tag + "_nugget"])
+    A = O.make_A(X, delta, nugget, 0)
+    beta, sig, st = dev.fit_state(delta, nugget, 1.0, 0)
+    assert abs(sig - O.sigma_analytic_mucm(A, H, y)) < 1e-11 * sig
+    user_beta = np.array([0.3, -0.2, 0.1, 0.4, 1.5])
+    dev.fit_state(delta, nugget, 0.9, 0, beta=user_beta)
+    Xs = G["Xs"][:40]
+    mean, var = dev.predict(Xs)
+    mref, Vref = O.posterior(Xs, O.make_H_linear(Xs), X, y, H, A, user_beta, 0.9, delta, nugget, 0)
+    assert np.allclose(mean, mref, rtol=1e-8, atol=1e-10)
+    assert np.allclose(var, np.diag(Vref), rtol=1e-8, atol=1e-8 * np.diag(Vref).max())
+
+
+def test_grid_prediction_matches_explicit_points_and_ragged_sizes(dev, golden_dir):
+    G = np.load(os.path.join(golden_dir, "post_n200_d4.npz"))
+    _setup(dev, G, "gp4ml_k_fixT", 0, 4)
+    levels = np.array([5, 4, 3, 7])
+    lo, hi = np.zeros(4), np.array([1.0, 1.0, 0.5, 2.0])
+    total = int(np.prod(levels))
+    idx = np.arange(total)
+    digs = np.stack(np.unravel_index(idx, levels), axis=1)
+    pts = lo + (digs + 0.5) * (hi - lo) / levels
+    m_all, v_all = dev.predict(pts)
+    for start, count in [(0, total), (17, 131), (400, 20), (1, 1)]:
+        mg, vg = dev.predict_grid(levels, lo, hi, start, count)
+        assert np.allclose(mg, m_all[start:start + count], rtol=1e-12, atol=1e-13)
+        assert np.allclose(vg, v_all[start:start + count], rtol=1e-10, atol=1e-14)
+    # device-resident in/out, chunked (chunk < m) and not a multiple of 128
+    os.environ["GPE_PRED_CHUNK"] = "256"
+    try:
+        from gp_emu_uqsa_b200 import _lib
+        d2 = _lib.Device(0)
+        X, y = G["X"], G["y"]
+        d2.set_training(X, y, O.make_H_linear(X)); d2.set_basis([0, 1, 2, 3], [1] * 4)
+        d2.fit_state(G["gp4ml_k_fixT_delta"], float(G["gp4ml_k_fixT_nugget"]), float(G["gp4ml_k_fixT_sigma"]), 0)
+        P = torch.tensor(pts[:389], device="cuda")
+        mo = torch.empty(389, dtype=torch.float64, device="cuda"); vo = torch.empty_like(mo)
+        d2.predict(P, out=(mo, vo))
+        assert np.allclose(mo.cpu().numpy(), m_all[:389], rtol=1e-12, atol=1e-13)
+        assert np.allclose(vo.cpu().numpy(), v_all[:389], rtol=1e-10, atol=1e-14)
+        d2.close()
+    finally:
+        del os.environ["GPE_PRED_CHUNK"]
+
+
+def test_implausibility_vs_reference_golden(dev, golden_dir):
+    """Identical non-implausible index sets (north_star) vs history_match.nonimp_data outputs."""
+    G = np.load(os.path.join(golden_dir, "hm_n100_d3.npz"))
+    pts = G["pts_scaled"]
+    means, variances = [], []
+    for o in range(2):
+        X, y = G["Xtrain%d" % o], G["ytrain%d" % o]
+        dev.set_training(X, y, O.make_H_linear(X)); dev.set_basis([0, 1, 2], [1, 1, 1])
+        dev.fit_state(G["delta%d" % o], float(G["nugget%d" % o]), float(G["sigma%d" % o]), 0, beta=G["beta%d" % o])
+        mu, v = dev.predict(pts)
+        assert np.allclose(mu, G["means"][o], rtol=1e-8, atol=1e-10)
+        assert np.allclose(v, G["vars"][o], rtol=1e-7, atol=1e-8 * G["vars"][o].max())
+        means.append(mu); variances.append(v)
+    means, variances = np.array(means), np.array(variances)
+    for maxno in (1, 2):
+        Imax, keep, count, cmin, ccnt = dev.implausibility(means, variances, G["zs"], G["var_extra"], float(G["cm"]), maxno, ncell=4)
+        Iref, kref, cref = O.implausibility(means, variances, G["zs"], G["var_extra"], float(G["cm"]), maxno)
+        assert np.allclose(Imax, Iref, rtol=1e-14, atol=0)
+        guard = np.abs(Iref[:, 0] - float(G["cm"])) < 1e-9          # guard band for index-set flips
+        assert not guard.any()
+        assert np.array_equal(keep.astype(bool), kref)
+        assert int(keep.sum()) == int(G["count_maxno%d" % maxno])
+        assert np.allclose(pts[keep.astype(bool)], G["kept_maxno%d" % maxno], atol=1e-15)
+        assert np.array_equal(count, cref.astype(np.uint64))
+        cells = Iref.reshape(4, -1, maxno)
+        imp_ref, odp_ref = O.implausibility_cells([c for c in cells], float(G["cm"]))
+        assert np.allclose(cmin, imp_ref, rtol=1e-14)
+        assert np.allclose(ccnt / cells.shape[1], odp_ref)
