@@ -1,0 +1,394 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native GP_emu_UQSA hot path.
+
+Metric (BASELINE.json): batched llh+grad evaluations/sec at n=4096, d=16 (config 3: 256 multistart
+guesses over 8 GPUs = 32 per GPU, weak scaling), plus posterior predictions/sec on the 10^8-point
+grid of config 4 (reported under "extra").  One "step" = one batched llh+gradient evaluation of
+32 hyper-parameter vectors per GPU (theta perturbed every step so nothing is cached).
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched by torchrun)
+    python bench.py --impl reference ...                      (CPU oracle port on the host cores)
+
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "llh+grad evals/sec (n=4096,d=16) and posterior preds/sec, 1/2/4/8 B200"
+N_TRAIN, D_IN, B_PER_GPU = 4096, 16, 32
+N_PRED, D_PRED = 2000, 8
+PRED_POINTS_PER_STEP = 1 << 20
+FP64_PEAK_FALLBACK_TFLOPS = 37.19     # tools/ub_fp64.cu on this pool's B200 (profiles/r01_ub_fp64_peaks.json)
+
+
+def synth(n, d, seed=0):
+    """BASELINE.md section 3 generator."""
+    rng = np.random.default_rng(seed)
+    X = rng.random((n, d))
+    w = rng.normal(size=d)
+    y = np.sin(X @ w) + 0.1 * (X ** 2).sum(1)
+    return X, y
+
+
+def linear_H(X):
+    return np.column_stack([np.ones(X.shape[0]), X])
+
+
+def draw_thetas(B_total, d, y, seed=0):
+    """Multistart guesses exactly as Optimize.optimal draws them (_emulatoroptimise.py:206-211):
+    row per parameter, uniform in the transformed auto bounds (delta in [1e-3, range=1],
+    sigma in [1e-3, sqrt(range y)]), from the global NumPy RNG."""
+    np.random.seed(seed)
+    bounds = [[0.001, 1.0]] * d + [[0.001, float(np.sqrt(np.amax(y) - np.amin(y)))]]
+    tb = 2.0 * np.log(np.array(bounds))
+    grid = np.zeros((d + 1, B_total))
+    for R in range(d + 1):
+        grid[R, :] = tb[R, 0] + (tb[R, 1] - tb[R, 0]) * np.random.random_sample(B_total)
+    return np.ascontiguousarray(grid.T)
+
+
+def flops_llh(n, d, q, p):
+    """F_llh ~ n^3 + n^2 (3d + p + 2q + 4)."""
+    return float(n) ** 3 + float(n) ** 2 * (3 * d + p + 2 * q + 4)
+
+
+def flops_pred(n, d, q):
+    """F_pred ~ n^2 + 2n (d + q + 3)."""
+    return float(n) ** 2 + 2.0 * n * (d + q + 3)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                       "-lms", "200"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.f.name)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def fp64_peak():
+    p = os.path.join(ROOT, "profiles", "r01_ub_fp64_peaks.json")
+    try:
+        with open(p) as f:
+            j = json.load(f)
+        return max(v for k, v in j.items() if k.startswith("dmma884") and isinstance(v, float) and v < 100), "measured (tools/ub_fp64.cu, DMMA.8x8x4)"
+    except Exception:
+        return FP64_PEAK_FALLBACK_TFLOPS, "fallback"
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def cpu_llh_sample(budget_s, threads_note=True):
+    """Time the oracle's loglikelihood_gp4ml (the reference's algorithm, NumPy/SciPy/OpenBLAS, all
+    host cores) on a bounded sample of the n=4096, d=16 workload: the largest leading row-subsample
+    whose evaluation fits the budget; evals/s at n=4096 is extrapolated with the measured n^3 cost law
+    when the sample is smaller than 4096 (said in `sample`)."""
+    from oracle import gp_oracle as O
+    X, y = synth(N_TRAIN, D_IN)
+    theta = draw_thetas(4, D_IN, y)[0]
+    theta[:D_IN] = 2 * np.log(0.5)        # delta = 0.5: a PD, well-conditioned point (cost is theta-independent)
+    t_est, n_used, t_used = None, None, None
+    for ns in (512, 1024, 2048, 4096):
+        if t_est is not None and t_est * (ns / n_used) ** 3 > budget_s:
+            break
+        Xs, ys = X[:ns], y[:ns]
+        H = linear_H(Xs)
+        t0 = time.perf_counter()
+        res = O.loglikelihood_gp4ml(theta, Xs, ys, H, 0, 1e-4)
+        t_used = time.perf_counter() - t0
+        assert res is not None
+        n_used, t_est = ns, t_used
+    scale = (N_TRAIN / n_used) ** 3
+    evals_per_s = 1.0 / (t_used * scale)
+    try:
+        from threadpoolctl import threadpool_info
+        thr = max([i.get("num_threads", 1) for i in threadpool_info()] + [1])
+    except Exception:
+        thr = os.cpu_count()
+    sample = "1 loglikelihood_gp4ml eval, n=%d, d=%d, %.2f s measured" % (n_used, D_IN, t_used)
+    if n_used != N_TRAIN:
+        sample += "; scaled to n=4096 by (4096/%d)^3" % n_used
+    return {"value": evals_per_s, "unit": "evals/s", "cores": int(thr), "kind": "port", "sample": sample,
+            "host_cpus": os.cpu_count(), "numpy": np.__version__}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    K, W = args.steps, args.warmup
+    per_step = max(3.0, 150.0 / max(1, K + W))
+    vals, last = [], None
+    for it in range(K + W):
+        last = cpu_llh_sample(per_step)
+        if it >= W:
+            vals.append(last["value"])
+    v = float(np.mean(vals))
+    last["value"] = v
+    line = {"metric": METRIC, "value": v, "unit": "evals/s", "n_gpus": args.gpus, "steps": K, "warmup": W,
+            "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "impl": "reference",
+            "config": {"workload": "config3: n=4096 d=16 q=17 llh+grad (gp4ml, fixed nugget 1e-4), CPU oracle port of "
+                                   "_emulatoroptimise.py:412-493 on the host cores"},
+            "cpu_baseline": last,
+            "e2e": {"value": v, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from gp_emu_uqsa_b200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the B200 path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    K, W = args.steps, args.warmup
+    n, d, B = N_TRAIN, D_IN, B_PER_GPU
+    q, p = d + 1, d + 1
+
+    X, y = synth(n, d)
+    H = linear_H(X)
+    thetas_all = draw_thetas(B * world, d, y)                 # every rank draws the same global list
+    theta_rank = thetas_all[rank * B:(rank + 1) * B].copy()   # block partition of the guess index
+
+    dev = _lib.Device(local)
+    dev.set_training(X, y, H)
+    stream = torch.cuda.ExternalStream(dev.stream_ptr, device=torch.device("cuda", local))
+
+    th_d = torch.tensor(theta_rank, device="cuda")
+    llh_d = torch.empty(B, dtype=torch.float64, device="cuda")
+    grad_d = torch.empty(B, p, dtype=torch.float64, device="cuda")
+    sig_d = torch.empty(B, dtype=torch.float64, device="cuda")
+    st_d = torch.zeros(B, dtype=torch.int32, device="cuda")
+    gather = [torch.empty(B, p + 2, dtype=torch.float64, device="cuda") for _ in range(world)] if world > 1 else None
+
+    def step_device(it):
+        th = th_d + 1e-3 * it
+        torch.cuda.current_stream().synchronize()
+        dev.llh_grad_batch(th, 0, fixed_nugget=1e-4, out=(llh_d, grad_d, sig_d, st_d))
+        if world > 1:      # the path's only exchange: gather (llh, theta, status) for the global argmin
+            pack = torch.cat([llh_d[:, None], th, st_d.double()[:, None]], dim=1)
+            dist.all_gather(gather, pack)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for it in range(W):
+        step_device(it)
+    barrier()
+    assert int(st_d.abs().sum().item()) == 0, "non-PD item in the benchmark batch"
+    dev.profile_enable(True)
+    dev.profile_read(reset=True)
+    clocks = ClockSampler(local)
+    clocks.start()
+    l0 = dev.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for it in range(K):
+        step_device(W + it)
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = dev.launches - l0
+    prof = dev.profile_read(reset=True)
+    dev.profile_enable(False)
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = B * world * K / (ms_max * 1e-3)
+
+    # ---- e2e: the same step through the public call with HOST buffers (pinned), copies inside
+    th_h = torch.empty(B, p, dtype=torch.float64).pin_memory()
+    llh_h = torch.empty(B, dtype=torch.float64).pin_memory()
+    grad_h = torch.empty(B, p, dtype=torch.float64).pin_memory()
+    sig_h = torch.empty(B, dtype=torch.float64).pin_memory()
+    st_h = torch.zeros(B, dtype=torch.int32).pin_memory()
+    th_np, llh_np, grad_np, sig_np, st_np = (a.numpy() for a in (th_h, llh_h, grad_h, sig_h, st_h))
+    Ke = max(2, min(K, 5))
+    barrier()
+    t0 = time.perf_counter()
+    for it in range(Ke):
+        th_np[:] = theta_rank + 1e-3 * (W + K + it)
+        dev.llh_grad_batch(th_np, 0, fixed_nugget=1e-4, out=(llh_np, grad_np, sig_np, st_np))
+        best = float(llh_np.min())          # device->host read of the step's result
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_val = B * world * Ke / float(te.item())
+    clk = clocks.stop()
+
+    # ---- posterior predictions/sec (config 4 slice), device-resident outputs, and its e2e
+    extra = {}
+    try:
+        Xp, yp = synth(N_PRED, D_PRED)
+        devp = _lib.Device(local)
+        devp.set_training(Xp, yp, linear_H(Xp))
+        devp.set_basis(list(range(D_PRED)), [1] * D_PRED)
+        devp.fit_state(np.full(D_PRED, 0.5), 1e-4, 1.0, 0)
+        levels = np.full(D_PRED, 10, dtype=np.int32)
+        lo, hi = np.zeros(D_PRED), np.ones(D_PRED)
+        total = 10 ** 8
+        shard = total // world
+        m = PRED_POINTS_PER_STEP
+        mean_d = torch.empty(m, dtype=torch.float64, device="cuda")
+        var_d = torch.empty(m, dtype=torch.float64, device="cuda")
+        pstream = torch.cuda.ExternalStream(devp.stream_ptr, device=torch.device("cuda", local))
+        Kp = max(2, min(K, 4))
+        for it in range(2):
+            devp.predict_grid(levels, lo, hi, rank * shard + it * m, m, out=(mean_d, var_d))
+        devp.profile_enable(True); devp.profile_read(reset=True)
+        barrier()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record(pstream)
+        for it in range(Kp):
+            devp.predict_grid(levels, lo, hi, rank * shard + (2 + it) * m, m, out=(mean_d, var_d))
+        p1.record(pstream)
+        barrier()
+        pms = torch.tensor([p0.elapsed_time(p1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(pms, op=dist.ReduceOp.MAX)
+        pprof = devp.profile_read(reset=True)
+        devp.profile_enable(False)
+        preds = m * world * Kp / (float(pms.item()) * 1e-3)
+        mean_h = np.empty(m); var_h = np.empty(m)
+        barrier()
+        t0 = time.perf_counter()
+        devp.predict_grid(levels, lo, hi, rank * shard, m, out=(mean_h, var_h))
+        pe = time.perf_counter() - t0
+        peak, peak_src = fp64_peak()
+        fpp = flops_pred(N_PRED, D_PRED, D_PRED + 1)
+        gms, gcnt = pprof["gemm_dmma_128"]
+        extra = {"posterior_preds_per_s": preds, "posterior_workload": "config4 slice: n=2000 d=8 q=9, 10^8-point tensor grid "
+                 "generated on device, %d points/step x %d steps per GPU, mean+diag var" % (m, Kp),
+                 "posterior_e2e_preds_per_s": m / pe, "posterior_d2h_bytes_per_pred": 16,
+                 "posterior_roofline": {"bound": "tensor", "achieved": preds / world * fpp * 1e-12, "peak": peak,
+                                        "unit": "TFLOP/s", "frac": preds / world * fpp * 1e-12 / peak,
+                                        "kernel_achieved": (m * Kp * float(2048) ** 2 * 1e-12) / (gms * 1e-3) if gms else None,
+                                        "note": "achieved = F_pred (n^2 + 2n(d+q+3)) x preds/s per GPU; kernel_achieved = padded "
+                                                "n^2 flops of the DMMA TRMM / its CUDA-event time"}}
+        devp.close()
+    except Exception as ex:      # the headline metric must still print
+        extra = {"posterior_error": repr(ex)}
+
+    if rank == 0:
+        peak, peak_src = fp64_peak()
+        F = flops_llh(n, d, q, p)
+        gemm_ms, gemm_cnt = prof["gemm_dmma_128"]
+        # dominant kernel: the 128x128-tile DMMA GEMM (Cholesky/TRTRI/LAUUM updates): algorithmic n^3 flops per eval
+        gemm_flops_per_step = B * float(n) ** 3
+        kern_ach = gemm_flops_per_step * K / (gemm_ms * 1e-3) * 1e-12 if gemm_ms else None
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        if os.path.exists(tp):
+            with open(tp) as f:
+                traffic = json.load(f).get("lauum_dram_bytes_per_launch")
+        line = {
+            "metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "config3: n=4096 d=16 q=17 p=17, gp4ml llh+grad, fixed nugget 1e-4, %d guesses/GPU per step "
+                                   "(256 over 8 GPUs), theta perturbed each step" % B,
+                       "l2": "working set 12.9 GB per step >> 126 MB L2 (inputs larger than L2, no flush needed)",
+                       "parallelism": "multistart guesses block-partitioned over ranks; one NCCL all_gather of (llh,theta,status) per step"},
+            "gpu_launches": int(launches),
+            "clocks": {"sm_mhz": clk["sm_mhz"], "sm_max_mhz": clk["sm_max_mhz"], "reasons": clk["reasons"], "samples": clk["samples"]},
+            "e2e": {"value": e2e_val, "unit": "evals/s", "h2d_bytes_per_step": int(B * p * 8),
+                    "d2h_bytes_per_step": int(B * (p + 2) * 8 + B * 4), "steps": Ke},
+            "roofline": {"bound": "tensor", "achieved": kern_ach, "peak": peak, "unit": "TFLOP/s",
+                         "frac": (kern_ach / peak) if kern_ach else None, "traffic": traffic,
+                         "kernel": "gemm_dmma_kernel<128,128,...> (all SYRK/TRMM/LAUUM launches of the step)",
+                         "peak_source": peak_src + "; MEASURED_PEAKS.json holds no FP64 figure",
+                         "algorithmic_flops_per_step": gemm_flops_per_step,
+                         "kernel_ms_per_step": gemm_ms / K if gemm_ms else None, "kernel_launches_per_step": gemm_cnt / K if K else None,
+                         "step_achieved": B * F / (ms_max / K * 1e-3) * 1e-12, "step_frac": B * F / (ms_max / K * 1e-3) * 1e-12 / peak,
+                         "by_kernel_ms_per_step": {k: v[0] / K for k, v in prof.items()}},
+            "extra": extra,
+        }
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = cpu_llh_sample(args.cpu_budget)
+        print(json.dumps(line))
+    dev.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--cpu-budget", type=float, default=25.0, help="seconds of CPU work for cpu_baseline")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

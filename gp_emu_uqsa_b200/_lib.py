@@ -38,6 +38,9 @@ def load():
         "gpe_destroy": (i, [p]),
         "gpe_last_error": (C.c_char_p, [p]),
         "gpe_launch_count": (ll, [p]),
+        "gpe_get_stream": (p, [p]),
+        "gpe_profile_enable": (i, [p, i]),
+        "gpe_profile_read": (i, [p, p, p, i]),
         "gpe_set_training": (i, [p, p, p, p, p, i, i, i]),
         "gpe_set_basis": (i, [p, p, p, i]),
         "gpe_cov_build": (i, [p, p, d, i, i, d, p]),
@@ -59,6 +62,7 @@ def load():
 
 
 EXPORTS = ["gpe_version", "gpe_create", "gpe_destroy", "gpe_last_error", "gpe_launch_count",
+           "gpe_get_stream", "gpe_profile_enable", "gpe_profile_read",
            "gpe_set_training", "gpe_set_basis", "gpe_cov_build", "gpe_cross_cov", "gpe_llh_grad_batch",
            "gpe_fit_state", "gpe_predict", "gpe_predict_grid", "gpe_predict_fullcov", "gpe_implausibility",
            "gpe_dbg_gemm", "gpe_dbg_potrf_inv"]
@@ -109,6 +113,22 @@ class Device:
     @property
     def launches(self):
         return int(self.L.gpe_launch_count(self.h))
+
+    @property
+    def stream_ptr(self):
+        """cudaStream_t of the handle (wrap with torch.cuda.ExternalStream to record events)."""
+        return int(self.L.gpe_get_stream(self.h) or 0)
+
+    PROFILE_CATEGORIES = ("gemm_dmma_128", "gemm_dmma_small", "potrf_leaf", "cov_build", "grad_reduce", "other")
+
+    def profile_enable(self, on=True):
+        self._ck(self.L.gpe_profile_enable(self.h, int(bool(on))))
+
+    def profile_read(self, reset=True):
+        ms = np.zeros(6)
+        cnt = np.zeros(6, dtype=np.int64)
+        self._ck(self.L.gpe_profile_read(self.h, _ptr(ms), _ptr(cnt), int(bool(reset))))
+        return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(self.PROFILE_CATEGORIES)}
 
     # ------------------------------------------------------------------ training set
     def set_training(self, X, y, H, r=None):

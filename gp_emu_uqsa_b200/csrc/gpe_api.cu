@@ -22,6 +22,23 @@ int gpe_handle::fail_msg(const char* what) {
     return -2;
 }
 
+cudaEvent_t gpe_handle::prof_begin(int cat) {
+    if (!prof_on) return nullptr;
+    cudaEvent_t e;
+    if (!prof_pool.empty()) { e = prof_pool.back(); prof_pool.pop_back(); }
+    else cudaEventCreate(&e);
+    cudaEventRecord(e, st);
+    (void)cat;
+    return e;
+}
+void gpe_handle::prof_end(int cat, cudaEvent_t e0) {
+    if (!prof_on || !e0) return;
+    cudaEvent_t e1;
+    if (!prof_pool.empty()) { e1 = prof_pool.back(); prof_pool.pop_back(); }
+    else cudaEventCreate(&e1);
+    cudaEventRecord(e1, st);
+    prof_recs.push_back({cat, e0, e1});
+}
 #define CK(call)                                                   \
     do {                                                           \
         cudaError_t e__ = (call);                                  \
@@ -108,7 +125,12 @@ static int run_gemm(gpe_handle* h, const double* A, const double* B, double* C, 
     GemmP p;
     p.A = A; p.B = B; p.C = C; p.lda = lda; p.ldb = ldb; p.ldc = ldc; p.sA = sA; p.sB = sB; p.sC = sC;
     p.M = M; p.N = N; p.K = K; p.alpha = alpha; p.accumulate = acc; p.kmode = kmode; p.lower = lower; p.batch = batch;
-    cudaError_t e = launch_gemm(p, layout, epi, h->st);
+    bool big = (M % 128 == 0) && (N % 128 == 0) && N != 32 && M != 32;
+    cudaError_t e;
+    {
+        ProfScope ps(h, big ? gpe_handle::CAT_GEMM_BIG : gpe_handle::CAT_GEMM_SMALL);
+        e = launch_gemm(p, layout, epi, h->st);
+    }
     h->launches++;
     if (e != cudaSuccess) return h->fail("launch_gemm", e);
     return 0;
@@ -127,7 +149,10 @@ static int potrf_inv_rec(gpe_handle* h, int off, int m, int B) {
     const int ld = h->npad;
     const long long sM = (long long)h->npad * h->npad;
     if (m == NB) {
-        launch_leaf(h->A, h->Li, ld, sM, sM, off, h->logdet_part, h->nleaf, h->status, B, h->st);
+        {
+            ProfScope ps(h, gpe_handle::CAT_LEAF);
+            launch_leaf(h->A, h->Li, ld, sM, sM, off, h->logdet_part, h->nleaf, h->status, B, h->st);
+        }
         h->launches++;
         return 0;
     }
@@ -164,16 +189,22 @@ int gpe_factor_and_reduce(gpe_handle* h, int B, int mode, int with_grad, const d
     if ((rc = potrf_inv_rec(h, 0, np, B))) return rc;
     // Wy = Linv [H | y]
     if ((rc = run_gemm(h, h->Li, h->HY, h->Wy, ld, NR, NR, sM, 0, sP, np, NR, np, 1.0, 0, KM_LE_I, 0, B, 1))) return rc;
-    launch_gram(h->Wy, np, B, h->GP, h->st);
-    launch_llh_finalize(h->Wy, h->GP, h->logdet_part, h->nleaf, h->n, h->q, np, mode, h->par, h->out, h->beta, h->Z,
-                        h->status, B, beta_override, Kout, h->st);
+    {
+        ProfScope ps(h, gpe_handle::CAT_OTHER);
+        launch_gram(h->Wy, np, B, h->GP, h->st);
+        launch_llh_finalize(h->Wy, h->GP, h->logdet_part, h->nleaf, h->n, h->q, np, mode, h->par, h->out, h->beta, h->Z,
+                            h->status, B, beta_override, Kout, h->st);
+    }
     h->launches += 2;
     // U = Linv^T Z = [A^-1 H K^-T | sqrt(f) A^-1 (y - H beta)]
     if ((rc = run_gemm(h, h->Li, h->Z, h->U, ld, NR, NR, sM, sP, sP, np, NR, np, 1.0, 0, KM_GE_I, 0, B, 2))) return rc;
     if (!with_grad) return 0;
     // LAUUM: A^-1 = Linv^T Linv (lower tiles) into the dead A buffer
     if ((rc = run_gemm(h, h->Li, h->Li, h->A, ld, ld, ld, sM, sM, sM, np, np, np, 1.0, 0, KM_GE_I, 1, B, 2))) return rc;
-    launch_grad_partial(h->X, h->r, h->n, h->d, np, h->winv, h->A, sM, h->U, h->q + 1, h->gpart, B, h->st);
+    {
+        ProfScope ps(h, gpe_handle::CAT_GRAD);
+        launch_grad_partial(h->X, h->r, h->n, h->d, np, h->winv, h->A, sM, h->U, h->q + 1, h->gpart, B, h->st);
+    }
     h->launches++;
     return 0;
 }
@@ -228,6 +259,34 @@ int gpe_destroy(gpe_handle* h) {
     h->free_training();
     cudaStreamDestroy(h->st);
     delete h;
+    return 0;
+}
+
+void* gpe_get_stream(gpe_handle* h) { return h ? (void*)h->st : nullptr; }
+
+int gpe_profile_enable(gpe_handle* h, int on) {
+    if (!h) return -2;
+    h->prof_on = on != 0;
+    return 0;
+}
+
+// Drain the recorded event pairs: ms[c] / count[c] per category since the last reset
+// (0 big DMMA GEMM tiles, 1 small/skinny GEMM, 2 leaf, 3 covariance build, 4 gradient reduction, 5 other).
+int gpe_profile_read(gpe_handle* h, double* ms, long long* count, int reset) {
+    if (!h) return -2;
+    cudaStreamSynchronize(h->st);
+    for (auto& r : h->prof_recs) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, r.e0, r.e1) == cudaSuccess) { h->prof_ms[r.cat] += t; h->prof_cnt[r.cat]++; }
+        h->prof_pool.push_back(r.e0);
+        h->prof_pool.push_back(r.e1);
+    }
+    h->prof_recs.clear();
+    for (int c = 0; c < gpe_handle::NCAT; c++) {
+        if (ms) ms[c] = h->prof_ms[c];
+        if (count) count[c] = h->prof_cnt[c];
+        if (reset) { h->prof_ms[c] = 0; h->prof_cnt[c] = 0; }
+    }
     return 0;
 }
 
@@ -308,11 +367,17 @@ int gpe_llh_grad_batch(gpe_handle* h, const double* theta, int B, int p, int mod
         int Bs = std::min(h->Bcap, B - b0);
         CK(cudaMemcpyAsync(h->theta_d, theta + (size_t)b0 * p, sizeof(double) * Bs * p, cudaMemcpyDefault, h->st));
         launch_prep_theta(h->theta_d, Bs, p, h->d, mode, fixed_nugget, h->par, h->winv, h->st);
-        launch_cov_build(h->X, h->r, h->n, h->d, h->npad, h->par, h->winv, h->A, sM, Bs, 0, h->st);
+        {
+            ProfScope ps(h, gpe_handle::CAT_COV);
+            launch_cov_build(h->X, h->r, h->n, h->d, h->npad, h->par, h->winv, h->A, sM, Bs, 0, h->st);
+        }
         h->launches += 2;
         if ((rc = gpe_factor_and_reduce(h, Bs, mode, 1, nullptr, nullptr))) return rc;
-        launch_grad_finalize(h->gpart, h->n, h->d, h->npad, p, mode, h->par, h->out, h->status, h->llh_d, h->grad_d,
-                             h->sig_d, Bs, h->st);
+        {
+            ProfScope ps(h, gpe_handle::CAT_OTHER);
+            launch_grad_finalize(h->gpart, h->n, h->d, h->npad, p, mode, h->par, h->out, h->status, h->llh_d, h->grad_d,
+                                 h->sig_d, Bs, h->st);
+        }
         h->launches++;
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(llh + b0, h->llh_d, sizeof(double) * Bs, cudaMemcpyDefault, h->st));

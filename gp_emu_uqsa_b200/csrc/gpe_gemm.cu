@@ -1,7 +1,19 @@
 // Dispatch for the batched DMMA GEMM family (see gpe_gemm.cuh).
 #include "gpe_gemm.cuh"
 
+#include <cstdlib>
+
 namespace gpe {
+
+// GPE_GEMM_WS=0 selects the single-role (block-barrier) 128x128 kernel, kept for A/B measurements.
+static bool use_ws() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("GPE_GEMM_WS");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1;
+}
 
 template <bool A_KC, bool B_KC>
 static cudaError_t dispatch_tiles(const GemmP& p, int epi, cudaStream_t st) {
@@ -18,9 +30,11 @@ static cudaError_t dispatch_tiles(const GemmP& p, int epi, cudaStream_t st) {
     bool big = (p.M % 128 == 0) && (p.N % 128 == 0) && (t128 >= 120);
     if (epi == EPI_SUMSQ) {
         // column norms are accumulated per 128-row tile: the partial buffer is sized for BM = 128
-        return launch_gemm_cfg<128, 128, 2, 4, A_KC, B_KC, EPI_SUMSQ>(p, st);
+        return use_ws() ? launch_gemm_ws<A_KC, B_KC, EPI_SUMSQ>(p, st)
+                        : launch_gemm_cfg<128, 128, 2, 4, A_KC, B_KC, EPI_SUMSQ>(p, st);
     }
-    if (big) return launch_gemm_cfg<128, 128, 2, 4, A_KC, B_KC, EPI_STORE>(p, st);
+    if (big) return use_ws() ? launch_gemm_ws<A_KC, B_KC, EPI_STORE>(p, st)
+                             : launch_gemm_cfg<128, 128, 2, 4, A_KC, B_KC, EPI_STORE>(p, st);
     return launch_gemm_cfg<64, 64, 2, 2, A_KC, B_KC, EPI_STORE>(p, st);
 }
 

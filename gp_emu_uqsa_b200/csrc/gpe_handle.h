@@ -1,6 +1,7 @@
 // Internal handle layout shared by the C-ABI translation units.
 #pragma once
 #include <string>
+#include <vector>
 
 #include "gpe_b200.h"
 #include "gpe_gemm.cuh"
@@ -11,6 +12,17 @@ struct gpe_handle {
     cudaStream_t st = nullptr;
     std::string err;
     long long launches = 0;
+
+    // optional per-category CUDA-event timing of every launch (gpe_profile_*)
+    enum { CAT_GEMM_BIG = 0, CAT_GEMM_SMALL = 1, CAT_LEAF = 2, CAT_COV = 3, CAT_GRAD = 4, CAT_OTHER = 5, NCAT = 6 };
+    bool prof_on = false;
+    struct ProfRec { int cat; cudaEvent_t e0, e1; };
+    std::vector<ProfRec> prof_recs;
+    std::vector<cudaEvent_t> prof_pool;
+    double prof_ms[NCAT] = {0};
+    long long prof_cnt[NCAT] = {0};
+    cudaEvent_t prof_begin(int cat);
+    void prof_end(int cat, cudaEvent_t e0);
 
     // training set (device)
     int n = 0, d = 0, q = 0, npad = 0, nleaf = 0;
@@ -47,6 +59,12 @@ struct gpe_handle {
     void free_batch_ws();
     void free_training();
     void free_fit();
+};
+
+struct ProfScope {
+    gpe_handle* h; int cat; cudaEvent_t e0;
+    ProfScope(gpe_handle* h_, int c) : h(h_), cat(c), e0(h_->prof_begin(c)) {}
+    ~ProfScope() { h->prof_end(cat, e0); }
 };
 
 bool gpe_is_device_ptr(const void* p);

@@ -307,8 +307,11 @@ int predict_chunk(gpe_handle* h, const double* P_dev, const double* Hs_dev, long
                   double* var_dev) {
     const int np = h->npad;
     size_t smem = (size_t)h->d * (64 + 130) * sizeof(double);
-    xcov_kernel<<<dim3(mc / 128, np / 64), 256, smem, h->st>>>(h->fXs, P_dev, h->fwinv, h->n, h->d, np, mc, count, h->fit_c,
-                                                               h->pC, mc);
+    {
+        ProfScope ps(h, gpe_handle::CAT_COV);
+        xcov_kernel<<<dim3(mc / 128, np / 64), 256, smem, h->st>>>(h->fXs, P_dev, h->fwinv, h->n, h->d, np, mc, count, h->fit_c,
+                                                                   h->pC, mc);
+    }
     h->launches++;
     int rc;
     // aux = [A^-1 H K^-T | e]^T C     (TN, skinny M = 32)
@@ -319,9 +322,12 @@ int predict_chunk(gpe_handle* h, const double* P_dev, const double* Hs_dev, long
         if ((rc = gpe_run_gemm(h, h->fLi, h->pC, h->pPart, np, mc, mc, 0, 0, 0, np, mc, np, 1.0, 0, KM_LE_I, 0, 1, 1, EPI_SUMSQ))) return rc;
         ntile = np / 128;
     }
-    predict_finalize_kernel<<<(unsigned)((count + 127) / 128), 128, 0, h->st>>>(
-        h->pPart, ntile, h->pAux, mc, P_dev, Hs_dev, basis_of(h), h->d, h->fK, h->fbeta, h->fit_sigma * h->fit_sigma, h->fit_astar,
-        count, mean_dev, var_dev);
+    {
+        ProfScope ps(h, gpe_handle::CAT_OTHER);
+        predict_finalize_kernel<<<(unsigned)((count + 127) / 128), 128, 0, h->st>>>(
+            h->pPart, ntile, h->pAux, mc, P_dev, Hs_dev, basis_of(h), h->d, h->fK, h->fbeta, h->fit_sigma * h->fit_sigma,
+            h->fit_astar, count, mean_dev, var_dev);
+    }
     h->launches++;
     return 0;
 }

@@ -39,6 +39,16 @@ const char* gpe_last_error(gpe_handle* h);
 /* number of kernels this library has launched on the handle since creation */
 long long gpe_launch_count(gpe_handle* h);
 
+/* The CUDA stream (cudaStream_t) every kernel of this handle is launched on: record CUDA
+ * events on it to time the path on the device. */
+void* gpe_get_stream(gpe_handle* h);
+/* Optional per-launch CUDA-event timing by kernel category (measurement only; the reference's
+ * unused @timeit helper, _emulatoroptimise.py:8-17, is the nearest analogue).  ms/count: 6 entries:
+ * 0 DMMA GEMM (128-wide tiles), 1 small/skinny GEMM, 2 Cholesky leaf, 3 covariance build,
+ * 4 gradient reduction, 5 other. */
+int gpe_profile_enable(gpe_handle* h, int on);
+int gpe_profile_read(gpe_handle* h, double* ms, long long* count, int reset);
+
 /* Training set of one emulator: Data.inputs/outputs/H/r (_emulatorclasses.py:539-584).
  * X [n,d] scaled inputs, y [n], H [n,q] (Data.make_H :558-566), r [n] or NULL (set_r :577-584). */
 int gpe_set_training(gpe_handle* h, const double* X, const double* y, const double* H,
