@@ -44,9 +44,10 @@ def load():
         "gpe_set_training": (i, [p, p, p, p, p, i, i, i]),
         "gpe_set_basis": (i, [p, p, p, i]),
         "gpe_cov_build": (i, [p, p, d, i, i, d, p]),
+        "gpe_cov_grad": (i, [p, p, d, i, i, d, p]),
         "gpe_cross_cov": (i, [p, p, d, i, p, i, p]),
         "gpe_llh_grad_batch": (i, [p, p, i, i, i, d, p, p, p, p]),
-        "gpe_fit_state": (i, [p, p, d, d, i, p, p, p, p]),
+        "gpe_fit_state": (i, [p, p, d, d, i, d, p, p, p, p]),
         "gpe_predict": (i, [p, p, p, ll, p, p]),
         "gpe_predict_grid": (i, [p, p, p, p, ll, ll, p, p]),
         "gpe_predict_fullcov": (i, [p, p, p, i, p, p, p]),
@@ -63,9 +64,26 @@ def load():
 
 EXPORTS = ["gpe_version", "gpe_create", "gpe_destroy", "gpe_last_error", "gpe_launch_count",
            "gpe_get_stream", "gpe_profile_enable", "gpe_profile_read",
-           "gpe_set_training", "gpe_set_basis", "gpe_cov_build", "gpe_cross_cov", "gpe_llh_grad_batch",
+           "gpe_set_training", "gpe_set_basis", "gpe_cov_build", "gpe_cov_grad", "gpe_cross_cov", "gpe_llh_grad_batch",
            "gpe_fit_state", "gpe_predict", "gpe_predict_grid", "gpe_predict_fullcov", "gpe_implausibility",
            "gpe_dbg_gemm", "gpe_dbg_potrf_inv"]
+
+
+def default_device_index():
+    """GPU of this process: GPE_DEVICE, else LOCAL_RANK (one process per GPU under torchrun), else 0."""
+    return int(os.environ.get("GPE_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+
+
+_scratch = None
+
+
+def scratch_device():
+    """A process-wide handle for one-off device work that is not tied to a training set
+    (kernel.var on arbitrary points, Cholesky of a small posterior covariance)."""
+    global _scratch
+    if _scratch is None:
+        _scratch = Device(default_device_index())
+    return _scratch
 
 
 def _ptr(a):
@@ -153,6 +171,13 @@ class Device:
         self._ck(self.L.gpe_cov_build(self.h, _ptr(delta), float(nugget), int(kind), int(bool(predict)), float(s2), _ptr(A)))
         return A
 
+    def cov_grad(self, delta, nugget, kind, which, s2):
+        """Dense grad_delta_A (which = dimension) / grad_nugget_A (which = -1)."""
+        delta = _f64(delta)
+        G = np.empty((self.n, self.n))
+        self._ck(self.L.gpe_cov_grad(self.h, _ptr(delta), float(nugget), int(kind), int(which), float(s2), _ptr(G)))
+        return G
+
     def cross_cov(self, delta, nugget, kind, Xs, out=None):
         delta, Xs = _f64(delta), _f64(Xs)
         m = Xs.shape[0]
@@ -177,13 +202,13 @@ class Device:
         return llh, grad, sig, status
 
     # ------------------------------------------------------------------ K4
-    def fit_state(self, delta, nugget, sigma, kind=0, beta=None):
+    def fit_state(self, delta, nugget, sigma, kind=0, beta=None, r_div=1.0):
         delta = _f64(delta)
         beta_in = None if beta is None else _f64(beta)
         beta_out = np.empty(self.q)
         sig = C.c_double(0.0)
         st = C.c_int(0)
-        self._ck(self.L.gpe_fit_state(self.h, _ptr(delta), float(nugget), float(sigma), int(kind), _ptr(beta_in),
+        self._ck(self.L.gpe_fit_state(self.h, _ptr(delta), float(nugget), float(sigma), int(kind), float(r_div), _ptr(beta_in),
                                       _ptr(beta_out), C.addressof(sig), C.addressof(st)))
         return beta_out, float(sig.value), int(st.value)
 

@@ -354,6 +354,42 @@ int gpe_cov_build(gpe_handle* h, const double* delta, double nugget, int kind, i
     return 0;
 }
 
+int gpe_cov_grad(gpe_handle* h, const double* delta, double nugget, int kind, int which, double s2, double* G_out) {
+    if (!h || !h->n || !delta || !G_out) return h ? h->fail_msg("bad argument / no training set") : -2;
+    if (which < -1 || which >= h->d) return h->fail_msg("which must be a delta index or -1 (nugget)");
+    CK(cudaSetDevice(h->device));
+    int rc;
+    if ((rc = gpe_ensure_batch_ws(h, 1))) return rc;
+    std::vector<double> dl(h->d);
+    CK(cudaMemcpy(dl.data(), delta, sizeof(double) * h->d, cudaMemcpyDefault));
+    ItemPar ip;
+    host_item_par(ip, nugget, kind, 1, 1.0, 1.0);
+    // grad_delta_A: s2 (1-nu) Delta^2 E  (alt: s2 Delta^2 E);  grad_nugget_A (kernel): -1/2 nu s2 E
+    ip.offs = (which >= 0) ? s2 * ip.c : -0.5 * nugget * s2;
+    std::vector<double> w(h->d);
+    for (int k = 0; k < h->d; k++) w[k] = 1.0 / dl[k];
+    CK(cudaMemcpyAsync(h->par, &ip, sizeof ip, cudaMemcpyHostToDevice, h->st));
+    CK(cudaMemcpyAsync(h->winv, w.data(), sizeof(double) * h->d, cudaMemcpyHostToDevice, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    size_t nn = (size_t)h->n * h->n;
+    bool dev = gpe_is_device_ptr(G_out);
+    double* dst = dev ? G_out : h->S;
+    if (which == -1 && kind == 1) {
+        // kernel_alt_nug.grad_nugget_A: diag(nu^2 s2)
+        std::vector<double> host(nn, 0.0);
+        for (int i = 0; i < h->n; i++) host[(size_t)i * h->n + i] = nugget * nugget * s2;
+        CK(cudaMemcpy(G_out, host.data(), nn * sizeof(double), cudaMemcpyDefault));
+        return 0;
+    }
+    launch_cov_build(h->X, h->r, h->n, h->d, h->npad, h->par, h->winv, h->A, 0, 1, 1, h->st, which >= 0 ? 1 : 2, which);
+    launch_unpad_sym(h->A, h->npad, h->n, dst, 0, h->st);
+    h->launches += 2;
+    if (!dev) CK(cudaMemcpyAsync(G_out, dst, nn * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    CK(cudaGetLastError());
+    return 0;
+}
+
 int gpe_llh_grad_batch(gpe_handle* h, const double* theta, int B, int p, int mode, double fixed_nugget,
                        double* llh, double* grad, double* sigma_hat, int* status) {
     if (!h || !h->n || !theta || B < 1 || !llh || !grad) return h ? h->fail_msg("bad argument / no training set") : -2;

@@ -49,7 +49,9 @@ constexpr int CT = 64;
 __global__ void __launch_bounds__(256) cov_build_kernel(const double* __restrict__ X, const double* __restrict__ r,
                                                         int n, int d, int npad, const ItemPar* __restrict__ par,
                                                         const double* __restrict__ winv, double* __restrict__ A,
-                                                        long long sA, int full) {
+                                                        long long sA, int full, int gmode, int gdim) {
+    // gmode 0: covariance; 1: d(s2 A)/d theta_delta[gdim] (grad_delta_A); 2: kernel grad_nugget_A
+    // (off-diagonal only; the alt-nugget form is a pure diagonal and is assembled by the caller)
     const int tj = blockIdx.x, ti = blockIdx.y, b = blockIdx.z;
     if (!full && tj > ti) return;
     extern __shared__ __align__(16) double sm[];
@@ -66,11 +68,11 @@ __global__ void __launch_bounds__(256) cov_build_kernel(const double* __restrict
     __syncthreads();
     const ItemPar ip = par[b];
     const int ty = tid >> 4, tx = tid & 15;
-    double D[4][4];
+    double D[4][4], G[4][4];
 #pragma unroll
     for (int a = 0; a < 4; a++)
 #pragma unroll
-        for (int c = 0; c < 4; c++) D[a][c] = 0.0;
+        for (int c = 0; c < 4; c++) { D[a][c] = 0.0; G[a][c] = 1.0; }
     for (int k = 0; k < d; k++) {
         double xi[4], xj[4];
 #pragma unroll
@@ -84,6 +86,7 @@ __global__ void __launch_bounds__(256) cov_build_kernel(const double* __restrict
             for (int c = 0; c < 4; c++) {
                 double df = xi[a] - xj[c];
                 D[a][c] = fma(df, df, D[a][c]);
+                if (gmode == 1 && k == gdim) G[a][c] = df * df;
             }
     }
     double* Ab = A + (size_t)b * sA;
@@ -99,9 +102,9 @@ __global__ void __launch_bounds__(256) cov_build_kernel(const double* __restrict
             for (int e = 0; e < 2; e++) {
                 int gj = gj0 + e;
                 double val;
-                if (gi >= n || gj >= n) val = (gi == gj) ? 1.0 : 0.0;     // identity padding
-                else if (gi == gj) val = ip.diagv + ip.radd * ri;
-                else val = ip.offs * exp(-D[a][2 * h + e]);
+                if (gi >= n || gj >= n) val = (gi == gj && gmode == 0) ? 1.0 : 0.0;     // identity padding
+                else if (gi == gj) val = (gmode == 0) ? ip.diagv + ip.radd * ri : 0.0;
+                else val = ip.offs * G[a][2 * h + e] * exp(-D[a][2 * h + e]);
                 v[e] = val;
             }
             *reinterpret_cast<double2*>(&Ab[(size_t)gi * npad + gj0]) = make_double2(v[0], v[1]);
@@ -110,10 +113,15 @@ __global__ void __launch_bounds__(256) cov_build_kernel(const double* __restrict
 }
 
 void launch_cov_build(const double* X, const double* r, int n, int d, int npad, const ItemPar* par,
-                      const double* winv, double* A, long long sA, int B, int full, cudaStream_t st) {
+                      const double* winv, double* A, long long sA, int B, int full, cudaStream_t st, int gmode, int gdim) {
     dim3 grid(npad / CT, npad / CT, B);
     size_t smem = (size_t)d * (CT + CT + 2) * sizeof(double);
-    cov_build_kernel<<<grid, 256, smem, st>>>(X, r, n, d, npad, par, winv, A, sA, full);
+    static size_t attr_sz = 0;
+    if (smem > 48 * 1024 && smem > attr_sz) {
+        cudaFuncSetAttribute(cov_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_sz = smem;
+    }
+    cov_build_kernel<<<grid, 256, smem, st>>>(X, r, n, d, npad, par, winv, A, sA, full, gmode, gdim);
 }
 
 __global__ void unpad_sym_kernel(const double* __restrict__ A, int npad, int n, double* __restrict__ out, int mirror) {

@@ -32,7 +32,8 @@ void launch_prep_theta(const double* theta, int B, int p, int d, int mode, doubl
 
 // K1: A[b] (ld = npad, batch stride sA) from X [n,d]; lower 64x64 tiles only unless full.
 void launch_cov_build(const double* X, const double* r, int n, int d, int npad, const ItemPar* par,
-                      const double* winv, double* A, long long sA, int B, int full, cudaStream_t st);
+                      const double* winv, double* A, long long sA, int B, int full, cudaStream_t st,
+                      int gmode = 0, int gdim = 0);
 
 // copy the n x n top-left of a padded matrix into a dense [n,n] output, mirroring the lower triangle
 void launch_unpad_sym(const double* A, int npad, int n, double* out, int mirror, cudaStream_t st);

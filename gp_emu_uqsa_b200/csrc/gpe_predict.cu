@@ -336,8 +336,8 @@ int predict_chunk(gpe_handle* h, const double* P_dev, const double* Hs_dev, long
 
 extern "C" {
 
-int gpe_fit_state(gpe_handle* h, const double* delta, double nugget, double sigma, int kind, const double* beta_in,
-                  double* beta_out, double* sigma_mucm_out, int* status) {
+int gpe_fit_state(gpe_handle* h, const double* delta, double nugget, double sigma, int kind, double r_div,
+                  const double* beta_in, double* beta_out, double* sigma_mucm_out, int* status) {
     if (!h || !h->n || !delta) return h ? h->fail_msg("bad argument / no training set") : -2;
     CK(cudaSetDevice(h->device));
     int rc;
@@ -345,7 +345,7 @@ int gpe_fit_state(gpe_handle* h, const double* delta, double nugget, double sigm
     const int np = h->npad, q = h->q;
     std::vector<double> dl(h->d), bin(NR, 0.0);
     CK(cudaMemcpy(dl.data(), delta, sizeof(double) * h->d, cudaMemcpyDefault));
-    if ((rc = gpe_upload_single_par(h, dl.data(), nugget, kind, 1, 1.0))) return rc;
+    if ((rc = gpe_upload_single_par(h, dl.data(), nugget, kind, 1, r_div > 0 ? r_div : 1.0))) return rc;
     if (!h->fLi) {
         CK(cudaMalloc((void**)&h->fLi, (size_t)np * np * sizeof(double)));
         CK(cudaMalloc((void**)&h->fE, (size_t)np * NR * sizeof(double)));

@@ -65,6 +65,12 @@ int gpe_set_basis(gpe_handle* h, const int* idx, const int* pow, int q);
 int gpe_cov_build(gpe_handle* h, const double* delta, double nugget, int kind, int predict,
                   double s2, double* A_out);
 
+/* kernel.grad_delta_A / grad_nugget_A (_emulatorkernels.py:53-71, :126-144) as dense [n,n]
+ * matrices, for callers that want them explicitly (the likelihood path never forms them):
+ * which = delta index, or -1 for the nugget.  s2 as in the reference's argument. */
+int gpe_cov_grad(gpe_handle* h, const double* delta, double nugget, int kind, int which, double s2,
+                 double* G_out);
+
 /* kernel.covar (_emulatorkernels.py:75-79, :148-152): C_out [n,m] = K(X, Xs). */
 int gpe_cross_cov(gpe_handle* h, const double* delta, double nugget, int kind,
                   const double* Xs, int m, double* C_out);
@@ -82,10 +88,12 @@ int gpe_llh_grad_batch(gpe_handle* h, const double* theta, int B, int p, int mod
  * (Data.remake + Optimize.optimalbeta + Optimize.sigma_analytic_mucm,
  * _emulatorclasses.py:553-555, _emulatoroptimise.py:382-408, :497-504).
  * The matrix factored is the one training.remake() leaves: correlation matrix (s2 = 1) plus
- * un-scaled r for the alt nugget.  beta_in NULL -> beta = optimalbeta(); else used as given.
+ * r / r_div for the alt nugget (r_div = 1 after remake(); = sigma^2 after Optimize.optimal's
+ * make_A(s2), :289).  beta_in NULL -> beta = optimalbeta(); else used as given.
  * Outputs (any may be NULL): beta_out [q], sigma_mucm_out (analytic MUCM sigma), status. */
 int gpe_fit_state(gpe_handle* h, const double* delta, double nugget, double sigma, int kind,
-                  const double* beta_in, double* beta_out, double* sigma_mucm_out, int* status);
+                  double r_div, const double* beta_in, double* beta_out, double* sigma_mucm_out,
+                  int* status);
 
 /* Posterior mean and diagonal variance (Posterior.make_covar/make_mean/make_var,
  * _emulatorclasses.py:607-631, diagonal as consumed at history_match.py:117-118,
