@@ -400,6 +400,7 @@ class Data:
         self.outputs = outputs
         self.basis, self.beliefs, self.par, self.K = basis, beliefs, par, K
         self.r = 0
+        self._r_made = 0
         self._dev = None
         self._loaded = None
         self._fit_key = None
@@ -423,6 +424,7 @@ class Data:
         """Record how A is to be built (reference :572-575); the matrix itself is built on device
         when ``A`` is next read.  NB remake() uses s2 = 1, i.e. adds un-scaled r (reference quirk)."""
         self._A_args = (float(s2), bool(predict))
+        self._r_made = self.r          # like the reference, A reflects r as of the last make_A()
         self._A = None
 
     @property
@@ -447,7 +449,6 @@ class Data:
             if message:
                 print("\n*** Updating array 'r' of constant variances***")
             self.r = r
-            self._A = None
         else:
             _die("\nWARNING: length of 'r' does not match number of data points")
 
@@ -455,7 +456,7 @@ class Data:
     def _fingerprint(self):
         X = np.asarray(self.inputs, dtype=float)
         y = np.zeros(X.shape[0]) if self.outputs is None else np.asarray(self.outputs, dtype=float)
-        r = np.asarray(self.r, dtype=float)
+        r = np.asarray(self._r_made, dtype=float)
         return (X.shape, float(X.sum()), float((X * X).sum()), float(y.sum()), float((y * y).sum()),
                 r.shape, float(r.sum()), float((r * r).sum()), self.H.shape, float(self.H.sum()))
 
@@ -466,7 +467,7 @@ class Data:
         fp = self._fingerprint()
         if fp != self._loaded:
             y = np.zeros(self.inputs.shape[0]) if self.outputs is None else self.outputs
-            r = self.r if np.ndim(self.r) else None
+            r = self._r_made if np.ndim(self._r_made) else None
             self._dev.set_training(self.inputs, y, self.H, r)
             if self.basis.poly is not None:
                 self._dev.set_basis(self.basis.basis_inf, self.basis.poly)
@@ -527,7 +528,7 @@ class Posterior:
             self.mean, self.var_diag = dev.predict(Dn.inputs, Hs)
             self.var = None
         else:
-            r_new = Dn.r if (np.ndim(Dn.r) and Dn.kind == 1) else None
+            r_new = np.asarray(Dn._r_made, dtype=float) / Dn._A_args[0] if (np.ndim(Dn._r_made) and Dn.kind == 1) else None
             self.mean, self.var = dev.predict_fullcov(Dn.inputs, Hs, r_new)
             self.var_diag = np.diag(self.var).copy()
 

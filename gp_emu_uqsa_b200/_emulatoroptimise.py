@@ -5,6 +5,7 @@ B200, all multistart guesses of a round in one call (``_lbfgsb_batch.minimize_ba
 ``torch.distributed`` initialised the guesses are block-partitioned over the ranks."""
 import numpy as np
 
+from . import _dist
 from . import _lib
 from ._lbfgsb_batch import minimize_batch
 
@@ -120,6 +121,7 @@ class Optimize:
 
     def _eval_batch(self, thetas):
         """(f, g, ok, sigma_hat) for a block of transformed parameter vectors -- one device call."""
+        self.data._r_made = self.data.r      # every reference evaluation starts with make_A(): current r
         dev = self.data.device()
         llh, grad, sig, st = dev.llh_grad_batch(thetas, self._mode(), fixed_nugget=float(self.data.K.n))
         return llh, grad, st == 0, sig
@@ -142,8 +144,8 @@ class Optimize:
         print("Using L-BFGS-G method (%s constraints)..." % ("with" if constrained else "no"))
 
         # the multistart batch: every rank draws the same guesses, owns a contiguous block of them
-        rank, world = _dist_rank_world()
-        lo, hi = _block(numguesses, rank, world)
+        rank, world = _dist.rank_world()
+        lo, hi = _dist.block(numguesses, rank, world)
         fixed_n = float(K.n)
 
         def eval_batch(X):
@@ -161,7 +163,7 @@ class Optimize:
                 pack[lo + k, 0], pack[lo + k, 1], pack[lo + k, 2:] = 1.0, res.fun, res.x
             else:
                 pack[lo + k, 0] = 0.0
-        pack = _allgather_blocks(pack, numguesses, rank, world)
+        pack = _dist.gather_blocks(pack, numguesses)
         K.n = fixed_n if self.beliefs.fix_nugget != "F" else K.n
 
         # sigma for the printed lines (mucm): one more batched evaluation at the optima
@@ -248,36 +250,3 @@ class Optimize:
         if st != 0:
             raise np.linalg.LinAlgError("Matrix is not positive definite")
         self.par.beta = bopt
-
-
-# ---------------------------------------------------------------------------------- distributed helpers
-def _dist_rank_world():
-    try:
-        import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized():
-            return dist.get_rank(), dist.get_world_size()
-    except ImportError:
-        pass
-    return 0, 1
-
-
-def _block(n, rank, world):
-    """Contiguous block partition of range(n): rank g owns [g*n/G, (g+1)*n/G)."""
-    return (n * rank) // world, (n * (rank + 1)) // world
-
-
-def _allgather_blocks(pack, n, rank, world):
-    """Every rank contributes its block of rows; all ranks end with the full table.  NCCL when the
-    process group is NCCL (tensors on the rank's GPU), gloo otherwise."""
-    if world == 1:
-        return pack
-    import torch
-    import torch.distributed as dist
-    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
-    mine = torch.from_numpy(np.nan_to_num(pack, nan=0.0)).to(dev)
-    mask = torch.zeros(n, 1, dtype=torch.float64, device=dev)
-    lo, hi = _block(n, rank, world)
-    mask[lo:hi] = 1.0
-    buf = mine * mask
-    dist.all_reduce(buf, op=dist.ReduceOp.SUM)       # disjoint blocks: the sum is the concatenation
-    return buf.cpu().numpy()

@@ -39,6 +39,7 @@ def load():
         "gpe_last_error": (C.c_char_p, [p]),
         "gpe_launch_count": (ll, [p]),
         "gpe_get_stream": (p, [p]),
+        "gpe_set_streams": (i, [p, i]),
         "gpe_profile_enable": (i, [p, i]),
         "gpe_profile_read": (i, [p, p, p, i]),
         "gpe_set_training": (i, [p, p, p, p, p, i, i, i]),
@@ -52,7 +53,11 @@ def load():
         "gpe_predict_grid": (i, [p, p, p, p, ll, ll, p, p]),
         "gpe_predict_fullcov": (i, [p, p, p, i, p, p, p]),
         "gpe_implausibility": (i, [p, p, p, i, ll, p, p, d, i, ll, p, p, p, p, p]),
+        "gpe_solve": (i, [p, p, i, p]),
+        "gpe_sens_contract": (i, [p, p, p, p, d, p, i, p, p]),
+        "gpe_sens_main_effect": (i, [p, p, p, p, p, p, d, p, i, p, i, p]),
         "gpe_dbg_gemm": (i, [p, p, p, p, i, i, i, ll, ll, ll, i, i, i, d, i, i, i, i, i]),
+        "gpe_potrf": (i, [p, p, i, i, p, p, p, p]),
         "gpe_dbg_potrf_inv": (i, [p, p, i, i, p, p, p]),
     }
     for name, (res, args) in proto.items():
@@ -63,9 +68,10 @@ def load():
 
 
 EXPORTS = ["gpe_version", "gpe_create", "gpe_destroy", "gpe_last_error", "gpe_launch_count",
-           "gpe_get_stream", "gpe_profile_enable", "gpe_profile_read",
+           "gpe_get_stream", "gpe_set_streams", "gpe_profile_enable", "gpe_profile_read",
            "gpe_set_training", "gpe_set_basis", "gpe_cov_build", "gpe_cov_grad", "gpe_cross_cov", "gpe_llh_grad_batch",
            "gpe_fit_state", "gpe_predict", "gpe_predict_grid", "gpe_predict_fullcov", "gpe_implausibility",
+           "gpe_solve", "gpe_sens_contract", "gpe_sens_main_effect", "gpe_potrf",
            "gpe_dbg_gemm", "gpe_dbg_potrf_inv"]
 
 
@@ -138,6 +144,10 @@ class Device:
         return int(self.L.gpe_get_stream(self.h) or 0)
 
     PROFILE_CATEGORIES = ("gemm_dmma_128", "gemm_dmma_small", "potrf_leaf", "cov_build", "grad_reduce", "other")
+
+    def set_streams(self, nstreams):
+        """Number of concurrent sub-batch streams of llh_grad_batch (1 = serial launches)."""
+        self._ck(self.L.gpe_set_streams(self.h, int(nstreams)))
 
     def profile_enable(self, on=True):
         self._ck(self.L.gpe_profile_enable(self.h, int(bool(on))))
@@ -264,6 +274,47 @@ class Device:
         self._ck(self.L.gpe_implausibility(self.h, _ptr(mean), _ptr(var), n_emul, m, _ptr(z), _ptr(var_extra), float(cm),
                                            int(maxno), int(ncell), _ptr(Imax), _ptr(keep), _ptr(count), _ptr(cmin), _ptr(ccnt)))
         return Imax, keep, count, cmin, ccnt
+
+    # ------------------------------------------------------------------ K6
+    def solve(self, Bm):
+        """A^-1 Bm for the matrix factored by fit_state; Bm [n] or [n,k]."""
+        Bm = _f64(Bm)
+        one = Bm.ndim == 1
+        B2 = Bm.reshape(self.n, -1)
+        out = np.empty_like(B2)
+        self._ck(self.L.gpe_solve(self.h, _ptr(B2), int(B2.shape[1]), _ptr(out)))
+        return out[:, 0] if one else out
+
+    def sens_contract(self, gamma, acoef, mvec, scale, V):
+        """(tr(A^-1 P), V^T P V) for the product-form matrix P (see gpe_sens_contract)."""
+        gamma, acoef, mvec, V = _f64(gamma), _f64(acoef), _f64(mvec), _f64(V)
+        nv = V.shape[1]
+        tr = C.c_double(0.0)
+        M = np.empty((nv, nv))
+        self._ck(self.L.gpe_sens_contract(self.h, _ptr(gamma), _ptr(acoef), _ptr(mvec), float(scale), _ptr(V), nv,
+                                          C.addressof(tr), _ptr(M)))
+        return float(tr.value), M
+
+    def sens_main_effect(self, t1, t2, cdiag, mvec, evec, scale, which, xw):
+        """Tw(x_w) . e for every input in `which` and every x_w value xw [len(which), points]."""
+        t1, t2, cdiag, mvec, evec, xw = (_f64(a) for a in (t1, t2, cdiag, mvec, evec, xw))
+        which = np.ascontiguousarray(which, dtype=np.int32)
+        out = np.empty_like(xw)
+        self._ck(self.L.gpe_sens_main_effect(self.h, _ptr(t1), _ptr(t2), _ptr(cdiag), _ptr(mvec), _ptr(evec), float(scale),
+                                             _ptr(which), len(which), _ptr(xw), int(xw.shape[1]), _ptr(out)))
+        return out
+
+    # ------------------------------------------------------------------ dense Cholesky
+    def cholesky(self, A):
+        """np.linalg.cholesky(A) on device (lower factor); raises LinAlgError when A is not PD."""
+        A = _f64(A)
+        n = A.shape[0]
+        Lf, st = np.empty_like(A), np.zeros(1, dtype=np.int32)
+        self._ck(self.L.gpe_potrf(self.h, _ptr(A), n, 1, _ptr(Lf), None, None, _ptr(st)))
+        self.n = self.d = self.q = 0          # replaces the handle's training set
+        if st[0] != 0:
+            raise np.linalg.LinAlgError("Matrix is not positive definite")
+        return Lf
 
     # ------------------------------------------------------------------ debug
     def dbg_potrf_inv(self, A):

@@ -22,21 +22,21 @@ int gpe_handle::fail_msg(const char* what) {
     return -2;
 }
 
-cudaEvent_t gpe_handle::prof_begin(int cat) {
+cudaEvent_t gpe_handle::prof_begin(int cat, cudaStream_t s) {
     if (!prof_on) return nullptr;
     cudaEvent_t e;
     if (!prof_pool.empty()) { e = prof_pool.back(); prof_pool.pop_back(); }
     else cudaEventCreate(&e);
-    cudaEventRecord(e, st);
+    cudaEventRecord(e, s);
     (void)cat;
     return e;
 }
-void gpe_handle::prof_end(int cat, cudaEvent_t e0) {
+void gpe_handle::prof_end(int cat, cudaEvent_t e0, cudaStream_t s) {
     if (!prof_on || !e0) return;
     cudaEvent_t e1;
     if (!prof_pool.empty()) { e1 = prof_pool.back(); prof_pool.pop_back(); }
     else cudaEventCreate(&e1);
-    cudaEventRecord(e1, st);
+    cudaEventRecord(e1, s);
     prof_recs.push_back({cat, e0, e1});
 }
 #define CK(call)                                                   \
@@ -119,7 +119,7 @@ int gpe_ensure_batch_ws(gpe_handle* h, int B) {
 }
 
 // ------------------------------------------------------------------------------------- GEMM helper
-static int run_gemm(gpe_handle* h, const double* A, const double* B, double* C, int lda, int ldb, int ldc,
+static int run_gemm(gpe_handle* h, cudaStream_t st, const double* A, const double* B, double* C, int lda, int ldb, int ldc,
                     long long sA, long long sB, long long sC, int M, int N, int K, double alpha, int acc,
                     int kmode, int lower, int batch, int layout, int epi = EPI_STORE) {
     GemmP p;
@@ -128,8 +128,8 @@ static int run_gemm(gpe_handle* h, const double* A, const double* B, double* C, 
     bool big = (M % 128 == 0) && (N % 128 == 0) && N != 32 && M != 32;
     cudaError_t e;
     {
-        ProfScope ps(h, big ? gpe_handle::CAT_GEMM_BIG : gpe_handle::CAT_GEMM_SMALL);
-        e = launch_gemm(p, layout, epi, h->st);
+        ProfScope ps(h, big ? gpe_handle::CAT_GEMM_BIG : gpe_handle::CAT_GEMM_SMALL, st);
+        e = launch_gemm(p, layout, epi, st);
     }
     h->launches++;
     if (e != cudaSuccess) return h->fail("launch_gemm", e);
@@ -138,20 +138,24 @@ static int run_gemm(gpe_handle* h, const double* A, const double* B, double* C, 
 int gpe_run_gemm(gpe_handle* h, const double* A, const double* B, double* C, int lda, int ldb, int ldc,
                  long long sA, long long sB, long long sC, int M, int N, int K, double alpha, int acc,
                  int kmode, int lower, int batch, int layout, int epi) {
-    return run_gemm(h, A, B, C, lda, ldb, ldc, sA, sB, sC, M, N, K, alpha, acc, kmode, lower, batch, layout, epi);
+    return run_gemm(h, h->st, A, B, C, lda, ldb, ldc, sA, sB, sC, M, N, K, alpha, acc, kmode, lower, batch, layout, epi);
 }
 
 // Recursive Cholesky + triangular inverse of the diagonal block [off, off+m) of every item:
 //   F(A11) ; L21 = A21 L11^-T ; A22 -= L21 L21^T ; F(A22) ; Linv21 = -L22^-1 (L21 L11^-1).
 // All four updates are DMMA GEMMs with a triangular operand (zero tiles skipped); only the
 // 128x128 diagonal leaves are factored by a panel kernel.  2n^3/3 flops, 5 launches per node.
-static int potrf_inv_rec(gpe_handle* h, int off, int m, int B) {
-    const int ld = h->npad;
+static int potrf_inv_rec(gpe_handle* h, const SubBatch& sb, int off, int m, int want_L) {
+    const int ld = h->npad, B = sb.B;
     const long long sM = (long long)h->npad * h->npad;
+    double* Ab = h->A + (size_t)sb.b0 * sM;
+    double* Sb = h->S + (size_t)sb.b0 * sM;
+    double* Lb = h->Li + (size_t)sb.b0 * sM;
     if (m == NB) {
         {
-            ProfScope ps(h, gpe_handle::CAT_LEAF);
-            launch_leaf(h->A, h->Li, ld, sM, sM, off, h->logdet_part, h->nleaf, h->status, B, h->st);
+            ProfScope ps(h, gpe_handle::CAT_LEAF, sb.st);
+            launch_leaf(Ab, Lb, ld, sM, sM, off, h->logdet_part + (size_t)sb.b0 * h->nleaf, h->nleaf, h->status + sb.b0, B, sb.st,
+                        want_L ? Sb : nullptr);
         }
         h->launches++;
         return 0;
@@ -159,51 +163,57 @@ static int potrf_inv_rec(gpe_handle* h, int off, int m, int B) {
     const int nb = m / NB;
     const int m1 = ((nb + 1) / 2) * NB, m2 = m - m1;
     int rc;
-    if ((rc = potrf_inv_rec(h, off, m1, B))) return rc;
-    double* A21 = h->A + (size_t)(off + m1) * ld + off;
-    double* A22 = h->A + (size_t)(off + m1) * ld + off + m1;
-    double* S21 = h->S + (size_t)(off + m1) * ld + off;
-    double* Li11 = h->Li + (size_t)off * ld + off;
-    double* Li22 = h->Li + (size_t)(off + m1) * ld + off + m1;
-    double* Li21 = h->Li + (size_t)(off + m1) * ld + off;
+    if ((rc = potrf_inv_rec(h, sb, off, m1, want_L))) return rc;
+    double* A21 = Ab + (size_t)(off + m1) * ld + off;
+    double* A22 = Ab + (size_t)(off + m1) * ld + off + m1;
+    double* S21 = Sb + (size_t)(off + m1) * ld + off;
+    double* Li11 = Lb + (size_t)off * ld + off;
+    double* Li22 = Lb + (size_t)(off + m1) * ld + off + m1;
+    double* Li21 = Lb + (size_t)(off + m1) * ld + off;
     // L21 = A21 * Linv11^T           (NT, Linv11 lower: k <= j)
-    if ((rc = run_gemm(h, A21, Li11, S21, ld, ld, ld, sM, sM, sM, m2, m1, m1, 1.0, 0, KM_LE_J, 0, B, 0))) return rc;
+    if ((rc = run_gemm(h, sb.st, A21, Li11, S21, ld, ld, ld, sM, sM, sM, m2, m1, m1, 1.0, 0, KM_LE_J, 0, B, 0))) return rc;
     // A22 -= L21 * L21^T             (SYRK, lower tiles)
-    if ((rc = run_gemm(h, S21, S21, A22, ld, ld, ld, sM, sM, sM, m2, m2, m1, -1.0, 1, KM_FULL, 1, B, 0))) return rc;
-    if ((rc = potrf_inv_rec(h, off + m1, m2, B))) return rc;
+    if ((rc = run_gemm(h, sb.st, S21, S21, A22, ld, ld, ld, sM, sM, sM, m2, m2, m1, -1.0, 1, KM_FULL, 1, B, 0))) return rc;
+    if ((rc = potrf_inv_rec(h, sb, off + m1, m2, want_L))) return rc;
     // T = L21 * Linv11               (NN, Linv11 lower: k >= j)  -> dead A21 block
-    if ((rc = run_gemm(h, S21, Li11, A21, ld, ld, ld, sM, sM, sM, m2, m1, m1, 1.0, 0, KM_GE_J, 0, B, 1))) return rc;
+    if ((rc = run_gemm(h, sb.st, S21, Li11, A21, ld, ld, ld, sM, sM, sM, m2, m1, m1, 1.0, 0, KM_GE_J, 0, B, 1))) return rc;
     // Linv21 = -Linv22 * T           (NN, Linv22 lower: k <= i)
-    if ((rc = run_gemm(h, Li22, A21, Li21, ld, ld, ld, sM, sM, sM, m2, m1, m2, -1.0, 0, KM_LE_I, 0, B, 1))) return rc;
+    if ((rc = run_gemm(h, sb.st, Li22, A21, Li21, ld, ld, ld, sM, sM, sM, m2, m1, m2, -1.0, 0, KM_LE_I, 0, B, 1))) return rc;
     return 0;
 }
-int gpe_potrf_inv(gpe_handle* h, int B) { return potrf_inv_rec(h, 0, h->npad, B); }
+int gpe_potrf_inv(gpe_handle* h, const SubBatch& sb, int want_L) { return potrf_inv_rec(h, sb, 0, h->npad, want_L); }
 
-// Everything after the covariance build for B items already described by h->par / h->winv.
+// Everything after the covariance build for the items of `sb`, already described by h->par / h->winv.
 // with_grad = 0 stops after the GLS/likelihood scalars (fit_state path).
-int gpe_factor_and_reduce(gpe_handle* h, int B, int mode, int with_grad, const double* beta_override, double* Kout) {
-    const int np = h->npad, ld = np;
+int gpe_factor_and_reduce(gpe_handle* h, const SubBatch& sb, int mode, int with_grad, const double* beta_override, double* Kout) {
+    const int np = h->npad, ld = np, B = sb.B, b0 = sb.b0;
     const long long sM = (long long)np * np, sP = (long long)np * NR;
+    cudaStream_t st = sb.st;
+    const int nslab = (np + GRAM_SLAB - 1) / GRAM_SLAB;
+    double* Ab = h->A + (size_t)b0 * sM;
+    double* Lb = h->Li + (size_t)b0 * sM;
+    double *Wy = h->Wy + (size_t)b0 * sP, *Z = h->Z + (size_t)b0 * sP, *U = h->U + (size_t)b0 * sP;
+    double* GP = h->GP + (size_t)b0 * nslab * NR * NR;
     int rc;
-    cudaMemsetAsync(h->status, 0, sizeof(int) * B, h->st);
-    if ((rc = potrf_inv_rec(h, 0, np, B))) return rc;
+    if ((rc = potrf_inv_rec(h, sb, 0, np, 0))) return rc;
     // Wy = Linv [H | y]
-    if ((rc = run_gemm(h, h->Li, h->HY, h->Wy, ld, NR, NR, sM, 0, sP, np, NR, np, 1.0, 0, KM_LE_I, 0, B, 1))) return rc;
+    if ((rc = run_gemm(h, st, Lb, h->HY, Wy, ld, NR, NR, sM, 0, sP, np, NR, np, 1.0, 0, KM_LE_I, 0, B, 1))) return rc;
     {
-        ProfScope ps(h, gpe_handle::CAT_OTHER);
-        launch_gram(h->Wy, np, B, h->GP, h->st);
-        launch_llh_finalize(h->Wy, h->GP, h->logdet_part, h->nleaf, h->n, h->q, np, mode, h->par, h->out, h->beta, h->Z,
-                            h->status, B, beta_override, Kout, h->st);
+        ProfScope ps(h, gpe_handle::CAT_OTHER, st);
+        launch_gram(Wy, np, B, GP, st);
+        launch_llh_finalize(Wy, GP, h->logdet_part + (size_t)b0 * h->nleaf, h->nleaf, h->n, h->q, np, mode, h->par + b0, h->out + b0,
+                            h->beta + (size_t)b0 * NR, Z, h->status + b0, B, beta_override, Kout, st);
     }
     h->launches += 2;
     // U = Linv^T Z = [A^-1 H K^-T | sqrt(f) A^-1 (y - H beta)]
-    if ((rc = run_gemm(h, h->Li, h->Z, h->U, ld, NR, NR, sM, sP, sP, np, NR, np, 1.0, 0, KM_GE_I, 0, B, 2))) return rc;
+    if ((rc = run_gemm(h, st, Lb, Z, U, ld, NR, NR, sM, sP, sP, np, NR, np, 1.0, 0, KM_GE_I, 0, B, 2))) return rc;
     if (!with_grad) return 0;
     // LAUUM: A^-1 = Linv^T Linv (lower tiles) into the dead A buffer
-    if ((rc = run_gemm(h, h->Li, h->Li, h->A, ld, ld, ld, sM, sM, sM, np, np, np, 1.0, 0, KM_GE_I, 1, B, 2))) return rc;
+    if ((rc = run_gemm(h, st, Lb, Lb, Ab, ld, ld, ld, sM, sM, sM, np, np, np, 1.0, 0, KM_GE_I, 1, B, 2))) return rc;
     {
-        ProfScope ps(h, gpe_handle::CAT_GRAD);
-        launch_grad_partial(h->X, h->r, h->n, h->d, np, h->winv, h->A, sM, h->U, h->q + 1, h->gpart, B, h->st);
+        ProfScope ps(h, gpe_handle::CAT_GRAD, st);
+        launch_grad_partial(h->X, h->r, h->n, h->d, np, h->winv + (size_t)b0 * h->d, Ab, sM, U, h->q + 1,
+                            h->gpart + (size_t)b0 * grad_ntiles(np) * grad_nvals(h->d), B, st);
     }
     h->launches++;
     return 0;
@@ -248,6 +258,12 @@ int gpe_create(int device, gpe_handle** out) {
     h->device = device;
     h->sms = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking) != cudaSuccess) { delete h; return -3; }
+    for (int s = 0; s < gpe_handle::MAX_SUB; s++) {
+        cudaStreamCreateWithFlags(&h->sub_st[s], cudaStreamNonBlocking);
+        cudaEventCreateWithFlags(&h->ev_join[s], cudaEventDisableTiming);
+    }
+    cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
+    if (const char* e = getenv("GPE_STREAMS")) h->nsub = std::max(1, std::min((int)gpe_handle::MAX_SUB, atoi(e)));
     *out = h;
     return 0;
 }
@@ -257,12 +273,24 @@ int gpe_destroy(gpe_handle* h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->st);
     h->free_training();
+    for (int s = 0; s < gpe_handle::MAX_SUB; s++) {
+        if (h->sub_st[s]) { cudaStreamSynchronize(h->sub_st[s]); cudaStreamDestroy(h->sub_st[s]); }
+        if (h->ev_join[s]) cudaEventDestroy(h->ev_join[s]);
+    }
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    for (auto e : h->prof_pool) cudaEventDestroy(e);
     cudaStreamDestroy(h->st);
     delete h;
     return 0;
 }
 
 void* gpe_get_stream(gpe_handle* h) { return h ? (void*)h->st : nullptr; }
+
+int gpe_set_streams(gpe_handle* h, int nstreams) {
+    if (!h || nstreams < 1) return -2;
+    h->nsub = std::min((int)gpe_handle::MAX_SUB, nstreams);
+    return 0;
+}
 
 int gpe_profile_enable(gpe_handle* h, int on) {
     if (!h) return -2;
@@ -399,16 +427,35 @@ int gpe_llh_grad_batch(gpe_handle* h, const double* theta, int B, int p, int mod
     int rc;
     if ((rc = gpe_ensure_batch_ws(h, B))) return rc;
     const long long sM = (long long)h->npad * h->npad;
+    const int gn = grad_ntiles(h->npad) * grad_nvals(h->d);
+    (void)gn;
     for (int b0 = 0; b0 < B; b0 += h->Bcap) {
         int Bs = std::min(h->Bcap, B - b0);
         CK(cudaMemcpyAsync(h->theta_d, theta + (size_t)b0 * p, sizeof(double) * Bs * p, cudaMemcpyDefault, h->st));
         launch_prep_theta(h->theta_d, Bs, p, h->d, mode, fixed_nugget, h->par, h->winv, h->st);
-        {
-            ProfScope ps(h, gpe_handle::CAT_COV);
-            launch_cov_build(h->X, h->r, h->n, h->d, h->npad, h->par, h->winv, h->A, sM, Bs, 0, h->st);
+        h->launches++;
+        CK(cudaMemsetAsync(h->status, 0, sizeof(int) * Bs, h->st));
+        // contiguous groups of the sub-batch, one stream each (a group needs >= 2 items to be worth a stream)
+        const int ns = std::max(1, std::min(h->nsub, Bs / 2));
+        if (ns > 1) CK(cudaEventRecord(h->ev_fork, h->st));
+        for (int g = 0; g < ns; g++) {
+            SubBatch sb;
+            sb.b0 = (int)((long long)Bs * g / ns);
+            sb.B = (int)((long long)Bs * (g + 1) / ns) - sb.b0;
+            sb.st = ns > 1 ? h->sub_st[g] : h->st;
+            if (ns > 1) CK(cudaStreamWaitEvent(sb.st, h->ev_fork, 0));
+            {
+                ProfScope ps(h, gpe_handle::CAT_COV, sb.st);
+                launch_cov_build(h->X, h->r, h->n, h->d, h->npad, h->par + sb.b0, h->winv + (size_t)sb.b0 * h->d,
+                                 h->A + (size_t)sb.b0 * sM, sM, sb.B, 0, sb.st);
+            }
+            h->launches++;
+            if ((rc = gpe_factor_and_reduce(h, sb, mode, 1, nullptr, nullptr))) return rc;
+            if (ns > 1) {
+                CK(cudaEventRecord(h->ev_join[g], sb.st));
+                CK(cudaStreamWaitEvent(h->st, h->ev_join[g], 0));
+            }
         }
-        h->launches += 2;
-        if ((rc = gpe_factor_and_reduce(h, Bs, mode, 1, nullptr, nullptr))) return rc;
         {
             ProfScope ps(h, gpe_handle::CAT_OTHER);
             launch_grad_finalize(h->gpart, h->n, h->d, h->npad, p, mode, h->par, h->out, h->status, h->llh_d, h->grad_d,
@@ -430,13 +477,13 @@ int gpe_dbg_gemm(gpe_handle* h, const double* A, const double* B, double* C, int
                  int kmode, int lower, int batch, int layout) {
     if (!h) return -2;
     CK(cudaSetDevice(h->device));
-    int rc = run_gemm(h, A, B, C, lda, ldb, ldc, sA, sB, sC, M, N, K, alpha, accumulate, kmode, lower, batch, layout);
+    int rc = run_gemm(h, h->st, A, B, C, lda, ldb, ldc, sA, sB, sC, M, N, K, alpha, accumulate, kmode, lower, batch, layout);
     if (rc) return rc;
     CK(cudaStreamSynchronize(h->st));
     return 0;
 }
 
-int gpe_dbg_potrf_inv(gpe_handle* h, const double* A, int n, int batch, double* Linv_out, double* logdet, int* status) {
+int gpe_potrf(gpe_handle* h, const double* A, int n, int batch, double* L_out, double* Linv_out, double* logdet, int* status) {
     if (!h || !A || n < 1 || batch < 1) return h ? h->fail_msg("bad argument") : -2;
     CK(cudaSetDevice(h->device));
     // temporary "training set" of the right size so the workspace exists
@@ -448,7 +495,7 @@ int gpe_dbg_potrf_inv(gpe_handle* h, const double* A, int n, int batch, double* 
     }
     int rc;
     if ((rc = gpe_ensure_batch_ws(h, batch))) return rc;
-    if (batch > h->Bcap) return h->fail_msg("debug batch exceeds workspace capacity");
+    if (batch > h->Bcap) return h->fail_msg("batch exceeds workspace capacity");
     const size_t nn = (size_t)npad * npad;
     // identity-padded copy
     std::vector<double> host((size_t)batch * nn, 0.0), src((size_t)batch * n * n);
@@ -460,15 +507,21 @@ int gpe_dbg_potrf_inv(gpe_handle* h, const double* A, int n, int batch, double* 
     }
     CK(cudaMemcpyAsync(h->A, host.data(), sizeof(double) * host.size(), cudaMemcpyHostToDevice, h->st));
     CK(cudaMemsetAsync(h->status, 0, sizeof(int) * batch, h->st));
-    if ((rc = potrf_inv_rec(h, 0, npad, batch))) return rc;
+    SubBatch sb{0, batch, h->st};
+    if ((rc = potrf_inv_rec(h, sb, 0, npad, L_out != nullptr))) return rc;
     CK(cudaStreamSynchronize(h->st));
     CK(cudaGetLastError());
-    CK(cudaMemcpy(host.data(), h->Li, sizeof(double) * host.size(), cudaMemcpyDeviceToHost));
     std::vector<double> outv((size_t)batch * n * n), ldp((size_t)batch * h->nleaf);
-    for (int b = 0; b < batch; b++)
-        for (int i = 0; i < n; i++)
-            for (int j = 0; j < n; j++) outv[((size_t)b * n + i) * n + j] = host[b * nn + (size_t)i * npad + j];
-    if (Linv_out) CK(cudaMemcpy(Linv_out, outv.data(), sizeof(double) * outv.size(), cudaMemcpyDefault));
+    auto unpad = [&](const double* devbuf, double* dst) -> int {
+        CK(cudaMemcpy(host.data(), devbuf, sizeof(double) * host.size(), cudaMemcpyDeviceToHost));
+        for (int b = 0; b < batch; b++)
+            for (int i = 0; i < n; i++)
+                for (int j = 0; j < n; j++) outv[((size_t)b * n + i) * n + j] = (j <= i) ? host[b * nn + (size_t)i * npad + j] : 0.0;
+        CK(cudaMemcpy(dst, outv.data(), sizeof(double) * outv.size(), cudaMemcpyDefault));
+        return 0;
+    };
+    if (Linv_out && (rc = unpad(h->Li, Linv_out))) return rc;
+    if (L_out && (rc = unpad(h->S, L_out))) return rc;
     CK(cudaMemcpy(ldp.data(), h->logdet_part, sizeof(double) * ldp.size(), cudaMemcpyDeviceToHost));
     if (logdet) {
         std::vector<double> ldv(batch, 0.0);
@@ -478,6 +531,10 @@ int gpe_dbg_potrf_inv(gpe_handle* h, const double* A, int n, int batch, double* 
     }
     if (status) CK(cudaMemcpy(status, h->status, sizeof(int) * batch, cudaMemcpyDefault));
     return 0;
+}
+
+int gpe_dbg_potrf_inv(gpe_handle* h, const double* A, int n, int batch, double* Linv_out, double* logdet, int* status) {
+    return gpe_potrf(h, A, n, batch, nullptr, Linv_out, logdet, status);
 }
 
 }  // extern "C"

@@ -21,8 +21,16 @@ struct gpe_handle {
     std::vector<cudaEvent_t> prof_pool;
     double prof_ms[NCAT] = {0};
     long long prof_cnt[NCAT] = {0};
-    cudaEvent_t prof_begin(int cat);
-    void prof_end(int cat, cudaEvent_t e0);
+    cudaEvent_t prof_begin(int cat, cudaStream_t s);
+    void prof_end(int cat, cudaEvent_t e0, cudaStream_t s);
+
+    // sub-batch streams: the multistart batch is split into contiguous groups that run the
+    // factorisation concurrently, so one group's latency-bound leaf panels and small recursion
+    // levels overlap the other groups' large DMMA GEMMs
+    enum { MAX_SUB = 8 };
+    int nsub = 4;
+    cudaStream_t sub_st[MAX_SUB] = {nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[MAX_SUB] = {nullptr};
 
     // training set (device)
     int n = 0, d = 0, q = 0, npad = 0, nleaf = 0;
@@ -50,6 +58,8 @@ struct gpe_handle {
     double *fbeta = nullptr;     // [NR]
     double *fwinv = nullptr;     // [d]
     double *fXs = nullptr;       // [d][npad] scaled training inputs, k-major
+    double *fAinv = nullptr;     // [npad][npad] A^-1 (lower 128-tiles), built on demand for the sensitivity traces
+    bool fAinv_valid = false;
     // prediction chunk workspace
     long long pchunk = 0;
     double *pC = nullptr, *pPart = nullptr, *pAux = nullptr, *pX = nullptr, *pH = nullptr, *pMean = nullptr, *pVar = nullptr;
@@ -62,15 +72,21 @@ struct gpe_handle {
 };
 
 struct ProfScope {
-    gpe_handle* h; int cat; cudaEvent_t e0;
-    ProfScope(gpe_handle* h_, int c) : h(h_), cat(c), e0(h_->prof_begin(c)) {}
-    ~ProfScope() { h->prof_end(cat, e0); }
+    gpe_handle* h; int cat; cudaStream_t s; cudaEvent_t e0;
+    ProfScope(gpe_handle* h_, int c, cudaStream_t s_ = nullptr) : h(h_), cat(c), s(s_ ? s_ : h_->st), e0(h_->prof_begin(c, s)) {}
+    ~ProfScope() { h->prof_end(cat, e0, s); }
+};
+
+// items [b0, b0 + B) of the batch workspace, processed on stream st
+struct SubBatch {
+    int b0, B;
+    cudaStream_t st;
 };
 
 bool gpe_is_device_ptr(const void* p);
 int gpe_ensure_batch_ws(gpe_handle* h, int B);
-int gpe_potrf_inv(gpe_handle* h, int B);
-int gpe_factor_and_reduce(gpe_handle* h, int B, int mode, int with_grad, const double* beta_override, double* Kout);
+int gpe_potrf_inv(gpe_handle* h, const SubBatch& sb, int want_L);
+int gpe_factor_and_reduce(gpe_handle* h, const SubBatch& sb, int mode, int with_grad, const double* beta_override, double* Kout);
 int gpe_upload_single_par(gpe_handle* h, const double* delta, double nugget, int kind, int predict, double s2_for_r);
 int gpe_run_gemm(gpe_handle* h, const double* A, const double* B, double* C, int lda, int ldb, int ldc,
                  long long sA, long long sB, long long sC, int M, int N, int K, double alpha, int acc,

@@ -149,7 +149,7 @@ constexpr int LS = NB + 1;
 __global__ void __launch_bounds__(1024, 1) leaf_potrf_trtri_kernel(const double* __restrict__ A, double* __restrict__ Linv,
                                                                     int ld, long long sA, long long sL, int off,
                                                                     double* __restrict__ logdet_part, int nleaf,
-                                                                    int* __restrict__ status) {
+                                                                    int* __restrict__ status, double* __restrict__ Lfac) {
     extern __shared__ __align__(16) double S[];  // [NB][LS] + dinv[NB]
     double* dinv = S + NB * LS;
     const int b = blockIdx.x, tid = threadIdx.x;
@@ -242,17 +242,24 @@ __global__ void __launch_bounds__(1024, 1) leaf_potrf_trtri_kernel(const double*
         double v = (j < i) ? S[j * LS + i] : ((j == i) ? dinv[i] : 0.0);
         Lb[(size_t)i * ld + j] = v;
     }
+    if (Lfac != nullptr) {   // the Cholesky factor of this block (np.linalg.cholesky consumers)
+        double* Fb = Lfac + (size_t)b * sL + (size_t)off * ld + off;
+        for (int e = tid; e < NB * NB; e += 1024) {
+            int i = e >> 7, j = e & (NB - 1);
+            Fb[(size_t)i * ld + j] = (j < i) ? S[i * LS + j] : ((j == i) ? 1.0 / dinv[i] : 0.0);
+        }
+    }
 }
 
 void launch_leaf(const double* A, double* Linv, int ld, long long sA, long long sL, int off,
-                 double* logdet_part, int nleaf, int* status, int B, cudaStream_t st) {
+                 double* logdet_part, int nleaf, int* status, int B, cudaStream_t st, double* Lfac) {
     size_t smem = (size_t)(NB * LS + NB) * sizeof(double);
     static bool attr = false;
     if (!attr) {
         cudaFuncSetAttribute(leaf_potrf_trtri_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr = true;
     }
-    leaf_potrf_trtri_kernel<<<B, 1024, smem, st>>>(A, Linv, ld, sA, sL, off, logdet_part, nleaf, status);
+    leaf_potrf_trtri_kernel<<<B, 1024, smem, st>>>(A, Linv, ld, sA, sL, off, logdet_part, nleaf, status, Lfac);
 }
 
 // =========================================================================== K3 pieces

@@ -40,7 +40,7 @@ void launch_unpad_sym(const double* A, int npad, int n, double* out, int mirror,
 
 // K2 leaf: Cholesky + triangular inverse of the 128x128 diagonal block at `off`.
 void launch_leaf(const double* A, double* Linv, int ld, long long sA, long long sL, int off,
-                 double* logdet_part, int nleaf, int* status, int B, cudaStream_t st);
+                 double* logdet_part, int nleaf, int* status, int B, cudaStream_t st, double* Lfac = nullptr);
 
 // [H | y | 0] -> padded panel HY [npad, NR] (shared by all batch items)
 void launch_build_hy(const double* H, const double* y, int n, int q, int npad, double* HY, cudaStream_t st);

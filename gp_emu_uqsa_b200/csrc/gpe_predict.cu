@@ -24,7 +24,8 @@ using namespace gpe;
 
 void gpe_handle::free_fit() {
     auto fr = [](double*& p) { if (p) cudaFree(p); p = nullptr; };
-    fr(fLi); fr(fE); fr(fK); fr(fbeta); fr(fwinv); fr(fXs);
+    fr(fLi); fr(fE); fr(fK); fr(fbeta); fr(fwinv); fr(fXs); fr(fAinv);
+    fAinv_valid = false;
     fr(pC); fr(pPart); fr(pAux); fr(pX); fr(pH); fr(pMean); fr(pVar);
     pchunk = 0;
     fitted = false;
@@ -363,7 +364,9 @@ int gpe_fit_state(gpe_handle* h, const double* delta, double nugget, double sigm
     launch_cov_build(h->X, h->r, h->n, h->d, np, h->par, h->winv, h->A, 0, 1, 0, h->st);
     h->launches++;
     CK(cudaMemsetAsync(h->fK, 0, sizeof(double) * NR * NR, h->st));
-    if ((rc = gpe_factor_and_reduce(h, 1, 0, 0, bov, h->fK))) return rc;
+    CK(cudaMemsetAsync(h->status, 0, sizeof(int), h->st));
+    SubBatch sb{0, 1, h->st};
+    if ((rc = gpe_factor_and_reduce(h, sb, 0, 0, bov, h->fK))) return rc;
     CK(cudaMemcpyAsync(h->fLi, h->Li, (size_t)np * np * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
     CK(cudaMemcpyAsync(h->fE, h->U, (size_t)np * NR * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
     CK(cudaMemcpyAsync(h->fwinv, h->winv, (size_t)h->d * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
@@ -382,6 +385,7 @@ int gpe_fit_state(gpe_handle* h, const double* delta, double nugget, double sigm
     h->fit_c = kind ? 1.0 : (1.0 - nugget);
     h->fit_astar = kind ? (1.0 + nugget * nugget) : 1.0;
     h->fitted = (st == 0);
+    h->fAinv_valid = false;
     if (beta_out) CK(cudaMemcpy(beta_out, bopt.data(), sizeof(double) * q, cudaMemcpyDefault));
     double sm = std::sqrt(io.quad / ((double)(h->n - q) - 2.0));
     if (sigma_mucm_out) CK(cudaMemcpy(sigma_mucm_out, &sm, sizeof(double), cudaMemcpyDefault));

@@ -42,6 +42,11 @@ long long gpe_launch_count(gpe_handle* h);
 /* The CUDA stream (cudaStream_t) every kernel of this handle is launched on: record CUDA
  * events on it to time the path on the device. */
 void* gpe_get_stream(gpe_handle* h);
+/* The multistart batch of gpe_llh_grad_batch is split into `nstreams` contiguous groups that run
+ * concurrently on their own CUDA streams (default 4, or GPE_STREAMS; 1 = strictly serial launches,
+ * which is what per-kernel timing with gpe_profile_* should be read under). */
+int gpe_set_streams(gpe_handle* h, int nstreams);
+
 /* Optional per-launch CUDA-event timing by kernel category (measurement only; the reference's
  * unused @timeit helper, _emulatoroptimise.py:8-17, is the nearest analogue).  ms/count: 6 entries:
  * 0 DMMA GEMM (128-wide tiles), 1 small/skinny GEMM, 2 Cholesky leaf, 3 covariance build,
@@ -126,15 +131,41 @@ int gpe_implausibility(gpe_handle* h, const double* mean, const double* var, int
                        unsigned long long* count_lt, double* cell_min,
                        unsigned long long* cell_count);
 
+/* out [n,k] = A^-1 Bm [n,k] for the training matrix factored by gpe_fit_state -- the
+ * np.linalg.solve(self.A, .) call sites of the sensitivity code
+ * (sensitivity/_sensitivityclasses.py:40-44 e, G; :187 A^-1 Rt; :451, :499 A^-1 T). */
+int gpe_solve(gpe_handle* h, const double* Bm, int k, double* out);
+
+/* Product-form n x n integrals of the sensitivity code -- Rtt (:90-102) and Pw (P_prod_calc +
+ * Pw_calc, :599-626):  P_kl = scale * u_k u_l * exp(-sum_i gamma_i (x_ki - x_li)^2),
+ * u_k = prod_i exp(-acoef_i (x_ki - mvec_i)^2)  (gamma_i = 0 for integrated-out inputs) --
+ * contracted without leaving the device:  trace_out = tr(A^-1 P)  (:191, :483-484) and
+ * M_out [nv,nv] = V^T P V for V [n,nv], nv <= 32 (V = [G | e]: G^T P G and e^T P e, :192-197, :488-495). */
+int gpe_sens_contract(gpe_handle* h, const double* gamma, const double* acoef, const double* mvec,
+                      double scale, const double* V, int nv, double* trace_out, double* M_out);
+
+/* Main-effect sweep (main_effect :277-285 with Tw_calc :628-633): for input which[w] and value
+ * xw[w,j]:  out[w,j] = sum_k evec_k * scale * prod_{i != P} t1_i exp(-t2_i (x_ki - mvec_i)^2)
+ *                                   * exp(-cdiag_P (xw - x_kP)^2)      ( = Tw . e ). */
+int gpe_sens_main_effect(gpe_handle* h, const double* t1, const double* t2, const double* cdiag,
+                         const double* mvec, const double* evec, double scale, const int* which,
+                         int nwhich, const double* xw, int points, double* out);
+
 /* Debug/test entry: one batched DMMA GEMM of the family used by the factorisation
  * (gpe_gemm.cuh).  layout 0 NT, 1 NN, 2 TN; device pointers only. */
 int gpe_dbg_gemm(gpe_handle* h, const double* A, const double* B, double* C, int lda, int ldb,
                  int ldc, long long sA, long long sB, long long sC, int M, int N, int K,
                  double alpha, int accumulate, int kmode, int lower, int batch, int layout);
 
-/* Debug/test entry: Cholesky + triangular inverse of `batch` SPD matrices A [batch,n,n]
- * (device or host): Linv_out [batch,n,n] lower-triangular L^-1, logdet [batch] = 2*sum(log L_ii),
- * status [batch]. */
+/* np.linalg.cholesky for `batch` SPD matrices A [batch,n,n] (device or host) -- the call sites
+ * outside the likelihood: posterior_sample (emulatorfunctions.py:283), noise_fit.py:131/:143,
+ * and V^-1 in Posterior.mahalanobis_distance (_emulatorclasses.py:672-673).  Outputs (any may be
+ * NULL): L_out [batch,n,n] lower Cholesky factor, Linv_out [batch,n,n] = L^-1,
+ * logdet [batch] = 2*sum(log L_ii), status [batch] (LAPACK info convention). */
+int gpe_potrf(gpe_handle* h, const double* A, int n, int batch, double* L_out, double* Linv_out,
+              double* logdet, int* status);
+
+/* Debug/test entry: gpe_potrf with only the inverse factor requested. */
 int gpe_dbg_potrf_inv(gpe_handle* h, const double* A, int n, int batch, double* Linv_out,
                       double* logdet, int* status);
 

@@ -183,10 +183,98 @@ def gen_hm(g, h, n, seed):
     return out
 
 
+def gen_sens(g, s, n, d, seed, points=25):
+    """Sensitivity (MUCM case 2): uncertainty / sensitivity / main_effect / totaleffectvariance of the
+    real reference for a fixed-hyper-parameter emulator."""
+    X, y, _ = synth(n, d, seed)
+    rng = np.random.default_rng(400 + seed)
+    out = {"X_raw": X, "y": y}
+    with tempfile.TemporaryDirectory() as tmp:
+        E = build(g, tmp, X, y, "F", "F", "T", 1e-4, "sens")
+        delta = 0.3 + 0.5 * rng.random(d)
+        sigma = 0.8 + 0.4 * rng.random()
+        E.par.delta = delta.copy(); E.K.d = E.par.delta; E.K.n = E.par.nugget
+        E.par.sigma = sigma
+        with RL.quiet():
+            E.training.remake()
+            E.opt_T.optimalbeta()
+            m = 0.4 + 0.2 * rng.random(d)
+            v = 0.01 + 0.03 * rng.random(d)
+            S = s.setup(E, list(m), list(v))
+            S.uncertainty()
+            S.sensitivity()
+            S.main_effect(plot=False, points=points)
+            S.totaleffectvariance()
+        out.update(X=E.training.inputs.copy(), H=E.training.H.copy(), A=E.training.A.copy(), delta=delta, sigma=sigma,
+                   nugget=float(E.par.nugget), beta=np.array(E.par.beta), m=m, v=v,
+                   input_range=np.array(E.all_data.input_range), uE=S.uE, uV=S.uV, uEV=S.uEV,
+                   senseindex=S.senseindex, effect=S.effect, mean_effect=S.mean_effect, EVTw=S.EVTw,
+                   e=S.e, G=S.G, W=S.W)
+    return out
+
+
+def gen_hm_api(g, h, n, seed):
+    """History matching through the reference's public functions: imp_plot (IMP/ODP matrices per input
+    pair), nonimp_data and new_wave_design (kept rows), for two trained 3-input emulators rebuilt from
+    their updated beliefs files.  The text of those checkpoint files is stored so the test can rebuild
+    byte-identical emulators without the reference."""
+    X, y, w = synth(n, 3, seed)
+    rng = np.random.default_rng(300 + seed)
+    y2 = np.cos(X @ rng.normal(size=3))
+    out = {}
+    with tempfile.TemporaryDirectory() as tmp, RL.cwd(tmp), RL.quiet():
+        emuls = []
+        for o, yy in enumerate((y, y2)):
+            cfg = RL.write_emulator_files(tmp, X, yy, mucm="F", fix_nugget="T", alt_nugget="F",
+                                          nugget=1e-4, name="hm%d" % o, tries=3)
+            np.random.seed(5 + o)
+            E = g.setup(cfg, datashuffle=False, scaleinputs=True)
+            g.train(E)
+            with open("hm%d_config_r" % o, "w") as f:
+                f.write("beliefs hm%d_beliefs-0f\ninputs hm%d_input-o0-0f\noutputs hm%d_output-o0-0f\n" % (o, o, o))
+                f.write("tv_config 10 0 0\ndelta_bounds [ ]\nsigma_bounds [ ]\nnugget_bounds [ ]\ntries 1\nconstraints bounds\n")
+            for fn in ("hm%d_config_r" % o, "hm%d_beliefs-0f" % o, "hm%d_input-o0-0f" % o, "hm%d_output-o0-0f" % o):
+                out["file_" + fn] = np.frombuffer(open(fn, "rb").read(), dtype=np.uint8)
+            emuls.append(g.setup("hm%d_config_r" % o, datashuffle=False, scaleinputs=True))
+        zs = [float(np.median(y)), float(np.median(y2))]
+        ve = [1e-2, 1e-2]
+        cm = 3.0
+        out.update(zs=np.array(zs), var_extra=np.array(ve), cm=cm)
+        np.random.seed(77)
+        h.imp_plot(emuls, zs, cm, ve, maxno=2, olhcmult=30, grid=4, plot=False, fileStr="g")
+        for s_ in ([0, 1], [0, 2], [1, 2]):
+            for m in (1, 2):
+                for kind in ("IMP", "ODP"):
+                    name = "g_%d_%s_%d_%d" % (m, kind, s_[0], s_[1])
+                    out[name] = np.loadtxt(name)
+            out["lhc_%d_%d" % tuple(s_)] = np.loadtxt("imp_input_%d_%d" % tuple(s_))
+        pts = rng.random((300, 3))
+        np.savetxt("sim_in", pts, fmt="%.17g")
+        np.savetxt("sim_out", np.column_stack([pts[:, 0], pts[:, 1]]), fmt="%.17g")
+        out["sim_in"] = pts
+        cnt = h.nonimp_data(emuls, zs, cm, ve, ["sim_in", "sim_out"], maxno=1)
+        out["nonimp_count"] = cnt
+        out["nonimp_in"] = np.atleast_2d(np.loadtxt("nonimp_sim_in"))
+        out["nonimp_out"] = np.atleast_2d(np.loadtxt("noninp_sim_out"))
+        np.random.seed(78)
+        cnt2 = h.new_wave_design(emuls, zs, cm, ve, ["nonimp_sim_in", "noninp_sim_out"], maxno=1, olhcmult=40, fileStr="w2")
+        out["wave_count"] = cnt2
+        out["wave_in"] = np.atleast_2d(np.loadtxt("w2_nonimp_sim_in"))
+        out["olhc_des"] = np.loadtxt("olhc_des")
+    return out
+
+
 def main():
     assert RL.available(), "reference not present"
     g, h, s, gn = RL.load()
     save = lambda name, d: (np.savez_compressed(os.path.join(HERE, name), **d), print("wrote", name))
+    if len(sys.argv) > 1 and sys.argv[1] == "sens":
+        save("sens_n60_d3.npz", gen_sens(g, s, 60, 3, 7))
+        save("sens_n150_d4.npz", gen_sens(g, s, 150, 4, 8))
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "hmapi":
+        save("hmapi_n100_d3.npz", gen_hm_api(g, h, 100, 6))
+        return
     save("llh_n60_d2.npz", gen_llh(g, 60, 2, 1, 3, nugget=1e-2))
     save("llh_n200_d4.npz", gen_llh(g, 200, 4, 2, 3, with_r=True))
     save("llh_n500_d8.npz", gen_llh(g, 500, 8, 3, 2))

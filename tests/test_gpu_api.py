@@ -1,0 +1,166 @@
+"""End-to-end parity of the reference-facing Python API (g.setup / g.train / g.posterior,
+sensitivity.*) on the B200 against goldens produced by the real reference
+(tests/golden/make_golden.py)."""
+import contextlib
+import io
+import os
+import shutil
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@contextlib.contextmanager
+def _cwd(path):
+    old = os.getcwd()
+    os.chdir(path)
+    try:
+        yield
+    finally:
+        os.chdir(old)
+
+
+@contextlib.contextmanager
+def _quiet():
+    with contextlib.redirect_stdout(io.StringIO()):
+        yield
+
+
+def test_toysim_setup_train_posterior_matches_reference(golden_dir, tmp_path):
+    """Config 1: examples/toy-sim as shipped (mucm T, fix_nugget T, tries 10, tv_config 10 0 2),
+    np.random.seed(0): same shuffle, same guesses, same best start -> same trained state."""
+    import gp_emu_uqsa_b200 as g
+    gold = np.load(os.path.join(golden_dir, "toysim.npz"))
+    for f in os.listdir(os.path.join(golden_dir, "toy-sim")):
+        shutil.copy(os.path.join(golden_dir, "toy-sim", f), tmp_path)
+    with _cwd(tmp_path), _quiet():
+        np.random.seed(0)
+        E = g.setup("toy-sim_config")
+        g.train(E)
+        mean, var = g.posterior(E, gold["xs"].copy())
+    # the trained state is the converged optimum of SciPy's L-BFGS-B: reproducible to optimiser tolerance
+    assert np.allclose(E.par.delta, gold["delta"], rtol=2e-4)
+    assert abs(E.par.sigma - gold["sigma"]) <= 2e-4 * gold["sigma"]
+    assert np.allclose(E.par.beta, gold["beta"], rtol=2e-4, atol=1e-5)
+    assert np.array_equal(E.training.inputs, gold["X"]) and np.array_equal(E.training.outputs, gold["y"])
+    assert np.allclose(mean, gold["mean"], rtol=1e-4, atol=1e-6)
+    assert np.allclose(var, gold["var"], rtol=5e-3, atol=1e-7)
+    # checkpoint files of the final build exist in the reference's naming
+    for name in ("toy-sim_beliefs-2f", "toy-sim_input-o0-2f", "toy-sim_output-o0-2f"):
+        assert os.path.exists(os.path.join(tmp_path, name))
+    # rebuilt emulator from the written files predicts the same
+    with _cwd(tmp_path), _quiet():
+        with open("recon_config", "w") as f:
+            f.write("beliefs toy-sim_beliefs-2f\ninputs toy-sim_input-o0-2f\noutputs toy-sim_output-o0-2f\n"
+                    "tv_config 10 0 0\ndelta_bounds [ ]\nnugget_bounds [ ]\nsigma_bounds [ ]\ntries 1\nconstraints none\n")
+        E2 = g.setup("recon_config", datashuffle=False)
+        m2, v2 = g.posterior(E2, gold["xs"].copy())
+    assert np.allclose(m2, mean, rtol=1e-6, atol=1e-7)      # '%.8f' text round trip of the data files
+
+
+def _emulator_from_golden(g, gold, tmp, mucm="F", alt="F"):
+    from oracle import ref_loader as RL          # test infrastructure: writes the four text files
+    with _cwd(tmp), _quiet():
+        cfg = RL.write_emulator_files(str(tmp), gold["X_raw"], gold["y"], mucm=mucm, fix_nugget="T", alt_nugget=alt,
+                                      nugget=float(gold["nugget"]), name="e")
+        E = g.setup(cfg, datashuffle=False, scaleinputs=True)
+        E.par.delta = gold["delta"].copy(); E.K.d = E.par.delta; E.K.n = E.par.nugget
+        E.par.sigma = float(gold["sigma"])
+        E.training.remake()
+        E.opt_T.optimalbeta()
+    return E
+
+
+@pytest.mark.parametrize("fname", ["sens_n60_d3.npz", "sens_n150_d4.npz"])
+def test_sensitivity_matches_reference(golden_dir, tmp_path, fname):
+    """uncertainty / sensitivity / main_effect / totaleffectvariance vs the real reference.
+    Tolerances: the measures are differences of O(1) integrals (E*[V_w] = EEE - EE2), so the
+    absolute error is referred to the scale of the terms (here var of the output ~ uEV)."""
+    import gp_emu_uqsa_b200 as g
+    import gp_emu_uqsa_b200.sensitivity as s
+    gold = np.load(os.path.join(golden_dir, fname))
+    E = _emulator_from_golden(g, gold, tmp_path)
+    assert np.allclose(E.training.inputs, gold["X"], rtol=0, atol=1e-15)
+    assert np.allclose(E.par.beta, gold["beta"], rtol=1e-9, atol=1e-11)
+    with _quiet():
+        S = s.setup(E, list(gold["m"]), list(gold["v"]))
+        S.uncertainty()
+        S.sensitivity()
+        S.main_effect(plot=False, points=gold["effect"].shape[1])
+        S.totaleffectvariance()
+    assert np.allclose(S.e, gold["e"], rtol=1e-7, atol=1e-9 * np.abs(gold["e"]).max())
+    assert np.allclose(S.G, gold["G"], rtol=1e-7, atol=1e-9 * np.abs(gold["G"]).max())
+    assert abs(S.uE - gold["uE"]) <= 1e-10 * abs(gold["uE"])
+    scale = abs(float(gold["uEV"]))
+    assert abs(S.uV - gold["uV"]) <= 1e-8 * scale
+    assert abs(S.uEV - gold["uEV"]) <= 1e-7 * scale
+    assert np.all(np.abs(S.senseindex - gold["senseindex"]) <= 1e-7 * scale)
+    assert np.all(np.abs(S.EVTw - gold["EVTw"]) <= 1e-7 * scale)
+    assert np.allclose(S.effect, gold["effect"], rtol=1e-8, atol=1e-10)
+    assert np.allclose(S.mean_effect, gold["mean_effect"], rtol=1e-8, atol=1e-10)
+    S.to_file(str(tmp_path / "sense_file"))
+    txt = open(tmp_path / "sense_file").read().split("\n")
+    assert txt[0].startswith("EE ") and txt[3].startswith("EVw ") and txt[4].startswith("EVTw ") and txt[5].startswith("xw ")
+
+
+def test_sensitivity_vs_oracle_larger_n(tmp_path):
+    """n = 700 (several leaf blocks, padded): GPU Sensitivity vs the NumPy oracle restatement."""
+    import gp_emu_uqsa_b200 as g
+    import gp_emu_uqsa_b200.sensitivity as s
+    from oracle.sens_oracle import SensOracle
+    rng = np.random.default_rng(11)
+    n, d = 700, 5
+    X = rng.random((n, d))
+    y = np.sin(X @ rng.normal(size=d)) + 0.1 * (X ** 2).sum(1)
+    gold = {"X_raw": X, "y": y, "nugget": 1e-4, "delta": 0.3 + 0.4 * rng.random(d), "sigma": 0.9}
+    E = _emulator_from_golden(g, gold, tmp_path)
+    m, v = list(0.4 + 0.2 * rng.random(d)), list(0.01 + 0.02 * rng.random(d))
+    with _quiet():
+        S = s.setup(E, m, v)
+        S.uncertainty(); S.sensitivity(); S.main_effect(points=20)
+    O = SensOracle(E.training.inputs, E.training.outputs, E.training.H, E.training.A, E.par.beta, E.par.sigma, E.par.nugget,
+                   E.par.delta, m, v)
+    uE, uV, uEV = O.uncertainty()
+    assert abs(S.uE - uE) <= 1e-10 * abs(uE)
+    assert abs(S.uV - uV) <= 1e-8 * abs(uEV) and abs(S.uEV - uEV) <= 1e-7 * abs(uEV)
+    assert np.all(np.abs(S.senseindex - O.sensitivity()) <= 1e-7 * abs(uEV))
+    eff, me = O.main_effect(E.all_data.input_range, points=20)
+    assert np.allclose(S.effect, eff, rtol=1e-8, atol=1e-10) and np.allclose(S.mean_effect, me, rtol=1e-8, atol=1e-10)
+
+
+def test_kernel_classes_match_oracle(tmp_path):
+    """kernel / kernel_alt_nug .var, .covar, .grad_delta_A, .grad_nugget_A as dense matrices."""
+    from gp_emu_uqsa_b200 import _emulatorkernels as K
+    from oracle import gp_oracle as O
+
+    class P:
+        delta = np.array([0.4, 0.7, 0.3])
+        nugget = 0.003
+    rng = np.random.default_rng(3)
+    X, Xv = rng.random((90, 3)), rng.random((37, 3))
+    for cls, kind in ((K.kernel, 0), (K.kernel_alt_nug, 1)):
+        k = cls(3, P)
+        for predict in (True, False):
+            A = k.var(X, predict)
+            assert np.allclose(A, O.cov_var(X, P.delta, P.nugget, kind, predict), rtol=1e-13, atol=1e-15)
+        C = k.covar(X, Xv)
+        assert np.allclose(C, O.cov_covar(X, Xv, P.delta, P.nugget, kind), rtol=1e-13, atol=1e-15)
+        k.var(X)
+        Gd = k.grad_delta_A(X[:, 1], 1, 0.7)
+        assert np.allclose(Gd, O.grad_delta_A(X, O.cov_exp_condensed(X, P.delta), P.delta, P.nugget, 1, 0.7, kind), rtol=1e-12, atol=1e-15)
+        Gn = k.grad_nugget_A(X, 0.7)
+        assert np.allclose(Gn, O.grad_nugget_A(X, O.cov_exp_condensed(X, P.delta), P.nugget, 0.7, kind), rtol=1e-12, atol=1e-15)
+
+
+def test_device_cholesky_and_posterior_sample(golden_dir, tmp_path):
+    from gp_emu_uqsa_b200 import _lib
+    rng = np.random.default_rng(5)
+    for n in (37, 128, 300):
+        M = rng.normal(size=(n, n))
+        A = M @ M.T + n * np.eye(n)
+        Lf = _lib.scratch_device().cholesky(A)
+        assert np.allclose(Lf, np.linalg.cholesky(A), rtol=1e-11, atol=1e-12)
+    with pytest.raises(np.linalg.LinAlgError):
+        _lib.scratch_device().cholesky(-np.eye(5))
