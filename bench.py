@@ -206,6 +206,7 @@ def run_b200(args):
     theta_rank = thetas_all[rank * B:(rank + 1) * B].copy()   # block partition of the guess index
 
     dev = _lib.Device(local)
+    dev.set_streams(args.streams)
     dev.set_training(X, y, H)
     stream = torch.cuda.ExternalStream(dev.stream_ptr, device=torch.device("cuda", local))
 
@@ -234,8 +235,6 @@ def run_b200(args):
         step_device(it)
     barrier()
     assert int(st_d.abs().sum().item()) == 0, "non-PD item in the benchmark batch"
-    dev.profile_enable(True)
-    dev.profile_read(reset=True)
     clocks = ClockSampler(local)
     clocks.start()
     l0 = dev.launches
@@ -248,8 +247,6 @@ def run_b200(args):
     barrier()
     ms = e0.elapsed_time(e1)
     launches = dev.launches - l0
-    prof = dev.profile_read(reset=True)
-    dev.profile_enable(False)
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -278,31 +275,59 @@ def run_b200(args):
     e2e_val = B * world * Ke / float(te.item())
     clk = clocks.stop()
 
-    # ---- posterior predictions/sec (config 4 slice), device-resident outputs, and its e2e
+    # ---- per-kernel CUDA-event timing: the same step with the sub-batch streams switched off, so that
+    # every launch runs alone on the handle's stream and its event pair measures that kernel only
+    dev.set_streams(1)
+    Kp_ = max(2, min(K, 3))
+    step_device(W + K)
+    barrier()
+    dev.profile_enable(True)
+    dev.profile_read(reset=True)
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record(stream)
+    for it in range(Kp_):
+        step_device(W + K + 1 + it)
+    s1.record(stream)
+    barrier()
+    serial_ms = s0.elapsed_time(s1) / Kp_
+    prof = dev.profile_read(reset=True)
+    dev.profile_enable(False)
+    dev.set_streams(args.streams)
+
+    # ---- posterior predictions/sec over the config-4 grid (10 levels^8 = 10^8 points, sharded by flat index
+    # range over the ranks), mean + diagonal variance kept in HBM, then the history-matching pass over two
+    # emulators (implausibility, keep mask, per-(dim0,dim1)-cell min and counts)
     extra = {}
     try:
         Xp, yp = synth(N_PRED, D_PRED)
-        devp = _lib.Device(local)
-        devp.set_training(Xp, yp, linear_H(Xp))
-        devp.set_basis(list(range(D_PRED)), [1] * D_PRED)
-        devp.fit_state(np.full(D_PRED, 0.5), 1e-4, 1.0, 0)
+        rng2 = np.random.default_rng(1)
+        yp2 = np.cos(Xp @ rng2.normal(size=D_PRED))
         levels = np.full(D_PRED, 10, dtype=np.int32)
         lo, hi = np.zeros(D_PRED), np.ones(D_PRED)
-        total = 10 ** 8
-        shard = total // world
-        m = PRED_POINTS_PER_STEP
-        mean_d = torch.empty(m, dtype=torch.float64, device="cuda")
-        var_d = torch.empty(m, dtype=torch.float64, device="cuda")
+        total = int(args.grid_points)
+        ncell_all = 100
+        cell_pts = total // ncell_all
+        c0, c1 = (ncell_all * rank) // world, (ncell_all * (rank + 1)) // world     # whole cells per rank
+        start, m = c0 * cell_pts, (c1 - c0) * cell_pts
+        devs = []
+        for yy in (yp, yp2):
+            dv = _lib.Device(local)
+            dv.set_training(Xp, yy, linear_H(Xp))
+            dv.set_basis(list(range(D_PRED)), [1] * D_PRED)
+            dv.fit_state(np.full(D_PRED, 0.5), 1e-4, 1.0, 0)
+            devs.append(dv)
+        devp = devs[0]
+        mean_d = torch.empty((2, m), dtype=torch.float64, device="cuda")
+        var_d = torch.empty((2, m), dtype=torch.float64, device="cuda")
         pstream = torch.cuda.ExternalStream(devp.stream_ptr, device=torch.device("cuda", local))
-        Kp = max(2, min(K, 4))
-        for it in range(2):
-            devp.predict_grid(levels, lo, hi, rank * shard + it * m, m, out=(mean_d, var_d))
+        warm = min(m, 1 << 18)
+        for it in range(3):
+            devp.predict_grid(levels, lo, hi, start, warm, out=(mean_d[0, :warm], var_d[0, :warm]))
         devp.profile_enable(True); devp.profile_read(reset=True)
         barrier()
         p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         p0.record(pstream)
-        for it in range(Kp):
-            devp.predict_grid(levels, lo, hi, rank * shard + (2 + it) * m, m, out=(mean_d, var_d))
+        devp.predict_grid(levels, lo, hi, start, m, out=(mean_d[0], var_d[0]))
         p1.record(pstream)
         barrier()
         pms = torch.tensor([p0.elapsed_time(p1)], dtype=torch.float64, device="cuda")
@@ -310,34 +335,71 @@ def run_b200(args):
             dist.all_reduce(pms, op=dist.ReduceOp.MAX)
         pprof = devp.profile_read(reset=True)
         devp.profile_enable(False)
-        preds = m * world * Kp / (float(pms.item()) * 1e-3)
-        mean_h = np.empty(m); var_h = np.empty(m)
+        preds = float(total) / (float(pms.item()) * 1e-3)
+        # history matching over the same shard: second emulator + implausibility reductions
         barrier()
         t0 = time.perf_counter()
-        devp.predict_grid(levels, lo, hi, rank * shard, m, out=(mean_h, var_h))
+        devs[1].predict_grid(levels, lo, hi, start, m, out=(mean_d[1], var_d[1]))
+        keep_d = torch.empty(m, dtype=torch.uint8, device="cuda")
+        zs = [float(np.median(yp)), float(np.median(yp2))]
+        _, _, cnt, cmin, ccnt = devp.implausibility(mean_d, var_d, zs, [1e-2, 1e-2], 3.0, maxno=1, ncell=c1 - c0,
+                                                     want_imax=False, out=(None, keep_d))
+        stats = torch.zeros(ncell_all + 1, dtype=torch.float64, device="cuda")
+        stats[c0:c1] = torch.from_numpy(cmin[:, 0]).cuda()
+        stats[ncell_all] = float(cnt[0])
+        if world > 1:      # the path's exchange: all-reduce of the cell statistics and the non-implausible count
+            dist.all_reduce(stats, op=dist.ReduceOp.SUM)
+        torch.cuda.synchronize()
+        hm_s = time.perf_counter() - t0
+        th = torch.tensor([hm_s], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(th, op=dist.ReduceOp.MAX)
+        # e2e: a slice of the shard through the call with HOST output buffers
+        me = min(m, 1 << 22)
+        mean_h = np.empty(me); var_h = np.empty(me)
+        barrier()
+        t0 = time.perf_counter()
+        devp.predict_grid(levels, lo, hi, start, me, out=(mean_h, var_h))
         pe = time.perf_counter() - t0
         peak, peak_src = fp64_peak()
         fpp = flops_pred(N_PRED, D_PRED, D_PRED + 1)
         gms, gcnt = pprof["gemm_dmma_128"]
-        extra = {"posterior_preds_per_s": preds, "posterior_workload": "config4 slice: n=2000 d=8 q=9, 10^8-point tensor grid "
-                 "generated on device, %d points/step x %d steps per GPU, mean+diag var" % (m, Kp),
-                 "posterior_e2e_preds_per_s": m / pe, "posterior_d2h_bytes_per_pred": 16,
+        nchunks = gcnt
+        extra = {"posterior_preds_per_s": preds,
+                 "posterior_workload": "config4: n=2000 d=8 q=9, %.0e-point tensor grid (10 levels/dim) generated on device from the flat "
+                                       "index, sharded over %d GPU(s) by index range, mean + diagonal variance written to HBM "
+                                       "(%.2f GB per GPU)" % (total, world, 16.0 * m / 1e9),
+                 "posterior_ms": float(pms.item()),
+                 "posterior_e2e_preds_per_s": me * world / pe, "posterior_d2h_bytes_per_pred": 16,
                  "posterior_roofline": {"bound": "tensor", "achieved": preds / world * fpp * 1e-12, "peak": peak,
                                         "unit": "TFLOP/s", "frac": preds / world * fpp * 1e-12 / peak,
-                                        "kernel_achieved": (m * Kp * float(2048) ** 2 * 1e-12) / (gms * 1e-3) if gms else None,
-                                        "note": "achieved = F_pred (n^2 + 2n(d+q+3)) x preds/s per GPU; kernel_achieved = padded "
-                                                "n^2 flops of the DMMA TRMM / its CUDA-event time"}}
-        devp.close()
+                                        "kernel": "gemm_dmma_ws_kernel<NN, EPI_SUMSQ> (Z = L^-1 C with fused column norms)",
+                                        "kernel_achieved": (float(m) * float(N_PRED) ** 2 * 1e-12) / (gms * 1e-3) if gms else None,
+                                        "kernel_launches": nchunks,
+                                        "by_kernel_ms": {k: v[0] for k, v in pprof.items()},
+                                        "note": "achieved = F_pred (n^2 + 2n(d+q+3)) x preds/s per GPU; kernel_achieved = n^2 flops per "
+                                                "point / CUDA-event time of the TRMM launches (timed inside the full pass)"},
+                 "history_match": {"points_per_s": float(total) / float(th.item()),
+                                   "workload": "second emulator prediction + implausibility over 2 emulators (cm=3, maxno=1): keep mask, "
+                                               "count and per-cell min over the 10x10 (dim0,dim1) cells; all-reduce of cell statistics",
+                                   "non_implausible": int(stats[ncell_all].item()), "seconds": float(th.item())}}
+        for dv in devs:
+            dv.close()
     except Exception as ex:      # the headline metric must still print
-        extra = {"posterior_error": repr(ex)}
+        import traceback
+        extra = {"posterior_error": repr(ex), "trace": traceback.format_exc()[-600:]}
 
     if rank == 0:
         peak, peak_src = fp64_peak()
         F = flops_llh(n, d, q, p)
         gemm_ms, gemm_cnt = prof["gemm_dmma_128"]
-        # dominant kernel: the 128x128-tile DMMA GEMM (Cholesky/TRTRI/LAUUM updates): algorithmic n^3 flops per eval
-        gemm_flops_per_step = B * float(n) ** 3
-        kern_ach = gemm_flops_per_step * K / (gemm_ms * 1e-3) * 1e-12 if gemm_ms else None
+        lau_ms, lau_cnt = prof["lauum"]
+        # dominant kernel: the LAUUM launch (A^-1 = L^-T L^-1, gemm_dmma_ws_kernel<TN>): algorithmic n^3/3 flops per item
+        lau_flops = B * float(n) ** 3 / 3.0
+        kern_ach = lau_flops * lau_cnt / (lau_ms * 1e-3) * 1e-12 if lau_ms else None
+        fam_flops = B * float(n) ** 3                       # potrf + trtri + lauum, all DMMA launches of a step
+        fam_ms = gemm_ms + lau_ms
+        fam_ach = fam_flops * Kp_ / (fam_ms * 1e-3) * 1e-12 if fam_ms else None
         traffic = None
         tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
         if os.path.exists(tp):
@@ -350,19 +412,26 @@ def run_b200(args):
             "config": {"workload": "config3: n=4096 d=16 q=17 p=17, gp4ml llh+grad, fixed nugget 1e-4, %d guesses/GPU per step "
                                    "(256 over 8 GPUs), theta perturbed each step" % B,
                        "l2": "working set 12.9 GB per step >> 126 MB L2 (inputs larger than L2, no flush needed)",
-                       "parallelism": "multistart guesses block-partitioned over ranks; one NCCL all_gather of (llh,theta,status) per step"},
+                       "parallelism": "multistart guesses block-partitioned over ranks; one NCCL all_gather of (llh,theta,status) per step",
+                       "streams": args.streams},
             "gpu_launches": int(launches),
             "clocks": {"sm_mhz": clk["sm_mhz"], "sm_max_mhz": clk["sm_max_mhz"], "reasons": clk["reasons"], "samples": clk["samples"]},
             "e2e": {"value": e2e_val, "unit": "evals/s", "h2d_bytes_per_step": int(B * p * 8),
                     "d2h_bytes_per_step": int(B * (p + 2) * 8 + B * 4), "steps": Ke},
             "roofline": {"bound": "tensor", "achieved": kern_ach, "peak": peak, "unit": "TFLOP/s",
                          "frac": (kern_ach / peak) if kern_ach else None, "traffic": traffic,
-                         "kernel": "gemm_dmma_kernel<128,128,...> (all SYRK/TRMM/LAUUM launches of the step)",
+                         "kernel": "gemm_dmma_ws_kernel<TN> LAUUM launch (A^-1 = L^-T L^-1, %d items, lower 128x128 tiles)" % B,
                          "peak_source": peak_src + "; MEASURED_PEAKS.json holds no FP64 figure",
-                         "algorithmic_flops_per_step": gemm_flops_per_step,
-                         "kernel_ms_per_step": gemm_ms / K if gemm_ms else None, "kernel_launches_per_step": gemm_cnt / K if K else None,
+                         "algorithmic_flops_per_launch": lau_flops, "algorithmic_bytes_per_launch": B * 8.0 * n * n,
+                         "kernel_ms_per_launch": lau_ms / lau_cnt if lau_cnt else None,
+                         "kernel_timing": "CUDA-event pair around every launch, measured live in this run in a separate pass of %d steps "
+                                          "with the sub-batch streams off (serial launches, %.2f ms/step); the timed region runs %d "
+                                          "concurrent sub-batch streams" % (Kp_, serial_ms, args.streams),
+                         "dmma_family": {"what": "all 128x128-tile DMMA launches of a step (SYRK/TRMM updates + LAUUM), algorithmic n^3 flops/item",
+                                         "achieved": fam_ach, "frac": fam_ach / peak if fam_ach else None, "ms_per_step": fam_ms / Kp_,
+                                         "launches_per_step": (gemm_cnt + lau_cnt) / Kp_},
                          "step_achieved": B * F / (ms_max / K * 1e-3) * 1e-12, "step_frac": B * F / (ms_max / K * 1e-3) * 1e-12 / peak,
-                         "by_kernel_ms_per_step": {k: v[0] / K for k, v in prof.items()}},
+                         "by_kernel_ms_per_step": {k: v[0] / Kp_ for k, v in prof.items()}},
             "extra": extra,
         }
         if world == 1 and not args.no_cpu:
@@ -382,6 +451,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-budget", type=float, default=25.0, help="seconds of CPU work for cpu_baseline")
+    ap.add_argument("--streams", type=int, default=8, help="concurrent sub-batch streams of gpe_llh_grad_batch")
+    ap.add_argument("--grid-points", type=float, default=1e8, help="size of the prediction grid (config 4: 1e8)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

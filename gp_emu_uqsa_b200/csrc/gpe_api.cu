@@ -121,14 +121,14 @@ int gpe_ensure_batch_ws(gpe_handle* h, int B) {
 // ------------------------------------------------------------------------------------- GEMM helper
 static int run_gemm(gpe_handle* h, cudaStream_t st, const double* A, const double* B, double* C, int lda, int ldb, int ldc,
                     long long sA, long long sB, long long sC, int M, int N, int K, double alpha, int acc,
-                    int kmode, int lower, int batch, int layout, int epi = EPI_STORE) {
+                    int kmode, int lower, int batch, int layout, int epi = EPI_STORE, int cat = -1) {
     GemmP p;
     p.A = A; p.B = B; p.C = C; p.lda = lda; p.ldb = ldb; p.ldc = ldc; p.sA = sA; p.sB = sB; p.sC = sC;
     p.M = M; p.N = N; p.K = K; p.alpha = alpha; p.accumulate = acc; p.kmode = kmode; p.lower = lower; p.batch = batch;
     bool big = (M % 128 == 0) && (N % 128 == 0) && N != 32 && M != 32;
     cudaError_t e;
     {
-        ProfScope ps(h, big ? gpe_handle::CAT_GEMM_BIG : gpe_handle::CAT_GEMM_SMALL, st);
+        ProfScope ps(h, cat >= 0 ? cat : (big ? gpe_handle::CAT_GEMM_BIG : gpe_handle::CAT_GEMM_SMALL), st);
         e = launch_gemm(p, layout, epi, st);
     }
     h->launches++;
@@ -209,7 +209,8 @@ int gpe_factor_and_reduce(gpe_handle* h, const SubBatch& sb, int mode, int with_
     if ((rc = run_gemm(h, st, Lb, Z, U, ld, NR, NR, sM, sP, sP, np, NR, np, 1.0, 0, KM_GE_I, 0, B, 2))) return rc;
     if (!with_grad) return 0;
     // LAUUM: A^-1 = Linv^T Linv (lower tiles) into the dead A buffer
-    if ((rc = run_gemm(h, st, Lb, Lb, Ab, ld, ld, ld, sM, sM, sM, np, np, np, 1.0, 0, KM_GE_I, 1, B, 2))) return rc;
+    if ((rc = run_gemm(h, st, Lb, Lb, Ab, ld, ld, ld, sM, sM, sM, np, np, np, 1.0, 0, KM_GE_I, 1, B, 2, EPI_STORE,
+                       gpe_handle::CAT_LAUUM))) return rc;
     {
         ProfScope ps(h, gpe_handle::CAT_GRAD, st);
         launch_grad_partial(h->X, h->r, h->n, h->d, np, h->winv + (size_t)b0 * h->d, Ab, sM, U, h->q + 1,
@@ -299,7 +300,8 @@ int gpe_profile_enable(gpe_handle* h, int on) {
 }
 
 // Drain the recorded event pairs: ms[c] / count[c] per category since the last reset
-// (0 big DMMA GEMM tiles, 1 small/skinny GEMM, 2 leaf, 3 covariance build, 4 gradient reduction, 5 other).
+// (0 big DMMA GEMM tiles, 1 small/skinny GEMM, 2 leaf, 3 covariance build, 4 gradient reduction, 5 other,
+// 6 the LAUUM launch A^-1 = L^-T L^-1, the single largest launch of an evaluation).
 int gpe_profile_read(gpe_handle* h, double* ms, long long* count, int reset) {
     if (!h) return -2;
     cudaStreamSynchronize(h->st);

@@ -14,7 +14,7 @@ struct gpe_handle {
     long long launches = 0;
 
     // optional per-category CUDA-event timing of every launch (gpe_profile_*)
-    enum { CAT_GEMM_BIG = 0, CAT_GEMM_SMALL = 1, CAT_LEAF = 2, CAT_COV = 3, CAT_GRAD = 4, CAT_OTHER = 5, NCAT = 6 };
+    enum { CAT_GEMM_BIG = 0, CAT_GEMM_SMALL = 1, CAT_LEAF = 2, CAT_COV = 3, CAT_GRAD = 4, CAT_OTHER = 5, CAT_LAUUM = 6, NCAT = 7 };
     bool prof_on = false;
     struct ProfRec { int cat; cudaEvent_t e0, e1; };
     std::vector<ProfRec> prof_recs;
@@ -28,7 +28,7 @@ struct gpe_handle {
     // factorisation concurrently, so one group's latency-bound leaf panels and small recursion
     // levels overlap the other groups' large DMMA GEMMs
     enum { MAX_SUB = 8 };
-    int nsub = 4;
+    int nsub = 8;
     cudaStream_t sub_st[MAX_SUB] = {nullptr};
     cudaEvent_t ev_fork = nullptr, ev_join[MAX_SUB] = {nullptr};
 

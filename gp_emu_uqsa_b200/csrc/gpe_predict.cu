@@ -219,14 +219,30 @@ __global__ void __launch_bounds__(256) implaus_kernel(const double* __restrict__
         if (live && Imax != nullptr) Imax[(size_t)r * ds.maxno + k] = vk;
     }
     if (live && keep != nullptr) keep[r] = (top[0] < ds.cm) ? 1 : 0;
+    // cells are contiguous runs of cell_pts points, so a warp (32 consecutive points) almost always
+    // sits inside one cell: reduce in the warp first, one atomic per warp instead of one per point
+    const long long cell = (cell_pts > 0 && live) ? r / cell_pts : -1;
+    const long long cell0 = __shfl_sync(0xffffffffu, cell, 0);
+    const bool uniform = cell_pts > 0 && __all_sync(0xffffffffu, cell == cell0) && cell0 >= 0;
     for (int k = 0; k < ds.maxno; k++) {
         // k-th output statistic refers to the (k+1)-th largest: top[maxno-1-k]
         double vk = top[ds.maxno - 1 - k];
         bool lt = live && (vk < ds.cm);
         unsigned bal = __ballot_sync(0xffffffffu, lt);
         if ((threadIdx.x & 31) == 0 && bal && count_lt != nullptr) atomicAdd(&count_lt[k], (unsigned long long)__popc(bal));
-        if (cell_pts > 0 && live) {
-            long long cell = r / cell_pts;
+        if (cell_pts <= 0) continue;
+        if (uniform) {
+            unsigned long long bits = (unsigned long long)__double_as_longlong(vk);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                unsigned long long other = __shfl_xor_sync(0xffffffffu, bits, o);
+                bits = other < bits ? other : bits;
+            }
+            if ((threadIdx.x & 31) == 0) {
+                if (cell_min_bits != nullptr) atomicMin(&cell_min_bits[(size_t)cell0 * ds.maxno + k], bits);
+                if (bal && cell_count != nullptr) atomicAdd(&cell_count[(size_t)cell0 * ds.maxno + k], (unsigned long long)__popc(bal));
+            }
+        } else if (live) {
             if (cell_min_bits != nullptr) atomicMin(&cell_min_bits[(size_t)cell * ds.maxno + k], (unsigned long long)__double_as_longlong(vk));
             if (lt && cell_count != nullptr) atomicAdd(&cell_count[(size_t)cell * ds.maxno + k], 1ull);
         }

@@ -43,14 +43,15 @@ long long gpe_launch_count(gpe_handle* h);
  * events on it to time the path on the device. */
 void* gpe_get_stream(gpe_handle* h);
 /* The multistart batch of gpe_llh_grad_batch is split into `nstreams` contiguous groups that run
- * concurrently on their own CUDA streams (default 4, or GPE_STREAMS; 1 = strictly serial launches,
+ * concurrently on their own CUDA streams (default 8, or GPE_STREAMS; 1 = strictly serial launches,
  * which is what per-kernel timing with gpe_profile_* should be read under). */
 int gpe_set_streams(gpe_handle* h, int nstreams);
 
 /* Optional per-launch CUDA-event timing by kernel category (measurement only; the reference's
- * unused @timeit helper, _emulatoroptimise.py:8-17, is the nearest analogue).  ms/count: 6 entries:
- * 0 DMMA GEMM (128-wide tiles), 1 small/skinny GEMM, 2 Cholesky leaf, 3 covariance build,
- * 4 gradient reduction, 5 other. */
+ * unused @timeit helper, _emulatoroptimise.py:8-17, is the nearest analogue).  ms/count: 7 entries:
+ * 0 DMMA GEMM (128-wide tiles; SYRK/TRMM updates of the factorisation and the prediction TRMM),
+ * 1 small/skinny GEMM, 2 Cholesky leaf, 3 covariance build, 4 gradient reduction, 5 other,
+ * 6 LAUUM (A^-1 = L^-T L^-1, the largest single launch of a likelihood evaluation). */
 int gpe_profile_enable(gpe_handle* h, int on);
 int gpe_profile_read(gpe_handle* h, double* ms, long long* count, int reset);
 
