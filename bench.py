@@ -25,6 +25,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+RESULT_OUT = sys.stdout
 METRIC = "llh+grad evals/sec (n=4096,d=16) and posterior preds/sec, 1/2/4/8 B200"
 N_TRAIN, D_IN, B_PER_GPU = 4096, 16, 32
 N_PRED, D_PRED = 2000, 8
@@ -179,7 +180,7 @@ def run_reference(args):
                                    "_emulatoroptimise.py:412-493 on the host cores"},
             "cpu_baseline": last,
             "e2e": {"value": v, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    print(json.dumps(line), file=RESULT_OUT, flush=True)
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
@@ -436,14 +437,25 @@ def run_b200(args):
         }
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_llh_sample(args.cpu_budget)
-        print(json.dumps(line))
+        print(json.dumps(line), file=RESULT_OUT, flush=True)
     dev.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+def _private_stdout():
+    """Library chatter on fd 1 (e.g. NCCL's version banner) must not mix with the ONE JSON line:
+    keep a private copy of stdout for the result and point fd 1 at stderr for everything else."""
+    sys.stdout.flush()
+    keep = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(keep, "w")
+
+
 def main():
+    global RESULT_OUT
+    RESULT_OUT = _private_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

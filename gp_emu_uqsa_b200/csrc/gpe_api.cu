@@ -64,7 +64,14 @@ static void dev_free(T*& p) {
     p = nullptr;
 }
 
+void gpe_handle::drop_graphs() {
+    for (auto& g : graphs)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+    graphs.clear();
+}
+
 void gpe_handle::free_batch_ws() {
+    drop_graphs();
     dev_free(A); dev_free(S); dev_free(Li); dev_free(Wy); dev_free(Z); dev_free(U); dev_free(GP);
     dev_free(logdet_part); dev_free(par); dev_free(out); dev_free(winv); dev_free(beta);
     dev_free(status); dev_free(gpart); dev_free(theta_d); dev_free(llh_d); dev_free(grad_d); dev_free(sig_d);
@@ -265,6 +272,7 @@ int gpe_create(int device, gpe_handle** out) {
     }
     cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
     if (const char* e = getenv("GPE_STREAMS")) h->nsub = std::max(1, std::min((int)gpe_handle::MAX_SUB, atoi(e)));
+    if (const char* e = getenv("GPE_GRAPHS")) h->use_graphs = e[0] != '0';
     *out = h;
     return 0;
 }
@@ -290,6 +298,7 @@ void* gpe_get_stream(gpe_handle* h) { return h ? (void*)h->st : nullptr; }
 int gpe_set_streams(gpe_handle* h, int nstreams) {
     if (!h || nstreams < 1) return -2;
     h->nsub = std::min((int)gpe_handle::MAX_SUB, nstreams);
+    h->drop_graphs();
     return 0;
 }
 
@@ -420,6 +429,45 @@ int gpe_cov_grad(gpe_handle* h, const double* delta, double nugget, int kind, in
     return 0;
 }
 
+// Device work of one resident sub-batch: theta_d -> (llh_d, grad_d, sig_d, status).  Everything is
+// enqueued on h->st and its sub-batch streams (fork/join by events), so the same code path is used
+// eagerly and under stream capture.
+static int enqueue_llh_chunk(gpe_handle* h, int Bs, int p, int mode, double fixed_nugget) {
+    const long long sM = (long long)h->npad * h->npad;
+    int rc;
+    launch_prep_theta(h->theta_d, Bs, p, h->d, mode, fixed_nugget, h->par, h->winv, h->st);
+    h->launches++;
+    CK(cudaMemsetAsync(h->status, 0, sizeof(int) * Bs, h->st));
+    // contiguous groups of the sub-batch, one stream each (a group needs >= 2 items to be worth a stream)
+    const int ns = std::max(1, std::min(h->nsub, Bs / 2));
+    if (ns > 1) CK(cudaEventRecord(h->ev_fork, h->st));
+    for (int g = 0; g < ns; g++) {
+        SubBatch sb;
+        sb.b0 = (int)((long long)Bs * g / ns);
+        sb.B = (int)((long long)Bs * (g + 1) / ns) - sb.b0;
+        sb.st = ns > 1 ? h->sub_st[g] : h->st;
+        if (ns > 1) CK(cudaStreamWaitEvent(sb.st, h->ev_fork, 0));
+        {
+            ProfScope ps(h, gpe_handle::CAT_COV, sb.st);
+            launch_cov_build(h->X, h->r, h->n, h->d, h->npad, h->par + sb.b0, h->winv + (size_t)sb.b0 * h->d,
+                             h->A + (size_t)sb.b0 * sM, sM, sb.B, 0, sb.st);
+        }
+        h->launches++;
+        if ((rc = gpe_factor_and_reduce(h, sb, mode, 1, nullptr, nullptr))) return rc;
+        if (ns > 1) {
+            CK(cudaEventRecord(h->ev_join[g], sb.st));
+            CK(cudaStreamWaitEvent(h->st, h->ev_join[g], 0));
+        }
+    }
+    {
+        ProfScope ps(h, gpe_handle::CAT_OTHER);
+        launch_grad_finalize(h->gpart, h->n, h->d, h->npad, p, mode, h->par, h->out, h->status, h->llh_d, h->grad_d,
+                             h->sig_d, Bs, h->st);
+    }
+    h->launches++;
+    return 0;
+}
+
 int gpe_llh_grad_batch(gpe_handle* h, const double* theta, int B, int p, int mode, double fixed_nugget,
                        double* llh, double* grad, double* sigma_hat, int* status) {
     if (!h || !h->n || !theta || B < 1 || !llh || !grad) return h ? h->fail_msg("bad argument / no training set") : -2;
@@ -428,42 +476,40 @@ int gpe_llh_grad_batch(gpe_handle* h, const double* theta, int B, int p, int mod
     CK(cudaSetDevice(h->device));
     int rc;
     if ((rc = gpe_ensure_batch_ws(h, B))) return rc;
-    const long long sM = (long long)h->npad * h->npad;
-    const int gn = grad_ntiles(h->npad) * grad_nvals(h->d);
-    (void)gn;
     for (int b0 = 0; b0 < B; b0 += h->Bcap) {
         int Bs = std::min(h->Bcap, B - b0);
         CK(cudaMemcpyAsync(h->theta_d, theta + (size_t)b0 * p, sizeof(double) * Bs * p, cudaMemcpyDefault, h->st));
-        launch_prep_theta(h->theta_d, Bs, p, h->d, mode, fixed_nugget, h->par, h->winv, h->st);
-        h->launches++;
-        CK(cudaMemsetAsync(h->status, 0, sizeof(int) * Bs, h->st));
-        // contiguous groups of the sub-batch, one stream each (a group needs >= 2 items to be worth a stream)
-        const int ns = std::max(1, std::min(h->nsub, Bs / 2));
-        if (ns > 1) CK(cudaEventRecord(h->ev_fork, h->st));
-        for (int g = 0; g < ns; g++) {
-            SubBatch sb;
-            sb.b0 = (int)((long long)Bs * g / ns);
-            sb.B = (int)((long long)Bs * (g + 1) / ns) - sb.b0;
-            sb.st = ns > 1 ? h->sub_st[g] : h->st;
-            if (ns > 1) CK(cudaStreamWaitEvent(sb.st, h->ev_fork, 0));
-            {
-                ProfScope ps(h, gpe_handle::CAT_COV, sb.st);
-                launch_cov_build(h->X, h->r, h->n, h->d, h->npad, h->par + sb.b0, h->winv + (size_t)sb.b0 * h->d,
-                                 h->A + (size_t)sb.b0 * sM, sM, sb.B, 0, sb.st);
-            }
-            h->launches++;
-            if ((rc = gpe_factor_and_reduce(h, sb, mode, 1, nullptr, nullptr))) return rc;
-            if (ns > 1) {
-                CK(cudaEventRecord(h->ev_join[g], sb.st));
-                CK(cudaStreamWaitEvent(h->st, h->ev_join[g], 0));
+        gpe_handle::LlhGraph* gr = nullptr;
+        if (h->use_graphs && !h->prof_on) {
+            for (auto& g : h->graphs)
+                if (g.Bs == Bs && g.p == p && g.mode == mode && g.nsub == h->nsub && g.nug == fixed_nugget) gr = &g;
+            if (!gr) {
+                h->graphs.push_back({Bs, p, mode, h->nsub, fixed_nugget, 0, nullptr, 0});
+                gr = &h->graphs.back();
             }
         }
-        {
-            ProfScope ps(h, gpe_handle::CAT_OTHER);
-            launch_grad_finalize(h->gpart, h->n, h->d, h->npad, p, mode, h->par, h->out, h->status, h->llh_d, h->grad_d,
-                                 h->sig_d, Bs, h->st);
+        if (gr && gr->exec) {
+            CK(cudaGraphLaunch(gr->exec, h->st));
+            h->launches += gr->launches;
+        } else if (gr && gr->seen >= 1) {
+            // second sighting of this shape: capture the launch sequence (all sub-batch streams join the
+            // capture through the fork event), instantiate, replay
+            const long long l0 = h->launches;
+            cudaGraph_t graph = nullptr;
+            CK(cudaStreamBeginCapture(h->st, cudaStreamCaptureModeRelaxed));
+            rc = enqueue_llh_chunk(h, Bs, p, mode, fixed_nugget);
+            cudaError_t ce = cudaStreamEndCapture(h->st, &graph);
+            if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+            if (ce != cudaSuccess) return h->fail("cudaStreamEndCapture", ce);
+            gr->launches = h->launches - l0;
+            ce = cudaGraphInstantiate(&gr->exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (ce != cudaSuccess) { gr->exec = nullptr; return h->fail("cudaGraphInstantiate", ce); }
+            CK(cudaGraphLaunch(gr->exec, h->st));
+        } else {
+            if (gr) gr->seen++;
+            if ((rc = enqueue_llh_chunk(h, Bs, p, mode, fixed_nugget))) return rc;
         }
-        h->launches++;
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(llh + b0, h->llh_d, sizeof(double) * Bs, cudaMemcpyDefault, h->st));
         CK(cudaMemcpyAsync(grad + (size_t)b0 * p, h->grad_d, sizeof(double) * Bs * p, cudaMemcpyDefault, h->st));

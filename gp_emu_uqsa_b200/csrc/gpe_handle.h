@@ -32,6 +32,14 @@ struct gpe_handle {
     cudaStream_t sub_st[MAX_SUB] = {nullptr};
     cudaEvent_t ev_fork = nullptr, ev_join[MAX_SUB] = {nullptr};
 
+    // CUDA graphs of the likelihood step: the launch sequence of a (batch size, mode) pair is
+    // captured the second time it is seen and replayed afterwards (one cudaGraphLaunch instead of
+    // ~650 launches per stream), so the host never limits the small-n, many-stream case
+    bool use_graphs = true;
+    struct LlhGraph { int Bs, p, mode, nsub; double nug; int seen; cudaGraphExec_t exec; long long launches; };
+    std::vector<LlhGraph> graphs;
+    void drop_graphs();
+
     // training set (device)
     int n = 0, d = 0, q = 0, npad = 0, nleaf = 0;
     double *X = nullptr, *y = nullptr, *H = nullptr, *r = nullptr, *HY = nullptr;

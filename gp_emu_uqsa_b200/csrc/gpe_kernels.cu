@@ -696,8 +696,6 @@ __global__ void __launch_bounds__(256) grad_partial_kernel(const double* __restr
     __syncthreads();
     const int ty = tid >> 4, tx = tid & 15;
     const double* Ab = Ainv + (size_t)b * sAinv;
-    const bool diag_tile = (ti == tj);
-    const double wgt = diag_tile ? 1.0 : 2.0;
     double t[4][4];
     double sE = 0.0, sD = 0.0, sDr = 0.0;
     {
@@ -745,12 +743,14 @@ __global__ void __launch_bounds__(256) grad_partial_kernel(const double* __restr
                     int gj = gj0 + e;
                     double wv = (e ? av.y : av.x) - dot[a][2 * h + e];
                     double tv = 0.0;
+                    // A^-1 is valid on and below the diagonal only (LAUUM computes lower fragments):
+                    // every off-diagonal pair is taken once from the lower triangle with weight 2
                     if (gi < n && gj < n) {
                         if (gi == gj) {
                             sD += wv;
                             if (r != nullptr) sDr = fma(wv, r[gi], sDr);
-                        } else {
-                            tv = wgt * wv * exp(-D[a][2 * h + e]);
+                        } else if (gi > gj) {
+                            tv = 2.0 * wv * exp(-D[a][2 * h + e]);
                         }
                     }
                     t[a][2 * h + e] = tv;

@@ -98,7 +98,6 @@ __global__ void __launch_bounds__(256) sens_pw_kernel(const double* __restrict__
             }
     }
     const bool lower = tj <= ti;
-    const double wgt = (ti == tj) ? 1.0 : 2.0;
     double acc = 0.0;
 #pragma unroll
     for (int a = 0; a < 4; a++) {
@@ -110,16 +109,18 @@ __global__ void __launch_bounds__(256) sens_pw_kernel(const double* __restrict__
             pv.x = scale * ui[li] * uj[lj0] * exp(-D[a][2 * hh]);
             pv.y = scale * ui[li] * uj[lj0 + 1] * exp(-D[a][2 * hh + 1]);
             *reinterpret_cast<double2*>(&P[(size_t)gi * npad + gj0]) = pv;
-            if (lower) {
+            if (lower) {      // A^-1 is valid on and below the diagonal only: off-diagonal pairs weigh 2
                 double2 av = *reinterpret_cast<const double2*>(&Ainv[(size_t)gi * npad + gj0]);
-                acc = fma(av.x, pv.x, acc);
-                acc = fma(av.y, pv.y, acc);
+                double w0 = (gj0 < gi) ? 2.0 : ((gj0 == gi) ? 1.0 : 0.0);
+                double w1 = (gj0 + 1 < gi) ? 2.0 : ((gj0 + 1 == gi) ? 1.0 : 0.0);
+                acc = fma(w0 * av.x, pv.x, acc);
+                acc = fma(w1 * av.y, pv.y, acc);
             }
         }
     }
     if (lower) {
         double tot = block_sum(acc, red);
-        if (tid == 0) tpart[(size_t)ti * (ti + 1) / 2 + tj] = wgt * tot;
+        if (tid == 0) tpart[(size_t)ti * (ti + 1) / 2 + tj] = tot;
     }
 }
 

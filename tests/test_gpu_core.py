@@ -48,9 +48,9 @@ def test_gemm_layouts(dev, M, N, K, batch, layout):
     assert torch.allclose(Cm2, ref, rtol=1e-12, atol=1e-11)
 
 
-def test_gemm_triangular_kmodes(dev):
+@pytest.mark.parametrize("n,batch", [(512, 2), (1024, 8), (1536, 4)])   # 64x64 tiles / warp-specialised 128x128 tiles
+def test_gemm_triangular_kmodes(dev, n, batch):
     from gp_emu_uqsa_b200 import _lib
-    n, batch = 512, 2
     g = torch.Generator(device="cuda").manual_seed(7)
     T = torch.randn(batch, n, n, dtype=torch.float64, device="cuda", generator=g) * _tril_mask(n, "cuda")
     F = torch.randn(batch, n, n, dtype=torch.float64, device="cuda", generator=g)
@@ -71,6 +71,16 @@ def test_gemm_triangular_kmodes(dev):
     want = T.transpose(1, 2) @ T
     m = _tril_mask(n, "cuda")
     assert torch.allclose(Cm * m, want * m, rtol=1e-12, atol=1e-11)
+    # TN, A lower stored [k][m] against a dense panel: C = T^T F, k >= i  (back substitution panels)
+    dev.dbg_gemm(T, F, Cm, n, n, n, n, n, n, sz, sz, sz, kmode=_lib.KM_GE_I, batch=batch, layout=2)
+    assert torch.allclose(Cm, T.transpose(1, 2) @ F, rtol=1e-12, atol=1e-11)
+    # NT, lower-only accumulate: C -= F F^T (SYRK); entries above the diagonal of C are left alone
+    C0 = torch.randn(batch, n, n, dtype=torch.float64, device="cuda", generator=g)
+    Cm = C0.clone()
+    torch.cuda.synchronize()        # the handle launches on its own (non-blocking) stream
+    dev.dbg_gemm(F, F, Cm, n, n, n, n, n, n, sz, sz, sz, alpha=-1.0, accumulate=1, kmode=_lib.KM_FULL, lower=1, batch=batch, layout=0)
+    want = C0 - F @ F.transpose(1, 2)
+    assert torch.allclose(Cm * m, want * m, rtol=1e-12, atol=1e-10)
 
 
 @pytest.mark.parametrize("n,batch", [(60, 2), (128, 3), (200, 2), (640, 2), (1000, 1)])
