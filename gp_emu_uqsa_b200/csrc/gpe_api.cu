@@ -126,6 +126,14 @@ int gpe_ensure_batch_ws(gpe_handle* h, int B) {
 }
 
 // ------------------------------------------------------------------------------------- GEMM helper
+// does launch_gemm pick the warp-specialised 128x128 kernel with a machine-filling grid? (mirrors dispatch_tiles)
+static bool gemm_is_big(int M, int N, int lower, int batch) {
+    if (M % 128 || N % 128 || M == 32 || N == 32) return false;
+    long long t128 = (long long)(M / 128) * (N / 128) * batch;
+    if (lower) t128 = t128 / 2 + (M / 128) * batch / 2;
+    return t128 >= 120;
+}
+
 static int run_gemm(gpe_handle* h, cudaStream_t st, const double* A, const double* B, double* C, int lda, int ldb, int ldc,
                     long long sA, long long sB, long long sC, int M, int N, int K, double alpha, int acc,
                     int kmode, int lower, int batch, int layout, int epi = EPI_STORE, int cat = -1) {
@@ -160,8 +168,9 @@ static int potrf_inv_rec(gpe_handle* h, const SubBatch& sb, int off, int m, int 
     double* Lb = h->Li + (size_t)sb.b0 * sM;
     if (m == NB) {
         {
-            ProfScope ps(h, gpe_handle::CAT_LEAF, sb.st);
-            launch_leaf(Ab, Lb, ld, sM, sM, off, h->logdet_part + (size_t)sb.b0 * h->nleaf, h->nleaf, h->status + sb.b0, B, sb.st,
+            cudaStream_t st = sb.stream(true);
+            ProfScope ps(h, gpe_handle::CAT_LEAF, st);
+            launch_leaf(Ab, Lb, ld, sM, sM, off, h->logdet_part + (size_t)sb.b0 * h->nleaf, h->nleaf, h->status + sb.b0, B, st,
                         want_L ? Sb : nullptr);
         }
         h->launches++;
@@ -178,14 +187,14 @@ static int potrf_inv_rec(gpe_handle* h, const SubBatch& sb, int off, int m, int 
     double* Li22 = Lb + (size_t)(off + m1) * ld + off + m1;
     double* Li21 = Lb + (size_t)(off + m1) * ld + off;
     // L21 = A21 * Linv11^T           (NT, Linv11 lower: k <= j)
-    if ((rc = run_gemm(h, sb.st, A21, Li11, S21, ld, ld, ld, sM, sM, sM, m2, m1, m1, 1.0, 0, KM_LE_J, 0, B, 0))) return rc;
+    if ((rc = run_gemm(h, sb.stream(!gemm_is_big(m2, m1, 0, B)), A21, Li11, S21, ld, ld, ld, sM, sM, sM, m2, m1, m1, 1.0, 0, KM_LE_J, 0, B, 0))) return rc;
     // A22 -= L21 * L21^T             (SYRK, lower tiles)
-    if ((rc = run_gemm(h, sb.st, S21, S21, A22, ld, ld, ld, sM, sM, sM, m2, m2, m1, -1.0, 1, KM_FULL, 1, B, 0))) return rc;
+    if ((rc = run_gemm(h, sb.stream(!gemm_is_big(m2, m2, 1, B)), S21, S21, A22, ld, ld, ld, sM, sM, sM, m2, m2, m1, -1.0, 1, KM_FULL, 1, B, 0))) return rc;
     if ((rc = potrf_inv_rec(h, sb, off + m1, m2, want_L))) return rc;
     // T = L21 * Linv11               (NN, Linv11 lower: k >= j)  -> dead A21 block
-    if ((rc = run_gemm(h, sb.st, S21, Li11, A21, ld, ld, ld, sM, sM, sM, m2, m1, m1, 1.0, 0, KM_GE_J, 0, B, 1))) return rc;
+    if ((rc = run_gemm(h, sb.stream(!gemm_is_big(m2, m1, 0, B)), S21, Li11, A21, ld, ld, ld, sM, sM, sM, m2, m1, m1, 1.0, 0, KM_GE_J, 0, B, 1))) return rc;
     // Linv21 = -Linv22 * T           (NN, Linv22 lower: k <= i)
-    if ((rc = run_gemm(h, sb.st, Li22, A21, Li21, ld, ld, ld, sM, sM, sM, m2, m1, m2, -1.0, 0, KM_LE_I, 0, B, 1))) return rc;
+    if ((rc = run_gemm(h, sb.stream(!gemm_is_big(m2, m1, 0, B)), Li22, A21, Li21, ld, ld, ld, sM, sM, sM, m2, m1, m2, -1.0, 0, KM_LE_I, 0, B, 1))) return rc;
     return 0;
 }
 int gpe_potrf_inv(gpe_handle* h, const SubBatch& sb, int want_L) { return potrf_inv_rec(h, sb, 0, h->npad, want_L); }
@@ -195,7 +204,7 @@ int gpe_potrf_inv(gpe_handle* h, const SubBatch& sb, int want_L) { return potrf_
 int gpe_factor_and_reduce(gpe_handle* h, const SubBatch& sb, int mode, int with_grad, const double* beta_override, double* Kout) {
     const int np = h->npad, ld = np, B = sb.B, b0 = sb.b0;
     const long long sM = (long long)np * np, sP = (long long)np * NR;
-    cudaStream_t st = sb.st;
+    cudaStream_t st;
     const int nslab = (np + GRAM_SLAB - 1) / GRAM_SLAB;
     double* Ab = h->A + (size_t)b0 * sM;
     double* Lb = h->Li + (size_t)b0 * sM;
@@ -204,6 +213,7 @@ int gpe_factor_and_reduce(gpe_handle* h, const SubBatch& sb, int mode, int with_
     int rc;
     if ((rc = potrf_inv_rec(h, sb, 0, np, 0))) return rc;
     // Wy = Linv [H | y]
+    st = sb.stream(true);
     if ((rc = run_gemm(h, st, Lb, h->HY, Wy, ld, NR, NR, sM, 0, sP, np, NR, np, 1.0, 0, KM_LE_I, 0, B, 1))) return rc;
     {
         ProfScope ps(h, gpe_handle::CAT_OTHER, st);
@@ -216,6 +226,7 @@ int gpe_factor_and_reduce(gpe_handle* h, const SubBatch& sb, int mode, int with_
     if ((rc = run_gemm(h, st, Lb, Z, U, ld, NR, NR, sM, sP, sP, np, NR, np, 1.0, 0, KM_GE_I, 0, B, 2))) return rc;
     if (!with_grad) return 0;
     // LAUUM: A^-1 = Linv^T Linv (lower tiles) into the dead A buffer
+    st = sb.stream(false);
     if ((rc = run_gemm(h, st, Lb, Lb, Ab, ld, ld, ld, sM, sM, sM, np, np, np, 1.0, 0, KM_GE_I, 1, B, 2, EPI_STORE,
                        gpe_handle::CAT_LAUUM))) return rc;
     {
@@ -266,10 +277,15 @@ int gpe_create(int device, gpe_handle** out) {
     h->device = device;
     h->sms = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking) != cudaSuccess) { delete h; return -3; }
+    int prio_least = 0, prio_greatest = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
     for (int s = 0; s < gpe_handle::MAX_SUB; s++) {
-        cudaStreamCreateWithFlags(&h->sub_st[s], cudaStreamNonBlocking);
+        cudaStreamCreateWithPriority(&h->sub_st[s], cudaStreamNonBlocking, prio_least);
+        cudaStreamCreateWithPriority(&h->sub_hi[s], cudaStreamNonBlocking, prio_greatest);
         cudaEventCreateWithFlags(&h->ev_join[s], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&h->ev_sw[s], cudaEventDisableTiming);
     }
+    if (const char* e = getenv("GPE_PRIO")) h->use_prio = e[0] != '0';
     cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
     if (const char* e = getenv("GPE_STREAMS")) h->nsub = std::max(1, std::min((int)gpe_handle::MAX_SUB, atoi(e)));
     if (const char* e = getenv("GPE_GRAPHS")) h->use_graphs = e[0] != '0';
@@ -284,7 +300,9 @@ int gpe_destroy(gpe_handle* h) {
     h->free_training();
     for (int s = 0; s < gpe_handle::MAX_SUB; s++) {
         if (h->sub_st[s]) { cudaStreamSynchronize(h->sub_st[s]); cudaStreamDestroy(h->sub_st[s]); }
+        if (h->sub_hi[s]) { cudaStreamSynchronize(h->sub_hi[s]); cudaStreamDestroy(h->sub_hi[s]); }
         if (h->ev_join[s]) cudaEventDestroy(h->ev_join[s]);
+        if (h->ev_sw[s]) cudaEventDestroy(h->ev_sw[s]);
     }
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     for (auto e : h->prof_pool) cudaEventDestroy(e);
@@ -446,6 +464,7 @@ static int enqueue_llh_chunk(gpe_handle* h, int Bs, int p, int mode, double fixe
         sb.b0 = (int)((long long)Bs * g / ns);
         sb.B = (int)((long long)Bs * (g + 1) / ns) - sb.b0;
         sb.st = ns > 1 ? h->sub_st[g] : h->st;
+        if (ns > 1 && h->use_prio) { sb.hi = h->sub_hi[g]; sb.ev = h->ev_sw[g]; }
         if (ns > 1) CK(cudaStreamWaitEvent(sb.st, h->ev_fork, 0));
         {
             ProfScope ps(h, gpe_handle::CAT_COV, sb.st);
@@ -455,7 +474,7 @@ static int enqueue_llh_chunk(gpe_handle* h, int Bs, int p, int mode, double fixe
         h->launches++;
         if ((rc = gpe_factor_and_reduce(h, sb, mode, 1, nullptr, nullptr))) return rc;
         if (ns > 1) {
-            CK(cudaEventRecord(h->ev_join[g], sb.st));
+            CK(cudaEventRecord(h->ev_join[g], sb.stream(false)));
             CK(cudaStreamWaitEvent(h->st, h->ev_join[g], 0));
         }
     }

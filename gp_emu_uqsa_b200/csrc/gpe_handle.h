@@ -29,8 +29,10 @@ struct gpe_handle {
     // levels overlap the other groups' large DMMA GEMMs
     enum { MAX_SUB = 8 };
     int nsub = 8;
-    cudaStream_t sub_st[MAX_SUB] = {nullptr};
-    cudaEvent_t ev_fork = nullptr, ev_join[MAX_SUB] = {nullptr};
+    cudaStream_t sub_st[MAX_SUB] = {nullptr};      // low priority: the large DMMA GEMMs, covariance build, gradient reduction
+    cudaStream_t sub_hi[MAX_SUB] = {nullptr};      // high priority: leaf panels, small recursion levels, skinny panels
+    cudaEvent_t ev_fork = nullptr, ev_join[MAX_SUB] = {nullptr}, ev_sw[MAX_SUB] = {nullptr};
+    bool use_prio = false;     // measured neutral on B200: off unless GPE_PRIO=1
 
     // CUDA graphs of the likelihood step: the launch sequence of a (batch size, mode) pair is
     // captured the second time it is seen and replayed afterwards (one cudaGraphLaunch instead of
@@ -85,10 +87,26 @@ struct ProfScope {
     ~ProfScope() { h->prof_end(cat, e0, s); }
 };
 
-// items [b0, b0 + B) of the batch workspace, processed on stream st
+// items [b0, b0 + B) of the batch workspace.  A group owns a low-priority stream `st` for its large
+// kernels and (optionally) a high-priority stream `hi` for its latency-bound small ones: the block
+// scheduler hands freed SMs to high-priority grids first, so one group's leaf panels and small
+// recursion levels run inside another group's big GEMM instead of waiting for its tail.  `stream(small)`
+// returns the stream for the next launch and orders it after everything the group has enqueued so far.
 struct SubBatch {
     int b0, B;
     cudaStream_t st;
+    cudaStream_t hi = nullptr;
+    cudaEvent_t ev = nullptr;
+    mutable bool on_hi = false;
+    cudaStream_t stream(bool small) const {
+        if (!hi || small == on_hi) return on_hi ? hi : st;
+        cudaStream_t from = on_hi ? hi : st, to = small ? hi : st;
+        cudaEventRecord(ev, from);
+        cudaStreamWaitEvent(to, ev, 0);
+        on_hi = small;
+        return to;
+    }
+    cudaStream_t current() const { return on_hi ? hi : st; }
 };
 
 bool gpe_is_device_ptr(const void* p);
