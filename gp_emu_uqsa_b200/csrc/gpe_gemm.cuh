@@ -113,7 +113,12 @@ __global__ void __launch_bounds__(WMW* WNW * 32, 1) gemm_dmma_kernel(GemmP p) {
     constexpr int A_LD = TileShape<BM, A_KC>::LD, B_LD = TileShape<BN, B_KC>::LD;
     extern __shared__ __align__(16) double smem[];
 
-    const int tj = blockIdx.x, ti = blockIdx.y, b = blockIdx.z;
+    // Heaviest tiles first: with a triangular operand the k-range grows with tj (KM_LE_J) or ti (KM_LE_I);
+    // walking those indices downwards leaves the short tiles for the tail of the launch
+    // (B200: TRMM 8.80 -> 8.68 ms at n = 2048 x 32 items, prediction 6.86 -> 6.98 Mpred/s).
+    const int tj = (p.kmode == KM_LE_J) ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;
+    const int ti = (p.kmode == KM_LE_I) ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y;
+    const int b = blockIdx.z;
     if (p.lower && (ti + 1) * BM <= tj * BN) return;
     const int m0 = ti * BM, n0 = tj * BN;
 
@@ -282,7 +287,12 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_dmma_ws_kernel(GemmP p) {
     extern __shared__ __align__(16) double smem[];
     __shared__ __align__(8) uint64_t full_bar[GEMM_STAGES], empty_bar[GEMM_STAGES];
 
-    const int tj = blockIdx.x, ti = blockIdx.y, b = blockIdx.z;
+    // Heaviest tiles first: with a triangular operand the k-range grows with tj (KM_LE_J) or ti (KM_LE_I);
+    // walking those indices downwards leaves the short tiles for the tail of the launch
+    // (B200: TRMM 8.80 -> 8.68 ms at n = 2048 x 32 items, prediction 6.86 -> 6.98 Mpred/s).
+    const int tj = (p.kmode == KM_LE_J) ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;
+    const int ti = (p.kmode == KM_LE_I) ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y;
+    const int b = blockIdx.z;
     if (p.lower && (ti + 1) * BM <= tj * BN) return;
     const int m0 = ti * BM, n0 = tj * BN;
     int kbeg = 0, kend = p.K;

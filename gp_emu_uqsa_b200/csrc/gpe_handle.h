@@ -27,7 +27,7 @@ struct gpe_handle {
     // sub-batch streams: the multistart batch is split into contiguous groups that run the
     // factorisation concurrently, so one group's latency-bound leaf panels and small recursion
     // levels overlap the other groups' large DMMA GEMMs
-    enum { MAX_SUB = 8 };
+    enum { MAX_SUB = 16 };
     int nsub = 8;
     cudaStream_t sub_st[MAX_SUB] = {nullptr};      // low priority: the large DMMA GEMMs, covariance build, gradient reduction
     cudaStream_t sub_hi[MAX_SUB] = {nullptr};      // high priority: leaf panels, small recursion levels, skinny panels
