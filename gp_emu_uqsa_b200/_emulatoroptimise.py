@@ -164,6 +164,7 @@ class Optimize:
             else:
                 pack[lo + k, 0] = 0.0
         pack = _dist.gather_blocks(pack, numguesses)
+        self.last_table = pack                     # rows [ok, fun, theta...] per guess, in guess order
         K.n = fixed_n if self.beliefs.fix_nugget != "F" else K.n
 
         # sigma for the printed lines (mucm): one more batched evaluation at the optima
@@ -173,7 +174,7 @@ class Optimize:
             _, _, ok2, sig = self._eval_batch(pack[okrows, 2:])
             sig_print = {int(c): float(s) for c, s, o in zip(okrows, sig, ok2) if o}
 
-        first_try, best_min, best_x = True, 10000000.0, None
+        first_try, best_min, best_x, best_C = True, 10000000.0, None, -1
         for C in range(numguesses):
             if pack[C, 0] != 1.0:
                 print("Trying next guess...")
@@ -187,7 +188,7 @@ class Optimize:
                 sig_str = "  sig: " + str(np.around(self.par.sigma, decimals=4))
             print("  hp: ", np.around(K.untransform(x), decimals=4), " llh: ", -1.0 * np.around(fun, decimals=4), sig_str)
             if fun < best_min or first_try:
-                best_min, best_x, first_try = fun, K.untransform(x), False
+                best_min, best_x, first_try, best_C = fun, K.untransform(x), False, C
         print("********")
         if first_try:
             print("ERROR: No optimization was made due to non-PSD errors. Increase 'tries'. Exiting.")
@@ -200,7 +201,7 @@ class Optimize:
             K.set_params(best_x[:-1])
             self.par.delta, self.par.nugget = K.d, K.n
             self.par.sigma = best_x[-1]
-        self.best_llh = best_min
+        self.best_llh, self.best_guess = best_min, best_C
         self.data.make_A(self.par.sigma ** 2)      # including r still (reference :289)
         self.data.make_H()
 

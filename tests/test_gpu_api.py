@@ -164,3 +164,42 @@ def test_device_cholesky_and_posterior_sample(golden_dir, tmp_path):
         assert np.allclose(Lf, np.linalg.cholesky(A), rtol=1e-11, atol=1e-12)
     with pytest.raises(np.linalg.LinAlgError):
         _lib.scratch_device().cholesky(-np.eye(5))
+
+
+@pytest.mark.parametrize("mucm,fix", [("F", "T"), ("T", "F")])
+def test_multistart_optimiser_matches_sequential_reference_algorithm(tmp_path, mucm, fix):
+    """Config-2 style (reduced): the batched lock-step multistart must find, start by start, what the
+    reference's sequential loop finds (SciPy L-BFGS-B on the oracle's llh+grad, same guesses from the
+    same seeded RNG, same bounds), and select the same best guess."""
+    import gp_emu_uqsa_b200 as g
+    from scipy.optimize import minimize
+    from oracle import gp_oracle as O
+    from oracle import ref_loader as RL
+    rng = np.random.default_rng(21)
+    n, d, B = 300, 6, 8
+    X = rng.random((n, d))
+    y = np.sin(X @ rng.normal(size=d)) + 0.1 * (X ** 2).sum(1)
+    with _cwd(tmp_path), _quiet():
+        cfg = RL.write_emulator_files(str(tmp_path), X, y, mucm=mucm, fix_nugget=fix, alt_nugget="F", nugget=1e-4,
+                                      name="c2", tries=B, constraints="bounds")
+        E = g.setup(cfg, datashuffle=False, scaleinputs=True)
+        np.random.seed(4)
+        E.opt_T.llh_optimize()
+    table = E.opt_T.last_table
+    # the oracle side: same guesses (row per parameter from the global RNG), sequential minimize
+    Xs, H = E.training.inputs, E.training.H
+    bounds_t = 2.0 * np.log(np.array(E.config.bounds))
+    p = bounds_t.shape[0]
+    np.random.seed(4)
+    grid = np.array([bounds_t[R, 0] + (bounds_t[R, 1] - bounds_t[R, 0]) * np.random.random_sample(B) for R in range(p)])
+    llh = O.loglikelihood_mucm if mucm == "T" else O.loglikelihood_gp4ml
+    funs = []
+    for C in range(B):
+        res = minimize(lambda t: llh(t, Xs, y, H, 0, 1e-4), grid[:, C], method="L-BFGS-B", jac=True, bounds=[list(b) for b in bounds_t])
+        funs.append(res.fun)
+    funs = np.array(funs)
+    assert np.all(table[:, 0] == 1.0)
+    close = np.abs(table[:, 1] - funs) <= 1e-6 * np.abs(funs)
+    assert close.sum() >= B - 1, (table[:, 1], funs)           # a start may settle in a neighbouring optimum
+    assert E.opt_T.best_guess == int(np.argmin(funs))
+    assert abs(E.opt_T.best_llh - funs.min()) <= 1e-8 * abs(funs.min())
