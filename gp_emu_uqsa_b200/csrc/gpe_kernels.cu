@@ -362,9 +362,13 @@ __global__ void __launch_bounds__(LT, 1) leaf_potrf_trtri_v2_kernel(const double
                     cb[c] = (c < nb && cc < NB) ? S[cc * LS + j0 + k] : 0.0;
                 }
 #pragma unroll
-                for (int a = 0; a < 4; a++)
+                for (int a = 0; a < 4; a++) {
+                    if (a >= na) break;                 // uniform: row groups beyond the trailing block
 #pragma unroll
-                    for (int c = 0; c < 8; c++) acc[a][c] = fma(ra[a], cb[c], acc[a][c]);
+                    for (int c = 0; c < 8; c++)
+                        if (c < nb && c <= 2 * a + 1)   // uniform: column group c lies right of every row of group a
+                            acc[a][c] = fma(ra[a], cb[c], acc[a][c]);
+                }
             }
 #pragma unroll
             for (int a = 0; a < 4; a++) {

@@ -1,0 +1,113 @@
+"""BASELINE.json's full sizes (n = 4096, d = 16 likelihood batch; n = 2000, d = 8 posterior) checked
+through size-independent properties -- the oracle needs a minute per evaluation there, so these are
+the checks that scale: factor * inverse = I, log-det consistency, gradient vs finite differences of
+the value, permutation invariance, the MUCM output-scale law, interpolation at the training points,
+grid-index vs explicit-point prediction, implausibility counts vs a direct evaluation."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+
+def _synth(n, d, seed=0):
+    rng = np.random.default_rng(seed)
+    X = rng.random((n, d))
+    w = rng.normal(size=d)
+    return X, np.sin(X @ w) + 0.1 * (X ** 2).sum(1)
+
+
+@pytest.fixture(scope="module")
+def dev():
+    from gp_emu_uqsa_b200 import _lib
+    d = _lib.Device(0)
+    yield d
+    d.close()
+
+
+def test_factor_times_inverse_is_identity_n4096(dev):
+    from gp_emu_uqsa_b200 import _lib
+    n, d = 4096, 16
+    X, y = _synth(n, d)
+    dev.set_training(X, y, np.column_stack([np.ones(n), X]))
+    A = dev.cov_build(np.full(d, 0.6), 1e-4, 0, True, 1.0)
+    Lf, Li = np.empty_like(A), np.empty_like(A)
+    ld, st = np.empty(1), np.zeros(1, dtype=np.int32)
+    dev._ck(dev.L.gpe_potrf(dev.h, _lib._ptr(A), n, 1, _lib._ptr(Lf), _lib._ptr(Li), _lib._ptr(ld), _lib._ptr(st)))
+    dev.n = dev.d = dev.q = 0
+    assert st[0] == 0
+    assert np.allclose(np.triu(Lf, 1), 0) and np.allclose(np.triu(Li, 1), 0)
+    R = Li @ Lf - np.eye(n)
+    assert np.abs(R).max() < 1e-9, np.abs(R).max()
+    assert abs(ld[0] - 2.0 * np.log(np.diag(Lf)).sum()) <= 1e-11 * abs(ld[0])
+    resid = Lf @ Lf.T - A
+    assert np.abs(resid).max() <= 1e-13 * n
+
+
+def test_llh_gradient_permutation_and_scale_laws_n4096(dev):
+    n, d = 4096, 16
+    X, y = _synth(n, d)
+    H = np.column_stack([np.ones(n), X])
+    rng = np.random.default_rng(5)
+    hp = np.column_stack([0.4 + 0.5 * rng.random((2, d)), 0.8 + 0.4 * rng.random(2)])
+    theta = 2 * np.log(hp)
+    eps = 1e-4
+    dirs = rng.normal(size=(2, d + 1))
+    dirs /= np.linalg.norm(dirs, axis=1)[:, None]
+    batch = [theta[0], theta[1]]
+    for v in dirs:                                          # central differences around theta[0]
+        batch += [theta[0] + eps * v, theta[0] - eps * v]
+    dev.set_training(X, y, H)
+    llh, grad, sig, st = dev.llh_grad_batch(np.array(batch), 0, fixed_nugget=1e-4)
+    assert (st == 0).all()
+    for k, v in enumerate(dirs):
+        fd = (llh[2 + 2 * k] - llh[3 + 2 * k]) / (2 * eps)
+        assert abs(fd - grad[0] @ v) <= 2e-6 * max(1.0, np.abs(grad[0]).max()), (fd, grad[0] @ v)
+    # same data in another order: the likelihood is a function of the set of points
+    perm = rng.permutation(n)
+    dev.set_training(X[perm], y[perm], H[perm])
+    llh_p, grad_p, _, st = dev.llh_grad_batch(theta, 0, fixed_nugget=1e-4)
+    assert (st == 0).all()
+    assert np.allclose(llh_p, llh[:2], rtol=1e-10, atol=0)
+    assert np.allclose(grad_p, grad[:2], rtol=0, atol=1e-8 * np.abs(grad[:2]).max())
+    # MUCM: y -> c y  =>  sigma_hat -> c sigma_hat, LLH -> LLH + (n - q) ln c
+    th_m = theta[:, :d]
+    dev.set_training(X, y, H)
+    l1, g1, s1, st1 = dev.llh_grad_batch(th_m, 1, fixed_nugget=1e-4)
+    dev.set_training(X, 3.0 * y, H)
+    l3, g3, s3, st3 = dev.llh_grad_batch(th_m, 1, fixed_nugget=1e-4)
+    assert (st1 == 0).all() and (st3 == 0).all()
+    assert np.allclose(s3, 3.0 * s1, rtol=1e-10)
+    assert np.allclose(l3, l1 + (n - (d + 1)) * np.log(3.0), rtol=1e-10)
+    assert np.allclose(g3, 9.0 * g1, rtol=1e-7, atol=1e-9 * np.abs(g3).max())      # reference quirk: grad carries sigma_hat^2
+
+
+def test_posterior_properties_n2000_and_grid_consistency(dev):
+    n, d = 2000, 8
+    X, y = _synth(n, d, seed=2)
+    dev.set_training(X, y, np.column_stack([np.ones(n), X]))
+    dev.set_basis(list(range(d)), [1] * d)
+    beta, _, st = dev.fit_state(np.full(d, 0.5), 1e-4, 1.0, 0)
+    assert st == 0
+    mean, var = dev.predict(X[:700])                        # at training points: interpolation up to the nugget
+    assert np.abs(mean - y[:700]).max() < 2e-3 and var.min() > -1e-12 and var.max() < 5e-3
+    # flat-index grid == the same points given explicitly (ragged count, crossing chunk boundaries)
+    levels = np.full(d, 10, dtype=np.int32)
+    start, count = 123457, 70001
+    gm, gv = dev.predict_grid(levels, np.zeros(d), np.ones(d), start, count)
+    idx = np.arange(start, start + count)
+    P = np.empty((count, d))
+    for k in range(d - 1, -1, -1):
+        P[:, k] = 0.0 + (idx % 10 + 0.5) * ((1.0 - 0.0) / 10.0)      # the device's formula: lo + (digit + 0.5) * step
+        idx = idx // 10
+    em, ev = dev.predict(P)
+    assert np.allclose(gm, em, rtol=1e-13, atol=1e-15) and np.allclose(gv, ev, rtol=1e-12, atol=1e-16)
+    assert ev.min() > 0
+    # implausibility reductions vs direct evaluation of history_match.py:121-136 on the same arrays
+    z, ve, cm = float(np.median(y)), 1e-2, 3.0
+    Imax, keep, cnt, cmin, ccnt = dev.implausibility(gm[None, :70000], gv[None, :70000], [z], [ve], cm, maxno=1, ncell=7)
+    I = np.sqrt((gm[:70000] - z) ** 2 / (gv[:70000] + ve))
+    assert np.array_equal(Imax[:, 0], I) or np.allclose(Imax[:, 0], I, rtol=1e-15)
+    assert np.array_equal(keep.astype(bool), I < cm) and cnt[0] == (I < cm).sum()
+    assert np.allclose(cmin[:, 0], I.reshape(7, -1).min(1), rtol=1e-15)
+    assert np.array_equal(ccnt[:, 0], (I.reshape(7, -1) < cm).sum(1))
