@@ -13,6 +13,7 @@
 // Measured roof (tools/ub_fp64.cu on B200): 37.2 TFLOP/s, DMMA == DFMA peak.
 #pragma once
 #include "gpe_common.cuh"
+#include <cstdlib>
 
 namespace gpe {
 
@@ -278,10 +279,12 @@ inline cudaError_t launch_gemm_cfg(const GemmP& p, cudaStream_t st) {
 constexpr int WS_CONSUMERS = 8;
 constexpr int WS_THREADS = (WS_CONSUMERS + 1) * 32;
 
-template <bool A_KC, bool B_KC, int EPI>
+// WMW = warp rows of the 8 math warps: 2 -> 2x4 warps of 64x32 (column-triangular and dense launches),
+// 4 -> 4x2 warps of 32x64 (row-triangular launches: four row levels for the per-warp k range below).
+template <bool A_KC, bool B_KC, int EPI, int WMW = 2>
 __global__ void __launch_bounds__(WS_THREADS, 1) gemm_dmma_ws_kernel(GemmP p) {
-    constexpr int BM = 128, BN = 128, WNW = 4;
-    constexpr int WTM = 64, WTN = 32, FM = 8, FN = 4;
+    constexpr int BM = 128, BN = 128, WNW = WS_CONSUMERS / WMW;
+    constexpr int WTM = BM / WMW, WTN = BN / WNW, FM = WTM / 8, FN = WTN / 8;
     constexpr int A_EL = TileShape<BM, A_KC>::ELEMS, B_EL = TileShape<BN, B_KC>::ELEMS;
     constexpr int A_LD = TileShape<BM, A_KC>::LD, B_LD = TileShape<BN, B_KC>::LD;
     extern __shared__ __align__(16) double smem[];
@@ -337,8 +340,28 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_dmma_ws_kernel(GemmP p) {
     }
 
     // ===== consumer warps =====
-    const int wm0 = (warp / WNW) * WTM, wn0 = (warp % WNW) * WTN;
+    // Warp w runs on SM sub-partition w % 4.  Column ownership is mirrored for the second warp row
+    // (warps 4..7 take columns 3,2,1,0), so each sub-partition hosts one warp from the light and one from
+    // the heavy end of a triangular operand (see the per-warp k range below).
+    // (4x2 grid: warps 0..3 take rows 0..3 of column 0, warps 4..7 rows 3..0 of column 1.)
+    const int wrow = (WMW == 2) ? warp / 4 : (warp < 4 ? warp : 7 - warp);
+    const int wcol = (WMW == 2) ? (warp < 4 ? warp : 7 - warp) : warp / 4;
+    const int wm0 = wrow * WTM, wn0 = wcol * WTN;
     const int fr = lane >> 2, fc = lane & 3;
+    // Per-warp k range.  The CTA-level range [kbeg, kend) already drops the k-tiles that are zero for the
+    // whole 128x128 tile; inside the 128-wide diagonal block of the triangular operand a 64x32 warp tile
+    // still meets only zeros for part of it (B lower: columns n see k <= n, or k >= n when stored [k][n];
+    // A lower: rows likewise).  Those k-tiles are waited for and released but not multiplied:
+    // 37.5 % (column modes) / 25 % (row modes) of the diagonal block's DMMAs, with no change to the
+    // inner loop.
+    int wk_lo = 0, wk_hi = KT;
+    switch (p.kmode) {
+        case KM_LE_J: wk_hi = min(KT, (n0 + wn0 + WTN - kbeg + GEMM_BK - 1) / GEMM_BK); break;
+        case KM_GE_J: wk_lo = max(0, (n0 + wn0 - kbeg) / GEMM_BK); break;
+        case KM_LE_I: wk_hi = min(KT, (m0 + wm0 + WTM - kbeg + GEMM_BK - 1) / GEMM_BK); break;
+        case KM_GE_I: wk_lo = max(0, (m0 + wm0 - kbeg) / GEMM_BK); break;
+        default: break;
+    }
     double acc[FM][FN][2];
 #pragma unroll
     for (int i = 0; i < FM; i++)
@@ -356,17 +379,19 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_dmma_ws_kernel(GemmP p) {
         mbar_wait(&full_bar[s], (kt / GEMM_STAGES) & 1);
         const double* at = As + s * A_EL + a_off;
         const double* bt = Bs + s * B_EL + b_off;
+        if (kt >= wk_lo && kt < wk_hi) {
 #pragma unroll
-        for (int kk = 0; kk < GEMM_BK / 4; kk++) {
-            double af[FM], bf[FN];
+            for (int kk = 0; kk < GEMM_BK / 4; kk++) {
+                double af[FM], bf[FN];
 #pragma unroll
-            for (int i = 0; i < FM; i++) af[i] = at[kk * a_kk + i * a_fstep];
+                for (int i = 0; i < FM; i++) af[i] = at[kk * a_kk + i * a_fstep];
 #pragma unroll
-            for (int j = 0; j < FN; j++) bf[j] = bt[kk * b_kk + j * b_fstep];
+                for (int j = 0; j < FN; j++) bf[j] = bt[kk * b_kk + j * b_fstep];
 #pragma unroll
-            for (int i = 0; i < FM; i++)
+                for (int i = 0; i < FM; i++)
 #pragma unroll
-                for (int j = 0; j < FN; j++) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+                    for (int j = 0; j < FN; j++) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+            }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty_bar[s]);
@@ -391,7 +416,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_dmma_ws_kernel(GemmP p) {
             }
     } else {
         named_bar_sync(1, WS_THREADS);      // every stage consumed, producer drained: smem is free
-        double* red = smem;                 // [2][BN]
+        double* red = smem;                 // [WMW][BN]
 #pragma unroll
         for (int j = 0; j < FN; j++) {
             double s0 = 0.0, s1 = 0.0;
@@ -406,19 +431,23 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_dmma_ws_kernel(GemmP p) {
                 s1 += __shfl_xor_sync(0xffffffffu, s1, o);
             }
             if (fr == 0) {
-                red[(warp / WNW) * BN + wn0 + 8 * j + 2 * fc] = s0;
-                red[(warp / WNW) * BN + wn0 + 8 * j + 2 * fc + 1] = s1;
+                red[wrow * BN + wn0 + 8 * j + 2 * fc] = s0;
+                red[wrow * BN + wn0 + 8 * j + 2 * fc + 1] = s1;
             }
         }
         named_bar_sync(2, WS_CONSUMERS * 32);
-        for (int c = tid; c < BN; c += WS_CONSUMERS * 32)
-            p.C[(size_t)b * p.sC + (size_t)ti * p.ldc + n0 + c] = red[c] + red[BN + c];
+        for (int c = tid; c < BN; c += WS_CONSUMERS * 32) {
+            double tot = 0.0;
+#pragma unroll
+            for (int w = 0; w < WMW; w++) tot += red[w * BN + c];
+            p.C[(size_t)b * p.sC + (size_t)ti * p.ldc + n0 + c] = tot;
+        }
     }
 }
 
-template <bool A_KC, bool B_KC, int EPI>
-inline cudaError_t launch_gemm_ws(const GemmP& p, cudaStream_t st) {
-    auto kern = gemm_dmma_ws_kernel<A_KC, B_KC, EPI>;
+template <bool A_KC, bool B_KC, int EPI, int WMW>
+inline cudaError_t launch_gemm_ws_shape(const GemmP& p, cudaStream_t st) {
+    auto kern = gemm_dmma_ws_kernel<A_KC, B_KC, EPI, WMW>;
     constexpr size_t smem = gemm_smem_bytes<128, 128, A_KC, B_KC>();
     static bool attr_set = false;
     if (!attr_set) {
@@ -430,6 +459,18 @@ inline cudaError_t launch_gemm_ws(const GemmP& p, cudaStream_t st) {
     dim3 grid(p.N / 128, p.M / 128, p.batch);
     kern<<<grid, WS_THREADS, smem, st>>>(p);
     return cudaGetLastError();
+}
+
+// row-triangular launches (k <= i, k >= i) get the 4x2 warp grid, everything else the 2x4 grid
+template <bool A_KC, bool B_KC, int EPI>
+inline cudaError_t launch_gemm_ws(const GemmP& p, cudaStream_t st) {
+    static int force2 = -1;
+    if (force2 < 0) {
+        const char* e = getenv("GPE_WS_SHAPE");
+        force2 = (e && e[0] == '2') ? 1 : 0;
+    }
+    if (!force2 && (p.kmode == KM_LE_I || p.kmode == KM_GE_I)) return launch_gemm_ws_shape<A_KC, B_KC, EPI, 4>(p, st);
+    return launch_gemm_ws_shape<A_KC, B_KC, EPI, 2>(p, st);
 }
 
 // Layout ids: 0 = (A_KC,B_KC) "NT", 1 = (A_KC,!B_KC) "NN", 2 = (!A_KC,!B_KC) "TN".
