@@ -150,6 +150,11 @@ static int run_gemm(gpe_handle* h, cudaStream_t st, const double* A, const doubl
     if (e != cudaSuccess) return h->fail("launch_gemm", e);
     return 0;
 }
+int gpe_run_gemm_on(gpe_handle* h, cudaStream_t st, const double* A, const double* B, double* C, int lda, int ldb, int ldc,
+                    long long sA, long long sB, long long sC, int M, int N, int K, double alpha, int acc,
+                    int kmode, int lower, int batch, int layout, int epi) {
+    return run_gemm(h, st, A, B, C, lda, ldb, ldc, sA, sB, sC, M, N, K, alpha, acc, kmode, lower, batch, layout, epi);
+}
 int gpe_run_gemm(gpe_handle* h, const double* A, const double* B, double* C, int lda, int ldb, int ldc,
                  long long sA, long long sB, long long sC, int M, int N, int K, double alpha, int acc,
                  int kmode, int lower, int batch, int layout, int epi) {

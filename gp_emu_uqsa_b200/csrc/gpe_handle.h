@@ -72,7 +72,10 @@ struct gpe_handle {
     bool fAinv_valid = false;
     // prediction chunk workspace
     long long pchunk = 0;
-    double *pC = nullptr, *pPart = nullptr, *pAux = nullptr, *pX = nullptr, *pH = nullptr, *pMean = nullptr, *pVar = nullptr;
+    // two slots: consecutive chunks alternate between two streams so that one chunk's cross-covariance /
+    // skinny product / finalize overlap the other's TRMM
+    struct PredSlot { double *C = nullptr, *Part = nullptr, *Aux = nullptr, *X = nullptr, *H = nullptr, *Mean = nullptr, *Var = nullptr; };
+    PredSlot ps[2];
 
     int fail(const char* what, cudaError_t e);
     int fail_msg(const char* what);
@@ -114,6 +117,9 @@ int gpe_ensure_batch_ws(gpe_handle* h, int B);
 int gpe_potrf_inv(gpe_handle* h, const SubBatch& sb, int want_L);
 int gpe_factor_and_reduce(gpe_handle* h, const SubBatch& sb, int mode, int with_grad, const double* beta_override, double* Kout);
 int gpe_upload_single_par(gpe_handle* h, const double* delta, double nugget, int kind, int predict, double s2_for_r);
+int gpe_run_gemm_on(gpe_handle* h, cudaStream_t st, const double* A, const double* B, double* C, int lda, int ldb, int ldc,
+                    long long sA, long long sB, long long sC, int M, int N, int K, double alpha, int acc,
+                    int kmode, int lower, int batch, int layout, int epi);
 int gpe_run_gemm(gpe_handle* h, const double* A, const double* B, double* C, int lda, int ldb, int ldc,
                  long long sA, long long sB, long long sC, int M, int N, int K, double alpha, int acc,
                  int kmode, int lower, int batch, int layout, int epi);

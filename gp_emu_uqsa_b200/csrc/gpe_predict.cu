@@ -26,7 +26,7 @@ void gpe_handle::free_fit() {
     auto fr = [](double*& p) { if (p) cudaFree(p); p = nullptr; };
     fr(fLi); fr(fE); fr(fK); fr(fbeta); fr(fwinv); fr(fXs); fr(fAinv);
     fAinv_valid = false;
-    fr(pC); fr(pPart); fr(pAux); fr(pX); fr(pH); fr(pMean); fr(pVar);
+    for (auto& sl : ps) { fr(sl.C); fr(sl.Part); fr(sl.Aux); fr(sl.X); fr(sl.H); fr(sl.Mean); fr(sl.Var); }
     pchunk = 0;
     fitted = false;
 }
@@ -292,16 +292,18 @@ __global__ void fullcov_finalize_kernel(const double* __restrict__ ZtZ, int mp, 
 int ensure_predict_ws(gpe_handle* h, long long mc) {
     if (mc <= h->pchunk) return 0;
     auto fr = [](double*& p) { if (p) cudaFree(p); p = nullptr; };
-    fr(h->pC); fr(h->pPart); fr(h->pAux); fr(h->pX); fr(h->pH); fr(h->pMean); fr(h->pVar);
     h->pchunk = 0;
     size_t ntile = h->npad / 128;
-    CK(cudaMalloc((void**)&h->pC, (size_t)h->npad * mc * sizeof(double)));
-    CK(cudaMalloc((void**)&h->pPart, ntile * mc * sizeof(double)));
-    CK(cudaMalloc((void**)&h->pAux, (size_t)NR * mc * sizeof(double)));
-    CK(cudaMalloc((void**)&h->pX, (size_t)mc * h->d * sizeof(double)));
-    CK(cudaMalloc((void**)&h->pH, (size_t)mc * NR * sizeof(double)));
-    CK(cudaMalloc((void**)&h->pMean, (size_t)mc * sizeof(double)));
-    CK(cudaMalloc((void**)&h->pVar, (size_t)mc * sizeof(double)));
+    for (auto& sl : h->ps) {
+        fr(sl.C); fr(sl.Part); fr(sl.Aux); fr(sl.X); fr(sl.H); fr(sl.Mean); fr(sl.Var);
+        CK(cudaMalloc((void**)&sl.C, (size_t)h->npad * mc * sizeof(double)));
+        CK(cudaMalloc((void**)&sl.Part, ntile * mc * sizeof(double)));
+        CK(cudaMalloc((void**)&sl.Aux, (size_t)NR * mc * sizeof(double)));
+        CK(cudaMalloc((void**)&sl.X, (size_t)mc * h->d * sizeof(double)));
+        CK(cudaMalloc((void**)&sl.H, (size_t)mc * NR * sizeof(double)));
+        CK(cudaMalloc((void**)&sl.Mean, (size_t)mc * sizeof(double)));
+        CK(cudaMalloc((void**)&sl.Var, (size_t)mc * sizeof(double)));
+    }
     h->pchunk = mc;
     return 0;
 }
@@ -319,30 +321,30 @@ long long default_chunk(gpe_handle* h) {
     return (c + 127) / 128 * 128;
 }
 
-// One chunk: points already in P_dev [mc, d] (rows >= count arbitrary but finite).
-int predict_chunk(gpe_handle* h, const double* P_dev, const double* Hs_dev, long long count, int mc, double* mean_dev,
-                  double* var_dev) {
+// One chunk on stream `st` with the buffers of `sl`: points already in P_dev [mc, d] (rows >= count
+// arbitrary but finite).
+int predict_chunk(gpe_handle* h, gpe_handle::PredSlot& sl, cudaStream_t st, const double* P_dev, const double* Hs_dev,
+                  long long count, int mc, double* mean_dev, double* var_dev) {
     const int np = h->npad;
     size_t smem = (size_t)h->d * (64 + 130) * sizeof(double);
     {
-        ProfScope ps(h, gpe_handle::CAT_COV);
-        xcov_kernel<<<dim3(mc / 128, np / 64), 256, smem, h->st>>>(h->fXs, P_dev, h->fwinv, h->n, h->d, np, mc, count, h->fit_c,
-                                                                   h->pC, mc);
+        ProfScope ps(h, gpe_handle::CAT_COV, st);
+        xcov_kernel<<<dim3(mc / 128, np / 64), 256, smem, st>>>(h->fXs, P_dev, h->fwinv, h->n, h->d, np, mc, count, h->fit_c, sl.C, mc);
     }
     h->launches++;
     int rc;
     // aux = [A^-1 H K^-T | e]^T C     (TN, skinny M = 32)
-    if ((rc = gpe_run_gemm(h, h->fE, h->pC, h->pAux, NR, mc, mc, 0, 0, 0, NR, mc, np, 1.0, 0, KM_FULL, 0, 1, 2, EPI_STORE))) return rc;
+    if ((rc = gpe_run_gemm_on(h, st, h->fE, sl.C, sl.Aux, NR, mc, mc, 0, 0, 0, NR, mc, np, 1.0, 0, KM_FULL, 0, 1, 2, EPI_STORE))) return rc;
     int ntile = 0;
     if (var_dev != nullptr) {
         // column norms of Z = Linv C    (NN, Linv lower: k <= i), reduced in the epilogue
-        if ((rc = gpe_run_gemm(h, h->fLi, h->pC, h->pPart, np, mc, mc, 0, 0, 0, np, mc, np, 1.0, 0, KM_LE_I, 0, 1, 1, EPI_SUMSQ))) return rc;
+        if ((rc = gpe_run_gemm_on(h, st, h->fLi, sl.C, sl.Part, np, mc, mc, 0, 0, 0, np, mc, np, 1.0, 0, KM_LE_I, 0, 1, 1, EPI_SUMSQ))) return rc;
         ntile = np / 128;
     }
     {
-        ProfScope ps(h, gpe_handle::CAT_OTHER);
-        predict_finalize_kernel<<<(unsigned)((count + 127) / 128), 128, 0, h->st>>>(
-            h->pPart, ntile, h->pAux, mc, P_dev, Hs_dev, basis_of(h), h->d, h->fK, h->fbeta, h->fit_sigma * h->fit_sigma,
+        ProfScope ps(h, gpe_handle::CAT_OTHER, st);
+        predict_finalize_kernel<<<(unsigned)((count + 127) / 128), 128, 0, st>>>(
+            sl.Part, ntile, sl.Aux, mc, P_dev, Hs_dev, basis_of(h), h->d, h->fK, h->fbeta, h->fit_sigma * h->fit_sigma,
             h->fit_astar, count, mean_dev, var_dev);
     }
     h->launches++;
@@ -417,38 +419,53 @@ static int predict_common(gpe_handle* h, const double* Xs, const double* Hs, con
     long long chunk = std::min<long long>(default_chunk(h), (m + 127) / 128 * 128);
     int rc;
     if ((rc = ensure_predict_ws(h, chunk))) return rc;
-    // staging buffers are reused across chunks; every copy/kernel is ordered on h->st
+    // Chunks alternate between two (stream, buffer slot) pairs: a slot's staging buffers are reused only
+    // by later chunks of the same stream, which orders them.
     const bool x_dev = Xs && gpe_is_device_ptr(Xs), h_dev = Hs && gpe_is_device_ptr(Hs);
     const bool mean_dev = gpe_is_device_ptr(mean), var_dev = var && gpe_is_device_ptr(var);
     const int d = h->d, q = h->q;
-    for (long long s = 0; s < m; s += chunk) {
+    const bool two = m > chunk && !h->prof_on;
+    if (two) {
+        CK(cudaEventRecord(h->ev_fork, h->st));
+        for (int k = 0; k < 2; k++) CK(cudaStreamWaitEvent(h->sub_st[k], h->ev_fork, 0));
+    }
+    int ci = 0;
+    for (long long s = 0; s < m; s += chunk, ci++) {
+        gpe_handle::PredSlot& sl = h->ps[two ? (ci & 1) : 0];
+        cudaStream_t st = two ? h->sub_st[ci & 1] : h->st;
         long long cnt = std::min(chunk, m - s);
         int mc = (int)((cnt + 127) / 128 * 128);
         const double* P = nullptr;
         if (grid) {
-            grid_points_kernel<<<(mc + 255) / 256, 256, 0, h->st>>>(*grid, start + s, cnt, mc, h->pX);
+            grid_points_kernel<<<(mc + 255) / 256, 256, 0, st>>>(*grid, start + s, cnt, mc, sl.X);
             h->launches++;
-            P = h->pX;
+            P = sl.X;
         } else if (x_dev && cnt == mc) {
             P = Xs + (size_t)s * d;
         } else {
-            if (cnt < mc) CK(cudaMemsetAsync(h->pX, 0, (size_t)mc * d * sizeof(double), h->st));
-            CK(cudaMemcpyAsync(h->pX, Xs + (size_t)s * d, (size_t)cnt * d * sizeof(double), cudaMemcpyDefault, h->st));
-            P = h->pX;
+            if (cnt < mc) CK(cudaMemsetAsync(sl.X, 0, (size_t)mc * d * sizeof(double), st));
+            CK(cudaMemcpyAsync(sl.X, Xs + (size_t)s * d, (size_t)cnt * d * sizeof(double), cudaMemcpyDefault, st));
+            P = sl.X;
         }
         const double* Hc = nullptr;
         if (Hs) {
             if (h_dev) Hc = Hs + (size_t)s * q;
             else {
-                CK(cudaMemcpyAsync(h->pH, Hs + (size_t)s * q, (size_t)cnt * q * sizeof(double), cudaMemcpyDefault, h->st));
-                Hc = h->pH;
+                CK(cudaMemcpyAsync(sl.H, Hs + (size_t)s * q, (size_t)cnt * q * sizeof(double), cudaMemcpyDefault, st));
+                Hc = sl.H;
             }
         }
-        double* mo = mean_dev ? mean + s : h->pMean;
-        double* vo = var ? (var_dev ? var + s : h->pVar) : nullptr;
-        if ((rc = predict_chunk(h, P, Hc, cnt, mc, mo, vo))) return rc;
-        if (!mean_dev) CK(cudaMemcpyAsync(mean + s, h->pMean, cnt * sizeof(double), cudaMemcpyDeviceToHost, h->st));
-        if (var && !var_dev) CK(cudaMemcpyAsync(var + s, h->pVar, cnt * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+        double* mo = mean_dev ? mean + s : sl.Mean;
+        double* vo = var ? (var_dev ? var + s : sl.Var) : nullptr;
+        if ((rc = predict_chunk(h, sl, st, P, Hc, cnt, mc, mo, vo))) return rc;
+        if (!mean_dev) CK(cudaMemcpyAsync(mean + s, sl.Mean, cnt * sizeof(double), cudaMemcpyDeviceToHost, st));
+        if (var && !var_dev) CK(cudaMemcpyAsync(var + s, sl.Var, cnt * sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
+    if (two) {
+        for (int k = 0; k < 2; k++) {
+            CK(cudaEventRecord(h->ev_join[k], h->sub_st[k]));
+            CK(cudaStreamWaitEvent(h->st, h->ev_join[k], 0));
+        }
     }
     CK(cudaStreamSynchronize(h->st));
     CK(cudaGetLastError());
