@@ -253,52 +253,60 @@ __global__ void __launch_bounds__(1024, 1) leaf_potrf_trtri_kernel(const double*
     }
 }
 
-// ---- v2 leaf: blocked, barrier-light --------------------------------------------------------------
+// ---- v3 leaf: blocked, barrier-light, O(n^3) parts on the FP64 tensor pipe -------------------------
 // The v1 kernel above spends one block barrier, one FP64 sqrt and one FP64 divide per column on a
-// 1024-thread CTA (ncu/CUDA events: 238 us per 128x128 block, the longest latency chain of an
-// evaluation).  v2 keeps the block in shared memory and works in 8-wide panels:
+// 1024-thread CTA (238 us per launch of 128x128 blocks, the longest latency chain of an evaluation).
+// v3 keeps the block in shared memory and works in 8-wide panels:
 //   potrf  (16 panels): (1) the 8x8 diagonal block is factored by ONE warp in registers -- lane i owns
 //          row i, pivots and columns travel by shuffles, 1/sqrt(pivot) comes from rsqrt() so there is
 //          no divide on the chain; (2) the rows below are solved against it, one thread per row;
-//          (3) the trailing block gets its rank-8 update from a 16x32 thread grid with 4x8 register
-//          micro-tiles (12 shared loads per 32 FMA).  3 barriers per panel instead of 8.
+//          (3) the trailing block gets its rank-8 update as two DMMA.8x8x4 per lower 8x8 fragment,
+//          operands and accumulator read straight from shared memory.  3 barriers per panel.
 //   trtri: the 8x8 diagonal inverses (one thread per column), then log2(128/8) = 4 doubling levels
-//          X21 = -X22 (L21 X11), every output an independent dot product; 9 barriers in total.
+//          X21 = -X22 (L21 X11), both products as DMMA fragments with the triangular k ranges; 9 barriers.
 // L is kept in the lower triangle (diagonal included), X = L^-1 transposed in the upper triangle, its
 // diagonal (1/L_ii) in dinv[]; the log-determinant is summed from the stored pivots afterwards.
-constexpr int LT = 512;          // threads of the v2 leaf
+// History (tools/perf_leaf.py, 32 blocks per launch): v1 238 us; v2 (same structure, scalar-FMA trailing
+// update and inverse levels with register micro-tiles) 107 us, of which 33 us trailing update and 43 us
+// inverse levels -- issue-bound, one FMA per instruction; v3 58.7 us.  The row stride is 132 (= 4 mod 16
+// doubles, the same rule as the GEMM tiles) so the 8x4 / 4x8 fragment loads are bank-conflict-free; the
+// few row-per-thread accesses of the panel solve pay a 4-way conflict instead.
+constexpr int LT = 512;          // threads of the leaf CTA
 constexpr int PW = 8;            // panel width
+constexpr int L3 = NB + 4;
+constexpr int T3MAX = 64 * 68;
 
-__global__ void __launch_bounds__(LT, 1) leaf_potrf_trtri_v2_kernel(const double* __restrict__ A, double* __restrict__ Linv,
+__global__ void __launch_bounds__(LT, 1) leaf_potrf_trtri_v3_kernel(const double* __restrict__ A, double* __restrict__ Linv,
                                                                      int ld, long long sA, long long sL, int off,
                                                                      double* __restrict__ logdet_part, int nleaf,
                                                                      int* __restrict__ status, double* __restrict__ Lfac) {
-    extern __shared__ __align__(16) double S[];      // [NB][LS]
-    double* Tm = S + NB * LS;                        // [64*65] product scratch of the inverse levels
-    double* dinv = Tm + 64 * 65;                     // [NB] 1 / L_ii
+    extern __shared__ __align__(16) double S[];      // [NB][L3]
+    double* Tm = S + NB * L3;                        // [T3MAX] product scratch of the inverse levels
+    double* dinv = Tm + T3MAX;                       // [NB] 1 / L_ii
     double* pv = dinv + NB;                          // [NB] pivots
     __shared__ double red[32];
     __shared__ int s_bad;
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int fr = lane >> 2, fc = lane & 3;
+    constexpr int NW = LT / 32;
     const double* Ab = A + (size_t)b * sA + (size_t)off * ld + off;
     for (int e = tid; e < NB * NB; e += LT) {
         int i = e >> 7, j = e & (NB - 1);
-        S[i * LS + j] = (j <= i) ? Ab[(size_t)i * ld + j] : 0.0;
+        S[i * L3 + j] = (j <= i) ? Ab[(size_t)i * ld + j] : 0.0;
     }
     if (tid == 0) s_bad = 0;
     __syncthreads();
 
-    // ------------------------------------------------------------------ potrf
-    const int tx = tid & 15, ty = tid >> 4;          // trailing-update thread grid 16 x 32
+    // ------------------------------------------------------------------ potrf, 8-wide panels
     for (int j0 = 0; j0 < NB; j0 += PW) {
-        if (warp == 0) {
+        if (warp == 0) {                 // 8x8 diagonal block in registers: lane i owns row i
             double a[PW];
 #pragma unroll
-            for (int c = 0; c < PW; c++) a[c] = (lane < PW && c <= lane) ? S[(j0 + lane) * LS + j0 + c] : 0.0;
+            for (int c = 0; c < PW; c++) a[c] = (lane < PW && c <= lane) ? S[(j0 + lane) * L3 + j0 + c] : 0.0;
 #pragma unroll
             for (int j = 0; j < PW; j++) {
                 double pj = __shfl_sync(0xffffffffu, a[j], j);
-                if (!(pj > 0.0)) {               // LAPACK dpotrf: pivot <= 0 or NaN -> info = j + 1
+                if (!(pj > 0.0)) {       // LAPACK dpotrf: pivot <= 0 or NaN -> info = j + 1
                     if (lane == 0 && s_bad == 0) s_bad = off + j0 + j + 1;
                     pj = 1.0;
                 }
@@ -319,14 +327,14 @@ __global__ void __launch_bounds__(LT, 1) leaf_potrf_trtri_v2_kernel(const double
             if (lane < PW) {
 #pragma unroll
                 for (int c = 0; c < PW; c++)
-                    if (c <= lane) S[(j0 + lane) * LS + j0 + c] = a[c];
+                    if (c <= lane) S[(j0 + lane) * L3 + j0 + c] = a[c];
             }
         }
         __syncthreads();
         const int base = j0 + PW, R = NB - base;
         if (R == 0) break;
-        if (tid < R) {                              // panel solve: row r against the diagonal block
-            double* row = S + (base + tid) * LS + j0;
+        if (tid < R) {                   // panel solve: row r against the diagonal block
+            double* row = S + (base + tid) * L3 + j0;
             double x[PW];
 #pragma unroll
             for (int c = 0; c < PW; c++) x[c] = row[c];
@@ -334,56 +342,32 @@ __global__ void __launch_bounds__(LT, 1) leaf_potrf_trtri_v2_kernel(const double
             for (int j = 0; j < PW; j++) {
                 double sacc = x[j];
 #pragma unroll
-                for (int k = 0; k < j; k++) sacc = fma(-x[k], S[(j0 + j) * LS + j0 + k], sacc);
+                for (int k = 0; k < j; k++) sacc = fma(-x[k], S[(j0 + j) * L3 + j0 + k], sacc);
                 x[j] = sacc * dinv[j0 + j];
             }
 #pragma unroll
             for (int c = 0; c < PW; c++) row[c] = x[c];
         }
         __syncthreads();
-        {                                           // rank-8 update of the trailing lower triangle
-            const int na = (R + 31) >> 5, nb = (R + 15) >> 4;
-            double acc[4][8];
-#pragma unroll
-            for (int a = 0; a < 4; a++)
-#pragma unroll
-                for (int c = 0; c < 8; c++) acc[a][c] = 0.0;
-#pragma unroll
-            for (int k = 0; k < PW; k++) {
-                double ra[4], cb[8];
-#pragma unroll
-                for (int a = 0; a < 4; a++) {
-                    int r = base + ty + 32 * a;
-                    ra[a] = (a < na && r < NB) ? S[r * LS + j0 + k] : 0.0;
-                }
-#pragma unroll
-                for (int c = 0; c < 8; c++) {
-                    int cc = base + tx + 16 * c;
-                    cb[c] = (c < nb && cc < NB) ? S[cc * LS + j0 + k] : 0.0;
-                }
-#pragma unroll
-                for (int a = 0; a < 4; a++) {
-                    if (a >= na) break;                 // uniform: row groups beyond the trailing block
-#pragma unroll
-                    for (int c = 0; c < 8; c++)
-                        if (c < nb && c <= 2 * a + 1)   // uniform: column group c lies right of every row of group a
-                            acc[a][c] = fma(ra[a], cb[c], acc[a][c]);
-                }
-            }
-#pragma unroll
-            for (int a = 0; a < 4; a++) {
-                int r = base + ty + 32 * a;
-#pragma unroll
-                for (int c = 0; c < 8; c++) {
-                    int cc = base + tx + 16 * c;
-                    if (r < NB && cc <= r) S[r * LS + cc] -= acc[a][c];
-                }
+        {                                // A22 -= L21 L21^T on the lower 8x8 fragments: 2 DMMAs each
+            const int nbk = R >> 3, F = nbk * (nbk + 1) / 2;
+            for (int f = warp; f < F; f += NW) {
+                int rb = (int)((sqrtf(8.0f * (float)f + 1.0f) - 1.0f) * 0.5f);
+                while ((rb + 1) * (rb + 2) / 2 <= f) rb++;
+                while (rb * (rb + 1) / 2 > f) rb--;
+                const int cb = f - rb * (rb + 1) / 2;
+                const double* ar = S + (base + 8 * rb + fr) * L3 + j0 + fc;
+                const double* br = S + (base + 8 * cb + fr) * L3 + j0 + fc;
+                double* cp = S + (base + 8 * rb + fr) * L3 + base + 8 * cb + 2 * fc;
+                double2 c = *reinterpret_cast<double2*>(cp);
+                dmma884(c.x, c.y, -ar[0], br[0]);
+                dmma884(c.x, c.y, -ar[4], br[4]);
+                *reinterpret_cast<double2*>(cp) = c;
             }
         }
         __syncthreads();
     }
-    // log-determinant from the pivots: 2 sum log L_ii = sum log pivot_i
-    {
+    {                                    // log-determinant from the pivots: 2 sum log L_ii = sum log pivot_i
         double v = (tid < NB) ? log(pv[tid]) : 0.0;
         double tot = block_sum(v, red);
         if (tid == 0) {
@@ -399,79 +383,96 @@ __global__ void __launch_bounds__(LT, 1) leaf_potrf_trtri_v2_kernel(const double
         }
     }
     // ------------------------------------------------------------------ trtri
-    if (tid < NB) {                                  // inverses of the 8x8 diagonal blocks, one thread per column
+    // X = L^-1 is kept transposed in the upper triangle (X[i][j], i > j, at S[j][i]), its diagonal in dinv.
+    if (tid < NB) {                      // inverses of the 8x8 diagonal blocks, one thread per column
         const int o = tid & ~(PW - 1), c = tid & (PW - 1);
         double x[PW];
 #pragma unroll
         for (int i = 0; i < PW; i++) {
             double sacc = 0.0;
 #pragma unroll
-            for (int k = 0; k < i; k++) sacc = fma(S[(o + i) * LS + o + k], x[k], sacc);
+            for (int k = 0; k < i; k++) sacc = fma(S[(o + i) * L3 + o + k], x[k], sacc);
             x[i] = (i == c) ? dinv[o + i] : ((i > c) ? -sacc * dinv[o + i] : 0.0);
         }
 #pragma unroll
         for (int i = 0; i < PW; i++)
-            if (i > c) S[tid * LS + o + i] = x[i];
+            if (i > c) S[tid * L3 + o + i] = x[i];
     }
     __syncthreads();
-    for (int h = PW; h < NB; h <<= 1) {
-        const int hh = h * h, tot = (NB / 2) * h;    // (NB / 2h) nodes x h^2 outputs
-        // T = L21 X11 :  T[r][c] = sum_{k >= c} L[o+h+r][o+k] X[o+k][o+c]
-        for (int e = tid; e < tot; e += LT) {
-            const int node = e / hh, rem = e - node * hh, c = rem / h, r = rem - c * h, o = node * 2 * h;
-            const double* lrow = S + (o + h + r) * LS + o;
-            const double* xrow = S + (o + c) * LS + o;          // X[o+k][o+c] lives at S[o+c][o+k]
-            double sacc = lrow[c] * dinv[o + c];
-            for (int k = c + 1; k < h; k++) sacc = fma(lrow[k], xrow[k], sacc);
-            Tm[node * h * (h + 1) + r * (h + 1) + c] = sacc;
+    for (int h = PW; h < NB; h <<= 1) {  // doubling levels: X21 = -X22 (L21 X11) per node of size 2h
+        const int hb = h >> 3, fpn = hb * hb, F = (NB / (2 * h)) * fpn, ldT = h + 4;
+        // T = L21 X11: fragment (rb, cb); X11 is lower triangular: k4 steps from 2 cb on
+        for (int f = warp; f < F; f += NW) {
+            const int node = f / fpn, rem = f - node * fpn, rb = rem / hb, cb = rem - rb * hb, o = node * 2 * h;
+            const double* ar = S + (o + h + 8 * rb + fr) * L3 + o + fc;          // L21[8rb+fr][k]
+            const int n = 8 * cb + fr;                                          // this lane's column of X11
+            const double* xr = S + (o + n) * L3 + o + fc;                       // X11[k][n] lives at S[o+n][o+k]
+            double c0 = 0.0, c1 = 0.0;
+            for (int sidx = 2 * cb; sidx < 2 * hb; sidx++) {
+                const int k = 4 * sidx + fc;
+                const double bv = (k > n) ? xr[4 * sidx] : ((k == n) ? dinv[o + n] : 0.0);
+                dmma884(c0, c1, ar[4 * sidx], bv);
+            }
+            double* tp = Tm + node * h * ldT + (8 * rb + fr) * ldT + 8 * cb + 2 * fc;
+            tp[0] = c0;
+            tp[1] = c1;
         }
         __syncthreads();
-        // X21 = -X22 T :  X21[r][c] = -sum_{k <= r} X[o+h+r][o+h+k] T[k][c]   -> stored at S[o+c][o+h+r]
-        for (int e = tid; e < tot; e += LT) {
-            const int node = e / hh, rem = e - node * hh, c = rem / h, r = rem - c * h, o = node * 2 * h;
-            const double* tcol = Tm + node * h * (h + 1) + c;
-            const double* xcol = S + (o + h) * LS + o + h + r;  // X[o+h+r][o+h+k] lives at S[o+h+k][o+h+r]
-            double sacc = dinv[o + h + r] * tcol[r * (h + 1)];
-            for (int k = 0; k < r; k++) sacc = fma(xcol[k * LS], tcol[k * (h + 1)], sacc);
-            S[(o + c) * LS + o + h + r] = -sacc;
+        // X21 = -X22 T: X22 lower triangular: k4 steps up to 2 rb + 1; result stored transposed
+        for (int f = warp; f < F; f += NW) {
+            const int node = f / fpn, rem = f - node * fpn, rb = rem / hb, cb = rem - rb * hb, o = node * 2 * h;
+            const int r = 8 * rb + fr;                                          // this lane's row of X22
+            const double* xc = S + (o + h + fc) * L3 + o + h + r;               // X22[r][k] lives at S[o+h+k][o+h+r]
+            const double* tr = Tm + node * h * ldT + fc * ldT + 8 * cb + fr;    // T[k][8cb+fr]
+            double c0 = 0.0, c1 = 0.0;
+            for (int sidx = 0; sidx <= 2 * rb + 1; sidx++) {
+                const int k = 4 * sidx + fc;
+                const double av = (k < r) ? xc[4 * sidx * L3] : ((k == r) ? dinv[o + h + r] : 0.0);
+                dmma884(c0, c1, av, tr[4 * sidx * ldT]);
+            }
+            double* xo = S + (o + 8 * cb + 2 * fc) * L3 + o + h + r;
+            xo[0] = -c0;
+            xo[L3] = -c1;
         }
         __syncthreads();
     }
     double* Lb = Linv + (size_t)b * sL + (size_t)off * ld + off;
     for (int e = tid; e < NB * NB; e += LT) {
         int i = e >> 7, j = e & (NB - 1);
-        Lb[(size_t)i * ld + j] = (j < i) ? S[j * LS + i] : ((j == i) ? dinv[i] : 0.0);
+        Lb[(size_t)i * ld + j] = (j < i) ? S[j * L3 + i] : ((j == i) ? dinv[i] : 0.0);
     }
     if (Lfac != nullptr) {
         double* Fb = Lfac + (size_t)b * sL + (size_t)off * ld + off;
         for (int e = tid; e < NB * NB; e += LT) {
             int i = e >> 7, j = e & (NB - 1);
-            Fb[(size_t)i * ld + j] = (j <= i) ? S[i * LS + j] : 0.0;
+            Fb[(size_t)i * ld + j] = (j <= i) ? S[i * L3 + j] : 0.0;
         }
     }
 }
 
-static bool leaf_v1() {
+// GPE_LEAF=1 selects the v1 leaf (kept for A/B measurements); default is v3.
+static int leaf_version() {
     static int v = -1;
     if (v < 0) {
-        const char* e = getenv("GPE_LEAF_V1");
-        v = (e && e[0] == '1') ? 1 : 0;
+        const char* e = getenv("GPE_LEAF");
+        v = (e && atoi(e) == 1) ? 1 : 3;
     }
-    return v == 1;
+    return v;
 }
 
 void launch_leaf(const double* A, double* Linv, int ld, long long sA, long long sL, int off,
                  double* logdet_part, int nleaf, int* status, int B, cudaStream_t st, double* Lfac) {
     static bool attr = false;
     const size_t smem1 = (size_t)(NB * LS + NB) * sizeof(double);
-    const size_t smem2 = (size_t)(NB * LS + 64 * 65 + 2 * NB) * sizeof(double);
+    const size_t smem3 = (size_t)(NB * L3 + T3MAX + 2 * NB) * sizeof(double);
     if (!attr) {
         cudaFuncSetAttribute(leaf_potrf_trtri_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
-        cudaFuncSetAttribute(leaf_potrf_trtri_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+        cudaFuncSetAttribute(leaf_potrf_trtri_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3);
         attr = true;
     }
-    if (leaf_v1()) leaf_potrf_trtri_kernel<<<B, 1024, smem1, st>>>(A, Linv, ld, sA, sL, off, logdet_part, nleaf, status, Lfac);
-    else leaf_potrf_trtri_v2_kernel<<<B, LT, smem2, st>>>(A, Linv, ld, sA, sL, off, logdet_part, nleaf, status, Lfac);
+    const int v = leaf_version();
+    if (v == 1) leaf_potrf_trtri_kernel<<<B, 1024, smem1, st>>>(A, Linv, ld, sA, sL, off, logdet_part, nleaf, status, Lfac);
+    else leaf_potrf_trtri_v3_kernel<<<B, LT, smem3, st>>>(A, Linv, ld, sA, sL, off, logdet_part, nleaf, status, Lfac);
 }
 
 // =========================================================================== K3 pieces
