@@ -203,3 +203,41 @@ def test_multistart_optimiser_matches_sequential_reference_algorithm(tmp_path, m
     assert close.sum() >= B - 1, (table[:, 1], funs)           # a start may settle in a neighbouring optimum
     assert E.opt_T.best_guess == int(np.argmin(funs))
     assert abs(E.opt_T.best_llh - funs.min()) <= 1e-8 * abs(funs.min())
+
+
+def test_one_input_emulator_and_noise_prior_on_new_points(tmp_path):
+    """Edge cases of the reference-facing layer: a 1-input emulator (inputs file with one column,
+    reference :313-316) through setup / posterior, and the heteroscedastic prior of new points
+    (xp.set_r(r); xp.make_A(s2, predict) before Posterior -- noise_fit.py:118-123) against the oracle."""
+    import gp_emu_uqsa_b200 as g
+    from gp_emu_uqsa_b200 import _emulatorclasses as C
+    from oracle import gp_oracle as O
+    from oracle import ref_loader as RL
+    rng = np.random.default_rng(8)
+    n = 90
+    X = np.sort(rng.random((n, 1)), axis=0)
+    y = np.sin(6 * X[:, 0]) + 0.05 * rng.normal(size=n)
+    with _cwd(tmp_path), _quiet():
+        cfg = RL.write_emulator_files(str(tmp_path), X, y, mucm="F", fix_nugget="T", alt_nugget="T", nugget=0.03, name="one",
+                                      delta=[0.2], sigma=0.7)
+        E = g.setup(cfg, datashuffle=False, scaleinputs=True)
+        r = 0.01 + 0.02 * rng.random(n)
+        E.training.set_r(r)
+        E.training.remake()
+        E.opt_T.optimalbeta()
+        xs = rng.random((40, 1))
+        mean, var = g.posterior(E, xs[:, 0].copy())          # 1-D array in, like the reference allows
+        # new points with their own r and s2 = sigma^2
+        xp = C.Data(xs, None, E.basis, E.par, E.beliefs, E.K)
+        rn = 0.02 + 0.01 * rng.random(40)
+        xp.set_r(rn)
+        xp.make_A(s2=E.par.sigma ** 2, predict=True)
+        p2 = C.Posterior(xp, E.training, E.par, E.beliefs, E.K)
+    Xt, H = E.training.inputs, E.training.H
+    A = O.make_A(Xt, E.par.delta, E.par.nugget, 1, r, 1.0, True)
+    Hs = np.column_stack([np.ones(40), xs[:, 0]])
+    m_ref, V_ref = O.posterior(xs, Hs, Xt, y, H, A, E.par.beta, E.par.sigma, E.par.delta, E.par.nugget, 1)
+    assert np.allclose(mean, m_ref, rtol=1e-9, atol=1e-11) and np.allclose(var, V_ref, rtol=1e-8, atol=1e-10 * np.abs(V_ref).max())
+    m2, V2 = O.posterior(xs, Hs, Xt, y, H, A, E.par.beta, E.par.sigma, E.par.delta, E.par.nugget, 1, r_new=rn / E.par.sigma ** 2)
+    assert np.allclose(p2.mean, m2, rtol=1e-9, atol=1e-11) and np.allclose(p2.var, V2, rtol=1e-8, atol=1e-10 * np.abs(V2).max())
+    assert np.allclose(np.diag(p2.var) - np.diag(var), rn, rtol=1e-7)      # sigma^2 * (r / sigma^2) on the diagonal
