@@ -35,6 +35,8 @@ def minimize_batch(eval_batch, x0s, bounds=None, shard=None):
     def worker(i):
         def fun(x):
             with cond:
+                if state.get("abort"):
+                    raise _EvalFailed()
                 pending[i] = np.array(x, dtype=float, copy=True)
                 cond.notify_all()
                 while i not in ready:
@@ -66,7 +68,19 @@ def minimize_batch(eval_batch, x0s, bounds=None, shard=None):
                 break
             idx = sorted(pending)
             X = np.stack([pending.pop(i) for i in idx])
-        f, g, ok = eval_batch(X)
+        try:
+            f, g, ok = eval_batch(X)
+        except BaseException:
+            # a device/library error: release every parked start as "failed" so no thread is left waiting,
+            # then let the error reach the caller
+            with cond:
+                for i in idx:
+                    ready[i] = (float("nan"), np.zeros(x0s.shape[1]), False)
+                state["abort"] = True
+                cond.notify_all()
+            for t in threads:
+                t.join()
+            raise
         rounds += 1
         evals += len(idx)
         with cond:

@@ -292,6 +292,13 @@ int gpe_create(int device, gpe_handle** out) {
     }
     if (const char* e = getenv("GPE_PRIO")) h->use_prio = e[0] != '0';
     cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
+    {   // keep freed temporaries cached in the device's default pool instead of returning them to the driver
+        cudaMemPool_t pool = nullptr;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
     if (const char* e = getenv("GPE_STREAMS")) h->nsub = std::max(1, std::min((int)gpe_handle::MAX_SUB, atoi(e)));
     if (const char* e = getenv("GPE_GRAPHS")) h->use_graphs = e[0] != '0';
     *out = h;

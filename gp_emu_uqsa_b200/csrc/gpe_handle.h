@@ -112,6 +112,25 @@ struct SubBatch {
     cudaStream_t current() const { return on_hi ? hi : st; }
 };
 
+// Stream-ordered temporary device buffer (cudaMallocAsync / cudaFreeAsync on the handle's stream): released
+// on every exit path of the entry point that owns it, after the work already enqueued on that stream; the
+// device's default memory pool keeps the memory cached between calls (release threshold set in gpe_create),
+// so repeated calls do not pay a device allocation.  Declare at function scope, before the first launch.
+struct TmpDev {
+    cudaStream_t st;
+    void* p = nullptr;
+    explicit TmpDev(gpe_handle* h) : st(h->st) {}
+    TmpDev(const TmpDev&) = delete;
+    TmpDev& operator=(const TmpDev&) = delete;
+    ~TmpDev() { if (p) cudaFreeAsync(p, st); }
+    template <class T>
+    cudaError_t get(T** out, size_t count) {
+        cudaError_t e = cudaMallocAsync(&p, count ? count * sizeof(T) : sizeof(T), st);
+        *out = (e == cudaSuccess) ? static_cast<T*>(p) : nullptr;
+        return e;
+    }
+};
+
 bool gpe_is_device_ptr(const void* p);
 int gpe_ensure_batch_ws(gpe_handle* h, int B);
 int gpe_potrf_inv(gpe_handle* h, const SubBatch& sb, int want_L);

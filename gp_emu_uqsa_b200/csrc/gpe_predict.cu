@@ -499,11 +499,12 @@ int gpe_cross_cov(gpe_handle* h, const double* delta, double nugget, int kind, c
     std::vector<double> w(d), dl(d);
     CK(cudaMemcpy(dl.data(), delta, sizeof(double) * d, cudaMemcpyDefault));
     for (int k = 0; k < d; k++) w[k] = 1.0 / dl[k];
-    double *wd = nullptr, *xs = nullptr, *P = nullptr, *Cm = nullptr, *Cd = nullptr;
-    CK(cudaMalloc((void**)&wd, sizeof(double) * d));
-    CK(cudaMalloc((void**)&xs, sizeof(double) * d * np));
-    CK(cudaMalloc((void**)&P, sizeof(double) * (size_t)mc * d));
-    CK(cudaMalloc((void**)&Cm, sizeof(double) * (size_t)np * mc));
+    double *wd = nullptr, *xs = nullptr, *P = nullptr, *Cm = nullptr;
+    TmpDev t_wd(h), t_xs(h), t_P(h), t_Cm(h);
+    CK(t_wd.get(&wd, (size_t)d));
+    CK(t_xs.get(&xs, (size_t)d * np));
+    CK(t_P.get(&P, (size_t)mc * d));
+    CK(t_Cm.get(&Cm, (size_t)np * mc));
     CK(cudaMemcpyAsync(wd, w.data(), sizeof(double) * d, cudaMemcpyHostToDevice, h->st));
     CK(cudaMemsetAsync(P, 0, sizeof(double) * (size_t)mc * d, h->st));
     CK(cudaMemcpyAsync(P, Xs, sizeof(double) * (size_t)m * d, cudaMemcpyDefault, h->st));
@@ -515,7 +516,6 @@ int gpe_cross_cov(gpe_handle* h, const double* delta, double nugget, int kind, c
     CK(cudaMemcpy2DAsync(C_out, sizeof(double) * m, Cm, sizeof(double) * mc, sizeof(double) * m, h->n,
                          dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, h->st));
     CK(cudaStreamSynchronize(h->st));
-    cudaFree(wd); cudaFree(xs); cudaFree(P); cudaFree(Cm); (void)Cd;
     CK(cudaGetLastError());
     return 0;
 }
@@ -530,22 +530,23 @@ int gpe_predict_fullcov(gpe_handle* h, const double* Xs, const double* Hs, int m
     const int mp = (m + 127) / 128 * 128;
     double *P = nullptr, *Hd = nullptr, *Cm = nullptr, *Zm = nullptr, *ZtZ = nullptr, *aux = nullptr, *G = nullptr, *rn = nullptr,
            *md = nullptr, *Vd = nullptr;
-    CK(cudaMalloc((void**)&P, sizeof(double) * (size_t)mp * d));
-    CK(cudaMalloc((void**)&Cm, sizeof(double) * (size_t)np * mp));
-    CK(cudaMalloc((void**)&Zm, sizeof(double) * (size_t)np * mp));
-    CK(cudaMalloc((void**)&ZtZ, sizeof(double) * (size_t)mp * mp));
-    CK(cudaMalloc((void**)&aux, sizeof(double) * (size_t)NR * mp));
-    CK(cudaMalloc((void**)&G, sizeof(double) * (size_t)NR * mp));
-    CK(cudaMalloc((void**)&md, sizeof(double) * (size_t)mp));
-    CK(cudaMalloc((void**)&Vd, sizeof(double) * (size_t)m * m));
+    TmpDev t_P(h), t_Cm(h), t_Zm(h), t_ZtZ(h), t_aux(h), t_G(h), t_md(h), t_Vd(h), t_Hd(h), t_rn(h);
+    CK(t_P.get(&P, (size_t)mp * d));
+    CK(t_Cm.get(&Cm, (size_t)np * mp));
+    CK(t_Zm.get(&Zm, (size_t)np * mp));
+    CK(t_ZtZ.get(&ZtZ, (size_t)mp * mp));
+    CK(t_aux.get(&aux, (size_t)NR * mp));
+    CK(t_G.get(&G, (size_t)NR * mp));
+    CK(t_md.get(&md, (size_t)mp));
+    CK(t_Vd.get(&Vd, (size_t)m * m));
     CK(cudaMemsetAsync(P, 0, sizeof(double) * (size_t)mp * d, h->st));
     CK(cudaMemcpyAsync(P, Xs, sizeof(double) * (size_t)m * d, cudaMemcpyDefault, h->st));
     if (Hs) {
-        CK(cudaMalloc((void**)&Hd, sizeof(double) * (size_t)m * q));
+        CK(t_Hd.get(&Hd, (size_t)m * q));
         CK(cudaMemcpyAsync(Hd, Hs, sizeof(double) * (size_t)m * q, cudaMemcpyDefault, h->st));
     }
     if (r_new) {
-        CK(cudaMalloc((void**)&rn, sizeof(double) * m));
+        CK(t_rn.get(&rn, (size_t)m));
         CK(cudaMemcpyAsync(rn, r_new, sizeof(double) * m, cudaMemcpyDefault, h->st));
     }
     size_t smem = (size_t)d * (64 + 130) * sizeof(double);
@@ -571,8 +572,6 @@ int gpe_predict_fullcov(gpe_handle* h, const double* Xs, const double* Hs, int m
         cudaMemcpyAsync(V, Vd, sizeof(double) * (size_t)m * m, cudaMemcpyDefault, h->st);
     }
     cudaStreamSynchronize(h->st);
-    cudaFree(P); cudaFree(Hd); cudaFree(Cm); cudaFree(Zm); cudaFree(ZtZ); cudaFree(aux); cudaFree(G); cudaFree(rn);
-    cudaFree(md); cudaFree(Vd);
     if (rc) return rc;
     CK(cudaGetLastError());
     return 0;
@@ -596,21 +595,22 @@ int gpe_implausibility(gpe_handle* h, const double* mean, const double* var, int
     double *mtmp = nullptr, *vtmp = nullptr, *Id = nullptr;
     unsigned char* kd = nullptr;
     unsigned long long *cnt = nullptr, *cmin = nullptr, *ccnt = nullptr;
+    TmpDev t_m(h), t_v(h), t_I(h), t_k(h), t_cnt(h), t_cmin(h), t_ccnt(h);
     if (!in_dev) {
-        CK(cudaMalloc((void**)&mtmp, sizeof(double) * (size_t)n_emul * m));
-        CK(cudaMalloc((void**)&vtmp, sizeof(double) * (size_t)n_emul * m));
+        CK(t_m.get(&mtmp, (size_t)n_emul * m));
+        CK(t_v.get(&vtmp, (size_t)n_emul * m));
         CK(cudaMemcpyAsync(mtmp, mean, sizeof(double) * (size_t)n_emul * m, cudaMemcpyHostToDevice, h->st));
         CK(cudaMemcpyAsync(vtmp, var, sizeof(double) * (size_t)n_emul * m, cudaMemcpyHostToDevice, h->st));
         md = mtmp; vd = vtmp;
     }
     const bool I_dev = Imax && gpe_is_device_ptr(Imax), k_dev = keep && gpe_is_device_ptr(keep);
-    if (Imax) { if (I_dev) Id = Imax; else CK(cudaMalloc((void**)&Id, sizeof(double) * (size_t)m * maxno)); }
-    if (keep) { if (k_dev) kd = keep; else CK(cudaMalloc((void**)&kd, (size_t)m)); }
-    CK(cudaMalloc((void**)&cnt, sizeof(unsigned long long) * maxno));
+    if (Imax) { if (I_dev) Id = Imax; else CK(t_I.get(&Id, (size_t)m * maxno)); }
+    if (keep) { if (k_dev) kd = keep; else CK(t_k.get(&kd, (size_t)m)); }
+    CK(t_cnt.get(&cnt, (size_t)maxno));
     CK(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long) * maxno, h->st));
     if (ncell > 0) {
-        CK(cudaMalloc((void**)&cmin, sizeof(unsigned long long) * ncell * maxno));
-        CK(cudaMalloc((void**)&ccnt, sizeof(unsigned long long) * ncell * maxno));
+        CK(t_cmin.get(&cmin, (size_t)ncell * maxno));
+        CK(t_ccnt.get(&ccnt, (size_t)ncell * maxno));
         CK(cudaMemsetAsync(cmin, 0x7f, sizeof(unsigned long long) * ncell * maxno, h->st));   // large positive double
         CK(cudaMemsetAsync(ccnt, 0, sizeof(unsigned long long) * ncell * maxno, h->st));
     }
@@ -622,8 +622,6 @@ int gpe_implausibility(gpe_handle* h, const double* mean, const double* var, int
     if (ncell > 0 && cell_min) CK(cudaMemcpyAsync(cell_min, cmin, sizeof(double) * ncell * maxno, cudaMemcpyDefault, h->st));
     if (ncell > 0 && cell_count) CK(cudaMemcpyAsync(cell_count, ccnt, sizeof(unsigned long long) * ncell * maxno, cudaMemcpyDefault, h->st));
     CK(cudaStreamSynchronize(h->st));
-    cudaFree(mtmp); cudaFree(vtmp); if (!I_dev) cudaFree(Id); if (!k_dev) cudaFree(kd);
-    cudaFree(cnt); cudaFree(cmin); cudaFree(ccnt);
     CK(cudaGetLastError());
     return 0;
 }

@@ -187,14 +187,16 @@ int gpe_solve(gpe_handle* h, const double* Bm, int k, double* out) {
     const int np = h->npad, n = h->n;
     double *src = nullptr, *dst = nullptr, *p0 = nullptr, *p1 = nullptr, *p2 = nullptr;
     const bool in_dev = gpe_is_device_ptr(Bm), out_dev = gpe_is_device_ptr(out);
-    CK(cudaMalloc((void**)&p0, (size_t)np * NR * sizeof(double)));
-    CK(cudaMalloc((void**)&p1, (size_t)np * NR * sizeof(double)));
-    CK(cudaMalloc((void**)&p2, (size_t)np * NR * sizeof(double)));
+    TmpDev t_p0(h), t_p1(h), t_p2(h), t_src(h), t_dst(h);
+    CK(t_p0.get(&p0, (size_t)np * NR));
+    CK(t_p1.get(&p1, (size_t)np * NR));
+    CK(t_p2.get(&p2, (size_t)np * NR));
+    CK(t_src.get(&src, (size_t)n * NR));
+    CK(t_dst.get(&dst, (size_t)n * NR));
     int rc = 0;
     for (int c0 = 0; c0 < k && !rc; c0 += NR) {
         int kc = std::min(NR, k - c0);
         // gather the column block [n, kc] (strided in the source) into a dense staging buffer
-        if (!src) CK(cudaMalloc((void**)&src, (size_t)n * NR * sizeof(double)));
         CK(cudaMemcpy2DAsync(src, sizeof(double) * kc, Bm + c0, sizeof(double) * k, sizeof(double) * kc, n,
                              in_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->st));
         pack_panel_kernel<<<(np * NR + 255) / 256, 256, 0, h->st>>>(src, n, kc, np, p0);
@@ -203,7 +205,6 @@ int gpe_solve(gpe_handle* h, const double* Bm, int k, double* out) {
         rc = gpe_run_gemm(h, h->fLi, p0, p1, np, NR, NR, 0, 0, 0, np, NR, np, 1.0, 0, KM_LE_I, 0, 1, 1, EPI_STORE);
         if (!rc) rc = gpe_run_gemm(h, h->fLi, p1, p2, np, NR, NR, 0, 0, 0, np, NR, np, 1.0, 0, KM_GE_I, 0, 1, 2, EPI_STORE);
         if (rc) break;
-        if (!dst) CK(cudaMalloc((void**)&dst, (size_t)n * NR * sizeof(double)));
         unpack_panel_kernel<<<(n * kc + 255) / 256, 256, 0, h->st>>>(p2, n, kc, dst);
         h->launches++;
         CK(cudaMemcpy2DAsync(out + c0, sizeof(double) * k, dst, sizeof(double) * kc, sizeof(double) * kc, n,
@@ -211,7 +212,6 @@ int gpe_solve(gpe_handle* h, const double* Bm, int k, double* out) {
         CK(cudaStreamSynchronize(h->st));
     }
     cudaStreamSynchronize(h->st);
-    cudaFree(src); cudaFree(dst); cudaFree(p0); cudaFree(p1); cudaFree(p2);
     if (rc) return rc;
     CK(cudaGetLastError());
     return 0;
@@ -233,12 +233,13 @@ int gpe_sens_contract(gpe_handle* h, const double* gamma, const double* acoef, c
     CK(cudaMemcpy(hostbuf.data() + 2 * d, mvec, sizeof(double) * d, cudaMemcpyDefault));
     const int nt = np / ST, ntile = nt * (nt + 1) / 2;
     double *coef = nullptr, *tpart = nullptr, *Vsrc = nullptr, *Vp = nullptr, *Yp = nullptr, *outd = nullptr;
-    CK(cudaMalloc((void**)&coef, sizeof(double) * 3 * d));
-    CK(cudaMalloc((void**)&tpart, sizeof(double) * ntile));
-    CK(cudaMalloc((void**)&Vsrc, sizeof(double) * (size_t)n * nv));
-    CK(cudaMalloc((void**)&Vp, sizeof(double) * (size_t)np * NR));
-    CK(cudaMalloc((void**)&Yp, sizeof(double) * (size_t)np * NR));
-    CK(cudaMalloc((void**)&outd, sizeof(double) * (1 + NR * NR)));
+    TmpDev t_coef(h), t_tpart(h), t_Vsrc(h), t_Vp(h), t_Yp(h), t_outd(h);
+    CK(t_coef.get(&coef, (size_t)3 * d));
+    CK(t_tpart.get(&tpart, (size_t)ntile));
+    CK(t_Vsrc.get(&Vsrc, (size_t)n * nv));
+    CK(t_Vp.get(&Vp, (size_t)np * NR));
+    CK(t_Yp.get(&Yp, (size_t)np * NR));
+    CK(t_outd.get(&outd, (size_t)(1 + NR * NR)));
     CK(cudaMemcpyAsync(coef, hostbuf.data(), sizeof(double) * 3 * d, cudaMemcpyHostToDevice, h->st));
     CK(cudaMemcpyAsync(Vsrc, V, sizeof(double) * (size_t)n * nv, cudaMemcpyDefault, h->st));
     pack_panel_kernel<<<(np * NR + 255) / 256, 256, 0, h->st>>>(Vsrc, n, nv, np, Vp);
@@ -259,7 +260,6 @@ int gpe_sens_contract(gpe_handle* h, const double* gamma, const double* acoef, c
     std::vector<double> res(1 + NR * NR);
     cudaMemcpyAsync(res.data(), outd, sizeof(double) * res.size(), cudaMemcpyDeviceToHost, h->st);
     cudaStreamSynchronize(h->st);
-    cudaFree(coef); cudaFree(tpart); cudaFree(Vsrc); cudaFree(Vp); cudaFree(Yp); cudaFree(outd);
     if (rc) return rc;
     CK(cudaGetLastError());
     if (trace_out) CK(cudaMemcpy(trace_out, res.data(), sizeof(double), cudaMemcpyDefault));
@@ -292,9 +292,10 @@ int gpe_sens_main_effect(gpe_handle* h, const double* t1, const double* t2, cons
         if (wh[w] < 0 || wh[w] >= d) return h->fail_msg("input index out of range");
     double *db = nullptr, *od = nullptr;
     int* wd = nullptr;
-    CK(cudaMalloc((void**)&db, sizeof(double) * hb.size()));
-    CK(cudaMalloc((void**)&od, sizeof(double) * (size_t)nwhich * points));
-    CK(cudaMalloc((void**)&wd, sizeof(int) * nwhich));
+    TmpDev t_db(h), t_od(h), t_wd(h);
+    CK(t_db.get(&db, hb.size()));
+    CK(t_od.get(&od, (size_t)nwhich * points));
+    CK(t_wd.get(&wd, (size_t)nwhich));
     CK(cudaMemcpyAsync(db, hb.data(), sizeof(double) * hb.size(), cudaMemcpyHostToDevice, h->st));
     CK(cudaMemcpyAsync(wd, wh.data(), sizeof(int) * nwhich, cudaMemcpyHostToDevice, h->st));
     sens_main_effect_kernel<<<dim3(points, nwhich), 256, 0, h->st>>>(h->X, n, d, db, db + d, db + 2 * d, db + 3 * d, db + 4 * d, scale,
@@ -302,7 +303,6 @@ int gpe_sens_main_effect(gpe_handle* h, const double* t1, const double* t2, cons
     h->launches++;
     cudaMemcpyAsync(out, od, sizeof(double) * (size_t)nwhich * points, cudaMemcpyDefault, h->st);
     cudaStreamSynchronize(h->st);
-    cudaFree(db); cudaFree(od); cudaFree(wd);
     CK(cudaGetLastError());
     return 0;
 }
