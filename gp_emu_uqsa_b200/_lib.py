@@ -58,6 +58,7 @@ def load():
         "gpe_sens_main_effect": (i, [p, p, p, p, p, p, d, p, i, p, i, p]),
         "gpe_dbg_gemm": (i, [p, p, p, p, i, i, i, ll, ll, ll, i, i, i, d, i, i, i, i, i]),
         "gpe_potrf": (i, [p, p, i, i, p, p, p, p]),
+        "gpe_pdist_argmin": (i, [p, p, i, i, i, p, i, p]),
         "gpe_dbg_potrf_inv": (i, [p, p, i, i, p, p, p]),
     }
     for name, (res, args) in proto.items():
@@ -71,7 +72,7 @@ EXPORTS = ["gpe_version", "gpe_create", "gpe_destroy", "gpe_last_error", "gpe_la
            "gpe_get_stream", "gpe_set_streams", "gpe_profile_enable", "gpe_profile_read",
            "gpe_set_training", "gpe_set_basis", "gpe_cov_build", "gpe_cov_grad", "gpe_cross_cov", "gpe_llh_grad_batch",
            "gpe_fit_state", "gpe_predict", "gpe_predict_grid", "gpe_predict_fullcov", "gpe_implausibility",
-           "gpe_solve", "gpe_sens_contract", "gpe_sens_main_effect", "gpe_potrf",
+           "gpe_solve", "gpe_sens_contract", "gpe_sens_main_effect", "gpe_potrf", "gpe_pdist_argmin",
            "gpe_dbg_gemm", "gpe_dbg_potrf_inv"]
 
 
@@ -315,6 +316,16 @@ class Device:
         if st[0] != 0:
             raise np.linalg.LinAlgError("Matrix is not positive definite")
         return Lf
+
+    # ------------------------------------------------------------------ design criterion
+    def pdist_argmin(self, designs, extra=None):
+        """np.argmin(pdist(concat(design, extra), 'sqeuclidean')) for every design of designs [N, n, dim]."""
+        designs = _f64(designs)
+        N, n, dim = designs.shape
+        extra = None if extra is None else _f64(extra).reshape(-1, dim)
+        out = np.empty(N, dtype=np.int64)
+        self._ck(self.L.gpe_pdist_argmin(self.h, _ptr(designs), N, n, dim, _ptr(extra), 0 if extra is None else extra.shape[0], _ptr(out)))
+        return out
 
     # ------------------------------------------------------------------ debug
     def dbg_potrf_inv(self, A):

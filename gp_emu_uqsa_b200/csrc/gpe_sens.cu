@@ -165,6 +165,58 @@ __global__ void __launch_bounds__(256) sens_main_effect_kernel(const double* __r
     if (threadIdx.x == 0) out[(size_t)w * points + j] = tot;
 }
 
+// Maximin criterion of the Latin-hypercube design (design_inputs.py:73): argmin over the condensed
+// squared-distance vector of one candidate design (+ shared extra points).  The distance is accumulated
+// exactly like scipy's pdist('sqeuclidean') kernel -- sequentially over the dimensions, separate multiply
+// and add (no FMA contraction) -- so values, and therefore the index of the first minimum, are bit-identical.
+constexpr int PD_ROWS = 32;
+struct PdBest { double val; long long idx; };
+
+__global__ void __launch_bounds__(256) pdist_argmin_kernel(const double* __restrict__ designs, int n, int dim,
+                                                           const double* __restrict__ extra, int ne,
+                                                           PdBest* __restrict__ part) {
+    __shared__ double rowpt[64];
+    __shared__ double rv[8];
+    __shared__ long long ri[8];
+    const int P = n + ne, blk = blockIdx.x, des = blockIdx.y, tid = threadIdx.x;
+    const double* D = designs + (size_t)des * n * dim;
+    auto point = [&](int r) -> const double* { return r < n ? D + (size_t)r * dim : extra + (size_t)(r - n) * dim; };
+    double best = 1.0e300;
+    long long bidx = 0x7fffffffffffffffll;
+    const int r0 = blk * PD_ROWS, r1 = min(P - 1, r0 + PD_ROWS);
+    for (int i = r0; i < r1; i++) {
+        __syncthreads();
+        if (tid < dim) rowpt[tid] = point(i)[tid];
+        __syncthreads();
+        const long long base = (long long)i * P - (long long)i * (i + 1) / 2 - i - 1;      // + j
+        for (int j = i + 1 + tid; j < P; j += 256) {
+            const double* pj = point(j);
+            double acc = 0.0;
+            for (int k = 0; k < dim; k++) {
+                const double diff = __dsub_rn(rowpt[k], pj[k]);
+                acc = __dadd_rn(acc, __dmul_rn(diff, diff));
+            }
+            if (acc < best) { best = acc; bidx = base + j; }       // indices only grow: first minimum kept
+        }
+    }
+    // block reduce: smallest value, ties -> smallest index
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        double ov = __shfl_xor_sync(0xffffffffu, best, o);
+        long long oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+        if (ov < best || (ov == best && oi < bidx)) { best = ov; bidx = oi; }
+    }
+    __syncthreads();
+    if ((tid & 31) == 0) { rv[tid >> 5] = best; ri[tid >> 5] = bidx; }
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < 8; w++)
+            if (rv[w] < best || (rv[w] == best && ri[w] < bidx)) { best = rv[w]; bidx = ri[w]; }
+        part[(size_t)des * gridDim.x + blk].val = best;
+        part[(size_t)des * gridDim.x + blk].idx = bidx;
+    }
+}
+
 int ensure_ainv(gpe_handle* h) {
     if (h->fAinv_valid) return 0;
     const int np = h->npad;
@@ -304,6 +356,47 @@ int gpe_sens_main_effect(gpe_handle* h, const double* t1, const double* t2, cons
     cudaMemcpyAsync(out, od, sizeof(double) * (size_t)nwhich * points, cudaMemcpyDefault, h->st);
     cudaStreamSynchronize(h->st);
     CK(cudaGetLastError());
+    return 0;
+}
+
+int gpe_pdist_argmin(gpe_handle* h, const double* designs, int N, int n, int dim, const double* extra, int ne,
+                     long long* argmin_out) {
+    if (!h || !designs || !argmin_out || N < 1 || n < 1 || dim < 1 || dim > 64 || ne < 0 || (ne > 0 && !extra) || n + ne < 2)
+        return h ? h->fail_msg("bad argument (1 <= dim <= 64, at least two points)") : -2;
+    CK(cudaSetDevice(h->device));
+    const int P = n + ne, nblk = (P - 1 + PD_ROWS - 1) / PD_ROWS;
+    double *dd = nullptr, *de = nullptr;
+    PdBest* dp = nullptr;
+    TmpDev t_d(h), t_e(h), t_p(h);
+    const double* dsrc = designs;
+    if (!gpe_is_device_ptr(designs)) {
+        CK(t_d.get(&dd, (size_t)N * n * dim));
+        CK(cudaMemcpyAsync(dd, designs, sizeof(double) * (size_t)N * n * dim, cudaMemcpyHostToDevice, h->st));
+        dsrc = dd;
+    }
+    const double* esrc = extra;
+    if (ne > 0 && !gpe_is_device_ptr(extra)) {
+        CK(t_e.get(&de, (size_t)ne * dim));
+        CK(cudaMemcpyAsync(de, extra, sizeof(double) * (size_t)ne * dim, cudaMemcpyHostToDevice, h->st));
+        esrc = de;
+    }
+    CK(t_p.get(&dp, (size_t)N * nblk));
+    pdist_argmin_kernel<<<dim3(nblk, N), 256, 0, h->st>>>(dsrc, n, dim, esrc, ne, dp);
+    h->launches++;
+    std::vector<PdBest> part((size_t)N * nblk);
+    CK(cudaMemcpyAsync(part.data(), dp, sizeof(PdBest) * part.size(), cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    CK(cudaGetLastError());
+    std::vector<long long> res(N);
+    for (int k = 0; k < N; k++) {
+        PdBest b = part[(size_t)k * nblk];
+        for (int t = 1; t < nblk; t++) {
+            const PdBest& c = part[(size_t)k * nblk + t];
+            if (c.val < b.val || (c.val == b.val && c.idx < b.idx)) b = c;
+        }
+        res[k] = b.idx;
+    }
+    CK(cudaMemcpy(argmin_out, res.data(), sizeof(long long) * N, cudaMemcpyDefault));
     return 0;
 }
 

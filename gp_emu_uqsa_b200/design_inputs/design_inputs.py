@@ -1,16 +1,35 @@
 """Maximin Latin-hypercube design (reference: gp_emu_uqsa/design_inputs/design_inputs.py).
 
-Host code: the design is driven by the global NumPy RNG and must consume it exactly like the
-reference (one ``uniform`` and one ``shuffle`` per dimension per candidate design) so that history
-matching, which calls this inside its loops, reproduces the reference's designs under a fixed seed.
-It is a "next" row of the scope table, not part of the GPU hot path."""
+The design is driven by the global NumPy RNG and must consume it exactly like the reference (one
+``uniform`` and one ``shuffle`` per dimension per candidate design) so that history matching, which
+calls this inside its loops, reproduces the reference's designs under a fixed seed; that part stays on
+the host.  The O(N n^2 dim) maximin criterion of the N candidates is what costs time once prediction
+is fast: ``device_criterion`` evaluates it for all candidates in one launch
+(``gpe_pdist_argmin``, bit-identical to scipy's pdist + argmin) and is what history_match / noise_fit
+pass in; called on its own, ``optLatinHyperCube`` uses scipy like the reference (it is a host utility
+that works without a GPU and is not part of the hot path)."""
 import numpy as _np
 import scipy.spatial.distance as _dist
 
 __all__ = ["optLatinHyperCube"]
 
 
-def optLatinHyperCube(dim=None, n=None, N=None, minmax=None, filename="inputs", fextra=None):
+def _host_criterion(designs, fextra):
+    """argmin of the condensed squared-distance vector per candidate design (reference :73)."""
+    out = _np.empty(designs.shape[0], dtype=_np.int64)
+    for k in range(designs.shape[0]):
+        xt = _np.concatenate([designs[k], fextra]) if fextra is not None else designs[k]
+        out[k] = _np.argmin(_dist.pdist(xt, 'sqeuclidean'))
+    return out
+
+
+def device_criterion(designs, fextra):
+    """The same criterion for all candidates in one device launch (gpe_pdist_argmin)."""
+    from .. import _lib
+    return _lib.scratch_device().pdist_argmin(designs, fextra)
+
+
+def optLatinHyperCube(dim=None, n=None, N=None, minmax=None, filename="inputs", fextra=None, _criterion=None):
     """Generate N random Latin hypercubes of n points in `dim` dimensions, keep the "best", scale it
     to `minmax` and save it to `filename` ('%.8f' text).  Returns None.
 
@@ -32,20 +51,26 @@ def optLatinHyperCube(dim=None, n=None, N=None, minmax=None, filename="inputs", 
     else:
         print("\nGenerating", N, "oLHC samples of", n, "points and checking maximin criterion (pick design with maximum "
               "minimum distance between design points)...")
-    x = _np.zeros((n, dim))
-    best_D, best_k, best_maximin = None, None, None
+    if N < 1 or n < 1:      # the reference dies on an unbound name here (e.g. 2-input imp_plot: dim = 0)
+        raise UnboundLocalError("optLatinHyperCube: no candidate design was generated (N = 0)")
+    # all candidates first (the RNG draws do not depend on the criterion), then the criterion in one go
+    designs = _np.empty((N, n, dim))
     for k in range(0, N):
         for i in range(0, dim):
             u = _np.random.uniform(0.0, 1.0, n)
             b = _np.arange(0, n, 1)
             _np.random.shuffle(b)
-            x[:, i] = (b + u) / float(n)
-        xt = _np.concatenate([x, fextra]) if fextra is not None else x
-        maximin = _np.argmin(_dist.pdist(xt, 'sqeuclidean'))
-        if k == 0 or maximin > best_maximin:
-            best_D, best_k, best_maximin = _np.copy(x), k, maximin
-    if best_D is None:      # N == 0: the reference dies on an unbound name here (e.g. 2-input imp_plot)
-        raise UnboundLocalError("optLatinHyperCube: no candidate design was generated (N = 0)")
+            designs[k, :, i] = (b + u) / float(n)
+    fx = None if fextra is None else _np.ascontiguousarray(fextra, dtype=float).reshape(-1, dim)
+    if n + (0 if fx is None else fx.shape[0]) < 2:
+        crit = _np.zeros(N, dtype=_np.int64)
+    else:
+        crit = (_criterion or _host_criterion)(designs, fx)
+    best_k, best_maximin = 0, crit[0]
+    for k in range(1, N):
+        if crit[k] > best_maximin:
+            best_k, best_maximin = k, crit[k]
+    best_D = _np.copy(designs[best_k])
     D = best_D
     print("Optimal LHC design was no.", best_k)
     print("Saving inputs to file...")

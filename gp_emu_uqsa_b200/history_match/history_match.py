@@ -80,7 +80,7 @@ def imp_plot(emuls, zs, cm, var_extra, maxno=1, olhcmult=100, grid=10, act=[], f
         olhc_range = [it[1] for it in sorted(minmax.items(), key=lambda x: int(x[0])) if int(it[0]) != s[0] and int(it[0]) != s[1]]
         print("olhc_range:", olhc_range)
         filename = "imp_input_" + str(s[0]) + '_' + str(s[1])
-        _gd.optLatinHyperCube(dim, n, N, olhc_range, filename)       # every rank: same seeded RNG stream
+        _gd.optLatinHyperCube(dim, n, N, olhc_range, filename, _criterion=_gd.device_criterion)   # every rank: same seeded RNG stream
         x_other = _np.loadtxt(filename).reshape(n, dim)
         other_dim = [act_ref[str(key)] for key in act_ref if int(key) not in s]
         print("\nCalculating Implausibilities...")
@@ -179,7 +179,7 @@ def new_wave_design(emuls, zs, cm, var_extra, datafiles, maxno=1, olhcmult=100, 
     olhc_range = [it[1] for it in sorted(minmax.items(), key=lambda x: int(x[0]))]
     print("olhc_range:", olhc_range)
     filename = "olhc_des"
-    _gd.optLatinHyperCube(dim, n, N, olhc_range, filename, fextra=sim_x)
+    _gd.optLatinHyperCube(dim, n, N, olhc_range, filename, fextra=sim_x, _criterion=_gd.device_criterion)
     x = _np.loadtxt(filename).reshape(n, dim)
     print("\nCalculating Implausibilities...")
     keep = _flat_keep(emuls, zs, cm, var_extra, x, act_ref, maxno)

@@ -137,7 +137,7 @@ def noisefit(data, noise, stopat=20, olhcmult=100, samples=200, fileStr=""):
     ndim = x[0].size
     n = ndim * int(olhcmult)
     olhc_range = [[np.amin(col), np.amax(col)] for col in x.T]
-    _gd.optLatinHyperCube(ndim, n, int(n), olhc_range, "x_range_input")
+    _gd.optLatinHyperCube(ndim, n, int(n), olhc_range, "x_range_input", _criterion=_gd.device_criterion)
     x_range = np.loadtxt("x_range_input").reshape(n, ndim)
     p_plot = _emuc.Posterior(_points(GN, x_range), GN.training, GN.par, GN.beliefs, GN.K, diag_only=True)
     p_plot.interval()

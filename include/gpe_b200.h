@@ -152,6 +152,14 @@ int gpe_sens_main_effect(gpe_handle* h, const double* t1, const double* t2, cons
                          const double* mvec, const double* evec, double scale, const int* which,
                          int nwhich, const double* xw, int points, double* out);
 
+/* Maximin criterion of the optimised Latin hypercube (design_inputs/design_inputs.py:59-77):
+ * argmin_out[k] = np.argmin(pdist(concat(designs[k], extra), 'sqeuclidean')) for N candidate designs
+ * designs [N, n, dim] and shared extra points [ne, dim] (fextra; NULL / 0 if none).  Distances are
+ * accumulated like scipy's kernel (sequential over dimensions, no FMA), so the indices are identical.
+ * Needs no training set.  (The reference compares these *indices* between designs -- a known quirk.) */
+int gpe_pdist_argmin(gpe_handle* h, const double* designs, int N, int n, int dim, const double* extra, int ne,
+                     long long* argmin_out);
+
 /* Debug/test entry: one batched DMMA GEMM of the family used by the factorisation
  * (gpe_gemm.cuh).  layout 0 NT, 1 NN, 2 TN; device pointers only. */
 int gpe_dbg_gemm(gpe_handle* h, const double* A, const double* B, double* C, int lda, int ldb,

@@ -94,3 +94,18 @@ def test_noisefit_runs_on_device(tmp_path):
     assert xin.shape == (20, 2) and out.shape == (20, 3)
     assert np.all(np.isfinite(out)) and np.all(out > 0) and np.all(out[:, 1] <= out[:, 0]) and np.all(out[:, 0] <= out[:, 2])
     assert 0.01 < np.median(out[:, 0]) < 2.0
+
+
+@pytest.mark.parametrize("n,dim,ne", [(30, 1, 0), (100, 3, 0), (257, 8, 0), (120, 3, 202), (64, 10, 1000)])
+def test_device_maximin_criterion_is_bit_identical_to_scipy(n, dim, ne):
+    """gpe_pdist_argmin == np.argmin(scipy pdist 'sqeuclidean') for every candidate design, including
+    near-ties (duplicated points make exact ties: the first index must win)."""
+    import gp_emu_uqsa_b200.design_inputs.design_inputs as d
+    rng = np.random.default_rng(n + dim + ne)
+    designs = rng.random((7, n, dim))
+    designs[3, n // 2] = designs[3, 1]            # exact tie at distance 0 with another pair below
+    designs[3, n - 1] = designs[3, 0]
+    extra = rng.random((ne, dim)) if ne else None
+    want = d._host_criterion(designs, extra)
+    got = d.device_criterion(designs, extra)
+    assert np.array_equal(got, want)
