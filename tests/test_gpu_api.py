@@ -241,3 +241,85 @@ def test_one_input_emulator_and_noise_prior_on_new_points(tmp_path):
     m2, V2 = O.posterior(xs, Hs, Xt, y, H, A, E.par.beta, E.par.sigma, E.par.delta, E.par.nugget, 1, r_new=rn / E.par.sigma ** 2)
     assert np.allclose(p2.mean, m2, rtol=1e-9, atol=1e-11) and np.allclose(p2.var, V2, rtol=1e-8, atol=1e-10 * np.abs(V2).max())
     assert np.allclose(np.diag(p2.var) - np.diag(var), rn, rtol=1e-7)      # sigma^2 * (r / sigma^2) on the diagonal
+
+
+def test_surfebm_example_reproduces_shipped_sense_file(golden_dir, tmp_path):
+    """The reference's own known-answer file: examples/sensitivity_surfebm/test_sense_file (MUCM's 2-input
+    'surfebm' example: 40 points, linear mean, gp4ml, nugget 1e-6, tries 20, constraints standard).  The
+    shipped script -- setup(shuffle, no scaling), train, sensitivity setup with m = 0.5, v = 0.02,
+    uncertainty / sensitivity / main_effect / to_file -- is run as is; the trained optimum and hence the
+    measures agree with the shipped file to the optimiser's convergence (the reference re-run here agrees
+    to 3e-7 ... 9e-5)."""
+    import gp_emu_uqsa_b200 as g
+    import gp_emu_uqsa_b200.sensitivity as s
+    src = os.path.join(golden_dir, "surfebm")
+    for f in os.listdir(src):
+        shutil.copy(os.path.join(src, f), tmp_path)
+    with _cwd(tmp_path), _quiet():
+        np.random.seed(3)
+        emul = g.setup("surfebm_config", datashuffle=True, scaleinputs=False)
+        g.train(emul, auto=True)
+        sens = s.setup(emul, [0.50, 0.50], [0.02, 0.02])
+        sens.uncertainty()
+        sens.sensitivity()
+        sens.main_effect(plot=False, points=100)
+        sens.to_file("my_sense_file")
+        sens.interaction_effect(0, 1)
+        sens.totaleffectvariance()
+        table = s.sense_table([sens, ], ["input 0", "input 1"], ["output 0"])
+
+    def read(path):
+        out = {}
+        for line in open(path):
+            w = line.split()
+            out[w[0]] = np.array([float(t) for t in w[1:]])
+        return out
+    want, got = read(os.path.join(src, "test_sense_file")), read(tmp_path / "my_sense_file")
+    assert list(want) == list(got)                       # same records in the same order
+    assert np.allclose(emul.par.delta, [0.544224, 0.096815], rtol=2e-4) and abs(emul.par.sigma - 0.935126) < 3e-4
+    assert np.allclose(got["EE"], want["EE"], rtol=1e-5)
+    assert np.allclose(got["VE"], want["VE"], rtol=1e-3)
+    assert np.allclose(got["EV"], want["EV"], rtol=2e-4)
+    assert np.allclose(got["EVw"], want["EVw"], rtol=2e-4)
+    assert np.allclose(got["xw"], want["xw"], rtol=0, atol=1e-11)
+    scale = max(np.abs(want["ME0"]).max(), np.abs(want["ME1"]).max())
+    assert np.abs(got["ME0"] - want["ME0"]).max() <= 5e-4 * scale and np.abs(got["ME1"] - want["ME1"]).max() <= 5e-4 * scale
+    assert sens.interaction.shape == (25, 25) and table.shape == (1, 3)
+
+
+def test_multi_output_example_reproduces_shipped_sense_files(golden_dir, tmp_path):
+    """examples/sensitivity_multi_outputs as shipped (3 inputs, 2 outputs, n = 100, tries 20, constraints
+    bounds): the reference's shipped sense_file0 / sense_file1 are reproduced to the optimiser's convergence
+    (the real reference re-run agrees with its own shipped files to 3e-4)."""
+    import gp_emu_uqsa_b200 as g
+    import gp_emu_uqsa_b200.sensitivity as s
+    src = os.path.join(golden_dir, "toysim3D")
+    for f in os.listdir(src):
+        shutil.copy(os.path.join(src, f), tmp_path)
+
+    def read(path):
+        out = {}
+        for line in open(path):
+            w = line.split()
+            out[w[0]] = np.array([float(t) for t in w[1:]])
+        return out
+    sense_list = []
+    for i in range(2):
+        with _cwd(tmp_path), _quiet():
+            np.random.seed(1)
+            emul = g.setup("toysim3D_config" + str(i), datashuffle=True, scaleinputs=True)
+            g.train(emul, auto=True)
+            sens = s.setup(emul, [0.50] * 3, [0.02] * 3)
+            sens.uncertainty()
+            sens.sensitivity()
+            sens.main_effect(plot=False, points=100)
+            sens.to_file("my_sense_file" + str(i))
+        sense_list.append(sens)
+        want, got = read(os.path.join(src, "sense_file" + str(i))), read(tmp_path / ("my_sense_file" + str(i)))
+        assert list(want) == list(got)
+        for key in ("EE", "VE", "EV", "EVw"):
+            assert np.allclose(got[key], want[key], rtol=1e-3), (i, key, got[key], want[key])
+        scale = max(np.abs(want["ME%d" % j]).max() for j in range(3))
+        assert max(np.abs(got["ME%d" % j] - want["ME%d" % j]).max() for j in range(3)) <= 1e-3 * scale
+    table = s.sense_table(sense_list, [], ["y[0]", "y[1]"], rowHeight=4)
+    assert table.shape == (2, 4)
