@@ -264,6 +264,25 @@ def gen_hm_api(g, h, n, seed):
     return out
 
 
+def gen_toysim_recon(g):
+    """examples/toy-sim/reconstruct: an emulator rebuilt from shipped (old-format) beliefs + data files, no
+    training; posterior mean / covariance of the real reference at fixed points."""
+    import shutil
+    out = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        src = os.path.join(RL.REF_ROOT, "examples", "toy-sim", "reconstruct")
+        for f in os.listdir(src):
+            if f.startswith("toy-sim_"):
+                shutil.copy(os.path.join(src, f), tmp)
+        with RL.cwd(tmp), RL.quiet():
+            E = g.setup("toy-sim_config_recon", datashuffle=False, scaleinputs=True)
+            xs = np.random.default_rng(9).random((64, 2))
+            mean, var = g.posterior(E, xs.copy())
+        out.update(xs=xs, mean=mean, var=var, X=E.training.inputs.copy(), y=E.training.outputs.copy(),
+                   nT=E.training.inputs.shape[0], nV=E.validation.inputs.shape[0])
+    return out
+
+
 def main():
     assert RL.available(), "reference not present"
     g, h, s, gn = RL.load()
@@ -271,6 +290,9 @@ def main():
     if len(sys.argv) > 1 and sys.argv[1] == "sens":
         save("sens_n60_d3.npz", gen_sens(g, s, 60, 3, 7))
         save("sens_n150_d4.npz", gen_sens(g, s, 150, 4, 8))
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "recon":
+        save("toysim_recon.npz", gen_toysim_recon(g))
         return
     if len(sys.argv) > 1 and sys.argv[1] == "hmapi":
         save("hmapi_n100_d3.npz", gen_hm_api(g, h, 100, 6))

@@ -323,3 +323,26 @@ def test_multi_output_example_reproduces_shipped_sense_files(golden_dir, tmp_pat
         assert max(np.abs(got["ME%d" % j] - want["ME%d" % j]).max() for j in range(3)) <= 1e-3 * scale
     table = s.sense_table(sense_list, [], ["y[0]", "y[1]"], rowHeight=4)
     assert table.shape == (2, 4)
+
+
+def test_reconstructed_emulator_from_shipped_old_format_files(golden_dir, tmp_path):
+    """examples/toy-sim/reconstruct: the reference's shipped checkpoint (old beliefs format: no active_index /
+    alt_nugget keys, fix_nugget F, mucm T) is loaded without training and predicts what the real reference
+    predicts; g.plot evaluates the shipped script's two grids (900-point line, 30 x 30 map)."""
+    import gp_emu_uqsa_b200 as g
+    gold = np.load(os.path.join(golden_dir, "toysim_recon.npz"))
+    src = os.path.join(golden_dir, "toy-sim-recon")
+    for f in os.listdir(src):
+        shutil.copy(os.path.join(src, f), tmp_path)
+    with _cwd(tmp_path), _quiet():
+        E = g.setup("toy-sim_config_recon", datashuffle=False, scaleinputs=True)
+        mean, var = g.posterior(E, gold["xs"].copy())
+        p1 = g.plot(E, [0], [1], [0.3], "mean")
+        p2 = g.plot(E, [0, 1], [2], [0.3], "mean")
+    assert E.training.inputs.shape[0] == int(gold["nT"]) and E.validation.inputs.shape[0] == int(gold["nV"])
+    assert np.array_equal(E.training.inputs, gold["X"]) and np.array_equal(E.training.outputs, gold["y"])
+    assert np.allclose(mean, gold["mean"], rtol=1e-9, atol=1e-11)
+    assert np.allclose(var, gold["var"], rtol=1e-8, atol=1e-10 * np.abs(gold["var"]).max())
+    assert p1.mean.shape == (900,) and p2.mean.shape == (900,) and p1.var_diag.min() > 0 and p2.var_diag.min() > 0
+    # the line plot is the map's slice at x1 = 0.3 only approximately (different grids); both are finite and smooth
+    assert np.all(np.isfinite(p1.mean)) and np.all(np.isfinite(p2.mean))
