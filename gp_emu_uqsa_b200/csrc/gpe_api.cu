@@ -284,13 +284,15 @@ int gpe_create(int device, gpe_handle** out) {
     if (cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking) != cudaSuccess) { delete h; return -3; }
     int prio_least = 0, prio_greatest = 0;
     cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
+    if (const char* e = getenv("GPE_PRIO")) h->use_prio = e[0] != '0';
     for (int s = 0; s < gpe_handle::MAX_SUB; s++) {
         cudaStreamCreateWithPriority(&h->sub_st[s], cudaStreamNonBlocking, prio_least);
-        cudaStreamCreateWithPriority(&h->sub_hi[s], cudaStreamNonBlocking, prio_greatest);
         cudaEventCreateWithFlags(&h->ev_join[s], cudaEventDisableTiming);
-        cudaEventCreateWithFlags(&h->ev_sw[s], cudaEventDisableTiming);
+        if (h->use_prio) {          // the optional high-priority twin streams (experiment knob)
+            cudaStreamCreateWithPriority(&h->sub_hi[s], cudaStreamNonBlocking, prio_greatest);
+            cudaEventCreateWithFlags(&h->ev_sw[s], cudaEventDisableTiming);
+        }
     }
-    if (const char* e = getenv("GPE_PRIO")) h->use_prio = e[0] != '0';
     cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
     {   // keep freed temporaries cached in the device's default pool instead of returning them to the driver
         cudaMemPool_t pool = nullptr;

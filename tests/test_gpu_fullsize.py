@@ -111,3 +111,49 @@ def test_posterior_properties_n2000_and_grid_consistency(dev):
     assert np.array_equal(keep.astype(bool), I < cm) and cnt[0] == (I < cm).sum()
     assert np.allclose(cmin[:, 0], I.reshape(7, -1).min(1), rtol=1e-15)
     assert np.array_equal(ccnt[:, 0], (I.reshape(7, -1) < cm).sum(1))
+
+
+def test_config4_subsample_matches_oracle_and_index_sets_are_identical(dev):
+    """Config 4: n = 2000, d = 8 emulators, points of the 10^8 grid.  A random subsample of
+    grid indices is predicted on the GPU and by the oracle (chunked g.posterior arithmetic); mean / variance
+    agree to 1e-8, the non-implausible index sets of two emulators are identical, and no point sits within the
+    guard band |I - cm| < 1e-9 where a last-bit difference could flip the decision."""
+    from gp_emu_uqsa_b200 import _lib
+    from oracle import gp_oracle as O
+    n, d, m = 2000, 8, 3000
+    X, y = _synth(n, d)
+    y2 = np.cos(X @ np.random.default_rng(1).normal(size=d))
+    H = np.column_stack([np.ones(n), X])
+    delta = np.full(d, 0.5)
+    rng = np.random.default_rng(4)
+    idx = np.sort(rng.choice(10 ** 8, size=m, replace=False))
+    P = np.empty((m, d))
+    t = idx.copy()
+    for k in range(d - 1, -1, -1):
+        P[:, k] = 0.0 + (t % 10 + 0.5) * ((1.0 - 0.0) / 10.0)
+        t = t // 10
+    Hs = np.column_stack([np.ones(m), P])
+    means, variances = [], []
+    A = O.make_A(X, delta, 1e-4, 0)
+    for yy in (y, y2):
+        dev.set_training(X, yy, H)
+        dev.set_basis(list(range(d)), [1] * d)
+        beta, _, st = dev.fit_state(delta, 1e-4, 1.0, 0)
+        assert st == 0
+        gm, gv = dev.predict(P)
+        om, ov = O.posterior_diag_chunked(P, Hs, X, yy, H, A, beta, 1.0, delta, 1e-4, 0, chunk=1000)
+        assert np.allclose(beta, O.optimalbeta(A, H, yy), rtol=1e-8, atol=1e-10)
+        assert np.allclose(gm, om, rtol=1e-8, atol=1e-10)
+        assert np.allclose(gv, ov, rtol=1e-8, atol=1e-9 * ov.max())
+        # a single flat-index prediction equals the explicit-point one
+        g1, v1 = dev.predict_grid(np.full(d, 10, dtype=np.int32), np.zeros(d), np.ones(d), int(idx[7]), 1)
+        assert abs(g1[0] - gm[7]) <= 1e-12 * abs(gm[7]) and abs(v1[0] - gv[7]) <= 1e-11 * abs(gv[7])
+        means.append(gm); variances.append(gv)
+    zs, ve, cm = [float(np.median(y)), float(np.median(y2))], [1e-2, 1e-2], 3.0
+    Imax, keep, cnt, _, _ = dev.implausibility(np.array(means), np.array(variances), zs, ve, cm, maxno=1)
+    om1, ov1 = O.posterior_diag_chunked(P, Hs, X, y, H, A, O.optimalbeta(A, H, y), 1.0, delta, 1e-4, 0, chunk=1000)
+    om2, ov2 = O.posterior_diag_chunked(P, Hs, X, y2, H, A, O.optimalbeta(A, H, y2), 1.0, delta, 1e-4, 0, chunk=1000)
+    Iref, kref, _ = O.implausibility(np.array([om1, om2]), np.array([ov1, ov2]), zs, ve, cm, 1)
+    assert np.abs(np.asarray(Iref)[:, -1] - cm).min() > 1e-9          # guard band is empty on this sample
+    assert np.array_equal(keep.astype(bool), np.asarray(kref)) and int(cnt[0]) == int(np.asarray(kref).sum())
+    assert 0 < int(cnt[0]) < m
