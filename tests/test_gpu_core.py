@@ -83,7 +83,7 @@ def test_gemm_triangular_kmodes(dev, n, batch):
     assert torch.allclose(Cm * m, want * m, rtol=1e-12, atol=1e-10)
 
 
-@pytest.mark.parametrize("n,batch", [(60, 2), (128, 3), (200, 2), (640, 2), (1000, 1)])
+@pytest.mark.parametrize("n,batch", [(1, 1), (7, 3), (60, 2), (128, 3), (129, 2), (200, 2), (640, 2), (1000, 1), (2000, 2)])
 def test_potrf_inv(dev, n, batch):
     rng = np.random.default_rng(n)
     As = []
