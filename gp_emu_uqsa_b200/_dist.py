@@ -2,16 +2,17 @@
 guesses of Optimize.optimal and the point/cell ranges of prediction + implausibility.  One process
 per GPU (torchrun); NCCL when the process group is NCCL (buffers on the rank's GPU), gloo otherwise.
 Without an initialised process group everything degenerates to rank 0 of 1."""
+import sys
+
 import numpy as np
 
 
 def rank_world():
-    try:
-        import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized():
-            return dist.get_rank(), dist.get_world_size()
-    except ImportError:
-        pass
+    # a process group can only exist if the caller has imported torch.distributed already: do not pay the
+    # torch import (about a second) in single-process runs
+    dist = sys.modules.get("torch.distributed")
+    if dist is not None and dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
     return 0, 1
 
 
