@@ -16,10 +16,17 @@ _WORKER = r"""
 import contextlib, io, os, shutil, sys
 import numpy as np
 import torch.distributed as dist
-ROOT, port, rank, work = sys.argv[1], sys.argv[2], int(sys.argv[3]), sys.argv[4]
+ROOT, port, rank, work, backend = sys.argv[1], sys.argv[2], int(sys.argv[3]), sys.argv[4], sys.argv[5]
 sys.path.insert(0, ROOT)
-os.environ["GPE_DEVICE"] = "0"
-dist.init_process_group("gloo", init_method="tcp://127.0.0.1:" + port, rank=rank, world_size=2)
+if backend == "nccl":                 # one rank per GPU, cell statistics / guess tables travel over NCCL
+    import torch
+    os.environ["GPE_DEVICE"] = str(rank)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", init_method="tcp://127.0.0.1:" + port, rank=rank, world_size=2,
+                            device_id=torch.device("cuda", rank))
+else:                                 # single-GPU box: both ranks on cuda:0, gloo for the exchanges
+    os.environ["GPE_DEVICE"] = "0"
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:" + port, rank=rank, world_size=2)
 import gp_emu_uqsa_b200 as g
 import gp_emu_uqsa_b200.history_match as h
 gdir = os.path.join(ROOT, "tests", "golden")
@@ -68,10 +75,12 @@ print("rank", rank, "ok")
 
 
 def test_two_ranks_shard_multistart_and_history_match(tmp_path):
+    import torch
+    backend = "nccl" if torch.cuda.device_count() >= 2 else "gloo"
     script = tmp_path / "w.py"
     script.write_text(_WORKER)
     port = str(31500 + os.getpid() % 2000)
-    procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r), str(tmp_path)], stdout=subprocess.PIPE,
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r), str(tmp_path), backend], stdout=subprocess.PIPE,
                               stderr=subprocess.STDOUT) for r in (0, 1)]
     outs = [p.communicate(timeout=600)[0].decode() for p in procs]
     for r, (p, o) in enumerate(zip(procs, outs)):
