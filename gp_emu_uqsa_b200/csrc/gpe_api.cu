@@ -165,7 +165,19 @@ int gpe_run_gemm(gpe_handle* h, const double* A, const double* B, double* C, int
 //   F(A11) ; L21 = A21 L11^-T ; A22 -= L21 L21^T ; F(A22) ; Linv21 = -L22^-1 (L21 L11^-1).
 // All four updates are DMMA GEMMs with a triangular operand (zero tiles skipped); only the
 // 128x128 diagonal leaves are factored by a panel kernel.  2n^3/3 flops, 5 launches per node.
-static int potrf_inv_rec(gpe_handle* h, const SubBatch& sb, int off, int m, int want_L) {
+int gpe_handle::ensure_side(int g) {
+    if (side_st[g][0]) return 0;
+    int prio_least = 0, prio_greatest = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
+    for (int k = 0; k < MAX_DEPTH; k++) {
+        if (cudaStreamCreateWithPriority(&side_st[g][k], cudaStreamNonBlocking, prio_least) != cudaSuccess) return -1;
+        cudaEventCreateWithFlags(&ev_sf[g][k], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&ev_sj[g][k], cudaEventDisableTiming);
+    }
+    return 0;
+}
+
+static int potrf_inv_rec(gpe_handle* h, const SubBatch& sb, int off, int m, int want_L, int depth = 0) {
     const int ld = h->npad, B = sb.B;
     const long long sM = (long long)h->npad * h->npad;
     double* Ab = h->A + (size_t)sb.b0 * sM;
@@ -184,7 +196,7 @@ static int potrf_inv_rec(gpe_handle* h, const SubBatch& sb, int off, int m, int 
     const int nb = m / NB;
     const int m1 = ((nb + 1) / 2) * NB, m2 = m - m1;
     int rc;
-    if ((rc = potrf_inv_rec(h, sb, off, m1, want_L))) return rc;
+    if ((rc = potrf_inv_rec(h, sb, off, m1, want_L, depth + 1))) return rc;
     double* A21 = Ab + (size_t)(off + m1) * ld + off;
     double* A22 = Ab + (size_t)(off + m1) * ld + off + m1;
     double* S21 = Sb + (size_t)(off + m1) * ld + off;
@@ -193,11 +205,25 @@ static int potrf_inv_rec(gpe_handle* h, const SubBatch& sb, int off, int m, int 
     double* Li21 = Lb + (size_t)(off + m1) * ld + off;
     // L21 = A21 * Linv11^T           (NT, Linv11 lower: k <= j)
     if ((rc = run_gemm(h, sb.stream(!gemm_is_big(m2, m1, 0, B)), A21, Li11, S21, ld, ld, ld, sM, sM, sM, m2, m1, m1, 1.0, 0, KM_LE_J, 0, B, 0))) return rc;
+    // T = L21 * Linv11  (NN, Linv11 lower: k >= j) -> dead A21 block.  It needs only L21 and Linv11, not the
+    // factorisation of A22: with side streams it is launched now, beside the SYRK and the whole A22 sub-recursion
+    // (whose leaves and small levels cannot fill the machine), and joined before the last product of the node.
+    const bool fork = sb.side != nullptr && depth < gpe_handle::MAX_DEPTH;
+    if (fork) {
+        cudaStream_t side = sb.side[depth];
+        cudaEventRecord(sb.ef[depth], sb.current());
+        cudaStreamWaitEvent(side, sb.ef[depth], 0);
+        if ((rc = run_gemm(h, side, S21, Li11, A21, ld, ld, ld, sM, sM, sM, m2, m1, m1, 1.0, 0, KM_GE_J, 0, B, 1))) return rc;
+        cudaEventRecord(sb.ej[depth], side);
+    }
     // A22 -= L21 * L21^T             (SYRK, lower tiles)
     if ((rc = run_gemm(h, sb.stream(!gemm_is_big(m2, m2, 1, B)), S21, S21, A22, ld, ld, ld, sM, sM, sM, m2, m2, m1, -1.0, 1, KM_FULL, 1, B, 0))) return rc;
-    if ((rc = potrf_inv_rec(h, sb, off + m1, m2, want_L))) return rc;
-    // T = L21 * Linv11               (NN, Linv11 lower: k >= j)  -> dead A21 block
-    if ((rc = run_gemm(h, sb.stream(!gemm_is_big(m2, m1, 0, B)), S21, Li11, A21, ld, ld, ld, sM, sM, sM, m2, m1, m1, 1.0, 0, KM_GE_J, 0, B, 1))) return rc;
+    if ((rc = potrf_inv_rec(h, sb, off + m1, m2, want_L, depth + 1))) return rc;
+    if (fork) {
+        cudaStreamWaitEvent(sb.current(), sb.ej[depth], 0);
+    } else {
+        if ((rc = run_gemm(h, sb.stream(!gemm_is_big(m2, m1, 0, B)), S21, Li11, A21, ld, ld, ld, sM, sM, sM, m2, m1, m1, 1.0, 0, KM_GE_J, 0, B, 1))) return rc;
+    }
     // Linv21 = -Linv22 * T           (NN, Linv22 lower: k <= i)
     if ((rc = run_gemm(h, sb.stream(!gemm_is_big(m2, m1, 0, B)), Li22, A21, Li21, ld, ld, ld, sM, sM, sM, m2, m1, m2, -1.0, 0, KM_LE_I, 0, B, 1))) return rc;
     return 0;
@@ -303,6 +329,7 @@ int gpe_create(int device, gpe_handle** out) {
     }
     if (const char* e = getenv("GPE_STREAMS")) h->nsub = std::max(1, std::min((int)gpe_handle::MAX_SUB, atoi(e)));
     if (const char* e = getenv("GPE_GRAPHS")) h->use_graphs = e[0] != '0';
+    if (const char* e = getenv("GPE_SIDE")) h->use_side = e[0] != '0';
     *out = h;
     return 0;
 }
@@ -318,6 +345,12 @@ int gpe_destroy(gpe_handle* h) {
         if (h->ev_join[s]) cudaEventDestroy(h->ev_join[s]);
         if (h->ev_sw[s]) cudaEventDestroy(h->ev_sw[s]);
     }
+    for (int s = 0; s < gpe_handle::MAX_SUB; s++)
+        for (int k = 0; k < gpe_handle::MAX_DEPTH; k++) {
+            if (h->side_st[s][k]) { cudaStreamSynchronize(h->side_st[s][k]); cudaStreamDestroy(h->side_st[s][k]); }
+            if (h->ev_sf[s][k]) cudaEventDestroy(h->ev_sf[s][k]);
+            if (h->ev_sj[s][k]) cudaEventDestroy(h->ev_sj[s][k]);
+        }
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     for (auto e : h->prof_pool) cudaEventDestroy(e);
     cudaStreamDestroy(h->st);
@@ -479,6 +512,10 @@ static int enqueue_llh_chunk(gpe_handle* h, int Bs, int p, int mode, double fixe
         sb.B = (int)((long long)Bs * (g + 1) / ns) - sb.b0;
         sb.st = ns > 1 ? h->sub_st[g] : h->st;
         if (ns > 1 && h->use_prio) { sb.hi = h->sub_hi[g]; sb.ev = h->ev_sw[g]; }
+        if (ns > 1 && h->use_side) {
+            if (h->ensure_side(g)) return h->fail_msg("could not create side streams");
+            sb.side = h->side_st[g]; sb.ef = h->ev_sf[g]; sb.ej = h->ev_sj[g];
+        }
         if (ns > 1) CK(cudaStreamWaitEvent(sb.st, h->ev_fork, 0));
         {
             ProfScope ps(h, gpe_handle::CAT_COV, sb.st);

@@ -32,7 +32,14 @@ struct gpe_handle {
     cudaStream_t sub_st[MAX_SUB] = {nullptr};      // low priority: the large DMMA GEMMs, covariance build, gradient reduction
     cudaStream_t sub_hi[MAX_SUB] = {nullptr};      // high priority: leaf panels, small recursion levels, skinny panels
     cudaEvent_t ev_fork = nullptr, ev_join[MAX_SUB] = {nullptr}, ev_sw[MAX_SUB] = {nullptr};
-    bool use_prio = false;     // measured neutral on B200: off unless GPE_PRIO=1
+    bool use_prio = false;
+    // side streams, one per (group, recursion depth): the product T = L21 L11^-1 of a node does not depend on
+    // the factorisation of its A22 block, so it runs beside that whole sub-recursion (gpe_api.cu:potrf_inv_rec)
+    enum { MAX_DEPTH = 10 };
+    bool use_side = true;
+    cudaStream_t side_st[MAX_SUB][MAX_DEPTH] = {{nullptr}};
+    cudaEvent_t ev_sf[MAX_SUB][MAX_DEPTH] = {{nullptr}}, ev_sj[MAX_SUB][MAX_DEPTH] = {{nullptr}};
+    int ensure_side(int g);     // measured neutral on B200: off unless GPE_PRIO=1
 
     // CUDA graphs of the likelihood step: the launch sequence of a (batch size, mode) pair is
     // captured the second time it is seen and replayed afterwards (one cudaGraphLaunch instead of
@@ -101,6 +108,8 @@ struct SubBatch {
     cudaStream_t hi = nullptr;
     cudaEvent_t ev = nullptr;
     mutable bool on_hi = false;
+    cudaStream_t* side = nullptr;      // [MAX_DEPTH] side streams of this group (nullptr: everything in order on st)
+    cudaEvent_t *ef = nullptr, *ej = nullptr;
     cudaStream_t stream(bool small) const {
         if (!hi || small == on_hi) return on_hi ? hi : st;
         cudaStream_t from = on_hi ? hi : st, to = small ? hi : st;
