@@ -346,3 +346,22 @@ def test_reconstructed_emulator_from_shipped_old_format_files(golden_dir, tmp_pa
     assert p1.mean.shape == (900,) and p2.mean.shape == (900,) and p1.var_diag.min() > 0 and p2.var_diag.min() > 0
     # the line plot is the map's slice at x1 = 0.3 only approximately (different grids); both are finite and smooth
     assert np.all(np.isfinite(p1.mean)) and np.all(np.isfinite(p2.mean))
+
+
+def test_posterior_sample_consumes_rng_like_reference(golden_dir, tmp_path):
+    """g.posterior_sample: mean + chol(V) u with u = np.random.randn(m) from the global RNG
+    (emulatorfunctions.py:283-285); the Cholesky factor comes from the device (gpe_potrf)."""
+    import gp_emu_uqsa_b200 as g
+    gold = np.load(os.path.join(golden_dir, "toysim_recon.npz"))
+    src = os.path.join(golden_dir, "toy-sim-recon")
+    for f in os.listdir(src):
+        shutil.copy(os.path.join(src, f), tmp_path)
+    xs = gold["xs"][:12].copy()
+    with _cwd(tmp_path), _quiet():
+        E = g.setup("toy-sim_config_recon", datashuffle=False, scaleinputs=True)
+        np.random.seed(11)
+        sample = g.posterior_sample(E, xs.copy())
+    np.random.seed(11)
+    u = np.random.randn(12)
+    want = gold["mean"][:12] + np.linalg.cholesky(gold["var"][:12, :12]).dot(u)      # the real reference's mean / covariance
+    assert np.allclose(sample, want, rtol=1e-7, atol=1e-9)
