@@ -512,7 +512,7 @@ static int enqueue_llh_chunk(gpe_handle* h, int Bs, int p, int mode, double fixe
         sb.B = (int)((long long)Bs * (g + 1) / ns) - sb.b0;
         sb.st = ns > 1 ? h->sub_st[g] : h->st;
         if (ns > 1 && h->use_prio) { sb.hi = h->sub_hi[g]; sb.ev = h->ev_sw[g]; }
-        if (ns > 1 && h->use_side) {
+        if (h->nsub > 1 && h->use_side) {      // also for a single group (small batches): intra-item overlap only
             if (h->ensure_side(g)) return h->fail_msg("could not create side streams");
             sb.side = h->side_st[g]; sb.ef = h->ev_sf[g]; sb.ej = h->ev_sj[g];
         }
