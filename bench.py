@@ -370,6 +370,11 @@ def run_b200(args):
         fpp = flops_pred(N_PRED, D_PRED, D_PRED + 1)
         gms, gcnt = pprof["gemm_dmma_128"]
         nchunks = gcnt
+        ptraffic = {}
+        tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        if os.path.exists(tp):
+            with open(tp) as f:
+                ptraffic = json.load(f)
         extra = {"posterior_preds_per_s": preds,
                  "posterior_workload": "config4: n=2000 d=8 q=9, %.0e-point tensor grid (10 levels/dim) generated on device from the flat "
                                        "index, sharded over %d GPU(s) by index range, mean + diagonal variance written to HBM "
@@ -381,6 +386,8 @@ def run_b200(args):
                                         "kernel": "gemm_dmma_ws_kernel<NN, EPI_SUMSQ> (Z = L^-1 C with fused column norms)",
                                         "kernel_achieved": (float(mprof) * float(N_PRED) ** 2 * 1e-12) / (gms * 1e-3) if gms else None,
                                         "kernel_launches": nchunks,
+                                        "traffic": ptraffic.get("trmm_dram_bytes_per_launch"),
+                                        "algorithmic_bytes_per_launch": ptraffic.get("trmm_algorithmic_bytes_per_launch"),
                                         "by_kernel_ms": {k: v[0] for k, v in pprof.items()},
                                         "note": "achieved = F_pred (n^2 + 2n(d+q+3)) x preds/s per GPU; kernel_achieved = n^2 flops per "
                                                 "point / CUDA-event time of the TRMM launches in a separate serial-launch pass over "
