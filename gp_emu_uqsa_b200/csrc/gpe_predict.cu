@@ -67,7 +67,7 @@ __global__ void grid_points_kernel(GridDesc g, long long start, long long count,
 
 // K1x: C[k][j] = c * exp(-sum_dim ((x_k - p_j)/delta)^2) for a chunk of mc points.
 // CTA = 64 training rows x 128 points, 256 threads, each thread 8 rows x 4 points.
-__global__ void __launch_bounds__(256) xcov_kernel(const double* __restrict__ Xs /*[d][npad]*/, const double* __restrict__ P /*[mc][d]*/,
+__global__ void __launch_bounds__(256, 3) xcov_kernel(const double* __restrict__ Xs /*[d][npad]*/, const double* __restrict__ P /*[mc][d]*/,
                                                    const double* __restrict__ winv, int n, int d, int npad, int mc, long long count,
                                                    double cscale, double* __restrict__ Cm, int ldc) {
     extern __shared__ __align__(16) double sm[];
