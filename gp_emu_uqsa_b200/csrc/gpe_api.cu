@@ -613,7 +613,16 @@ int gpe_potrf(gpe_handle* h, const double* A, int n, int batch, double* L_out, d
     }
     int rc;
     if ((rc = gpe_ensure_batch_ws(h, batch))) return rc;
-    if (batch > h->Bcap) return h->fail_msg("batch exceeds workspace capacity");
+    if (batch > h->Bcap) {      // more matrices than the resident workspace holds: sub-batches, one after the other
+        const size_t per = (size_t)n * n;
+        for (int b0 = 0; b0 < batch; b0 += h->Bcap) {
+            const int bs = std::min(h->Bcap, batch - b0);
+            if ((rc = gpe_potrf(h, A + b0 * per, n, bs, L_out ? L_out + b0 * per : nullptr, Linv_out ? Linv_out + b0 * per : nullptr,
+                                logdet ? logdet + b0 : nullptr, status ? status + b0 : nullptr)))
+                return rc;
+        }
+        return 0;
+    }
     const size_t nn = (size_t)npad * npad;
     // identity-padded copy
     std::vector<double> host((size_t)batch * nn, 0.0), src((size_t)batch * n * n);
