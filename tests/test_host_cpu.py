@@ -201,3 +201,13 @@ def test_world_size_2_gloo_sharding(tmp_path):
     outs = [p.communicate(timeout=180)[0].decode() for p in procs]
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0 and ("rank %d ok" % r) in o, o
+
+
+def test_header_is_plain_c(tmp_path):
+    """The C-ABI header must be consumable from C (cgo / JNI / ctypes-style bindings): plain pointers and
+    sizes, no C++ or torch types."""
+    src = tmp_path / "t.c"
+    src.write_text('#include "gpe_b200.h"\nint main(void) { gpe_handle* h = 0; (void)h; return GPE_MODE_MUCM | GPE_MODE_ALT_NUGGET | GPE_MODE_NUGGET_FREE; }\n')
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), str(src)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
