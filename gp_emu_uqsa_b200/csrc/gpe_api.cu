@@ -561,8 +561,9 @@ int gpe_llh_grad_batch(gpe_handle* h, const double* theta, int B, int p, int mod
         if (gr && gr->exec) {
             CK(cudaGraphLaunch(gr->exec, h->st));
             h->launches += gr->launches;
-        } else if (gr && gr->seen >= 1) {
-            // second sighting of this shape: capture the launch sequence (all sub-batch streams join the
+        } else if (gr && gr->seen >= 2) {
+            // third sighting of this shape (a ragged multistart sees most batch sizes once or twice: those stay
+            // eager, capture + instantiate would cost more than it saves): capture the launch sequence (all sub-batch streams join the
             // capture through the fork event), instantiate, replay
             const long long l0 = h->launches;
             cudaGraph_t graph = nullptr;

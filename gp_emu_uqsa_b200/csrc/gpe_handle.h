@@ -42,7 +42,7 @@ struct gpe_handle {
     int ensure_side(int g);     // measured neutral on B200: off unless GPE_PRIO=1
 
     // CUDA graphs of the likelihood step: the launch sequence of a (batch size, mode) pair is
-    // captured the second time it is seen and replayed afterwards (one cudaGraphLaunch instead of
+    // captured the third time it is seen and replayed afterwards (one cudaGraphLaunch instead of
     // ~650 launches per stream), so the host never limits the small-n, many-stream case
     bool use_graphs = true;
     struct LlhGraph { int Bs, p, mode, nsub; double nug; int seen; cudaGraphExec_t exec; long long launches; };
