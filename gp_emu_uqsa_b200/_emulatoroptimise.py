@@ -3,6 +3,8 @@
 the host; every log-likelihood + gradient evaluation is served by ``gpe_llh_grad_batch`` on the
 B200, all multistart guesses of a round in one call (``_lbfgsb_batch.minimize_batch``); with
 ``torch.distributed`` initialised the guesses are block-partitioned over the ranks."""
+import os
+
 import numpy as np
 
 from . import _dist
@@ -153,7 +155,8 @@ class Optimize:
             return f, g, ok
 
         x0s = guessgrid.T[lo:hi]
-        res_local, rounds, evals = minimize_batch(eval_batch, x0s, self.cons if constrained else None) \
+        res_local, rounds, evals = minimize_batch(eval_batch, x0s, self.cons if constrained else None,
+                                                    driver=os.environ.get("GPE_LBFGSB_DRIVER") or None) \
             if hi > lo else ([], 0, 0)
         self.last_rounds, self.last_evals = rounds, evals
         # pack (ok, fun, x) per guess and exchange so that every rank sees all of them in guess order

@@ -134,18 +134,32 @@ def test_lockstep_lbfgsb_matches_sequential_scipy():
     x0s = rng.normal(size=(12, 5)) * 3
     x0s[4, 0] = 60.0
     bounds = [[-2.0, 2.0]] * 5
-    for bnd in (None, bounds):
-        x0 = x0s.copy()
-        if bnd is not None:
-            x0[4, 0] = 1.0
-        res, rounds, evals = minimize_batch(eval_batch, x0, bnd)
-        for i in range(12):
-            if bnd is None and i == 4:
-                assert res[i] is None
-                continue
-            ref = minimize(fg, list(x0[i]), method="L-BFGS-B", jac=True, **({} if bnd is None else {"bounds": bnd}))
-            assert res[i].nfev == ref.nfev and np.array_equal(res[i].x, ref.x) and res[i].fun == ref.fun
-        assert evals == sum(calls[-rounds:]) and rounds >= 3
+    half_open = [[None, 1.0], [0.0, None], [None, None], [-1, 1], [-3, 0.5]]
+    for driver in ("rc", "threads", None):             # reverse-communication, threaded, and the default choice
+        for bnd in (None, bounds, half_open):
+            x0 = x0s.copy()
+            if bnd is not None:
+                x0[4, 0] = 1.0
+            res, rounds, evals = minimize_batch(eval_batch, x0, bnd, driver=driver)
+            for i in range(12):
+                if bnd is None and i == 4:
+                    assert res[i] is None
+                    continue
+                ref = minimize(fg, list(x0[i]), method="L-BFGS-B", jac=True, **({} if bnd is None else {"bounds": bnd}))
+                assert res[i].nfev == ref.nfev and res[i].nit == ref.nit and res[i].status == ref.status
+                assert np.array_equal(res[i].x, ref.x) and res[i].fun == ref.fun and np.array_equal(res[i].jac, ref.jac)
+            assert evals == sum(calls[-rounds:]) and rounds >= 3
+
+
+def test_lockstep_lbfgsb_error_reaches_caller():
+    from gp_emu_uqsa_b200._lbfgsb_batch import minimize_batch
+
+    def boom(X):
+        raise RuntimeError("device error")
+
+    for driver in ("rc", "threads"):
+        with pytest.raises(RuntimeError, match="device error"):
+            minimize_batch(boom, np.ones((4, 3)), None, driver=driver)
 
 
 _GLOO_WORKER = r"""
