@@ -540,6 +540,7 @@ static int enqueue_llh_chunk(gpe_handle* h, int Bs, int p, int mode, double fixe
 
 int gpe_llh_grad_batch(gpe_handle* h, const double* theta, int B, int p, int mode, double fixed_nugget,
                        double* llh, double* grad, double* sigma_hat, int* status) {
+    if (h && h->n && B == 0) return 0;                           // a rank that owns no guess of the multistart
     if (!h || !h->n || !theta || B < 1 || !llh || !grad) return h ? h->fail_msg("bad argument / no training set") : -2;
     int p_expect = h->d + ((mode & GPE_MODE_NUGGET_FREE) ? 1 : 0) + ((mode & GPE_MODE_MUCM) ? 0 : 1);
     if (p != p_expect) return h->fail_msg("p does not match d and mode");

@@ -473,12 +473,14 @@ static int predict_common(gpe_handle* h, const double* Xs, const double* Hs, con
 }
 
 int gpe_predict(gpe_handle* h, const double* Xs, const double* Hs, long long m, double* mean, double* var) {
+    if (h && m == 0) return 0;                                   // empty chunk: nothing to do
     if (!h || !Xs || !mean || m < 1) return h ? h->fail_msg("bad argument") : -2;
     return predict_common(h, Xs, Hs, nullptr, 0, m, mean, var);
 }
 
 int gpe_predict_grid(gpe_handle* h, const int* levels, const double* lo, const double* hi, long long start,
                      long long count, double* mean, double* var) {
+    if (h && count == 0) return 0;                               // empty shard of the grid
     if (!h || !levels || !lo || !hi || !mean || count < 1) return h ? h->fail_msg("bad argument") : -2;
     if (h->d > MAXD) return h->fail_msg("grid prediction supports d <= 64");
     GridDesc g;
@@ -492,6 +494,7 @@ int gpe_predict_grid(gpe_handle* h, const int* levels, const double* lo, const d
 }
 
 int gpe_cross_cov(gpe_handle* h, const double* delta, double nugget, int kind, const double* Xs, int m, double* C_out) {
+    if (h && m == 0) return 0;
     if (!h || !h->n || !delta || !Xs || !C_out || m < 1) return h ? h->fail_msg("bad argument") : -2;
     CK(cudaSetDevice(h->device));
     const int np = h->npad, d = h->d;
@@ -522,6 +525,7 @@ int gpe_cross_cov(gpe_handle* h, const double* delta, double nugget, int kind, c
 
 int gpe_predict_fullcov(gpe_handle* h, const double* Xs, const double* Hs, int m, const double* r_new, double* mean,
                         double* V) {
+    if (h && m == 0) return 0;
     if (!h || !Xs || !mean || !V || m < 1) return h ? h->fail_msg("bad argument") : -2;
     if (!h->fitted) return h->fail_msg("gpe_fit_state has not succeeded on this handle");
     if (!Hs && !h->has_basis) return h->fail_msg("no H* given and no device basis set (gpe_set_basis)");
@@ -580,7 +584,7 @@ int gpe_predict_fullcov(gpe_handle* h, const double* Xs, const double* Hs, int m
 int gpe_implausibility(gpe_handle* h, const double* mean, const double* var, int n_emul, long long m, const double* z,
                        const double* var_extra, double cm, int maxno, long long ncell, double* Imax, unsigned char* keep,
                        unsigned long long* count_lt, double* cell_min, unsigned long long* cell_count) {
-    if (!h || !mean || !var || !z || !var_extra || n_emul < 1 || m < 1) return h ? h->fail_msg("bad argument") : -2;
+    if (!h || !z || !var_extra || n_emul < 1 || m < 0 || (m > 0 && (!mean || !var))) return h ? h->fail_msg("bad argument") : -2;
     if (n_emul > MAXEM || maxno < 1 || maxno > n_emul) return h->fail_msg("need 1 <= maxno <= n_emul <= 16");
     if (ncell > 0 && m % ncell) return h->fail_msg("m must be a multiple of ncell");
     CK(cudaSetDevice(h->device));
@@ -614,10 +618,12 @@ int gpe_implausibility(gpe_handle* h, const double* mean, const double* var, int
         CK(cudaMemsetAsync(cmin, 0x7f, sizeof(unsigned long long) * ncell * maxno, h->st));   // large positive double
         CK(cudaMemsetAsync(ccnt, 0, sizeof(unsigned long long) * ncell * maxno, h->st));
     }
-    implaus_kernel<<<(unsigned)((m + 255) / 256), 256, 0, h->st>>>(md, vd, m, ds, ncell > 0 ? m / ncell : 0, Id, kd, cnt, cmin, ccnt);
-    h->launches++;
-    if (Imax && !I_dev) CK(cudaMemcpyAsync(Imax, Id, sizeof(double) * (size_t)m * maxno, cudaMemcpyDeviceToHost, h->st));
-    if (keep && !k_dev) CK(cudaMemcpyAsync(keep, kd, (size_t)m, cudaMemcpyDeviceToHost, h->st));
+    if (m > 0) {                                                 // m == 0: zero counts, +huge cell minima
+        implaus_kernel<<<(unsigned)((m + 255) / 256), 256, 0, h->st>>>(md, vd, m, ds, ncell > 0 ? m / ncell : 0, Id, kd, cnt, cmin, ccnt);
+        h->launches++;
+    }
+    if (Imax && !I_dev && m > 0) CK(cudaMemcpyAsync(Imax, Id, sizeof(double) * (size_t)m * maxno, cudaMemcpyDeviceToHost, h->st));
+    if (keep && !k_dev && m > 0) CK(cudaMemcpyAsync(keep, kd, (size_t)m, cudaMemcpyDeviceToHost, h->st));
     if (count_lt) CK(cudaMemcpyAsync(count_lt, cnt, sizeof(unsigned long long) * maxno, cudaMemcpyDefault, h->st));
     if (ncell > 0 && cell_min) CK(cudaMemcpyAsync(cell_min, cmin, sizeof(double) * ncell * maxno, cudaMemcpyDefault, h->st));
     if (ncell > 0 && cell_count) CK(cudaMemcpyAsync(cell_count, ccnt, sizeof(unsigned long long) * ncell * maxno, cudaMemcpyDefault, h->st));

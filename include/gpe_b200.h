@@ -14,6 +14,8 @@
  *    a numerically failed item (non positive-definite covariance, the reference's
  *    LinAlgError -> None path, _emulatoroptimise.py:374-376, :489-491) is reported only
  *    through status[] (index+1 of the first non-positive pivot), never as an error code;
+ *  - a unit count of zero (no guesses, no prediction points, an empty grid shard) is a successful
+ *    no-op that touches no output, so an empty rank of a partitioned job needs no special case;
  *  - one handle per device per process; a handle is not thread-safe; calls are synchronous
  *    with respect to the returned host-visible results;
  *  - there is NO CPU fallback: every entry point fails if no sm_100 device is present.

