@@ -283,6 +283,45 @@ def gen_toysim_recon(g):
     return out
 
 
+NOISEFIT_CFG = (("data", "OUTPUTS", ("alt_nugget T", "constraints none", "[[0.05,10.0],[0.05,10.00]]", "[[0.1,3.0]]", "[[0.001,1.05]]")),
+                ("noise", "zp-outputs", ("alt_nugget F", "constraints bounds", "[[0.05,1.0],[0.05,10.00]]", "[[0.001,10.0]]", "[[0.0001,1.0]]")))
+
+
+def write_noisefit_case(design_module, n=150, seed=3, tries=3):
+    """The noisefit2D example (examples/noisefit2D/emulator.py:12-32) at reduced size, written into the cwd.
+    Shared by the generator below and by tests/test_gpu_hm.py (which passes its own design module)."""
+    np.random.seed(seed)
+    design_module.optLatinHyperCube(2, n, 20, [[0.0, 1.0], [0.0, 1.0]], "INPUTS")
+    x = np.loadtxt("INPUTS")
+    mean = 3.0 * x[:, 0] ** 3 + np.exp(np.cos(10.0 * x[:, 1]) * np.cos(5.0 * x[:, 0]) ** 2)
+    noise = 0.5 * (x[:, 1] * (np.cos(6 * x[:, 0]) ** 2 + 0.1))
+    np.savetxt("OUTPUTS", mean + noise * np.random.randn(x.shape[0]))
+    for name, outputs, extra in NOISEFIT_CFG:
+        with open("config-" + name, "w") as f:
+            f.write("beliefs beliefs-%s\ninputs INPUTS\noutputs %s\ntv_config 10 0 0\ndelta_bounds %s\nsigma_bounds %s\n"
+                    "nugget_bounds %s\ntries %d\n%s\n" % (name, outputs, extra[2], extra[3], extra[4], tries, extra[1]))
+        with open("beliefs-" + name, "w") as f:
+            f.write("active all\noutput 0\nbasis_str 1.0\nbasis_inf NA\nbeta 1.0\ndelta 1.0 1.0\nsigma 1.0\nnugget 0.00001\n"
+                    "fix_nugget F\n%s\nmucm F\n" % extra[0])
+
+
+def gen_noisefit(gn):
+    """noise_fit.noisefit of the real reference on the reduced noisefit2D case: two alternations, 50 posterior
+    samples; stores the design, the simulated outputs, the last zp-outputs and the result files."""
+    import gp_emu_uqsa.design_inputs as d
+    out = {}
+    with tempfile.TemporaryDirectory() as tmp, RL.cwd(tmp), RL.quiet():
+        write_noisefit_case(d)
+        np.random.seed(11)
+        gn.noisefit("config-data", "config-noise", stopat=2, olhcmult=10, samples=50)
+        for fn in ("INPUTS", "OUTPUTS", "zp-outputs", "noise-inputs", "noise-outputs"):
+            out[fn.replace("-", "_")] = np.loadtxt(fn)
+        for fn in sorted(os.listdir(".")):
+            if fn.startswith("beliefs-") and fn.endswith("f"):
+                out["file_" + fn] = np.frombuffer(open(fn, "rb").read(), dtype=np.uint8)
+    return out
+
+
 def main():
     assert RL.available(), "reference not present"
     g, h, s, gn = RL.load()
@@ -293,6 +332,9 @@ def main():
         return
     if len(sys.argv) > 1 and sys.argv[1] == "recon":
         save("toysim_recon.npz", gen_toysim_recon(g))
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "noisefit":
+        save("noisefit_n150.npz", gen_noisefit(gn))
         return
     if len(sys.argv) > 1 and sys.argv[1] == "hmapi":
         save("hmapi_n100_d3.npz", gen_hm_api(g, h, 100, 6))
