@@ -132,6 +132,24 @@ def gen_toysim(g):
     return out
 
 
+def gen_toysim_log(g):
+    """Everything the reference prints during g.setup + g.train of examples/toy-sim (seed 0): the per-guess
+    optimiser lines, the validation diagnostics (Mahalanobis distances, individual standard errors), the
+    include-V-into-T steps and the checkpoint file names -- the train/validation orchestration as text."""
+    import contextlib
+    import io
+    import shutil
+    with tempfile.TemporaryDirectory() as tmp:
+        for f in ("toy-sim_config", "toy-sim_beliefs", "toy-sim_input", "toy-sim_output"):
+            shutil.copy(os.path.join(RL.REF_ROOT, "examples", "toy-sim", f), tmp)
+        buf = io.StringIO()
+        with RL.cwd(tmp), contextlib.redirect_stdout(buf):
+            np.random.seed(0)
+            E = g.setup("toy-sim_config")
+            g.train(E)
+    return {"log": np.frombuffer(buf.getvalue().encode(), dtype=np.uint8)}
+
+
 def gen_hm(g, h, n, seed):
     """History matching: two emulators on 3 inputs; nonimp_data-style flat implausibility.
     Stores means/variances from the reference Posterior and the reference's own
@@ -332,6 +350,9 @@ def main():
         return
     if len(sys.argv) > 1 and sys.argv[1] == "recon":
         save("toysim_recon.npz", gen_toysim_recon(g))
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "toysimlog":
+        save("toysim_log.npz", gen_toysim_log(g))
         return
     if len(sys.argv) > 1 and sys.argv[1] == "noisefit":
         save("noisefit_n150.npz", gen_noisefit(gn))

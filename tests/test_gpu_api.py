@@ -365,3 +365,46 @@ def test_posterior_sample_consumes_rng_like_reference(golden_dir, tmp_path):
     u = np.random.randn(12)
     want = gold["mean"][:12] + np.linalg.cholesky(gold["var"][:12, :12]).dot(u)      # the real reference's mean / covariance
     assert np.allclose(sample, want, rtol=1e-7, atol=1e-9)
+
+
+_NUM = r"[-+]?(?:\d+\.\d*|\.\d+|\d+)(?:[eE][-+]?\d+)?"
+
+
+def test_toysim_training_log_matches_reference_line_by_line(golden_dir, tmp_path):
+    """Everything g.setup + g.train print for examples/toy-sim (seed 0) against the real reference's output
+    (tests/golden/make_golden.py toysimlog): same lines in the same order -- config/beliefs echo, bounds, one
+    line per multistart guess, best hyper-parameters, Mahalanobis distances, 'Bad predictions' lines, V-into-T
+    steps, checkpoint file names -- with every number equal to the optimiser's tolerance.  Guesses that end on
+    a flat part of the likelihood (not the round's best value) are compared by value, not by position."""
+    import re
+    import gp_emu_uqsa_b200 as g
+    want = bytes(np.load(os.path.join(golden_dir, "toysim_log.npz"))["log"]).decode().splitlines()
+    for f in os.listdir(os.path.join(golden_dir, "toy-sim")):
+        shutil.copy(os.path.join(golden_dir, "toy-sim", f), tmp_path)
+    buf = io.StringIO()
+    with _cwd(tmp_path), contextlib.redirect_stdout(buf):
+        np.random.seed(0)
+        E = g.setup("toy-sim_config")
+        g.train(E)
+    got = buf.getvalue().splitlines()
+    assert len(got) == len(want), "\n".join(got)
+    best = {}
+    rnd = 0
+    for w in want:                                  # best llh of each optimisation round in the reference's log
+        if w.startswith("Optimising"):
+            rnd += 1
+        if w.lstrip().startswith("hp:"):
+            best[rnd] = max(best.get(rnd, -np.inf), float(re.findall(_NUM, w.split("llh:")[1])[0]))
+    rnd = 0
+    for a, b in zip(got, want):
+        if b.startswith("Optimising"):
+            rnd += 1
+        assert re.sub(_NUM, "#", a).split() == re.sub(_NUM, "#", b).split(), (a, b)
+        na, nb = [float(v) for v in re.findall(_NUM, a)], [float(v) for v in re.findall(_NUM, b)]
+        if b.lstrip().startswith("hp:"):
+            k = len(nb) - 2                         # ... hp values, then llh, then sig
+            assert np.allclose(na[k:], nb[k:], rtol=2e-4, atol=2e-4), (a, b)
+            if nb[k] == best[rnd]:
+                assert np.allclose(na[:k], nb[:k], rtol=2e-3, atol=2e-4), (a, b)
+        else:
+            assert np.allclose(na, nb, rtol=2e-3, atol=1e-6), (a, b)
