@@ -59,6 +59,42 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// ---- exp() for the Gaussian kernel entries ------------------------------------------------------------------
+// CUDA's exp(double) materialises every polynomial coefficient with a pair of UMOV/IMAD.MOV (a DFMA immediate holds
+// only the high 32 bits of a double): 22 UMOV + 15 IMAD per call, which made the covariance and gradient kernels
+// issue-bound (ncu: FP64 pipe 53-57 % busy, 134 issue slots per entry for 50 FP64 instructions).  Here the
+// constants sit in the constant bank and are DFMA operands directly.  Same method and accuracy class as the library
+// routine: k = rint(x log2 e) by the 1.5*2^52 trick, r = x - k ln2 in two parts (fdlibm split), exp(r) on
+// |r| <= ln2/2 as 1 + r(1 + r q(r)) with the Taylor coefficients to r^13 (truncation 6e-18), scaled by 2^k through the
+// exponent field; arguments outside (-708, 708) (denormal, zero or infinite results) are scaled by two multiplications.
+// tools/ub_exp.cu measures it against exp(): max 1 ulp apart on 2^26 arguments of the kernel's range.
+static __constant__ double GPE_EXP_K[16] = {
+    1.4426950408889634074,       // log2(e)
+    -6.93147180369123816490e-01, // -ln2 hi (low 21 bits zero: k * hi is exact)
+    -1.90821492927058770002e-10, // -ln2 lo
+    1.0 / 6227020800.0, 1.0 / 479001600.0, 1.0 / 39916800.0, 1.0 / 3628800.0, 1.0 / 362880.0, 1.0 / 40320.0,
+    1.0 / 5040.0, 1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5, 0.0};
+__device__ __forceinline__ double gpe_exp(double x) {
+    const double magic = 6755399441055744.0;           // 1.5 * 2^52 (low word zero: a DFMA immediate)
+    const double t = fma(x, GPE_EXP_K[0], magic);
+    const int k = __double2loint(t);
+    const double kd = t - magic;
+    double r = fma(kd, GPE_EXP_K[1], x);
+    r = fma(kd, GPE_EXP_K[2], r);
+    double q = GPE_EXP_K[3];
+#pragma unroll
+    for (int i = 4; i <= 14; i++) q = fma(q, r, GPE_EXP_K[i]);
+    q = fma(q, r, 1.0);
+    q = fma(q, r, 1.0);
+    if (fabs(x) < 708.0) return __hiloint2double(__double2hiint(q) + (k << 20), __double2loint(q));
+    // rare: results that are denormal, zero, infinite or NaN -- scale in two steps so the last product rounds once
+    if (x != x) return x;
+    if (x > 710.0) return __longlong_as_double(0x7ff0000000000000ll);
+    if (x < -746.0) return 0.0;
+    const int k1 = k >> 1, k2 = k - k1;
+    return q * __hiloint2double((k1 + 1023) << 20, 0) * __hiloint2double((k2 + 1023) << 20, 0);
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -48,12 +48,15 @@ void launch_prep_theta(const double* theta, int B, int p, int d, int mode, doubl
 // cond(A) digits and break the 1e-10 parity target).
 constexpr int CT = 64;
 
+// GMODE 0: covariance (the hot path: no G registers, no spills under the 80-register cap of 3 CTAs/SM);
+// 1: d(s2 A)/d theta_delta[gdim] (grad_delta_A); 2: kernel grad_nugget_A (off-diagonal only; the alt-nugget form
+// is a pure diagonal and is assembled by the caller)
+template <int GMODE>
 __global__ void __launch_bounds__(256, 3) cov_build_kernel(const double* __restrict__ X, const double* __restrict__ r,
                                                         int n, int d, int npad, const ItemPar* __restrict__ par,
                                                         const double* __restrict__ winv, double* __restrict__ A,
-                                                        long long sA, int full, int gmode, int gdim) {
-    // gmode 0: covariance; 1: d(s2 A)/d theta_delta[gdim] (grad_delta_A); 2: kernel grad_nugget_A
-    // (off-diagonal only; the alt-nugget form is a pure diagonal and is assembled by the caller)
+                                                        long long sA, int full, int gdim) {
+    constexpr int gmode = GMODE;
     const int tj = blockIdx.x, ti = blockIdx.y, b = blockIdx.z;
     if (!full && tj > ti) return;
     extern __shared__ __align__(16) double sm[];
@@ -70,11 +73,14 @@ __global__ void __launch_bounds__(256, 3) cov_build_kernel(const double* __restr
     __syncthreads();
     const ItemPar ip = par[b];
     const int ty = tid >> 4, tx = tid & 15;
-    double D[4][4], G[4][4];
+    double D[4][4], G[GMODE == 1 ? 4 : 1][4];
 #pragma unroll
     for (int a = 0; a < 4; a++)
 #pragma unroll
-        for (int c = 0; c < 4; c++) { D[a][c] = 0.0; G[a][c] = 1.0; }
+        for (int c = 0; c < 4; c++) {
+            D[a][c] = 0.0;
+            if constexpr (GMODE == 1) G[a][c] = 1.0;
+        }
     for (int k = 0; k < d; k++) {
         double xi[4], xj[4];
 #pragma unroll
@@ -88,9 +94,15 @@ __global__ void __launch_bounds__(256, 3) cov_build_kernel(const double* __restr
             for (int c = 0; c < 4; c++) {
                 double df = xi[a] - xj[c];
                 D[a][c] = fma(df, df, D[a][c]);
-                if (gmode == 1 && k == gdim) G[a][c] = df * df;
+                if constexpr (GMODE == 1) { if (k == gdim) G[a][c] = df * df; }
             }
     }
+    // all 16 exponentials first, outside the padding / diagonal case analysis: straight-line code whose 16 polynomial
+    // chains interleave (inside the branches they ran one dependent chain at a time)
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int c = 0; c < 4; c++) D[a][c] = gpe_exp(-D[a][c]);
     double* Ab = A + (size_t)b * sA;
 #pragma unroll
     for (int a = 0; a < 4; a++) {
@@ -106,7 +118,8 @@ __global__ void __launch_bounds__(256, 3) cov_build_kernel(const double* __restr
                 double val;
                 if (gi >= n || gj >= n) val = (gi == gj && gmode == 0) ? 1.0 : 0.0;     // identity padding
                 else if (gi == gj) val = (gmode == 0) ? ip.diagv + ip.radd * ri : 0.0;
-                else val = ip.offs * G[a][2 * h + e] * exp(-D[a][2 * h + e]);
+                else if constexpr (GMODE == 1) val = ip.offs * G[a][2 * h + e] * D[a][2 * h + e];
+                else val = ip.offs * D[a][2 * h + e];
                 v[e] = val;
             }
             *reinterpret_cast<double2*>(&Ab[(size_t)gi * npad + gj0]) = make_double2(v[0], v[1]);
@@ -120,10 +133,14 @@ void launch_cov_build(const double* X, const double* r, int n, int d, int npad, 
     size_t smem = (size_t)d * (CT + CT + 2) * sizeof(double);
     static size_t attr_sz = 0;
     if (smem > 48 * 1024 && smem > attr_sz) {
-        cudaFuncSetAttribute(cov_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(cov_build_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(cov_build_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(cov_build_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr_sz = smem;
     }
-    cov_build_kernel<<<grid, 256, smem, st>>>(X, r, n, d, npad, par, winv, A, sA, full, gmode, gdim);
+    if (gmode == 0) cov_build_kernel<0><<<grid, 256, smem, st>>>(X, r, n, d, npad, par, winv, A, sA, full, gdim);
+    else if (gmode == 1) cov_build_kernel<1><<<grid, 256, smem, st>>>(X, r, n, d, npad, par, winv, A, sA, full, gdim);
+    else cov_build_kernel<2><<<grid, 256, smem, st>>>(X, r, n, d, npad, par, winv, A, sA, full, gdim);
 }
 
 __global__ void unpad_sym_kernel(const double* __restrict__ A, int npad, int n, double* __restrict__ out, int mirror) {
@@ -753,6 +770,10 @@ __global__ void __launch_bounds__(256, 3) grad_partial_kernel(const double* __re
                 }
         }
 #pragma unroll
+        for (int a = 0; a < 4; a++)
+#pragma unroll
+            for (int c = 0; c < 4; c++) D[a][c] = gpe_exp(-D[a][c]);      // 16 interleaved chains, no branches
+#pragma unroll
         for (int a = 0; a < 4; a++) {
             int gi = ti * CT + ty + 16 * a;
 #pragma unroll
@@ -770,7 +791,7 @@ __global__ void __launch_bounds__(256, 3) grad_partial_kernel(const double* __re
                             sD += wv;
                             if (r != nullptr) sDr = fma(wv, r[gi], sDr);
                         } else if (gi > gj) {
-                            tv = 2.0 * wv * exp(-D[a][2 * h + e]);
+                            tv = 2.0 * wv * D[a][2 * h + e];
                         }
                     }
                     t[a][2 * h + e] = tv;

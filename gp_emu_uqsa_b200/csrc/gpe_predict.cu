@@ -106,6 +106,10 @@ __global__ void __launch_bounds__(256, 3) xcov_kernel(const double* __restrict__
             }
     }
 #pragma unroll
+    for (int a = 0; a < 8; a++)
+#pragma unroll
+        for (int c = 0; c < 4; c++) D[a][c] = gpe_exp(-D[a][c]);      // straight-line: the chains interleave
+#pragma unroll
     for (int a = 0; a < 8; a++) {
         int gk = k0 + ty + 8 * a;
         bool live = gk < n;
@@ -113,8 +117,8 @@ __global__ void __launch_bounds__(256, 3) xcov_kernel(const double* __restrict__
         for (int hh = 0; hh < 2; hh++) {
             int gj = j0 + 64 * hh + 2 * tx;
             double2 v;
-            v.x = (live && gj < count) ? cscale * exp(-D[a][2 * hh]) : 0.0;
-            v.y = (live && gj + 1 < count) ? cscale * exp(-D[a][2 * hh + 1]) : 0.0;
+            v.x = (live && gj < count) ? cscale * D[a][2 * hh] : 0.0;
+            v.y = (live && gj + 1 < count) ? cscale * D[a][2 * hh + 1] : 0.0;
             *reinterpret_cast<double2*>(&Cm[(size_t)gk * ldc + gj]) = v;
         }
     }
@@ -283,7 +287,7 @@ __global__ void fullcov_finalize_kernel(const double* __restrict__ ZtZ, int mp, 
         double df = P[(size_t)i * d + k] * winv[k] - P[(size_t)j * d + k] * winv[k];
         D = fma(df, df, D);
     }
-    double prior = (i == j) ? (astar + (r_new ? r_new[i] : 0.0)) : cscale * exp(-D);
+    double prior = (i == j) ? (astar + (r_new ? r_new[i] : 0.0)) : cscale * gpe_exp(-D);
     double gg = 0.0;
     for (int a = 0; a < q; a++) gg = fma(Gbuf[(size_t)a * mp + i], Gbuf[(size_t)a * mp + j], gg);
     V[idx] = sigma2 * (prior - ZtZ[(size_t)i * mp + j] + gg);

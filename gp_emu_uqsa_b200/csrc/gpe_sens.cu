@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(256) sens_pw_kernel(const double* __restrict__
             u = 1.0;
             for (int k = 0; k < d; k++) {      // product of exponentials, dimension order, as the reference forms it
                 double dx = X[(size_t)g * d + k] - mvec[k];
-                u *= exp(-acoef[k] * (dx * dx));
+                u *= gpe_exp(-acoef[k] * (dx * dx));
             }
         }
         (tid < ST ? ui : uj)[row] = u;
@@ -106,8 +106,8 @@ __global__ void __launch_bounds__(256) sens_pw_kernel(const double* __restrict__
         for (int hh = 0; hh < 2; hh++) {
             int lj0 = 32 * hh + 2 * tx, gj0 = tj * ST + lj0;
             double2 pv;
-            pv.x = scale * ui[li] * uj[lj0] * exp(-D[a][2 * hh]);
-            pv.y = scale * ui[li] * uj[lj0 + 1] * exp(-D[a][2 * hh + 1]);
+            pv.x = scale * ui[li] * uj[lj0] * gpe_exp(-D[a][2 * hh]);
+            pv.y = scale * ui[li] * uj[lj0 + 1] * gpe_exp(-D[a][2 * hh + 1]);
             *reinterpret_cast<double2*>(&P[(size_t)gi * npad + gj0]) = pv;
             if (lower) {      // A^-1 is valid on and below the diagonal only: off-diagonal pairs weigh 2
                 double2 av = *reinterpret_cast<const double2*>(&Ainv[(size_t)gi * npad + gj0]);
@@ -156,10 +156,10 @@ __global__ void __launch_bounds__(256) sens_main_effect_kernel(const double* __r
         for (int i = 0; i < d; i++) {
             if (i == P) continue;
             double dx = X[(size_t)k * d + i] - mvec[i];
-            val *= t1[i] * exp(-t2[i] * (dx * dx));
+            val *= t1[i] * gpe_exp(-t2[i] * (dx * dx));
         }
         double dw = xv - X[(size_t)k * d + P];
-        s = fma(scale * val * exp(-(dw * dw) * cP), evec[k], s);
+        s = fma(scale * val * gpe_exp(-(dw * dw) * cP), evec[k], s);
     }
     double tot = block_sum(s, red);
     if (threadIdx.x == 0) out[(size_t)w * points + j] = tot;
