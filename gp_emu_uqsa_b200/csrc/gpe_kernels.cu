@@ -48,6 +48,15 @@ void launch_prep_theta(const double* theta, int B, int p, int d, int mode, doubl
 // cond(A) digits and break the 1e-10 parity target).
 constexpr int CT = 64;
 
+// lower-triangle tile index t = ti (ti + 1) / 2 + tj  ->  (ti, tj): 1-D grids launch no empty CTAs for the upper half
+__device__ __forceinline__ void tri_decode(int t, int& ti, int& tj) {
+    int r = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+    while ((r + 1) * (r + 2) / 2 <= t) r++;
+    while (r * (r + 1) / 2 > t) r--;
+    ti = r;
+    tj = t - r * (r + 1) / 2;
+}
+
 // GMODE 0: covariance (the hot path: no G registers, no spills under the 80-register cap of 3 CTAs/SM);
 // 1: d(s2 A)/d theta_delta[gdim] (grad_delta_A); 2: kernel grad_nugget_A (off-diagonal only; the alt-nugget form
 // is a pure diagonal and is assembled by the caller)
@@ -57,18 +66,20 @@ __global__ void __launch_bounds__(256, 3) cov_build_kernel(const double* __restr
                                                         const double* __restrict__ winv, double* __restrict__ A,
                                                         long long sA, int full, int gdim) {
     constexpr int gmode = GMODE;
-    const int tj = blockIdx.x, ti = blockIdx.y, b = blockIdx.z;
-    if (!full && tj > ti) return;
+    int tj = blockIdx.x, ti = blockIdx.y;
+    const int b = blockIdx.z;
+    if (!full) tri_decode(blockIdx.x, ti, tj);
     extern __shared__ __align__(16) double sm[];
     double* Xi = sm;                   // [d][CT]
     double* Xj = sm + (size_t)d * CT;  // [d][CT+2]
     const int tid = threadIdx.x;
     const double* w = winv + (size_t)b * d;
-    for (int e = tid; e < CT * d; e += 256) {
-        int row = e / d, k = e % d;
-        int gi = ti * CT + row, gj = tj * CT + row;
-        Xi[k * CT + row] = (gi < n) ? X[(size_t)gi * d + k] * w[k] : 0.0;
-        Xj[k * (CT + 2) + row] = (gj < n) ? X[(size_t)gj * d + k] * w[k] : 0.0;
+    {   // tile fill without integer division: thread -> (row, k mod 4); 4 lanes read 32 contiguous bytes of a row
+        const int row = tid >> 2, gi = ti * CT + row, gj = tj * CT + row;
+        for (int k = tid & 3; k < d; k += 4) {
+            Xi[k * CT + row] = (gi < n) ? X[(size_t)gi * d + k] * w[k] : 0.0;
+            Xj[k * (CT + 2) + row] = (gj < n) ? X[(size_t)gj * d + k] * w[k] : 0.0;
+        }
     }
     __syncthreads();
     const ItemPar ip = par[b];
@@ -129,7 +140,8 @@ __global__ void __launch_bounds__(256, 3) cov_build_kernel(const double* __restr
 
 void launch_cov_build(const double* X, const double* r, int n, int d, int npad, const ItemPar* par,
                       const double* winv, double* A, long long sA, int B, int full, cudaStream_t st, int gmode, int gdim) {
-    dim3 grid(npad / CT, npad / CT, B);
+    const int nt = npad / CT;
+    dim3 grid = full ? dim3(nt, nt, B) : dim3(nt * (nt + 1) / 2, 1, B);
     size_t smem = (size_t)d * (CT + CT + 2) * sizeof(double);
     static size_t attr_sz = 0;
     if (smem > 48 * 1024 && smem > attr_sz) {
@@ -693,8 +705,9 @@ __global__ void __launch_bounds__(256, 3) grad_partial_kernel(const double* __re
                                                            int n, int d, int npad, const double* __restrict__ winv,
                                                            const double* __restrict__ Ainv, long long sAinv,
                                                            const double* __restrict__ U, int nu, double* __restrict__ part) {
-    const int tj = blockIdx.x, ti = blockIdx.y, b = blockIdx.z;
-    if (tj > ti) return;
+    int ti, tj;
+    tri_decode(blockIdx.x, ti, tj);
+    const int b = blockIdx.z;
     extern __shared__ __align__(16) double sm[];
     double* Xi = sm;                                // [d][64]
     double* Xj = Xi + (size_t)d * CT;               // [d][66]
@@ -703,17 +716,20 @@ __global__ void __launch_bounds__(256, 3) grad_partial_kernel(const double* __re
     double* red = Uj + (size_t)nu * (CT + 2);       // [8][d+3]
     const int tid = threadIdx.x;
     const double* w = winv + (size_t)b * d;
-    for (int e = tid; e < CT * d; e += 256) {
-        int row = e / d, k = e % d;
-        int gi = ti * CT + row, gj = tj * CT + row;
-        Xi[k * CT + row] = (gi < n) ? X[(size_t)gi * d + k] * w[k] : 0.0;
-        Xj[k * (CT + 2) + row] = (gj < n) ? X[(size_t)gj * d + k] * w[k] : 0.0;
+    {   // tile fill without integer division: thread -> (row, k mod 4); 4 lanes read 32 contiguous bytes of a row
+        const int row = tid >> 2, gi = ti * CT + row, gj = tj * CT + row;
+        for (int k = tid & 3; k < d; k += 4) {
+            Xi[k * CT + row] = (gi < n) ? X[(size_t)gi * d + k] * w[k] : 0.0;
+            Xj[k * (CT + 2) + row] = (gj < n) ? X[(size_t)gj * d + k] * w[k] : 0.0;
+        }
     }
     const double* Ub = U + (size_t)b * npad * NR;
-    for (int e = tid; e < CT * nu; e += 256) {
-        int row = e / nu, c = e % nu;
-        Ui[c * CT + row] = Ub[(size_t)(ti * CT + row) * NR + c];
-        Uj[c * (CT + 2) + row] = Ub[(size_t)(tj * CT + row) * NR + c];
+    {
+        const int row = tid >> 2;
+        for (int c = tid & 3; c < nu; c += 4) {
+            Ui[c * CT + row] = Ub[(size_t)(ti * CT + row) * NR + c];
+            Uj[c * (CT + 2) + row] = Ub[(size_t)(tj * CT + row) * NR + c];
+        }
     }
     __syncthreads();
     const int ty = tid >> 4, tx = tid & 15;
@@ -802,7 +818,7 @@ __global__ void __launch_bounds__(256, 3) grad_partial_kernel(const double* __re
     }
     const int nv = d + 3;
     const int warp = tid >> 5, lane = tid & 31;
-    double* pout = part + ((size_t)b * gridDim.y * (gridDim.y + 1) / 2 + (size_t)ti * (ti + 1) / 2 + tj) * nv;
+    double* pout = part + ((size_t)b * gridDim.x + blockIdx.x) * nv;
     sE = warp_sum(sE); sD = warp_sum(sD); sDr = warp_sum(sDr);
     if (lane == 0) { red[warp * nv + d] = sE; red[warp * nv + d + 1] = sD; red[warp * nv + d + 2] = sDr; }
     for (int k0 = 0; k0 < d; k0 += GD) {
@@ -853,7 +869,7 @@ void launch_grad_partial(const double* X, const double* r, int n, int d, int npa
         cudaFuncSetAttribute(grad_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr_sz = smem;
     }
-    grad_partial_kernel<<<dim3(nt, nt, B), 256, smem, st>>>(X, r, n, d, npad, winv, Ainv, sAinv, U, nu, part);
+    grad_partial_kernel<<<dim3(nt * (nt + 1) / 2, 1, B), 256, smem, st>>>(X, r, n, d, npad, winv, Ainv, sAinv, U, nu, part);
 }
 
 // Sum the tile partials in a fixed order and apply the per-parameter prefactors

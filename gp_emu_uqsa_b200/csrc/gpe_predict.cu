@@ -79,9 +79,9 @@ __global__ void __launch_bounds__(256, 3) xcov_kernel(const double* __restrict__
         int k = e / 64, rr = e % 64;
         Xt[k * 64 + rr] = Xs[(size_t)k * npad + k0 + rr];
     }
-    for (int e = tid; e < d * 128; e += 256) {
-        int jj = e / d, k = e % d;
-        Pt[k * 130 + jj] = P[(size_t)(j0 + jj) * d + k] * winv[k];
+    {   // point tile without integer division: thread -> (point, k mod 2)
+        const int jj = tid >> 1;
+        for (int k = tid & 1; k < d; k += 2) Pt[k * 130 + jj] = P[(size_t)(j0 + jj) * d + k] * winv[k];
     }
     __syncthreads();
     const int ty = tid >> 5, tx = tid & 31;   // rows ty + 8a (a<8); points 2tx+{0,1}, 64+2tx+{0,1}
