@@ -23,6 +23,11 @@ static cudaError_t dispatch_tiles(const GemmP& p, int epi, cudaStream_t st) {
     }
     if (p.N == 32) {
         if (epi != EPI_STORE) return cudaErrorInvalidValue;
+        // few items: 128-row tiles would leave most SMs idle behind up to K/16 serial k-steps (n = 1000, one guess:
+        // 8 CTAs, 51 us); 32-row tiles give four times the CTAs, each a quarter of the work.  Same k order per
+        // output element, so the values do not depend on the tile shape.
+        if ((long long)(p.M / 128) * p.batch < NUM_SMS && p.M % 32 == 0)
+            return launch_gemm_cfg<32, 32, 2, 2, A_KC, B_KC, EPI_STORE>(p, st);
         return launch_gemm_cfg<128, 32, 4, 2, A_KC, B_KC, EPI_STORE>(p, st);
     }
     long long t128 = (long long)(p.M / 128) * (p.N / 128) * p.batch;
@@ -35,6 +40,11 @@ static cudaError_t dispatch_tiles(const GemmP& p, int epi, cudaStream_t st) {
     }
     if (big) return use_ws() ? launch_gemm_ws<A_KC, B_KC, EPI_STORE>(p, st)
                              : launch_gemm_cfg<128, 128, 2, 4, A_KC, B_KC, EPI_STORE>(p, st);
+    // latency regime (one or two guesses at n <= 2000): 64x64 tiles would occupy under half of the SMs
+    long long t64 = (long long)(p.M / 64) * (p.N / 64) * p.batch;
+    if (p.lower) t64 = t64 / 2 + (p.M / 64) * p.batch / 2;
+    if (t64 < NUM_SMS / 2 && p.M % 32 == 0 && p.N % 32 == 0)
+        return launch_gemm_cfg<32, 32, 2, 2, A_KC, B_KC, EPI_STORE>(p, st);
     return launch_gemm_cfg<64, 64, 2, 2, A_KC, B_KC, EPI_STORE>(p, st);
 }
 
