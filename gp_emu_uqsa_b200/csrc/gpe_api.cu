@@ -497,14 +497,26 @@ int gpe_cov_grad(gpe_handle* h, const double* delta, double nugget, int kind, in
 // Device work of one resident sub-batch: theta_d -> (llh_d, grad_d, sig_d, status).  Everything is
 // enqueued on h->st and its sub-batch streams (fork/join by events), so the same code path is used
 // eagerly and under stream capture.
-static int enqueue_llh_chunk(gpe_handle* h, int Bs, int p, int mode, double fixed_nugget) {
+static int enqueue_llh_chunk(gpe_handle* h, int Bs, int p, int mode, double fixed_nugget, bool capturing) {
     const long long sM = (long long)h->npad * h->npad;
     int rc;
     launch_prep_theta(h->theta_d, Bs, p, h->d, mode, fixed_nugget, h->par, h->winv, h->st);
     h->launches++;
     CK(cudaMemsetAsync(h->status, 0, sizeof(int) * Bs, h->st));
     // contiguous groups of the sub-batch, one stream each (a group needs >= 2 items to be worth a stream)
-    const int ns = std::max(1, std::min(h->nsub, Bs / 2));
+    // ... and only where the groups pay.  Launched eagerly, an evaluation below npad = 2048 is bound by the launch
+    // rate of the host thread: groups multiply the launches (n = 200, 10 guesses: 67 instead of 15; 0.52 -> 0.30 ms
+    // with one group; n = 1000, 16 guesses: 2.58 -> 1.74 ms).  Replayed from a CUDA graph the launches are free and the
+    // groups overlap one another's latency-bound leaves again (n = 1000, 16 guesses: 1.40 vs 1.77 ms; n = 500, 64
+    // guesses: 0.90 vs 1.10 ms); below npad = 512 nothing is left to overlap.
+    static int group_npad = -1, group_npad_graph = -1;
+    if (group_npad < 0) {
+        const char* e = getenv("GPE_GROUP_NPAD");
+        group_npad = e ? atoi(e) : 2048;
+        e = getenv("GPE_GROUP_NPAD_GRAPH");
+        group_npad_graph = e ? atoi(e) : 512;
+    }
+    const int ns = h->npad < (capturing ? group_npad_graph : group_npad) ? 1 : std::max(1, std::min(h->nsub, Bs / 2));
     if (ns > 1) CK(cudaEventRecord(h->ev_fork, h->st));
     for (int g = 0; g < ns; g++) {
         SubBatch sb;
@@ -569,7 +581,7 @@ int gpe_llh_grad_batch(gpe_handle* h, const double* theta, int B, int p, int mod
             const long long l0 = h->launches;
             cudaGraph_t graph = nullptr;
             CK(cudaStreamBeginCapture(h->st, cudaStreamCaptureModeRelaxed));
-            rc = enqueue_llh_chunk(h, Bs, p, mode, fixed_nugget);
+            rc = enqueue_llh_chunk(h, Bs, p, mode, fixed_nugget, true);
             cudaError_t ce = cudaStreamEndCapture(h->st, &graph);
             if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
             if (ce != cudaSuccess) return h->fail("cudaStreamEndCapture", ce);
@@ -580,7 +592,7 @@ int gpe_llh_grad_batch(gpe_handle* h, const double* theta, int B, int p, int mod
             CK(cudaGraphLaunch(gr->exec, h->st));
         } else {
             if (gr) gr->seen++;
-            if ((rc = enqueue_llh_chunk(h, Bs, p, mode, fixed_nugget))) return rc;
+            if ((rc = enqueue_llh_chunk(h, Bs, p, mode, fixed_nugget, false))) return rc;
         }
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(llh + b0, h->llh_d, sizeof(double) * Bs, cudaMemcpyDefault, h->st));
