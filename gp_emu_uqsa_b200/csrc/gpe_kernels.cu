@@ -300,6 +300,17 @@ __global__ void __launch_bounds__(1024, 1) leaf_potrf_trtri_kernel(const double*
 // inverse levels -- issue-bound, one FMA per instruction; v3 58.7 us.  The row stride is 132 (= 4 mod 16
 // doubles, the same rule as the GEMM tiles) so the 8x4 / 4x8 fragment loads are bank-conflict-free; the
 // few row-per-thread accesses of the panel solve pay a 4-way conflict instead.
+// Phase timing of the leaf for tools/leaf_phases.cu (compiled only there, with -DGPE_LEAF_TIMING): thread 0 adds the
+// cycles between barriers to g_leaf_cyc[phase].
+#ifdef GPE_LEAF_TIMING
+__device__ unsigned long long g_leaf_cyc[16];
+__device__ unsigned long long g_leaf_warp[3][16];   // first panel's trailing update per warp: [0] fragment-loop cycles, [2] start offset after the barrier
+#define LEAF_TICK(i) do { if (tid == 0) { long long now_ = clock64(); g_leaf_cyc[i] += (unsigned long long)(now_ - t_last_); t_last_ = now_; } } while (0)
+#define LEAF_TICK_INIT long long t_last_ = clock64()
+#else
+#define LEAF_TICK(i) do { } while (0)
+#define LEAF_TICK_INIT do { } while (0)
+#endif
 constexpr int LT = 512;          // threads of the leaf CTA
 constexpr int PW = 8;            // panel width
 constexpr int L3 = NB + 4;
@@ -318,13 +329,24 @@ __global__ void __launch_bounds__(LT, 1) leaf_potrf_trtri_v3_kernel(const double
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int fr = lane >> 2, fc = lane & 3;
     constexpr int NW = LT / 32;
+    __shared__ unsigned char tri_rb[128], tri_cb[128];   // lower-triangle enumeration f = rb (rb + 1) / 2 + cb, f < 120
+    LEAF_TICK_INIT;
     const double* Ab = A + (size_t)b * sA + (size_t)off * ld + off;
+#pragma unroll 8
     for (int e = tid; e < NB * NB; e += LT) {
         int i = e >> 7, j = e & (NB - 1);
         S[i * L3 + j] = (j <= i) ? Ab[(size_t)i * ld + j] : 0.0;
     }
+    if (tid < 120) {
+        int rb = (int)((sqrtf(8.0f * (float)tid + 1.0f) - 1.0f) * 0.5f);
+        while ((rb + 1) * (rb + 2) / 2 <= tid) rb++;
+        while (rb * (rb + 1) / 2 > tid) rb--;
+        tri_rb[tid] = (unsigned char)rb;
+        tri_cb[tid] = (unsigned char)(tid - rb * (rb + 1) / 2);
+    }
     if (tid == 0) s_bad = 0;
     __syncthreads();
+    LEAF_TICK(0);
 
     // ------------------------------------------------------------------ potrf, 8-wide panels
     for (int j0 = 0; j0 < NB; j0 += PW) {
@@ -360,6 +382,7 @@ __global__ void __launch_bounds__(LT, 1) leaf_potrf_trtri_v3_kernel(const double
             }
         }
         __syncthreads();
+        LEAF_TICK(1);
         const int base = j0 + PW, R = NB - base;
         if (R == 0) break;
         if (tid < R) {                   // panel solve: row r against the diagonal block
@@ -378,23 +401,48 @@ __global__ void __launch_bounds__(LT, 1) leaf_potrf_trtri_v3_kernel(const double
             for (int c = 0; c < PW; c++) row[c] = x[c];
         }
         __syncthreads();
-        {                                // A22 -= L21 L21^T on the lower 8x8 fragments: 2 DMMAs each
+        LEAF_TICK(2);
+#ifdef GPE_LEAF_TIMING
+        const long long t_last_w_ = clock64();
+#endif
+        {                                // A22 -= L21 L21^T on the lower 8x8 fragments: 2 DMMAs each, two fragments
+                                         // in flight per warp (their loads and DMMA chains overlap)
             const int nbk = R >> 3, F = nbk * (nbk + 1) / 2;
-            for (int f = warp; f < F; f += NW) {
-                int rb = (int)((sqrtf(8.0f * (float)f + 1.0f) - 1.0f) * 0.5f);
-                while ((rb + 1) * (rb + 2) / 2 <= f) rb++;
-                while (rb * (rb + 1) / 2 > f) rb--;
-                const int cb = f - rb * (rb + 1) / 2;
+#ifdef GPE_LEAF_TIMING
+            const long long tw0_ = clock64();
+#endif
+            for (int f = warp; f < F; f += 2 * NW) {
+                const int f2 = f + NW;
+                const bool two = f2 < F;
+                const int rb = tri_rb[f], cb = tri_cb[f];
+                const int rb2 = two ? tri_rb[f2] : rb, cb2 = two ? tri_cb[f2] : cb;
                 const double* ar = S + (base + 8 * rb + fr) * L3 + j0 + fc;
                 const double* br = S + (base + 8 * cb + fr) * L3 + j0 + fc;
                 double* cp = S + (base + 8 * rb + fr) * L3 + base + 8 * cb + 2 * fc;
+                const double* ar2 = S + (base + 8 * rb2 + fr) * L3 + j0 + fc;
+                const double* br2 = S + (base + 8 * cb2 + fr) * L3 + j0 + fc;
+                double* cp2 = S + (base + 8 * rb2 + fr) * L3 + base + 8 * cb2 + 2 * fc;
+                const double a0 = ar[0], a4 = ar[4], b0 = br[0], b4 = br[4];
+                const double a0b = ar2[0], a4b = ar2[4], b0b = br2[0], b4b = br2[4];
                 double2 c = *reinterpret_cast<double2*>(cp);
-                dmma884(c.x, c.y, -ar[0], br[0]);
-                dmma884(c.x, c.y, -ar[4], br[4]);
+                double2 c2 = *reinterpret_cast<double2*>(cp2);
+                dmma884(c.x, c.y, -a0, b0);
+                dmma884(c2.x, c2.y, -a0b, b0b);
+                dmma884(c.x, c.y, -a4, b4);
+                dmma884(c2.x, c2.y, -a4b, b4b);
                 *reinterpret_cast<double2*>(cp) = c;
+                if (two) *reinterpret_cast<double2*>(cp2) = c2;
             }
+#ifdef GPE_LEAF_TIMING
+            if (j0 == 0 && lane == 0) {
+                const long long tw1_ = clock64();
+                g_leaf_warp[0][warp] += (unsigned long long)(tw1_ - tw0_);
+                g_leaf_warp[2][warp] += (unsigned long long)(tw0_ - t_last_w_);
+            }
+#endif
         }
         __syncthreads();
+        LEAF_TICK(3);
     }
     {                                    // log-determinant from the pivots: 2 sum log L_ii = sum log pivot_i
         double v = (tid < NB) ? log(pv[tid]) : 0.0;
@@ -411,6 +459,7 @@ __global__ void __launch_bounds__(LT, 1) leaf_potrf_trtri_v3_kernel(const double
             }
         }
     }
+    LEAF_TICK(4);
     // ------------------------------------------------------------------ trtri
     // X = L^-1 is kept transposed in the upper triangle (X[i][j], i > j, at S[j][i]), its diagonal in dinv.
     if (tid < NB) {                      // inverses of the 8x8 diagonal blocks, one thread per column
@@ -428,6 +477,7 @@ __global__ void __launch_bounds__(LT, 1) leaf_potrf_trtri_v3_kernel(const double
             if (i > c) S[tid * L3 + o + i] = x[i];
     }
     __syncthreads();
+    LEAF_TICK(5);
     for (int h = PW; h < NB; h <<= 1) {  // doubling levels: X21 = -X22 (L21 X11) per node of size 2h
         const int hb = h >> 3, fpn = hb * hb, F = (NB / (2 * h)) * fpn, ldT = h + 4;
         // T = L21 X11: fragment (rb, cb); X11 is lower triangular: k4 steps from 2 cb on
@@ -436,47 +486,61 @@ __global__ void __launch_bounds__(LT, 1) leaf_potrf_trtri_v3_kernel(const double
             const double* ar = S + (o + h + 8 * rb + fr) * L3 + o + fc;          // L21[8rb+fr][k]
             const int n = 8 * cb + fr;                                          // this lane's column of X11
             const double* xr = S + (o + n) * L3 + o + fc;                       // X11[k][n] lives at S[o+n][o+k]
-            double c0 = 0.0, c1 = 0.0;
-            for (int sidx = 2 * cb; sidx < 2 * hb; sidx++) {
-                const int k = 4 * sidx + fc;
+            double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;                      // two chains: even / odd k4 steps
+            for (int sidx = 2 * cb; sidx < 2 * hb; sidx += 2) {
+                const int k = 4 * sidx + fc, k2 = k + 4;
                 const double bv = (k > n) ? xr[4 * sidx] : ((k == n) ? dinv[o + n] : 0.0);
+                const double bv2 = (k2 > n) ? xr[4 * sidx + 4] : ((k2 == n) ? dinv[o + n] : 0.0);
                 dmma884(c0, c1, ar[4 * sidx], bv);
+                dmma884(e0, e1, ar[4 * sidx + 4], bv2);
             }
+            c0 += e0;
+            c1 += e1;
             double* tp = Tm + node * h * ldT + (8 * rb + fr) * ldT + 8 * cb + 2 * fc;
             tp[0] = c0;
             tp[1] = c1;
         }
         __syncthreads();
+        LEAF_TICK(6);
         // X21 = -X22 T: X22 lower triangular: k4 steps up to 2 rb + 1; result stored transposed
         for (int f = warp; f < F; f += NW) {
             const int node = f / fpn, rem = f - node * fpn, rb = rem / hb, cb = rem - rb * hb, o = node * 2 * h;
             const int r = 8 * rb + fr;                                          // this lane's row of X22
             const double* xc = S + (o + h + fc) * L3 + o + h + r;               // X22[r][k] lives at S[o+h+k][o+h+r]
             const double* tr = Tm + node * h * ldT + fc * ldT + 8 * cb + fr;    // T[k][8cb+fr]
-            double c0 = 0.0, c1 = 0.0;
-            for (int sidx = 0; sidx <= 2 * rb + 1; sidx++) {
-                const int k = 4 * sidx + fc;
+            double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;
+            for (int sidx = 0; sidx <= 2 * rb + 1; sidx += 2) {                 // 2 rb + 2 steps: always an even count
+                const int k = 4 * sidx + fc, k2 = k + 4;
                 const double av = (k < r) ? xc[4 * sidx * L3] : ((k == r) ? dinv[o + h + r] : 0.0);
+                const double av2 = (k2 < r) ? xc[(4 * sidx + 4) * L3] : ((k2 == r) ? dinv[o + h + r] : 0.0);
                 dmma884(c0, c1, av, tr[4 * sidx * ldT]);
+                dmma884(e0, e1, av2, tr[(4 * sidx + 4) * ldT]);
             }
+            c0 += e0;
+            c1 += e1;
             double* xo = S + (o + 8 * cb + 2 * fc) * L3 + o + h + r;
             xo[0] = -c0;
             xo[L3] = -c1;
         }
         __syncthreads();
+        LEAF_TICK(7);
     }
     double* Lb = Linv + (size_t)b * sL + (size_t)off * ld + off;
+#pragma unroll 8
     for (int e = tid; e < NB * NB; e += LT) {
         int i = e >> 7, j = e & (NB - 1);
         Lb[(size_t)i * ld + j] = (j < i) ? S[j * L3 + i] : ((j == i) ? dinv[i] : 0.0);
     }
     if (Lfac != nullptr) {
         double* Fb = Lfac + (size_t)b * sL + (size_t)off * ld + off;
+#pragma unroll 8
         for (int e = tid; e < NB * NB; e += LT) {
             int i = e >> 7, j = e & (NB - 1);
             Fb[(size_t)i * ld + j] = (j <= i) ? S[i * L3 + j] : 0.0;
         }
     }
+    __syncthreads();
+    LEAF_TICK(8);
 }
 
 // GPE_LEAF=1 selects the v1 leaf (kept for A/B measurements); default is v3.
