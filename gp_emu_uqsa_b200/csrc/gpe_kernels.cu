@@ -586,25 +586,26 @@ void launch_build_hy(const double* H, const double* y, int n, int q, int npad, d
     build_hy_kernel<<<(npad * NR + 255) / 256, 256, 0, st>>>(H, y, n, q, npad, HY);
 }
 
-// Gram partials: GP[b][slab][c1][c2] = sum_{i in slab} Wy[i][c1] Wy[i][c2]
+// Gram partials: GP[b][slab][c1][c2] = sum_{i in slab} Wy[i][c1] Wy[i][c2].  One 128-row slab per CTA, loaded in one
+// pass (the 512-row slabs in 64-row steps were a chain of dependent global-load latencies: 20-36 us for one item);
+// four accumulator chains per entry (rows mod 4), added in a fixed order.
 __global__ void __launch_bounds__(1024) gram_kernel(const double* __restrict__ Wy, int npad, double* __restrict__ GP) {
-    __shared__ double T[64][NR + 1];
+    __shared__ double T[GRAM_SLAB][NR + 1];
     const int slab = blockIdx.x, b = blockIdx.y, nslab = gridDim.x;
     const int c1 = threadIdx.x / NR, c2 = threadIdx.x % NR;
     const double* Wb = Wy + ((size_t)b * npad + (size_t)slab * GRAM_SLAB) * NR;
-    int rows = min(GRAM_SLAB, npad - slab * GRAM_SLAB);
-    double acc = 0.0;
-    for (int r0 = 0; r0 < rows; r0 += 64) {
-        __syncthreads();
-        for (int e = threadIdx.x; e < 64 * NR; e += 1024) {
-            int rr = e / NR, cc = e % NR;
-            T[rr][cc] = (r0 + rr < rows) ? Wb[(size_t)(r0 + rr) * NR + cc] : 0.0;
-        }
-        __syncthreads();
+#pragma unroll
+    for (int e = threadIdx.x; e < GRAM_SLAB * NR; e += 1024) T[e / NR][e % NR] = Wb[e];
+    __syncthreads();
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
 #pragma unroll 8
-        for (int rr = 0; rr < 64; rr++) acc = fma(T[rr][c1], T[rr][c2], acc);
+    for (int rr = 0; rr < GRAM_SLAB; rr += 4) {
+        a0 = fma(T[rr][c1], T[rr][c2], a0);
+        a1 = fma(T[rr + 1][c1], T[rr + 1][c2], a1);
+        a2 = fma(T[rr + 2][c1], T[rr + 2][c2], a2);
+        a3 = fma(T[rr + 3][c1], T[rr + 3][c2], a3);
     }
-    GP[((size_t)b * nslab + slab) * NR * NR + threadIdx.x] = acc;
+    GP[((size_t)b * nslab + slab) * NR * NR + threadIdx.x] = (a0 + a1) + (a2 + a3);
 }
 
 void launch_gram(const double* Wy, int npad, int B, double* GP, cudaStream_t st) {
@@ -624,7 +625,7 @@ __global__ void __launch_bounds__(256) llh_finalize_kernel(const double* __restr
                                                            double* __restrict__ Kout) {
     __shared__ double G[NR][NR + 1];
     __shared__ double Kf[NR][NR + 1];
-    __shared__ double beta[NR], tv[NR];
+    __shared__ double beta[NR], tv[NR], rK[NR];   // rK[a] = 1 / K_aa
     __shared__ double red[32];
     __shared__ double s_quad, s_sqrtf, s_logdetQ;
     __shared__ int s_badQ;
@@ -651,27 +652,28 @@ __global__ void __launch_bounds__(256) llh_finalize_kernel(const double* __restr
                 if (i == 0 && s_badQ == 0) s_badQ = j + 1;
                 piv = 1.0;
             }
-            double kjj = sqrt(piv);
-            if (i == j) Kf[j][j] = kjj;
-            else if (i > j && i < q) Kf[i][j] = (G[i][j] - s) / kjj;
+            const double rk = rsqrt(piv);                // one reciprocal root per column, no divide on the chain
+            if (i == j) { Kf[j][j] = piv * rk; rK[j] = rk; }
+            else if (i > j && i < q) Kf[i][j] = (G[i][j] - s) * rk;
             else if (i < j) Kf[i][j] = 0.0;
             __syncwarp();
         }
+        // log det Q = sum log pivot_j (= 2 sum log K_jj), lanes in parallel
+        double lp = (i < q) ? -2.0 * log(rK[i]) : 0.0;
+        lp = warp_sum(lp);
         if (i == 0) {
             // K t = w^T u ; K^T beta = t
-            double ld = 0.0;
             for (int a = 0; a < q; a++) {
                 double s = G[a][q];
                 for (int k = 0; k < a; k++) s -= Kf[a][k] * tv[k];
-                tv[a] = s / Kf[a][a];
-                ld += log(Kf[a][a]);
+                tv[a] = s * rK[a];
             }
             for (int a = q - 1; a >= 0; a--) {
                 double s = tv[a];
                 for (int k = a + 1; k < q; k++) s -= Kf[k][a] * beta[k];
-                beta[a] = s / Kf[a][a];
+                beta[a] = s * rK[a];
             }
-            s_logdetQ = 2.0 * ld;
+            s_logdetQ = lp;
         }
     }
     __syncthreads();
@@ -739,7 +741,7 @@ __global__ void __launch_bounds__(256) llh_finalize_kernel(const double* __restr
             if (a < q) {
                 double s = wr[a];
                 for (int k = 0; k < a; k++) s = fma(-Kf[a][k], v[k], s);
-                v[a] = s / Kf[a][a];
+                v[a] = s * rK[a];
             } else {
                 v[a] = 0.0;
             }

@@ -7,7 +7,7 @@
 namespace gpe {
 
 constexpr int NR = 32;        // padded width of the skinny [H | y] panels (q + 1 <= NR)
-constexpr int GRAM_SLAB = 512;
+constexpr int GRAM_SLAB = 128;   // rows per Gram partial (= NB: npad is a multiple); fixed, so sums do not depend on the batch
 
 // Per batch item covariance parameters, built on device from the transformed theta.
 struct ItemPar {
