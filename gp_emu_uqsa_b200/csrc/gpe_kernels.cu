@@ -304,7 +304,6 @@ __global__ void __launch_bounds__(1024, 1) leaf_potrf_trtri_kernel(const double*
 // cycles between barriers to g_leaf_cyc[phase].
 #ifdef GPE_LEAF_TIMING
 __device__ unsigned long long g_leaf_cyc[16];
-__device__ unsigned long long g_leaf_warp[3][16];   // first panel's trailing update per warp: [0] fragment-loop cycles, [2] start offset after the barrier
 #define LEAF_TICK(i) do { if (tid == 0) { long long now_ = clock64(); g_leaf_cyc[i] += (unsigned long long)(now_ - t_last_); t_last_ = now_; } } while (0)
 #define LEAF_TICK_INIT long long t_last_ = clock64()
 #else
@@ -348,43 +347,44 @@ __global__ void __launch_bounds__(LT, 1) leaf_potrf_trtri_v3_kernel(const double
     __syncthreads();
     LEAF_TICK(0);
 
-    // ------------------------------------------------------------------ potrf, 8-wide panels
-    for (int j0 = 0; j0 < NB; j0 += PW) {
-        if (warp == 0) {                 // 8x8 diagonal block in registers: lane i owns row i
-            double a[PW];
+    // ------------------------------------------------------------------ potrf, 8-wide panels with look-ahead
+    // 8x8 diagonal block in registers of warp 0: lane i owns row i
+    auto factor_diag = [&](int j0) {
+        double a[PW];
 #pragma unroll
-            for (int c = 0; c < PW; c++) a[c] = (lane < PW && c <= lane) ? S[(j0 + lane) * L3 + j0 + c] : 0.0;
+        for (int c = 0; c < PW; c++) a[c] = (lane < PW && c <= lane) ? S[(j0 + lane) * L3 + j0 + c] : 0.0;
 #pragma unroll
-            for (int j = 0; j < PW; j++) {
-                double pj = __shfl_sync(0xffffffffu, a[j], j);
-                if (!(pj > 0.0)) {       // LAPACK dpotrf: pivot <= 0 or NaN -> info = j + 1
-                    if (lane == 0 && s_bad == 0) s_bad = off + j0 + j + 1;
-                    pj = 1.0;
-                }
-                const double rj = rsqrt(pj);
-                if (lane == j) {
-                    a[j] = pj * rj;
-                    pv[j0 + j] = pj;
-                    dinv[j0 + j] = rj;
-                } else {
-                    a[j] *= rj;
-                }
-#pragma unroll
-                for (int k = j + 1; k < PW; k++) {
-                    double lk = __shfl_sync(0xffffffffu, a[j], k);
-                    if (lane >= k) a[k] = fma(-a[j], lk, a[k]);
-                }
+        for (int j = 0; j < PW; j++) {
+            double pj = __shfl_sync(0xffffffffu, a[j], j);
+            if (!(pj > 0.0)) {           // LAPACK dpotrf: pivot <= 0 or NaN -> info = j + 1
+                if (lane == 0 && s_bad == 0) s_bad = off + j0 + j + 1;
+                pj = 1.0;
             }
-            if (lane < PW) {
+            const double rj = rsqrt(pj);           // (a hand-rolled seed + 2 Newton steps was slower: 2.75 k vs 2.48 k cycles per panel)
+            if (lane == j) {
+                a[j] = pj * rj;
+                pv[j0 + j] = pj;
+                dinv[j0 + j] = rj;
+            } else {
+                a[j] *= rj;
+            }
 #pragma unroll
-                for (int c = 0; c < PW; c++)
-                    if (c <= lane) S[(j0 + lane) * L3 + j0 + c] = a[c];
+            for (int k = j + 1; k < PW; k++) {
+                double lk = __shfl_sync(0xffffffffu, a[j], k);
+                if (lane >= k) a[k] = fma(-a[j], lk, a[k]);
             }
         }
-        __syncthreads();
-        LEAF_TICK(1);
+        if (lane < PW) {
+#pragma unroll
+            for (int c = 0; c < PW; c++)
+                if (c <= lane) S[(j0 + lane) * L3 + j0 + c] = a[c];
+        }
+    };
+    if (warp == 0) factor_diag(0);
+    __syncthreads();
+    LEAF_TICK(1);
+    for (int j0 = 0; j0 < NB - PW; j0 += PW) {
         const int base = j0 + PW, R = NB - base;
-        if (R == 0) break;
         if (tid < R) {                   // panel solve: row r against the diagonal block
             double* row = S + (base + tid) * L3 + j0;
             double x[PW];
@@ -402,17 +402,27 @@ __global__ void __launch_bounds__(LT, 1) leaf_potrf_trtri_v3_kernel(const double
         }
         __syncthreads();
         LEAF_TICK(2);
-#ifdef GPE_LEAF_TIMING
-        const long long t_last_w_ = clock64();
-#endif
-        {                                // A22 -= L21 L21^T on the lower 8x8 fragments: 2 DMMAs each, two fragments
-                                         // in flight per warp (their loads and DMMA chains overlap)
-            const int nbk = R >> 3, F = nbk * (nbk + 1) / 2;
-#ifdef GPE_LEAF_TIMING
-            const long long tw0_ = clock64();
-#endif
-            for (int f = warp; f < F; f += 2 * NW) {
-                const int f2 = f + NW;
+        // A22 -= L21 L21^T on the lower 8x8 fragments (2 DMMAs each).  Look-ahead: warp 0 updates the next diagonal
+        // block (fragment 0) and factors it at once -- the serial pivot chain of panel j + 1 -- while warps 1..15 do the
+        // other fragments, two in flight per warp.  (tools/leaf_phases.cu: the chain and the update were 29 % + 24 %
+        // of the leaf when they ran one after the other.)
+        const int nbk = R >> 3, F = nbk * (nbk + 1) / 2;
+        if (warp == 0) {
+            const double* ar = S + (base + fr) * L3 + j0 + fc;
+            double* cp = S + (base + fr) * L3 + base + 2 * fc;
+            double2 c = *reinterpret_cast<double2*>(cp);
+            dmma884(c.x, c.y, -ar[0], ar[0]);
+            dmma884(c.x, c.y, -ar[4], ar[4]);
+            *reinterpret_cast<double2*>(cp) = c;
+            __syncwarp();
+            factor_diag(base);
+        } else if (warp & 3) {
+            // warps 4, 8, 12 share warp 0's scheduler and FP64 pipe: they stay out of the update so the pivot chain
+            // runs undisturbed (12 workers: chain and update both ~2.1 k cycles per panel instead of 2.75 k)
+            constexpr int NWK = NW - NW / 4;
+            const int wid = warp - 1 - (warp >> 2);
+            for (int f = 1 + wid; f < F; f += 2 * NWK) {
+                const int f2 = f + NWK;
                 const bool two = f2 < F;
                 const int rb = tri_rb[f], cb = tri_cb[f];
                 const int rb2 = two ? tri_rb[f2] : rb, cb2 = two ? tri_cb[f2] : cb;
@@ -433,13 +443,6 @@ __global__ void __launch_bounds__(LT, 1) leaf_potrf_trtri_v3_kernel(const double
                 *reinterpret_cast<double2*>(cp) = c;
                 if (two) *reinterpret_cast<double2*>(cp2) = c2;
             }
-#ifdef GPE_LEAF_TIMING
-            if (j0 == 0 && lane == 0) {
-                const long long tw1_ = clock64();
-                g_leaf_warp[0][warp] += (unsigned long long)(tw1_ - tw0_);
-                g_leaf_warp[2][warp] += (unsigned long long)(tw0_ - t_last_w_);
-            }
-#endif
         }
         __syncthreads();
         LEAF_TICK(3);

@@ -26,7 +26,6 @@ int main() {
     cudaDeviceSynchronize();
     unsigned long long zero[16] = {0};
     cudaMemcpyToSymbol(gpe::g_leaf_cyc, zero, sizeof zero);
-    { unsigned long long z3[3][16] = {{0}}; cudaMemcpyToSymbol(gpe::g_leaf_warp, z3, sizeof z3); }
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     cudaEventRecord(e0);
     for (int r = 0; r < reps; r++) gpe::launch_leaf(dA, dL, n, 0, 0, 0, dld, 1, dst, B, 0, dF);
@@ -34,16 +33,12 @@ int main() {
     float ms; cudaEventElapsedTime(&ms, e0, e1);
     unsigned long long cyc[16];
     cudaMemcpyFromSymbol(cyc, gpe::g_leaf_cyc, sizeof cyc);
-    const char* name[9] = {"load", "potrf: 8x8 diagonal factor (1 warp)", "potrf: panel solve", "potrf: trailing update (DMMA)",
+    const char* name[9] = {"load", "potrf: first 8x8 diagonal factor", "potrf: panel solve", "potrf: trailing update || next diagonal factor",
                            "log-det + status", "trtri: 8x8 diagonal inverses", "trtri: T = L21 X11", "trtri: X21 = -X22 T", "store"};
     double tot = 0;
     for (int i = 0; i < 9; i++) tot += (double)cyc[i] / reps;
     printf("leaf: %.1f us per launch (events, back-to-back launches of one block); clock64 total %.0f cycles\n", ms * 1e3 / reps, tot);
     for (int i = 0; i < 9; i++) printf("  %-40s %8.0f cycles  %5.1f %%\n", name[i], (double)cyc[i] / reps, 100.0 * cyc[i] / reps / tot);
-    unsigned long long w[3][16];
-    cudaMemcpyFromSymbol(w, gpe::g_leaf_warp, sizeof w);
-    printf("first panel's trailing update per warp (cycles): start offset after the barrier / fragment loop\n");
-    for (int i = 0; i < 16; i++) printf("  warp %2d: %6.0f %6.0f\n", i, (double)w[2][i] / reps, (double)w[0][i] / reps);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { printf("CUDA error: %s\n", cudaGetErrorString(e)); return 1; }
     return 0;
