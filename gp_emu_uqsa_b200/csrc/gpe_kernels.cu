@@ -481,65 +481,111 @@ __global__ void __launch_bounds__(LT, 1) leaf_potrf_trtri_v3_kernel(const double
     }
     __syncthreads();
     LEAF_TICK(5);
-    for (int h = PW; h < NB; h <<= 1) {  // doubling levels: X21 = -X22 (L21 X11) per node of size 2h
-        const int hb = h >> 3, fpn = hb * hb, F = (NB / (2 * h)) * fpn, ldT = h + 4;
+    int lhb = 0;                         // log2(h / 8)
+    for (int h = PW; h < NB; h <<= 1, lhb++) {  // doubling levels: X21 = -X22 (L21 X11) per node of size 2h
+        const int hb = h >> 3, F = (NB / (2 * h)) << (2 * lhb), ldT = h + 4;
+        // Two fragments per warp in flight, each with two accumulator chains (even / odd k4 steps): four independent
+        // DMMA chains per warp.  The k ranges are warp-uniform, so the predicates around the DMMAs are too.
         // T = L21 X11: fragment (rb, cb); X11 is lower triangular: k4 steps from 2 cb on
-        for (int f = warp; f < F; f += NW) {
-            const int node = f / fpn, rem = f - node * fpn, rb = rem / hb, cb = rem - rb * hb, o = node * 2 * h;
-            const double* ar = S + (o + h + 8 * rb + fr) * L3 + o + fc;          // L21[8rb+fr][k]
-            const int n = 8 * cb + fr;                                          // this lane's column of X11
+        for (int f = warp; f < F; f += 2 * NW) {
+            const int fB = f + NW;
+            const bool two = fB < F;
+            const int g = two ? fB : f;
+            const int node = f >> (2 * lhb), rem = f & (hb * hb - 1), rb = rem >> lhb, cb = rem & (hb - 1), o = node * 2 * h;
+            const int nodeB = g >> (2 * lhb), remB = g & (hb * hb - 1), rbB = remB >> lhb, cbB = remB & (hb - 1), oB = nodeB * 2 * h;
+            const double* ar = S + (o + h + 8 * rb + fr) * L3 + o + fc;         // L21[8rb+fr][k]
+            const double* arB = S + (oB + h + 8 * rbB + fr) * L3 + oB + fc;
+            const int n = 8 * cb + fr, nB = 8 * cbB + fr;                       // this lane's column of X11
             const double* xr = S + (o + n) * L3 + o + fc;                       // X11[k][n] lives at S[o+n][o+k]
-            double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;                      // two chains: even / odd k4 steps
-            for (int sidx = 2 * cb; sidx < 2 * hb; sidx += 2) {
+            const double* xrB = S + (oB + nB) * L3 + oB + fc;
+            const double dn = dinv[o + n], dnB = dinv[oB + nB];
+            double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0, p0 = 0.0, p1 = 0.0, q0 = 0.0, q1 = 0.0;
+            for (int sidx = 2 * min(cb, cbB); sidx < 2 * hb; sidx += 2) {
                 const int k = 4 * sidx + fc, k2 = k + 4;
-                const double bv = (k > n) ? xr[4 * sidx] : ((k == n) ? dinv[o + n] : 0.0);
-                const double bv2 = (k2 > n) ? xr[4 * sidx + 4] : ((k2 == n) ? dinv[o + n] : 0.0);
-                dmma884(c0, c1, ar[4 * sidx], bv);
-                dmma884(e0, e1, ar[4 * sidx + 4], bv2);
+                if (sidx >= 2 * cb) {
+                    const double bv = (k > n) ? xr[4 * sidx] : ((k == n) ? dn : 0.0);
+                    const double bv2 = (k2 > n) ? xr[4 * sidx + 4] : ((k2 == n) ? dn : 0.0);
+                    dmma884(c0, c1, ar[4 * sidx], bv);
+                    dmma884(e0, e1, ar[4 * sidx + 4], bv2);
+                }
+                if (sidx >= 2 * cbB) {
+                    const double bv = (k > nB) ? xrB[4 * sidx] : ((k == nB) ? dnB : 0.0);
+                    const double bv2 = (k2 > nB) ? xrB[4 * sidx + 4] : ((k2 == nB) ? dnB : 0.0);
+                    dmma884(p0, p1, arB[4 * sidx], bv);
+                    dmma884(q0, q1, arB[4 * sidx + 4], bv2);
+                }
             }
-            c0 += e0;
-            c1 += e1;
             double* tp = Tm + node * h * ldT + (8 * rb + fr) * ldT + 8 * cb + 2 * fc;
-            tp[0] = c0;
-            tp[1] = c1;
+            tp[0] = c0 + e0;
+            tp[1] = c1 + e1;
+            if (two) {
+                double* tpB = Tm + nodeB * h * ldT + (8 * rbB + fr) * ldT + 8 * cbB + 2 * fc;
+                tpB[0] = p0 + q0;
+                tpB[1] = p1 + q1;
+            }
         }
         __syncthreads();
         LEAF_TICK(6);
-        // X21 = -X22 T: X22 lower triangular: k4 steps up to 2 rb + 1; result stored transposed
-        for (int f = warp; f < F; f += NW) {
-            const int node = f / fpn, rem = f - node * fpn, rb = rem / hb, cb = rem - rb * hb, o = node * 2 * h;
-            const int r = 8 * rb + fr;                                          // this lane's row of X22
+        // X21 = -X22 T: X22 lower triangular: k4 steps up to 2 rb + 1 (an even count); result stored transposed
+        for (int f = warp; f < F; f += 2 * NW) {
+            const int fB = f + NW;
+            const bool two = fB < F;
+            const int g = two ? fB : f;
+            const int node = f >> (2 * lhb), rem = f & (hb * hb - 1), rb = rem >> lhb, cb = rem & (hb - 1), o = node * 2 * h;
+            const int nodeB = g >> (2 * lhb), remB = g & (hb * hb - 1), rbB = remB >> lhb, cbB = remB & (hb - 1), oB = nodeB * 2 * h;
+            const int r = 8 * rb + fr, rB = 8 * rbB + fr;                       // this lane's row of X22
             const double* xc = S + (o + h + fc) * L3 + o + h + r;               // X22[r][k] lives at S[o+h+k][o+h+r]
+            const double* xcB = S + (oB + h + fc) * L3 + oB + h + rB;
             const double* tr = Tm + node * h * ldT + fc * ldT + 8 * cb + fr;    // T[k][8cb+fr]
-            double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;
-            for (int sidx = 0; sidx <= 2 * rb + 1; sidx += 2) {                 // 2 rb + 2 steps: always an even count
+            const double* trB = Tm + nodeB * h * ldT + fc * ldT + 8 * cbB + fr;
+            const double dr = dinv[o + h + r], drB = dinv[oB + h + rB];
+            double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0, p0 = 0.0, p1 = 0.0, q0 = 0.0, q1 = 0.0;
+            for (int sidx = 0; sidx <= 2 * max(rb, rbB) + 1; sidx += 2) {
                 const int k = 4 * sidx + fc, k2 = k + 4;
-                const double av = (k < r) ? xc[4 * sidx * L3] : ((k == r) ? dinv[o + h + r] : 0.0);
-                const double av2 = (k2 < r) ? xc[(4 * sidx + 4) * L3] : ((k2 == r) ? dinv[o + h + r] : 0.0);
-                dmma884(c0, c1, av, tr[4 * sidx * ldT]);
-                dmma884(e0, e1, av2, tr[(4 * sidx + 4) * ldT]);
+                if (sidx <= 2 * rb + 1) {
+                    const double av = (k < r) ? xc[4 * sidx * L3] : ((k == r) ? dr : 0.0);
+                    const double av2 = (k2 < r) ? xc[(4 * sidx + 4) * L3] : ((k2 == r) ? dr : 0.0);
+                    dmma884(c0, c1, av, tr[4 * sidx * ldT]);
+                    dmma884(e0, e1, av2, tr[(4 * sidx + 4) * ldT]);
+                }
+                if (sidx <= 2 * rbB + 1) {
+                    const double av = (k < rB) ? xcB[4 * sidx * L3] : ((k == rB) ? drB : 0.0);
+                    const double av2 = (k2 < rB) ? xcB[(4 * sidx + 4) * L3] : ((k2 == rB) ? drB : 0.0);
+                    dmma884(p0, p1, av, trB[4 * sidx * ldT]);
+                    dmma884(q0, q1, av2, trB[(4 * sidx + 4) * ldT]);
+                }
             }
-            c0 += e0;
-            c1 += e1;
             double* xo = S + (o + 8 * cb + 2 * fc) * L3 + o + h + r;
-            xo[0] = -c0;
-            xo[L3] = -c1;
+            xo[0] = -(c0 + e0);
+            xo[L3] = -(c1 + e1);
+            if (two) {
+                double* xoB = S + (oB + 8 * cbB + 2 * fc) * L3 + oB + h + rB;
+                xoB[0] = -(p0 + q0);
+                xoB[L3] = -(p1 + q1);
+            }
         }
         __syncthreads();
         LEAF_TICK(7);
     }
+    // results as 16-byte stores: L^-1 (lower, zeros above the diagonal) and, if asked for, the factor itself
     double* Lb = Linv + (size_t)b * sL + (size_t)off * ld + off;
 #pragma unroll 8
-    for (int e = tid; e < NB * NB; e += LT) {
-        int i = e >> 7, j = e & (NB - 1);
-        Lb[(size_t)i * ld + j] = (j < i) ? S[j * L3 + i] : ((j == i) ? dinv[i] : 0.0);
+    for (int e = tid; e < NB * NB / 2; e += LT) {
+        const int i = e >> 6, j = (e & 63) * 2;
+        double2 v;
+        v.x = (j < i) ? S[j * L3 + i] : ((j == i) ? dinv[i] : 0.0);
+        v.y = (j + 1 < i) ? S[(j + 1) * L3 + i] : ((j + 1 == i) ? dinv[i] : 0.0);
+        *reinterpret_cast<double2*>(&Lb[(size_t)i * ld + j]) = v;
     }
     if (Lfac != nullptr) {
         double* Fb = Lfac + (size_t)b * sL + (size_t)off * ld + off;
 #pragma unroll 8
-        for (int e = tid; e < NB * NB; e += LT) {
-            int i = e >> 7, j = e & (NB - 1);
-            Fb[(size_t)i * ld + j] = (j <= i) ? S[i * L3 + j] : 0.0;
+        for (int e = tid; e < NB * NB / 2; e += LT) {
+            const int i = e >> 6, j = (e & 63) * 2;
+            double2 v;
+            v.x = (j <= i) ? S[i * L3 + j] : 0.0;
+            v.y = (j + 1 <= i) ? S[i * L3 + j + 1] : 0.0;
+            *reinterpret_cast<double2*>(&Fb[(size_t)i * ld + j]) = v;
         }
     }
     __syncthreads();
