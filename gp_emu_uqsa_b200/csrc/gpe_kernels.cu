@@ -290,14 +290,18 @@ __global__ void __launch_bounds__(1024, 1) leaf_potrf_trtri_kernel(const double*
 //          row i, pivots and columns travel by shuffles, 1/sqrt(pivot) comes from rsqrt() so there is
 //          no divide on the chain; (2) the rows below are solved against it, one thread per row;
 //          (3) the trailing block gets its rank-8 update as two DMMA.8x8x4 per lower 8x8 fragment,
-//          operands and accumulator read straight from shared memory.  3 barriers per panel.
+//          operands and accumulator read straight from shared memory, two fragments in flight per warp.
+//          Look-ahead: in step (3) warp 0 updates only the next diagonal block and factors it at once
+//          (step (1) of the next panel) while the warps of the other three scheduler partitions do the
+//          rest of the update, so the serial pivot chain and the DMMA work overlap.  2 barriers per panel.
 //   trtri: the 8x8 diagonal inverses (one thread per column), then log2(128/8) = 4 doubling levels
 //          X21 = -X22 (L21 X11), both products as DMMA fragments with the triangular k ranges; 9 barriers.
 // L is kept in the lower triangle (diagonal included), X = L^-1 transposed in the upper triangle, its
 // diagonal (1/L_ii) in dinv[]; the log-determinant is summed from the stored pivots afterwards.
 // History (tools/perf_leaf.py, 32 blocks per launch): v1 238 us; v2 (same structure, scalar-FMA trailing
 // update and inverse levels with register micro-tiles) 107 us, of which 33 us trailing update and 43 us
-// inverse levels -- issue-bound, one FMA per instruction; v3 58.7 us.  The row stride is 132 (= 4 mod 16
+// inverse levels -- issue-bound, one FMA per instruction; v3 58.7 us; with look-ahead and four DMMA chains per
+// warp in the inverse levels 45 us (tools/leaf_phases.cu: 109.6 k -> 82 k cycles).  The row stride is 132 (= 4 mod 16
 // doubles, the same rule as the GEMM tiles) so the 8x4 / 4x8 fragment loads are bank-conflict-free; the
 // few row-per-thread accesses of the panel solve pay a 4-way conflict instead.
 // Phase timing of the leaf for tools/leaf_phases.cu (compiled only there, with -DGPE_LEAF_TIMING): thread 0 adds the
