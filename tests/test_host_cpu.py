@@ -225,3 +225,26 @@ def test_header_is_plain_c(tmp_path):
     r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), str(src)],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+def test_block_partition_properties():
+    """Units (guesses, grid cells, rows) are split into contiguous blocks that tile range(n) exactly, differ in size
+    by at most one and may be empty when there are fewer units than ranks (the C-ABI treats zero units as a no-op)."""
+    from hypothesis import given, settings, strategies as st
+    from gp_emu_uqsa_b200 import _dist
+
+    @settings(max_examples=300, deadline=None)
+    @given(st.integers(0, 10 ** 9), st.integers(1, 64))
+    def check(n, world):
+        edges = [_dist.block(n, r, world) for r in range(world)]
+        assert edges[0][0] == 0 and edges[-1][1] == n
+        for (lo, hi), (lo2, _) in zip(edges, edges[1:]):
+            assert lo <= hi == lo2
+        sizes = [hi - lo for lo, hi in edges]
+        assert max(sizes) - min(sizes) <= 1 and sum(sizes) == n
+
+    check()
+    # single-process defaults: no process group -> rank 0 of 1, collectives are identities
+    assert _dist.rank_world() == (0, 1)
+    x = np.arange(6.0).reshape(3, 2)
+    assert np.array_equal(_dist.gather_blocks(x.copy(), 3), x)
