@@ -17,7 +17,7 @@ For each it reports the quantities the likelihood and its gradient are made of: 
 max |A^-1 - A^-1_LAPACK| relative to max |A^-1|, over a range of condition numbers (correlation lengths 0.5 ... 4,
 nugget 1e-4 / 1e-6: cond(A) from 1e3 to beyond 1e8).
 
-    python tools/ozaki_study.py [n] [d]
+    python tools/ozaki_study.py [n] [d] [delta:nugget,delta:nugget,...]
 """
 import sys
 import time
@@ -122,7 +122,10 @@ def main():
     X, y = synth(n, d)
     print("n = %d, d = %d; relative differences against LAPACK (float64)" % (n, d))
     print("%-6s %-8s %-9s %-10s %-12s %-12s %-12s %-8s" % ("delta", "nugget", "cond(A)", "GEMM", "logdet", "y'A^-1 y", "max|dA^-1|", "seconds"))
-    for delta, nugget in ((0.5, 1e-4), (1.0, 1e-4), (2.0, 1e-4), (2.0, 1e-6), (4.0, 1e-6)):
+    cases = ((0.5, 1e-4), (1.0, 1e-4), (2.0, 1e-4), (2.0, 1e-6), (4.0, 1e-6))
+    if len(sys.argv) > 3:                                     # e.g. "1.0:1e-4,2.0:1e-4"
+        cases = tuple(tuple(float(v) for v in c.split(":")) for c in sys.argv[3].split(","))
+    for delta, nugget in cases:
         A = cov(X, np.full(d, delta), nugget)
         c = np.linalg.cond(A)
         Lr = np.linalg.cholesky(A)
