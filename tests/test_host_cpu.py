@@ -248,3 +248,26 @@ def test_block_partition_properties():
     assert _dist.rank_world() == (0, 1)
     x = np.arange(6.0).reshape(3, 2)
     assert np.array_equal(_dist.gather_blocks(x.copy(), 3), x)
+
+
+def test_int8_slice_gemm_emulation_reaches_float64_accuracy():
+    """tools/ozaki_study.py (the CPU parity study behind DESIGN section 11): its exact INT8-slice GEMM emulation must
+    converge to the float64 product as slices are added -- 2^-7 per slice, float64 level at 9-10 slices -- also for
+    rows whose entries span many decades, and the blocked factorisation built on it must reproduce LAPACK."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ozaki_study", os.path.join(ROOT, "tools", "ozaki_study.py"))
+    oz = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(oz)
+    rng = np.random.default_rng(0)
+    A = rng.normal(size=(96, 160)) * 10.0 ** rng.integers(-6, 3, size=(96, 1)) * 10.0 ** (-8 * rng.random((96, 160)))
+    B = rng.normal(size=(160, 64)) * 10.0 ** rng.integers(-3, 4, size=(1, 64))
+    ref = A @ B
+    bound = np.abs(A) @ np.abs(B)
+    errs = [np.max(np.abs(oz.make_gemm_ozaki(s)(A, B) - ref) / bound) for s in (6, 8, 10)]
+    assert errs[0] > errs[1] > errs[2] and errs[1] < 1e-10 and errs[2] < 5e-15, errs
+    X, y = oz.synth(300, 4)
+    Acov = oz.cov(X, np.full(4, 0.7), 1e-4)
+    Li, Ainv, ld = oz.factor_inverse(Acov.copy(), oz.make_gemm_ozaki(10))
+    L = np.linalg.cholesky(Acov)
+    assert abs(ld - 2 * np.log(np.diag(L)).sum()) <= 1e-12 * abs(ld)
+    assert np.abs(Li @ L - np.eye(300)).max() < 1e-9
