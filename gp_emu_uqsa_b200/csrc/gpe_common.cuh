@@ -13,6 +13,23 @@ namespace gpe {
 constexpr int NB = 128;        // leaf block / padding granule of every n x n matrix
 constexpr int NUM_SMS = 148;   // B200
 
+// ---- opt-in to more than 48 KB of dynamic shared memory: a per-device function attribute, set the first time a
+// kernel needs a given size on the current device (one static instance per launch site)
+struct SmemOptIn {
+    size_t have[16] = {};
+    template <class Kern>
+    cudaError_t ensure(Kern kernel, size_t bytes) {
+        if (bytes <= 48 * 1024) return cudaSuccess;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        dev &= 15;
+        if (bytes <= have[dev]) return cudaSuccess;
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (e == cudaSuccess) have[dev] = bytes;
+        return e;
+    }
+};
+
 // ---- cp.async (LDGSTS) 16-byte copies, the staging path for FP64 DMMA tiles -------------
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
     unsigned s = (unsigned)__cvta_generic_to_shared(smem);

@@ -255,12 +255,8 @@ template <int BM, int BN, int WMW, int WNW, bool A_KC, bool B_KC, int EPI>
 inline cudaError_t launch_gemm_cfg(const GemmP& p, cudaStream_t st) {
     auto kern = gemm_dmma_kernel<BM, BN, WMW, WNW, A_KC, B_KC, EPI>;
     constexpr size_t smem = gemm_smem_bytes<BM, BN, A_KC, B_KC>();
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
+    static SmemOptIn optin;
+    if (cudaError_t e = optin.ensure(kern, smem); e != cudaSuccess) return e;
     if (p.M % BM || p.N % BN || p.K % GEMM_BK) return cudaErrorInvalidValue;
     dim3 grid(p.N / BN, p.M / BM, p.batch);
     kern<<<grid, WMW * WNW * 32, smem, st>>>(p);
@@ -470,12 +466,8 @@ template <bool A_KC, bool B_KC, int EPI, int WMW>
 inline cudaError_t launch_gemm_ws_shape(const GemmP& p, cudaStream_t st) {
     auto kern = gemm_dmma_ws_kernel<A_KC, B_KC, EPI, WMW>;
     constexpr size_t smem = gemm_smem_bytes<128, 128, A_KC, B_KC>();
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
+    static SmemOptIn optin;
+    if (cudaError_t e = optin.ensure(kern, smem); e != cudaSuccess) return e;
     if (p.M % 128 || p.N % 128 || p.K % GEMM_BK) return cudaErrorInvalidValue;
     const bool rowtri = (p.kmode == KM_LE_I || p.kmode == KM_GE_I);
     dim3 grid = rowtri ? dim3((p.M / 128) * (p.N / 128), 1, p.batch) : dim3(p.N / 128, p.M / 128, p.batch);

@@ -143,13 +143,10 @@ void launch_cov_build(const double* X, const double* r, int n, int d, int npad, 
     const int nt = npad / CT;
     dim3 grid = full ? dim3(nt, nt, B) : dim3(nt * (nt + 1) / 2, 1, B);
     size_t smem = (size_t)d * (CT + CT + 2) * sizeof(double);
-    static size_t attr_sz = 0;
-    if (smem > 48 * 1024 && smem > attr_sz) {
-        cudaFuncSetAttribute(cov_build_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(cov_build_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(cov_build_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_sz = smem;
-    }
+    static SmemOptIn opt0, opt1, opt2;
+    opt0.ensure(cov_build_kernel<0>, smem);
+    opt1.ensure(cov_build_kernel<1>, smem);
+    opt2.ensure(cov_build_kernel<2>, smem);
     if (gmode == 0) cov_build_kernel<0><<<grid, 256, smem, st>>>(X, r, n, d, npad, par, winv, A, sA, full, gdim);
     else if (gmode == 1) cov_build_kernel<1><<<grid, 256, smem, st>>>(X, r, n, d, npad, par, winv, A, sA, full, gdim);
     else cov_build_kernel<2><<<grid, 256, smem, st>>>(X, r, n, d, npad, par, winv, A, sA, full, gdim);
@@ -608,14 +605,11 @@ static int leaf_version() {
 
 void launch_leaf(const double* A, double* Linv, int ld, long long sA, long long sL, int off,
                  double* logdet_part, int nleaf, int* status, int B, cudaStream_t st, double* Lfac) {
-    static bool attr = false;
+    static SmemOptIn opt1, opt3;
     const size_t smem1 = (size_t)(NB * LS + NB) * sizeof(double);
     const size_t smem3 = (size_t)(NB * L3 + T3MAX + 2 * NB) * sizeof(double);
-    if (!attr) {
-        cudaFuncSetAttribute(leaf_potrf_trtri_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
-        cudaFuncSetAttribute(leaf_potrf_trtri_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3);
-        attr = true;
-    }
+    opt1.ensure(leaf_potrf_trtri_kernel, smem1);
+    opt3.ensure(leaf_potrf_trtri_v3_kernel, smem3);
     const int v = leaf_version();
     if (v == 1) leaf_potrf_trtri_kernel<<<B, 1024, smem1, st>>>(A, Linv, ld, sA, sL, off, logdet_part, nleaf, status, Lfac);
     else leaf_potrf_trtri_v3_kernel<<<B, LT, smem3, st>>>(A, Linv, ld, sA, sL, off, logdet_part, nleaf, status, Lfac);
@@ -983,11 +977,8 @@ void launch_grad_partial(const double* X, const double* r, int n, int d, int npa
                          int B, cudaStream_t st) {
     int nt = npad / CT;
     size_t smem = ((size_t)(d + nu) * (CT + CT + 2) + 8 * (size_t)(d + 3)) * sizeof(double);
-    static size_t attr_sz = 0;
-    if (smem > 48 * 1024 && smem > attr_sz) {
-        cudaFuncSetAttribute(grad_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_sz = smem;
-    }
+    static SmemOptIn optin;
+    optin.ensure(grad_partial_kernel, smem);
     grad_partial_kernel<<<dim3(nt * (nt + 1) / 2, 1, B), 256, smem, st>>>(X, r, n, d, npad, winv, Ainv, sAinv, U, nu, part);
 }
 

@@ -124,6 +124,12 @@ __global__ void __launch_bounds__(256, 3) xcov_kernel(const double* __restrict__
     }
 }
 
+// d >= 32 needs more than 48 KB for the two k-major tiles
+static SmemOptIn& xcov_optin() {
+    static SmemOptIn o;
+    return o;
+}
+
 // per point: mean, variance from the GEMM outputs
 __global__ void __launch_bounds__(128) predict_finalize_kernel(const double* __restrict__ part, int ntile, const double* __restrict__ aux,
                                                                int ld, const double* __restrict__ P, const double* __restrict__ Hs,
@@ -333,6 +339,7 @@ int predict_chunk(gpe_handle* h, gpe_handle::PredSlot& sl, cudaStream_t st, cons
     size_t smem = (size_t)h->d * (64 + 130) * sizeof(double);
     {
         ProfScope ps(h, gpe_handle::CAT_COV, st);
+        xcov_optin().ensure(xcov_kernel, smem);
         xcov_kernel<<<dim3(mc / 128, np / 64), 256, smem, st>>>(h->fXs, P_dev, h->fwinv, h->n, h->d, np, mc, count, h->fit_c, sl.C, mc);
     }
     h->launches++;
@@ -517,6 +524,7 @@ int gpe_cross_cov(gpe_handle* h, const double* delta, double nugget, int kind, c
     CK(cudaMemcpyAsync(P, Xs, sizeof(double) * (size_t)m * d, cudaMemcpyDefault, h->st));
     scale_train_kernel<<<(d * np + 255) / 256, 256, 0, h->st>>>(h->X, wd, h->n, d, np, xs);
     size_t smem = (size_t)d * (64 + 130) * sizeof(double);
+    xcov_optin().ensure(xcov_kernel, smem);
     xcov_kernel<<<dim3(mc / 128, np / 64), 256, smem, h->st>>>(xs, P, wd, h->n, d, np, mc, m, kind ? 1.0 : 1.0 - nugget, Cm, mc);
     h->launches += 2;
     bool dev = gpe_is_device_ptr(C_out);
@@ -558,6 +566,7 @@ int gpe_predict_fullcov(gpe_handle* h, const double* Xs, const double* Hs, int m
         CK(cudaMemcpyAsync(rn, r_new, sizeof(double) * m, cudaMemcpyDefault, h->st));
     }
     size_t smem = (size_t)d * (64 + 130) * sizeof(double);
+    xcov_optin().ensure(xcov_kernel, smem);
     xcov_kernel<<<dim3(mp / 128, np / 64), 256, smem, h->st>>>(h->fXs, P, h->fwinv, h->n, d, np, mp, m, h->fit_c, Cm, mp);
     h->launches++;
     int rc = 0;

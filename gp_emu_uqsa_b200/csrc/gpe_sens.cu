@@ -296,11 +296,8 @@ int gpe_sens_contract(gpe_handle* h, const double* gamma, const double* acoef, c
     CK(cudaMemcpyAsync(Vsrc, V, sizeof(double) * (size_t)n * nv, cudaMemcpyDefault, h->st));
     pack_panel_kernel<<<(np * NR + 255) / 256, 256, 0, h->st>>>(Vsrc, n, nv, np, Vp);
     size_t smem = ((size_t)d * (ST + ST + 2) + 2 * ST) * sizeof(double);
-    static size_t attr_sz = 0;
-    if (smem > 48 * 1024 && smem > attr_sz) {
-        cudaFuncSetAttribute(sens_pw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_sz = smem;
-    }
+    static SmemOptIn optin;
+    optin.ensure(sens_pw_kernel, smem);
     sens_pw_kernel<<<dim3(nt, nt), 256, smem, h->st>>>(h->X, n, d, np, coef, coef + d, coef + 2 * d, scale, h->fAinv, h->S, tpart);
     h->launches += 2;
     // Y = P Vp   (P dense [np,np] row-major; rows/cols >= n are zero because u = 0 there)

@@ -169,3 +169,32 @@ def test_empty_and_single_unit_calls(dev, golden_dir):
     # implausibility of no points: zero counts, nothing kept
     Imax, keep, count, cmin, ccnt = dev.implausibility(np.empty((2, 0)), np.empty((2, 0)), [0.1, 0.2], [1e-2, 1e-2], 3.0, maxno=1)
     assert Imax.shape == (0, 1) and keep.shape == (0,) and int(count.sum()) == 0
+
+
+def test_many_inputs_d48_needs_large_shared_memory_tiles(dev):
+    """d = 48 inputs: the k-major X tiles of the covariance, gradient and cross-covariance kernels exceed the default
+    48 KB of dynamic shared memory (opt-in per kernel and device).  Likelihood + gradient and prediction against the
+    oracle at the usual tolerances."""
+    rng = np.random.default_rng(48)
+    n, d, m = 150, 48, 200
+    X = rng.random((n, d))
+    w = rng.normal(size=d) / np.sqrt(d)
+    y = np.sin(X @ w) + 0.05 * rng.normal(size=n)
+    H = np.ones((n, 1))
+    delta = 2.0 + rng.random(d)
+    sigma, nugget = 0.8, 1e-3
+    dev.set_training(X, y, H)
+    theta = np.r_[O.transform(delta), O.transform(np.array([sigma]))][None, :]
+    llh, grad, _, st = dev.llh_grad_batch(theta, 0, fixed_nugget=nugget)
+    want = O.loglikelihood_gp4ml(theta[0], X, y, H, kind=0, nugget_fixed=nugget)
+    assert st[0] == 0 and want is not None
+    assert abs(llh[0] - want[0]) <= 1e-10 * abs(want[0])
+    assert np.all(np.abs(grad[0] - want[1]) <= 1e-9 * np.abs(want[1]).max() + 1e-12)
+    beta, _, st = dev.fit_state(delta, nugget, sigma, kind=0)
+    assert st == 0
+    Xs = rng.random((m, d))
+    mean, var = dev.predict(Xs, Hs=np.ones((m, 1)))
+    A = O.make_A(X, delta, nugget, 0)
+    mo, vo = O.posterior_diag_chunked(Xs, np.ones((m, 1)), X, y, H, A, O.optimalbeta(A, H, y), sigma, delta, nugget, 0)
+    np.testing.assert_allclose(mean, mo, rtol=1e-8, atol=1e-10)
+    np.testing.assert_allclose(var, vo, rtol=1e-8, atol=1e-12)
