@@ -3,24 +3,41 @@
 
 Metric (BASELINE.json): batched llh+grad evaluations/sec at n=4096, d=16 (config 3: 256 multistart
 guesses over 8 GPUs = 32 per GPU, weak scaling), plus posterior predictions/sec on the 10^8-point
-grid of config 4 (reported under "extra").  One "step" = one batched llh+gradient evaluation of
-32 hyper-parameter vectors per GPU (theta perturbed every step so nothing is cached).
+grid of config 4 and the other BASELINE configs (reported under "extra").  One "step" = one batched
+llh+gradient evaluation of 32 hyper-parameter vectors per GPU (theta perturbed every step so nothing
+is cached).
 
     python bench.py --gpus N --steps K --warmup W            (N>1: launched by torchrun)
-    python bench.py --impl reference ...                      (CPU oracle port on the host cores)
+    python bench.py --impl reference ...                      (the reference's CPU algorithm, all host cores)
 
 Prints ONE JSON line on rank 0.
 """
-import argparse
-import json
 import os
-import subprocess
 import sys
-import tempfile
-import threading
-import time
 
-import numpy as np
+
+def _host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+# The CPU legs must run the BLAS on every host core; torchrun exports OMP_NUM_THREADS=1 to its workers, and OpenBLAS
+# sizes its pool when NumPy is first imported -- so this has to happen before `import numpy`.
+if ("reference" in sys.argv and os.environ.get("RANK", "0") == "0") or os.environ.get("WORLD_SIZE", "1") == "1":
+    for _k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_k] = str(_host_cores())
+
+import argparse      # noqa: E402
+import contextlib    # noqa: E402
+import io            # noqa: E402
+import json          # noqa: E402
+import subprocess    # noqa: E402
+import tempfile      # noqa: E402
+import time          # noqa: E402
+
+import numpy as np   # noqa: E402
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -29,8 +46,8 @@ RESULT_OUT = sys.stdout
 METRIC = "llh+grad evals/sec (n=4096,d=16) and posterior preds/sec, 1/2/4/8 B200"
 N_TRAIN, D_IN, B_PER_GPU = 4096, 16, 32
 N_PRED, D_PRED = 2000, 8
-PRED_POINTS_PER_STEP = 1 << 20
 FP64_PEAK_FALLBACK_TFLOPS = 37.19     # tools/ub_fp64.cu on this pool's B200 (profiles/r01_ub_fp64_peaks.json)
+HBM_PEAK_FALLBACK_GBS = 6552.0
 
 
 def synth(n, d, seed=0):
@@ -59,6 +76,17 @@ def draw_thetas(B_total, d, y, seed=0):
     return np.ascontiguousarray(grid.T)
 
 
+def bench_config(streams):
+    """`config` of the JSON line -- the SAME object for the B200 arm and the reference arm (what differs between
+    the arms is said in `impl` and `cpu_baseline.sample`, not here)."""
+    return {"workload": "config3: n=4096 d=16 q=17 p=17, gp4ml llh+grad (value + gradient of Optimize.loglikelihood_gp4ml, "
+                        "_emulatoroptimise.py:412-493), fixed nugget 1e-4, theta = the multistart draw of _emulatoroptimise.py:206-211 "
+                        "from the auto bounds, perturbed each step; 32 guesses per GPU per step (256 over 8 GPUs)",
+            "l2": "working set 12.9 GB per step >> 126 MB L2 (inputs larger than L2, no flush needed)",
+            "parallelism": "multistart guesses block-partitioned over ranks; one NCCL all_gather of (llh,theta,status) per step",
+            "streams": streams}
+
+
 def flops_llh(n, d, q, p):
     """F_llh ~ n^3 + n^2 (3d + p + 2q + 4)."""
     return float(n) ** 3 + float(n) ** 2 * (3 * d + p + 2 * q + 4)
@@ -67,6 +95,36 @@ def flops_llh(n, d, q, p):
 def flops_pred(n, d, q):
     """F_pred ~ n^2 + 2n (d + q + 3)."""
     return float(n) ** 2 + 2.0 * n * (d + q + 3)
+
+
+def write_emulator_files(workdir, X, y, name, mucm="F", fix_nugget="T", alt_nugget="F", nugget=1e-4, delta=0.5, tries=1,
+                         constraints="bounds"):
+    """config / beliefs / inputs / outputs text files of a synthetic emulator with a linear mean (the reference's
+    on-disk interface, README 'config file' / 'beliefs file')."""
+    d = X.shape[1]
+    p = lambda f: os.path.join(workdir, f)
+    np.savetxt(p(name + "_input"), X, fmt="%.17g")
+    np.savetxt(p(name + "_output"), y.reshape(-1, 1), fmt="%.17g")
+    with open(p(name + "_beliefs"), "w") as f:
+        f.write("active all\noutput 0\nbasis_str 1.0 %s\nbasis_inf NA %s\nbeta %s\n" %
+                (" ".join(["x"] * d), " ".join(map(str, range(d))), " ".join(["1.0"] * (d + 1))))
+        f.write("delta %s\nsigma 1.0\nnugget %r\nfix_nugget %s\nalt_nugget %s\nmucm %s\n" %
+                (" ".join([repr(float(delta))] * d), float(nugget), fix_nugget, alt_nugget, mucm))
+    with open(p(name + "_config"), "w") as f:
+        f.write("beliefs %s_beliefs\ninputs %s_input\noutputs %s_output\ntv_config 10 0 0\ndelta_bounds [ ]\nsigma_bounds [ ]\n"
+                "nugget_bounds [ ]\ntries %d\nconstraints %s\n" % (name, name, name, tries, constraints))
+    return name + "_config"
+
+
+@contextlib.contextmanager
+def quiet_in(workdir):
+    old = os.getcwd()
+    os.chdir(workdir)
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):
+            yield
+    finally:
+        os.chdir(old)
 
 
 class ClockSampler:
@@ -125,69 +183,279 @@ def fp64_peak():
         return FP64_PEAK_FALLBACK_TFLOPS, "fallback"
 
 
+def hbm_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json"
+    except Exception:
+        return HBM_PEAK_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
+
+
 # ------------------------------------------------------------------------------------------ CPU arm
-def cpu_llh_sample(budget_s, threads_note=True):
-    """Time the oracle's loglikelihood_gp4ml (the reference's algorithm, NumPy/SciPy/OpenBLAS, all
-    host cores) on a bounded sample of the n=4096, d=16 workload: the largest leading row-subsample
-    whose evaluation fits the budget; evals/s at n=4096 is extrapolated with the measured n^3 cost law
-    when the sample is smaller than 4096 (said in `sample`)."""
-    from oracle import gp_oracle as O
-    X, y = synth(N_TRAIN, D_IN)
-    theta = draw_thetas(4, D_IN, y)[0]
-    theta[:D_IN] = 2 * np.log(0.5)        # delta = 0.5: a PD, well-conditioned point (cost is theta-independent)
-    t_est, n_used, t_used = None, None, None
-    for ns in (512, 1024, 2048, 4096):
-        if t_est is not None and t_est * (ns / n_used) ** 3 > budget_s:
-            break
-        Xs, ys = X[:ns], y[:ns]
-        H = linear_H(Xs)
-        t0 = time.perf_counter()
-        res = O.loglikelihood_gp4ml(theta, Xs, ys, H, 0, 1e-4)
-        t_used = time.perf_counter() - t0
-        assert res is not None
-        n_used, t_est = ns, t_used
-    scale = (N_TRAIN / n_used) ** 3
-    evals_per_s = 1.0 / (t_used * scale)
+def _blas_info():
+    info = {"host_cpus": os.cpu_count(), "usable_cores": _host_cores(), "numpy": np.__version__}
+    try:
+        import scipy
+        info["scipy"] = scipy.__version__
+    except Exception:
+        pass
     try:
         from threadpoolctl import threadpool_info
-        thr = max([i.get("num_threads", 1) for i in threadpool_info()] + [1])
+        pools = threadpool_info()
+        info["blas"] = [{k: p_.get(k) for k in ("internal_api", "version", "num_threads", "threading_layer")} for p_ in pools]
+        info["threads"] = max([p_.get("num_threads", 1) for p_ in pools] + [1])
     except Exception:
-        thr = os.cpu_count()
-    sample = "1 loglikelihood_gp4ml eval, n=%d, d=%d, %.2f s measured" % (n_used, D_IN, t_used)
-    if n_used != N_TRAIN:
-        sample += "; scaled to n=4096 by (4096/%d)^3" % n_used
-    return {"value": evals_per_s, "unit": "evals/s", "cores": int(thr), "kind": "port", "sample": sample,
-            "host_cpus": os.cpu_count(), "numpy": np.__version__}
+        info["threads"] = _host_cores()
+    return info
+
+
+@contextlib.contextmanager
+def all_cores():
+    """BLAS pools at every usable host core for the duration (the env fix at the top covers pools created at
+    import; this covers a pool that was sized before)."""
+    try:
+        from threadpoolctl import threadpool_limits
+        with threadpool_limits(limits=_host_cores()):
+            yield
+    except ImportError:
+        yield
+
+
+def cpu_llh_eval(X, y, H, theta, mucm=False):
+    """One evaluation of the reference's algorithm (oracle port, NumPy/SciPy/OpenBLAS): seconds."""
+    from oracle import gp_oracle as O
+    t0 = time.perf_counter()
+    res = O.loglikelihood_mucm(theta[:X.shape[1]], X, y, H, 0, 1e-4) if mucm else O.loglikelihood_gp4ml(theta, X, y, H, 0, 1e-4)
+    dt = time.perf_counter() - t0
+    assert res is not None, "non-PD theta in the CPU leg"
+    return dt
+
+
+def cpu_other_legs():
+    """BASELINE.md section 3, items M1 (n = 1000), M2, HM and Sensitivity on the host cores: the oracle port of the
+    reference's algorithm on bounded samples.  Returns a dict for `extra.cpu`."""
+    from oracle import gp_oracle as O
+    from oracle import sens_oracle as SO
+    out = {}
+    # M1 at config 2's shape: n = 1000, d = 8
+    X, y = synth(1000, 8)
+    H = linear_H(X)
+    th = draw_thetas(4, 8, y)[0]
+    th[:8] = 2 * np.log(0.5)
+    tg = [cpu_llh_eval(X, y, H, th) for _ in range(3)]
+    tm = [cpu_llh_eval(X, y, H, th, mucm=True) for _ in range(3)]
+    out["llh_n1000_d8"] = {"gp4ml_s_per_eval_median_of_3": float(np.median(tg)), "mucm_s_per_eval_median_of_3": float(np.median(tm)),
+                           "evals_per_s": 1.0 / float(np.median(tg)),
+                           "note": "a 64-start llh_optimize needs about 64 x 13 such evaluations one after the other (BASELINE.md section 2)"}
+    # M2: g.posterior at n = 2000, d = 8 in m = 1000 chunks (mean + the full m x m covariance: the reference's only API)
+    Xp, yp = synth(N_PRED, D_PRED)
+    yp2 = np.cos(Xp @ np.random.default_rng(1).normal(size=D_PRED))
+    Hp = linear_H(Xp)
+    delta = np.full(D_PRED, 0.5)
+    A = O.make_A(Xp, delta, 1e-4, 0)
+    betas = [O.optimalbeta(A, Hp, yy) for yy in (yp, yp2)]
+    rng = np.random.default_rng(7)
+    P = (rng.integers(0, 10, size=(5000, D_PRED)) + 0.5) / 10.0          # points of the config-4 grid
+    Hs = linear_H(P)
+    tp = []
+    for c in range(5):
+        sl = slice(1000 * c, 1000 * (c + 1))
+        t0 = time.perf_counter()
+        O.posterior(P[sl], Hs[sl], Xp, yp, Hp, A, betas[0], 1.0, delta, 1e-4, 0)
+        tp.append(time.perf_counter() - t0)
+    out["posterior_n2000_d8"] = {"preds_per_s": 1000.0 / float(np.median(tp)), "s_per_1000_point_chunk_median_of_5": float(np.median(tp)),
+                                 "what": "Posterior.make_covar/make_mean/make_var (_emulatorclasses.py:607-631) per g.posterior call"}
+    # HM: the nonimp_data loop (history_match.py:222-250): both emulators' posteriors per chunk + implausibility
+    t0 = time.perf_counter()
+    mh = 2000
+    means, variances = [], []
+    for yy, bb in zip((yp, yp2), betas):
+        mu, var = O.posterior_diag_chunked(P[:mh], Hs[:mh], Xp, yy, Hp, A, bb, 1.0, delta, 1e-4, 0, chunk=1000)
+        means.append(mu); variances.append(var)
+    O.implausibility(np.array(means), np.array(variances), [float(np.median(yp)), float(np.median(yp2))], [1e-2, 1e-2], 3.0, 1)
+    out["history_match_2_emulators"] = {"points_per_s": mh / (time.perf_counter() - t0), "points": mh}
+    # Sensitivity at n = 200, d = 4 (the vectorised port is faster than the reference's Python double loops:
+    # BASELINE.md section 2 has 2.7 / 3.3 / 4.5 s for the reference itself at this size)
+    Xs_, ys_ = synth(200, 4)
+    Hs_ = linear_H(Xs_)
+    ds_ = np.full(4, 0.5)
+    As_ = O.make_A(Xs_, ds_, 1e-4, 0)
+    bs_ = O.optimalbeta(As_, Hs_, ys_)
+    t0 = time.perf_counter()
+    S = SO.SensOracle(Xs_, ys_, Hs_, As_, bs_, 1.0, 1e-4, ds_, [0.5] * 4, [0.02] * 4)
+    tt = {"setup": time.perf_counter() - t0}
+    rng_in = [[float(Xs_[:, k].min()), float(Xs_[:, k].max())] for k in range(4)]
+    for name, fn in (("uncertainty", S.uncertainty), ("sensitivity", S.sensitivity), ("main_effect", lambda: S.main_effect(rng_in, points=100))):
+        t0 = time.perf_counter()
+        fn()
+        tt[name] = time.perf_counter() - t0
+    out["sensitivity_n200_d4_s"] = tt
+    return out
 
 
 def run_reference(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    """The reference's own algorithm for the metric's path on the host cores: every timed step is ONE real
+    loglikelihood_gp4ml evaluation (value + gradient) at the full n = 4096, d = 16 -- a 1/32 sample of the B200 arm's
+    step of 32 guesses, nothing extrapolated.  Warm-up steps run the same code at n = 1024 (they only have to spin
+    the BLAS pool up).  Timed steps stop early when the wall-clock budget is reached; `steps` is what was measured."""
+    if int(os.environ.get("RANK", "0")) != 0:
         return
+    t_begin = time.perf_counter()
     K, W = args.steps, args.warmup
-    per_step = max(3.0, 150.0 / max(1, K + W))
-    vals, last = [], None
-    for it in range(K + W):
-        last = cpu_llh_sample(per_step)
-        if it >= W:
-            vals.append(last["value"])
-    v = float(np.mean(vals))
-    last["value"] = v
-    line = {"metric": METRIC, "value": v, "unit": "evals/s", "n_gpus": args.gpus, "steps": K, "warmup": W,
-            "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "impl": "reference",
-            "config": {"workload": "config3: n=4096 d=16 q=17 llh+grad (gp4ml, fixed nugget 1e-4), CPU oracle port of "
-                                   "_emulatoroptimise.py:412-493 on the host cores"},
-            "cpu_baseline": last,
-            "e2e": {"value": v, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    X, y = synth(N_TRAIN, D_IN)
+    H = linear_H(X)
+    thetas = draw_thetas(B_PER_GPU * max(1, args.gpus), D_IN, y)
+    with all_cores():
+        info = _blas_info()
+        for it in range(W):
+            cpu_llh_eval(X[:1024], y[:1024], H[:1024], thetas[it % B_PER_GPU])
+        extra_cpu, t_mucm = {}, None
+        try:
+            extra_cpu = cpu_other_legs()
+        except Exception as ex:
+            extra_cpu = {"error": repr(ex)}
+        times = []
+        for it in range(K):
+            spent = time.perf_counter() - t_begin
+            if times and spent + 1.1 * max(times) > args.ref_budget:
+                break
+            times.append(cpu_llh_eval(X, y, H, thetas[it % B_PER_GPU] + 1e-3 * it))
+        spent = time.perf_counter() - t_begin
+        if spent + 1.2 * max(times) < args.ref_budget + 60:      # one full-size MUCM evaluation when it still fits
+            t_mucm = cpu_llh_eval(X, y, H, thetas[0], mucm=True)
+    v = len(times) / float(sum(times))
+    extra_cpu["llh_n4096_d16"] = {"gp4ml_s_per_eval": [round(t, 3) for t in times], "gp4ml_s_per_eval_median": float(np.median(times)),
+                                  "mucm_s_per_eval": t_mucm}
+    cpu = {"value": v, "unit": "evals/s", "cores": int(info["threads"]), "kind": "port",
+           "sample": "%d full-size evaluations of loglikelihood_gp4ml (oracle port of _emulatoroptimise.py:412-493), n=4096 d=16, one per step "
+                     "(1 of the 32 guesses of the B200 arm's step), %.1f s each; %d warm-up steps at n=1024; nothing extrapolated"
+                     % (len(times), float(np.mean(times)), W)}
+    cpu.update(info)
+    line = {"metric": METRIC, "value": v, "unit": "evals/s", "n_gpus": args.gpus, "steps": len(times), "steps_requested": K, "warmup": W,
+            "ms_per_step": 1e3 * float(np.mean(times)), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "impl": "reference", "config": bench_config(args.streams), "cpu_baseline": cpu,
+            "e2e": {"value": v, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "wall_s": time.perf_counter() - t_begin, "extra": {"cpu": extra_cpu}}
     print(json.dumps(line), file=RESULT_OUT, flush=True)
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
+def extra_configs(args, rank, world, local):
+    """Driver-run numbers for BASELINE's other configurations through the reference-facing API (N = 1 only for the
+    single-emulator ones).  Wall-clock times of whole calls, host work included."""
+    import gp_emu_uqsa_b200 as g
+    import gp_emu_uqsa_b200.sensitivity as s
+    from gp_emu_uqsa_b200 import _lib
+    out = {}
+    tmp = tempfile.mkdtemp(prefix="gpe_bench_")
+    # ---- config 3 as an optimisation: 32 starts per GPU through Optimize.llh_optimize (ragged tail included)
+    X, y = synth(N_TRAIN, D_IN)
+    with quiet_in(tmp):
+        cfg = write_emulator_files(tmp, X, y, "c3", tries=B_PER_GPU * world)
+        E = g.setup(cfg, datashuffle=False, scaleinputs=True)
+        np.random.seed(0)
+        t0 = time.perf_counter()
+        E.opt_T.llh_optimize()
+        dt = time.perf_counter() - t0
+    o = E.opt_T
+    out["config3_optimisation"] = {"what": "Optimize.llh_optimize, n=4096 d=16 gp4ml fixed nugget, %d starts (%d per GPU), bounds constraints, "
+                                           "batched lock-step L-BFGS-B; first call (no warm-up: workspace allocation and graph capture included)"
+                                           % (B_PER_GPU * world, B_PER_GPU),
+                                   "seconds": dt, "rounds_this_rank": o.last_rounds, "evals_this_rank": o.last_evals,
+                                   "evals_per_s_this_rank": o.last_evals / dt, "best_llh": float(-o.best_llh), "best_guess": int(o.best_guess)}
+    dev = E.training.device()
+    # ---- steady-state of the other likelihood modes and of small batches at n = 4096 (device-resident theta)
+    th = draw_thetas(B_PER_GPU, D_IN, y)
+    modes = {"gp4ml_fixed_nugget": (0, th), "mucm_fixed_nugget": (1, th[:, :D_IN]),
+             "gp4ml_free_nugget": (4, np.column_stack([th[:, :D_IN], np.full(B_PER_GPU, 2 * np.log(1e-3)), th[:, D_IN]]))}
+    ss = {}
+    for name, (mode, tt) in modes.items():
+        for it in range(4):
+            if it == 3:
+                t0 = time.perf_counter()
+            llh, _, _, st = dev.llh_grad_batch(tt + 1e-3 * it, mode, fixed_nugget=1e-4)
+        ms = (time.perf_counter() - t0) * 1e3
+        ss[name] = {"ms_per_32": ms, "evals_per_s": B_PER_GPU / ms * 1e3, "all_pd": bool((st == 0).all())}
+    out["n4096_steady_state_by_mode"] = ss
+    sb = {}
+    for Bs in (1, 2, 4, 8):
+        ts = []
+        for it in range(5):
+            t0 = time.perf_counter()
+            dev.llh_grad_batch(th[:Bs] + 1e-3 * it, 0, fixed_nugget=1e-4)
+            ts.append((time.perf_counter() - t0) * 1e3)
+        sb["B=%d" % Bs] = {"ms": float(np.median(ts[2:])), "frac_of_fp64_peak": Bs * flops_llh(N_TRAIN, D_IN, D_IN + 1, D_IN + 1) /
+                           (float(np.median(ts[2:])) * 1e-3) * 1e-12 / fp64_peak()[0]}
+    out["n4096_small_batches"] = sb
+    del E
+    if world > 1 or rank != 0:
+        return out
+    # ---- config 2: n = 1000, d = 8, full 64-start optimisation in the four modes
+    X2, y2 = synth(1000, 8)
+    c2 = {}
+    for mucm, fix in (("F", "T"), ("F", "F"), ("T", "T"), ("T", "F")):
+        with quiet_in(tmp):
+            cfg = write_emulator_files(tmp, X2, y2, "c2_%s%s" % (mucm, fix), mucm=mucm, fix_nugget=fix, tries=64)
+            E2 = g.setup(cfg, datashuffle=False, scaleinputs=True)
+            np.random.seed(0)
+            t0 = time.perf_counter()
+            E2.opt_T.llh_optimize()
+            cold = time.perf_counter() - t0
+            np.random.seed(0)
+            t0 = time.perf_counter()
+            E2.opt_T.llh_optimize()
+            dt = time.perf_counter() - t0
+        o = E2.opt_T
+        c2["mucm=%s fix_nugget=%s" % (mucm, fix)] = {"seconds": dt, "seconds_first_call": cold, "rounds": o.last_rounds, "evals": o.last_evals,
+                                                     "evals_per_s": o.last_evals / dt, "best_llh": float(-o.best_llh), "best_guess": int(o.best_guess)}
+    out["config2_optimisation_n1000_d8_64_starts"] = c2
+    # ---- config 5: sensitivity at n = 2000, d = 8
+    X5, y5 = synth(2000, 8)
+    with quiet_in(tmp):
+        cfg = write_emulator_files(tmp, X5, y5, "c5")
+        E5 = g.setup(cfg, datashuffle=False, scaleinputs=True)
+        E5.training.remake(); E5.opt_T.optimalbeta()
+        t5 = {}
+        for rep in range(2):
+            t0 = time.perf_counter(); S = s.setup(E5, [0.5] * 8, [0.02] * 8); t5["setup"] = time.perf_counter() - t0
+            t0 = time.perf_counter(); S.uncertainty(); t5["uncertainty"] = time.perf_counter() - t0
+            t0 = time.perf_counter(); S.sensitivity(); t5["sensitivity"] = time.perf_counter() - t0
+            t0 = time.perf_counter(); S.main_effect(points=100); t5["main_effect_100_points"] = time.perf_counter() - t0
+    out["config5_sensitivity_n2000_d8_s"] = t5
+    # ---- config 5: noise fit, noisefit2D generator at n = 2000
+    if not args.no_noisefit:
+        import gp_emu_uqsa_b200.noise_fit as gn
+        nf = tempfile.mkdtemp(prefix="gpe_bench_nf_")
+        with quiet_in(nf):
+            np.random.seed(1)
+            x = np.random.rand(2000, 2)
+            mean = 3.0 * x[:, 0] ** 3 + np.exp(np.cos(10.0 * x[:, 1]) * np.cos(5.0 * x[:, 0]) ** 2)
+            noise = np.abs(0.5 * (x[:, 1] * (np.cos(6 * x[:, 0]) ** 2 + 0.1)))
+            np.savetxt("INPUTS", x)
+            np.savetxt("OUTPUTS", mean + noise * np.random.randn(2000))
+            for name, outputs, alt, cons, db, sbd, nb in (("data", "OUTPUTS", "T", "none", "[[0.05,10.0],[0.05,10.00]]", "[[0.1,3.0]]", "[[0.001,1.05]]"),
+                                                         ("noise", "zp-outputs", "F", "bounds", "[[0.05,1.0],[0.05,10.00]]", "[[0.001,10.0]]", "[[0.0001,1.0]]")):
+                with open("config-" + name, "w") as f:
+                    f.write("beliefs beliefs-%s\ninputs INPUTS\noutputs %s\ntv_config 10 0 0\ndelta_bounds %s\nsigma_bounds %s\n"
+                            "nugget_bounds %s\ntries 3\nconstraints %s\n" % (name, outputs, db, sbd, nb, cons))
+                with open("beliefs-" + name, "w") as f:
+                    f.write("active all\noutput 0\nbasis_str 1.0\nbasis_inf NA\nbeta 1.0\ndelta 1.0 1.0\nsigma 1.0\nnugget 0.00001\n"
+                            "fix_nugget F\nalt_nugget %s\nmucm F\n" % alt)
+            t0 = time.perf_counter()
+            gn.noisefit("config-data", "config-noise", stopat=2, olhcmult=100, samples=200)
+            dt = time.perf_counter() - t0
+            fit = np.loadtxt("noise-outputs")
+            xin = np.loadtxt("noise-inputs")
+        true = np.abs(0.5 * (xin[:, 1] * (np.cos(6 * xin[:, 0]) ** 2 + 0.1)))
+        out["config5_noisefit_n2000"] = {"seconds": dt, "corr_fit_vs_true_noise": float(np.corrcoef(fit[:, 0], true)[0, 1]),
+                                         "what": "noisefit(stopat=2, samples=200): five g.train calls, four 2000x2000 posterior covariances + Cholesky factors"}
+    return out
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
-    from gp_emu_uqsa_b200 import _lib
+    from gp_emu_uqsa_b200 import _dist, _lib
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -295,9 +563,10 @@ def run_b200(args):
     dev.profile_enable(False)
     dev.set_streams(args.streams)
 
-    # ---- posterior predictions/sec over the config-4 grid (10 levels^8 = 10^8 points, sharded by flat index
-    # range over the ranks), mean + diagonal variance kept in HBM, then the history-matching pass over two
-    # emulators (implausibility, keep mask, per-(dim0,dim1)-cell min and counts)
+    # ---- posterior predictions/sec over the config-4 grid (10 levels^8 = 10^8 points): the flat index is cut into
+    # equal tile-aligned ranges, one per rank (cells of the history-matching statistics may straddle ranks); mean +
+    # diagonal variance kept in HBM; then the history-matching pass over two emulators (implausibility, keep mask,
+    # per-(dim0,dim1)-cell min and counts, all-reduce of the cell statistics)
     extra = {}
     try:
         Xp, yp = synth(N_PRED, D_PRED)
@@ -308,8 +577,8 @@ def run_b200(args):
         total = int(args.grid_points)
         ncell_all = 100
         cell_pts = total // ncell_all
-        c0, c1 = (ncell_all * rank) // world, (ncell_all * (rank + 1)) // world     # whole cells per rank
-        start, m = c0 * cell_pts, (c1 - c0) * cell_pts
+        start, stop = _dist.block_aligned(total, rank, world)
+        m = stop - start
         devs = []
         for yy in (yp, yp2):
             dv = _lib.Device(local)
@@ -325,11 +594,13 @@ def run_b200(args):
         for it in range(3):
             devp.predict_grid(levels, lo, hi, start, warm, out=(mean_d[0, :warm], var_d[0, :warm]))
         barrier()
+        lp0 = devp.launches
         p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         p0.record(pstream)
         devp.predict_grid(levels, lo, hi, start, m, out=(mean_d[0], var_d[0]))
         p1.record(pstream)
         barrier()
+        pred_launches = devp.launches - lp0
         pms = torch.tensor([p0.elapsed_time(p1)], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(pms, op=dist.ReduceOp.MAX)
@@ -347,13 +618,21 @@ def run_b200(args):
         devs[1].predict_grid(levels, lo, hi, start, m, out=(mean_d[1], var_d[1]))
         keep_d = torch.empty(m, dtype=torch.uint8, device="cuda")
         zs = [float(np.median(yp)), float(np.median(yp2))]
-        _, _, cnt, cmin, ccnt = devp.implausibility(mean_d, var_d, zs, [1e-2, 1e-2], 3.0, maxno=1, ncell=c1 - c0,
-                                                     want_imax=False, out=(None, keep_d))
-        stats = torch.zeros(ncell_all + 1, dtype=torch.float64, device="cuda")
-        stats[c0:c1] = torch.from_numpy(cmin[:, 0]).cuda()
-        stats[ncell_all] = float(cnt[0])
-        if world > 1:      # the path's exchange: all-reduce of the cell statistics and the non-implausible count
-            dist.all_reduce(stats, op=dist.ReduceOp.SUM)
+        _, _, cnt, cmin, ccnt = devp.implausibility(mean_d, var_d, zs, [1e-2, 1e-2], 3.0, maxno=1, cell_pts=cell_pts,
+                                                     first_index=start, want_imax=False, out=(None, keep_d))
+        cmin_all = np.full(ncell_all, np.inf)
+        ccnt_all = np.zeros(ncell_all + 1, dtype=np.int64)
+        c0 = start // cell_pts
+        if m:
+            cmin_all[c0:c0 + cmin.shape[0]] = cmin[:, 0]
+            ccnt_all[c0:c0 + ccnt.shape[0]] = ccnt[:, 0].astype(np.int64)
+        ccnt_all[ncell_all] = int(cnt[0])
+        if world > 1:      # the path's exchange: all-reduce(min) of the cell minima, all-reduce(sum) of the counts
+            tmin = torch.from_numpy(cmin_all).cuda()
+            tcnt = torch.from_numpy(ccnt_all).cuda()
+            dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
+            dist.all_reduce(tcnt, op=dist.ReduceOp.SUM)
+            cmin_all, ccnt_all = tmin.cpu().numpy(), tcnt.cpu().numpy()
         torch.cuda.synchronize()
         hm_s = time.perf_counter() - t0
         th = torch.tensor([hm_s], dtype=torch.float64, device="cuda")
@@ -367,90 +646,140 @@ def run_b200(args):
         devp.predict_grid(levels, lo, hi, start, me, out=(mean_h, var_h))
         pe = time.perf_counter() - t0
         peak, peak_src = fp64_peak()
+        hbm, hbm_src = hbm_peak()
         fpp = flops_pred(N_PRED, D_PRED, D_PRED + 1)
         gms, gcnt = pprof["gemm_dmma_128"]
-        nchunks = gcnt
         ptraffic = {}
-        tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
-        if os.path.exists(tp):
-            with open(tp) as f:
-                ptraffic = json.load(f)
+        for tp in ("r02_traffic.json", "r01_traffic.json"):
+            tp = os.path.join(ROOT, "profiles", tp)
+            if os.path.exists(tp):
+                with open(tp) as f:
+                    ptraffic = json.load(f)
+                break
+        cov_ms, cov_cnt = pprof["cov_build"]
         extra = {"posterior_preds_per_s": preds,
                  "posterior_workload": "config4: n=2000 d=8 q=9, %.0e-point tensor grid (10 levels/dim) generated on device from the flat "
-                                       "index, sharded over %d GPU(s) by index range, mean + diagonal variance written to HBM "
-                                       "(%.2f GB per GPU)" % (total, world, 16.0 * m / 1e9),
-                 "posterior_ms": float(pms.item()),
+                                       "index, cut into %d equal tile-aligned index ranges (one per GPU), mean + diagonal variance written "
+                                       "to HBM (%.2f GB per GPU)" % (total, world, 16.0 * m / 1e9),
+                 "posterior_ms": float(pms.item()), "posterior_gpu_launches": int(pred_launches),
                  "posterior_e2e_preds_per_s": me * world / pe, "posterior_d2h_bytes_per_pred": 16,
                  "posterior_roofline": {"bound": "tensor", "achieved": preds / world * fpp * 1e-12, "peak": peak,
                                         "unit": "TFLOP/s", "frac": preds / world * fpp * 1e-12 / peak,
                                         "kernel": "gemm_dmma_ws_kernel<NN, EPI_SUMSQ> (Z = L^-1 C with fused column norms)",
                                         "kernel_achieved": (float(mprof) * float(N_PRED) ** 2 * 1e-12) / (gms * 1e-3) if gms else None,
-                                        "kernel_launches": nchunks,
+                                        "kernel_launches": gcnt,
                                         "traffic": ptraffic.get("trmm_dram_bytes_per_launch"),
-                                        "algorithmic_bytes_per_launch": ptraffic.get("trmm_algorithmic_bytes_per_launch"),
+                                        "algorithmic_bytes_per_point": 16,
                                         "by_kernel_ms": {k: v[0] for k, v in pprof.items()},
+                                        "cross_covariance": {"ms": cov_ms, "launches": cov_cnt,
+                                                             "tflops_alu": mprof * float(N_PRED) * (3 * D_PRED + 1) / (cov_ms * 1e-3) * 1e-12 if cov_ms else None,
+                                                             "note": "FP64 ALU + exp work (n (3d + exp) flops per point), not tensor-pipe work"},
                                         "note": "achieved = F_pred (n^2 + 2n(d+q+3)) x preds/s per GPU; kernel_achieved = n^2 flops per "
                                                 "point / CUDA-event time of the TRMM launches in a separate serial-launch pass over "
                                                 "%d points" % mprof},
                  "history_match": {"points_per_s": float(total) / float(th.item()),
                                    "workload": "second emulator prediction + implausibility over 2 emulators (cm=3, maxno=1): keep mask, "
-                                               "count and per-cell min over the 10x10 (dim0,dim1) cells; all-reduce of cell statistics",
-                                   "non_implausible": int(stats[ncell_all].item()), "seconds": float(th.item())}}
+                                               "count and per-cell min over the 10x10 (dim0,dim1) cells; all-reduce(min / sum) of cell statistics",
+                                   "non_implausible": int(ccnt_all[ncell_all]), "cells_sum_check": int(ccnt_all[:ncell_all].sum()),
+                                   "min_cell_implausibility": float(cmin_all.min()), "seconds": float(th.item())}}
         for dv in devs:
             dv.close()
+        del mean_d, var_d
+        torch.cuda.empty_cache()
     except Exception as ex:      # the headline metric must still print
         import traceback
         extra = {"posterior_error": repr(ex), "trace": traceback.format_exc()[-600:]}
 
+    dev.close()
+    torch.cuda.empty_cache()
+    if not args.no_extra:
+        try:
+            extra.update(extra_configs(args, rank, world, local))
+        except BaseException as ex:
+            import traceback
+            extra["extra_configs_error"] = repr(ex) + " | " + traceback.format_exc()[-600:]
+
     if rank == 0:
         peak, peak_src = fp64_peak()
+        hbm, hbm_src = hbm_peak()
         F = flops_llh(n, d, q, p)
         gemm_ms, gemm_cnt = prof["gemm_dmma_128"]
         lau_ms, lau_cnt = prof["lauum"]
-        # dominant kernel: the LAUUM launch (A^-1 = L^-T L^-1, gemm_dmma_ws_kernel<TN>): algorithmic n^3/3 flops per item
+        # dominant kernel: the LAUUM launch (A^-1 = L^-T L^-1, with the gradient reduction in its epilogue): algorithmic n^3/3 flops per item
         lau_flops = B * float(n) ** 3 / 3.0
         kern_ach = lau_flops * lau_cnt / (lau_ms * 1e-3) * 1e-12 if lau_ms else None
         fam_flops = B * float(n) ** 3                       # potrf + trtri + lauum, all DMMA launches of a step
         fam_ms = gemm_ms + lau_ms
         fam_ach = fam_flops * Kp_ / (fam_ms * 1e-3) * 1e-12 if fam_ms else None
         traffic = None
-        tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
-        if os.path.exists(tp):
-            with open(tp) as f:
-                traffic = json.load(f).get("lauum_dram_bytes_per_launch")
+        for tp in ("r02_traffic.json", "r01_traffic.json"):
+            tp = os.path.join(ROOT, "profiles", tp)
+            if os.path.exists(tp):
+                with open(tp) as f:
+                    traffic = json.load(f).get("lauum_dram_bytes_per_launch")
+                break
+        step_ach = B * F / (ms_max / K * 1e-3) * 1e-12
+        # streaming kernels (north_star: achieved HBM GB/s for the covariance build; FP64-ALU share beside it)
+        npad = (n + 127) // 128 * 128
+        streaming = {}
+        cov_ms, cov_cnt = prof["cov_build"]
+        if cov_ms:
+            byt = B * Kp_ * 8.0 * (npad * (npad + 64) / 2.0)             # lower 64x64 tiles written once
+            flo = B * Kp_ * (n * n / 2.0) * (3 * d + 1)
+            streaming["cov_build"] = {"ms_per_step": cov_ms / Kp_, "hbm_GBps": byt / (cov_ms * 1e-3) * 1e-9, "frac_of_hbm": byt / (cov_ms * 1e-3) * 1e-9 / hbm,
+                                      "fp64_alu_TFLOPs": flo / (cov_ms * 1e-3) * 1e-12, "frac_of_fp64": flo / (cov_ms * 1e-3) * 1e-12 / peak,
+                                      "algorithmic": "8 B x n^2/2 written, (n^2/2)(3d + exp) flops per item"}
+        gr_ms, gr_cnt = prof["grad_reduce"]
+        if gr_ms:
+            byt = B * Kp_ * 8.0 * (n * n / 2.0)
+            flo = B * Kp_ * (n * n / 2.0) * (5 * d + 2 * q + 1)
+            streaming["grad_reduce"] = {"ms_per_step": gr_ms / Kp_, "hbm_GBps": byt / (gr_ms * 1e-3) * 1e-9, "frac_of_hbm": byt / (gr_ms * 1e-3) * 1e-9 / hbm,
+                                        "fp64_alu_TFLOPs": flo / (gr_ms * 1e-3) * 1e-12, "frac_of_fp64": flo / (gr_ms * 1e-3) * 1e-12 / peak,
+                                        "algorithmic": "8 B x n^2/2 read, (n^2/2)(5d + 2q + exp) flops per item"}
         line = {
             "metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "config3: n=4096 d=16 q=17 p=17, gp4ml llh+grad, fixed nugget 1e-4, %d guesses/GPU per step "
-                                   "(256 over 8 GPUs), theta perturbed each step" % B,
-                       "l2": "working set 12.9 GB per step >> 126 MB L2 (inputs larger than L2, no flush needed)",
-                       "parallelism": "multistart guesses block-partitioned over ranks; one NCCL all_gather of (llh,theta,status) per step",
-                       "streams": args.streams},
+            "dtype": "f64", "data": "synthetic", "impl": "b200",
+            "config": bench_config(args.streams),
             "gpu_launches": int(launches),
             "clocks": {"sm_mhz": clk["sm_mhz"], "sm_max_mhz": clk["sm_max_mhz"], "reasons": clk["reasons"], "samples": clk["samples"]},
             "e2e": {"value": e2e_val, "unit": "evals/s", "h2d_bytes_per_step": int(B * p * 8),
                     "d2h_bytes_per_step": int(B * (p + 2) * 8 + B * 4), "steps": Ke},
-            "roofline": {"bound": "tensor", "achieved": kern_ach, "peak": peak, "unit": "TFLOP/s",
-                         "frac": (kern_ach / peak) if kern_ach else None, "traffic": traffic,
-                         "kernel": "gemm_dmma_ws_kernel<TN> LAUUM launch (A^-1 = L^-T L^-1, %d items, lower 128x128 tiles)" % B,
+            "roofline": {"bound": "tensor", "achieved": step_ach, "peak": peak, "unit": "TFLOP/s", "frac": step_ach / peak,
+                         "what": "the whole llh+grad step: 32 x F_llh (n^3 + n^2(3d+p+2q+4)) algorithmic flops / ms_per_step of the timed region",
+                         "traffic": traffic,
                          "peak_source": peak_src + "; MEASURED_PEAKS.json holds no FP64 figure",
-                         "algorithmic_flops_per_launch": lau_flops, "algorithmic_bytes_per_launch": B * 8.0 * n * n,
-                         "kernel_ms_per_launch": lau_ms / lau_cnt if lau_cnt else None,
+                         "dominant_kernel": {"kernel": "lauum_grad_kernel / gemm_dmma_ws_kernel<TN> LAUUM launch (A^-1 = L^-T L^-1, %d items, lower 128x128 tiles)" % B,
+                                             "achieved": kern_ach, "frac": (kern_ach / peak) if kern_ach else None,
+                                             "algorithmic_flops_per_launch": lau_flops, "algorithmic_bytes_per_launch": B * 8.0 * n * n,
+                                             "ms_per_launch": lau_ms / lau_cnt if lau_cnt else None},
                          "kernel_timing": "CUDA-event pair around every launch, measured live in this run in a separate pass of %d steps "
                                           "with the sub-batch streams off (serial launches, %.2f ms/step); the timed region runs %d "
                                           "concurrent sub-batch streams" % (Kp_, serial_ms, args.streams),
                          "dmma_family": {"what": "all 128x128-tile DMMA launches of a step (SYRK/TRMM updates + LAUUM), algorithmic n^3 flops/item",
                                          "achieved": fam_ach, "frac": fam_ach / peak if fam_ach else None, "ms_per_step": fam_ms / Kp_,
                                          "launches_per_step": (gemm_cnt + lau_cnt) / Kp_},
-                         "step_achieved": B * F / (ms_max / K * 1e-3) * 1e-12, "step_frac": B * F / (ms_max / K * 1e-3) * 1e-12 / peak,
+                         "step_achieved": step_ach, "step_frac": step_ach / peak,
+                         "streaming_kernels": streaming, "hbm_peak_GBps": hbm, "hbm_peak_source": hbm_src,
                          "by_kernel_ms_per_step": {k: v[0] / Kp_ for k, v in prof.items()}},
             "extra": extra,
         }
         if world == 1 and not args.no_cpu:
-            line["cpu_baseline"] = cpu_llh_sample(args.cpu_budget)
+            with all_cores():
+                info = _blas_info()
+                thetas = draw_thetas(B, d, y)
+                cpu_llh_eval(X[:1024], y[:1024], H[:1024], thetas[0])          # BLAS pool warm-up
+                t1 = cpu_llh_eval(X, y, H, thetas[0])
+                cpu = {"value": 1.0 / t1, "unit": "evals/s", "cores": int(info["threads"]), "kind": "port",
+                       "sample": "1 full-size evaluation of loglikelihood_gp4ml (oracle port of _emulatoroptimise.py:412-493), n=4096 d=16, "
+                                 "%.1f s; nothing extrapolated (the --impl reference arm times one per step)" % t1}
+                cpu.update(info)
+                line["cpu_baseline"] = cpu
+                try:
+                    line["extra"]["cpu"] = cpu_other_legs()
+                except Exception as ex:
+                    line["extra"]["cpu"] = {"error": repr(ex)}
         print(json.dumps(line), file=RESULT_OUT, flush=True)
-    dev.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -473,8 +802,10 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--cpu-budget", type=float, default=25.0, help="seconds of CPU work for cpu_baseline")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
+    ap.add_argument("--no-extra", action="store_true", help="skip the config 2 / 3-as-optimisation / 5 legs")
+    ap.add_argument("--no-noisefit", action="store_true", help="skip the noise-fit leg of config 5")
+    ap.add_argument("--ref-budget", type=float, default=700.0, help="wall-clock budget (s) of the --impl reference run")
     ap.add_argument("--streams", type=int, default=8, help="concurrent sub-batch streams of gpe_llh_grad_batch")
     ap.add_argument("--grid-points", type=float, default=1e8, help="size of the prediction grid (config 4: 1e8)")
     args = ap.parse_args()

@@ -9,6 +9,7 @@ import math
 
 import numpy as np
 
+from . import _dist
 from . import _lib
 
 _PRED_FULL_LIMIT = 8192     # largest m for which Posterior materialises the full m x m covariance
@@ -17,6 +18,20 @@ _PRED_FULL_LIMIT = 8192     # largest m for which Posterior materialises the ful
 def _die(msg):
     print(msg)
     raise SystemExit(1)
+
+
+_CK_W = {}
+
+
+def _checksum(a):
+    """sum_k bits(a_k) * w_k mod 2^64 with fixed odd multipliers w_k (wrap-around uint64 arithmetic)."""
+    bits = np.ascontiguousarray(a, dtype=np.float64).reshape(-1).view(np.uint64)
+    w = _CK_W.get(bits.size)
+    if w is None:
+        w = (np.arange(bits.size, dtype=np.uint64) * np.uint64(2) + np.uint64(1)) * np.uint64(0x9E3779B97F4A7C15)
+        if len(_CK_W) < 64:
+            _CK_W[bits.size] = w
+    return int((bits * w).sum(dtype=np.uint64))
 
 
 class Emulator:
@@ -163,8 +178,10 @@ class Beliefs:
             "input_minmax " + str(E.all_data.input_minmax),
         ]
         try:
-            with open(name, "w") as fh:
-                fh.write("\n".join(lines) + "\n")
+            if _dist.is_writer():             # multi-rank: one writer, everyone waits for the file
+                with open(name, "w") as fh:
+                    fh.write("\n".join(lines) + "\n")
+            _dist.barrier()
         except OSError:
             _die("ERROR: Problem writing to file.")
 
@@ -355,6 +372,7 @@ class All_Data:
             return
         print("Shuffling", self.x_full.shape[0], "data points")
         z = np.column_stack([self.x_full, self.y_full])
+        _dist.sync_numpy_rng()                    # multi-rank: every rank shuffles with rank 0's generator state
         np.random.shuffle(z)                      # same RNG consumption as the reference (:490)
         ncol = self.x_full.shape[1]
         self.x_full[:, :] = z[:, :ncol]
@@ -454,11 +472,13 @@ class Data:
 
     # ---- device side ----------------------------------------------------------------------
     def _fingerprint(self):
+        """Content key of what the device holds (inputs, outputs, r, H): a position-weighted 64-bit checksum of
+        the raw bits of every array, so permuted rows, swapped entries or a changed sign are seen, not only
+        changed moments; costs one pass per array (it is taken before every device call)."""
         X = np.asarray(self.inputs, dtype=float)
         y = np.zeros(X.shape[0]) if self.outputs is None else np.asarray(self.outputs, dtype=float)
         r = np.asarray(self._r_made, dtype=float)
-        return (X.shape, float(X.sum()), float((X * X).sum()), float(y.sum()), float((y * y).sum()),
-                r.shape, float(r.sum()), float((r * r).sum()), self.H.shape, float(self.H.sum()))
+        return tuple((a.shape, _checksum(a)) for a in (X, y, r, np.asarray(self.H, dtype=float)))
 
     def device(self):
         """The handle holding this data set on the GPU (created and re-uploaded on demand)."""
@@ -494,16 +514,57 @@ class Posterior:
     ``diag_only=True`` only the diagonal is produced (``gpe_predict``, any m) in ``var_diag``.
     The ``predict`` flag is stored and, as in the reference (:595, :621), has no effect."""
 
-    def __init__(self, Dnew, Dold, par, beliefs, K, predict=True, diag_only=False):
+    def __init__(self, Dnew, Dold, par, beliefs, K, predict=True, diag_only=False, lazy=False):
         self.Dnew, self.Dold, self.par, self.beliefs, self.K = Dnew, Dold, par, beliefs, K
         self.predict = predict
         self.diag_only = diag_only
-        self.remake()
+        # lazy: g.setup builds a Posterior from the *initial* beliefs before any training; the reference gets
+        # through that with LU solves even when those hyper-parameters give a matrix that is not numerically
+        # positive definite (train() replaces them).  Here the factorisation is a Cholesky, so the setup-time
+        # object defers it to the first read of mean / var / var_diag (or the next remake()).
+        self._stale = True
+        self._mean = self._var = self._var_diag = None
+        if not lazy:
+            self.remake()
 
     def remake(self):
         self._covar = None
         self.make_mean()
         self.make_var()
+
+    def _fresh(self):
+        if self._stale:
+            self._predict()
+
+    @property
+    def mean(self):
+        self._fresh()
+        return self._mean
+
+    @mean.setter
+    def mean(self, value):
+        self._mean = value
+
+    @property
+    def var(self):
+        self._fresh()
+        if self._var is None and self._mean is not None and self._mean.size:
+            raise _lib.GpeError("the full %d x %d posterior covariance was not formed (more than %d points, or diag_only): "
+                                "use var_diag, or predict in smaller blocks" % (self._mean.size, self._mean.size, _PRED_FULL_LIMIT))
+        return self._var
+
+    @var.setter
+    def var(self, value):
+        self._var = value
+
+    @property
+    def var_diag(self):
+        self._fresh()
+        return self._var_diag
+
+    @var_diag.setter
+    def var_diag(self, value):
+        self._var_diag = value
 
     @property
     def covar(self):
@@ -515,6 +576,7 @@ class Posterior:
         self._covar = self.Dold.device().cross_cov(self.K.d, self.K.n, self.Dold.kind, self.Dnew.inputs)
 
     def _predict(self):
+        self._stale = False
         Dn = self.Dnew
         m = Dn.inputs.shape[0]
         if m == 0:
@@ -583,6 +645,8 @@ class Posterior:
         for name, arr in ((E.config.inputs + tag, unscaled), (E.config.outputs + tag, self.Dold.outputs)):
             print("Writing T-data to:", name)
             try:
-                np.savetxt(name, arr, delimiter=" ", fmt="%.8f")
+                if _dist.is_writer():
+                    np.savetxt(name, arr, delimiter=" ", fmt="%.8f")
+                _dist.barrier()
             except OSError:
                 _die("ERROR: Problem writing to file.")

@@ -134,6 +134,7 @@ class Optimize:
         # initial guesses: one row of uniforms per parameter from the global RNG (reference :206-211)
         guessgrid = np.zeros([params, numguesses])
         print("Calculating initial guesses from bounds")
+        _dist.sync_numpy_rng()                     # multi-rank: every rank draws rank 0's guesses
         for R in range(params):
             BL, BU = bounds[R][0], bounds[R][1]
             guessgrid[R, :] = BL + (BU - BL) * np.random.random_sample(numguesses)

@@ -52,7 +52,7 @@ def load():
         "gpe_predict": (i, [p, p, p, ll, p, p]),
         "gpe_predict_grid": (i, [p, p, p, p, ll, ll, p, p]),
         "gpe_predict_fullcov": (i, [p, p, p, i, p, p, p]),
-        "gpe_implausibility": (i, [p, p, p, i, ll, p, p, d, i, ll, p, p, p, p, p]),
+        "gpe_implausibility": (i, [p, p, p, i, ll, p, p, d, i, ll, ll, ll, p, p, p, p, p]),
         "gpe_solve": (i, [p, p, i, p]),
         "gpe_sens_contract": (i, [p, p, p, p, d, p, i, p, p]),
         "gpe_sens_main_effect": (i, [p, p, p, p, p, p, d, p, i, p, i, p]),
@@ -258,7 +258,11 @@ class Device:
         return mean, V
 
     # ------------------------------------------------------------------ K5
-    def implausibility(self, mean, var, z, var_extra, cm, maxno=1, ncell=0, want_imax=True, out=None):
+    def implausibility(self, mean, var, z, var_extra, cm, maxno=1, ncell=0, want_imax=True, out=None, cell_pts=0, first_index=0):
+        """Implausibility of m points from per-emulator mean/var [n_emul, m].  Cells: either ``ncell`` equal
+        contiguous cells of the m points, or (``cell_pts`` > 0) runs of cell_pts points of the global flat index
+        ``first_index + r`` -- a shard of a larger point set that may start and end inside a cell; cmin / ccnt then
+        cover the cells first_index // cell_pts ... (first_index + m - 1) // cell_pts."""
         host = isinstance(mean, np.ndarray)
         if host:
             mean, var = _f64(np.atleast_2d(mean)), _f64(np.atleast_2d(var))
@@ -269,11 +273,18 @@ class Device:
             keep = np.empty(m, dtype=np.uint8)
         else:
             Imax, keep = out
+        if cell_pts:
+            ncell = (first_index + m - 1) // cell_pts - first_index // cell_pts + 1 if m else 0
+        elif ncell:
+            if m % ncell:
+                raise GpeError("m must be a multiple of ncell")
+            cell_pts, first_index = m // ncell, 0
         count = np.zeros(maxno, dtype=np.uint64)
         cmin = np.empty((ncell, maxno)) if ncell else None
         ccnt = np.zeros((ncell, maxno), dtype=np.uint64) if ncell else None
         self._ck(self.L.gpe_implausibility(self.h, _ptr(mean), _ptr(var), n_emul, m, _ptr(z), _ptr(var_extra), float(cm),
-                                           int(maxno), int(ncell), _ptr(Imax), _ptr(keep), _ptr(count), _ptr(cmin), _ptr(ccnt)))
+                                           int(maxno), int(cell_pts), int(first_index), int(ncell), _ptr(Imax), _ptr(keep),
+                                           _ptr(count), _ptr(cmin), _ptr(ccnt)))
         return Imax, keep, count, cmin, ccnt
 
     # ------------------------------------------------------------------ K6
@@ -312,7 +323,6 @@ class Device:
         n = A.shape[0]
         Lf, st = np.empty_like(A), np.zeros(1, dtype=np.int32)
         self._ck(self.L.gpe_potrf(self.h, _ptr(A), n, 1, _ptr(Lf), None, None, _ptr(st)))
-        self.n = self.d = self.q = 0          # replaces the handle's training set
         if st[0] != 0:
             raise np.linalg.LinAlgError("Matrix is not positive definite")
         return Lf
@@ -335,7 +345,6 @@ class Device:
         b, n = A.shape[0], A.shape[1]
         Li, ld, st = np.empty_like(A), np.empty(b), np.zeros(b, dtype=np.int32)
         self._ck(self.L.gpe_dbg_potrf_inv(self.h, _ptr(A), n, b, _ptr(Li), _ptr(ld), _ptr(st)))
-        self.n = self.d = self.q = 0          # the debug entry replaces the training set
         return Li, ld, st
 
     def dbg_gemm(self, A, B, Cm, M, N, K, lda, ldb, ldc, sA=0, sB=0, sC=0, alpha=1.0, accumulate=0, kmode=0,

@@ -7,7 +7,12 @@
 #include <cstring>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 using namespace gpe;
+
+NvtxRange::NvtxRange(const char* name) { nvtxRangePushA(name); }
+NvtxRange::~NvtxRange() { nvtxRangePop(); }
 
 // ------------------------------------------------------------------------------------- utils
 int gpe_handle::fail(const char* what, cudaError_t e) {
@@ -76,6 +81,7 @@ void gpe_handle::free_batch_ws() {
     dev_free(logdet_part); dev_free(par); dev_free(out); dev_free(winv); dev_free(beta);
     dev_free(status); dev_free(gpart); dev_free(theta_d); dev_free(llh_d); dev_free(grad_d); dev_free(sig_d);
     Bcap = 0;
+    Bcap_final = false;
 }
 
 void gpe_handle::free_training() {
@@ -89,7 +95,9 @@ void gpe_handle::free_training() {
 // skinny panels.  180 GB of HBM3e holds the whole 256-guess batch of config 3 (103 GB), but the
 // default cap keeps sub-batches of <= 64 so the factorisation working set stays L2-friendly.
 int gpe_ensure_batch_ws(gpe_handle* h, int B) {
-    if (B <= h->Bcap) return 0;
+    // A workspace that already has the largest obtainable size is kept: batches beyond it run as sub-batches
+    // (re-allocating here on every call would also destroy the CUDA graphs before they are ever replayed).
+    if (B <= h->Bcap || (h->Bcap > 0 && h->Bcap_final)) return 0;
     size_t per_item = 3ull * h->npad * h->npad * sizeof(double) + 3ull * h->npad * NR * sizeof(double);
     size_t free_b = 0, total_b = 0;
     h->free_batch_ws();
@@ -122,6 +130,7 @@ int gpe_ensure_batch_ws(gpe_handle* h, int B) {
     CK(dev_alloc(&h->grad_d, (size_t)want * (h->d + 2)));
     CK(dev_alloc(&h->sig_d, (size_t)want));
     h->Bcap = want;
+    h->Bcap_final = want >= cap_env || want >= fit;
     return 0;
 }
 
@@ -177,17 +186,17 @@ int gpe_handle::ensure_side(int g) {
     return 0;
 }
 
-static int potrf_inv_rec(gpe_handle* h, const SubBatch& sb, int off, int m, int want_L, int depth = 0) {
-    const int ld = h->npad, B = sb.B;
-    const long long sM = (long long)h->npad * h->npad;
-    double* Ab = h->A + (size_t)sb.b0 * sM;
-    double* Sb = h->S + (size_t)sb.b0 * sM;
-    double* Lb = h->Li + (size_t)sb.b0 * sM;
+static int potrf_inv_rec(gpe_handle* h, const FactorWs& ws, const SubBatch& sb, int off, int m, int want_L, int depth = 0) {
+    const int ld = ws.npad, B = sb.B;
+    const long long sM = (long long)ws.npad * ws.npad;
+    double* Ab = ws.A + (size_t)sb.b0 * sM;
+    double* Sb = ws.S + (size_t)sb.b0 * sM;
+    double* Lb = ws.Li + (size_t)sb.b0 * sM;
     if (m == NB) {
         {
             cudaStream_t st = sb.stream(true);
             ProfScope ps(h, gpe_handle::CAT_LEAF, st);
-            launch_leaf(Ab, Lb, ld, sM, sM, off, h->logdet_part + (size_t)sb.b0 * h->nleaf, h->nleaf, h->status + sb.b0, B, st,
+            launch_leaf(Ab, Lb, ld, sM, sM, off, ws.logdet_part + (size_t)sb.b0 * ws.nleaf, ws.nleaf, ws.status + sb.b0, B, st,
                         want_L ? Sb : nullptr);
         }
         h->launches++;
@@ -196,7 +205,7 @@ static int potrf_inv_rec(gpe_handle* h, const SubBatch& sb, int off, int m, int 
     const int nb = m / NB;
     const int m1 = ((nb + 1) / 2) * NB, m2 = m - m1;
     int rc;
-    if ((rc = potrf_inv_rec(h, sb, off, m1, want_L, depth + 1))) return rc;
+    if ((rc = potrf_inv_rec(h, ws, sb, off, m1, want_L, depth + 1))) return rc;
     double* A21 = Ab + (size_t)(off + m1) * ld + off;
     double* A22 = Ab + (size_t)(off + m1) * ld + off + m1;
     double* S21 = Sb + (size_t)(off + m1) * ld + off;
@@ -218,7 +227,7 @@ static int potrf_inv_rec(gpe_handle* h, const SubBatch& sb, int off, int m, int 
     }
     // A22 -= L21 * L21^T             (SYRK, lower tiles)
     if ((rc = run_gemm(h, sb.stream(!gemm_is_big(m2, m2, 1, B)), S21, S21, A22, ld, ld, ld, sM, sM, sM, m2, m2, m1, -1.0, 1, KM_FULL, 1, B, 0))) return rc;
-    if ((rc = potrf_inv_rec(h, sb, off + m1, m2, want_L, depth + 1))) return rc;
+    if ((rc = potrf_inv_rec(h, ws, sb, off + m1, m2, want_L, depth + 1))) return rc;
     if (fork) {
         cudaStreamWaitEvent(sb.current(), sb.ej[depth], 0);
     } else {
@@ -228,7 +237,21 @@ static int potrf_inv_rec(gpe_handle* h, const SubBatch& sb, int off, int m, int 
     if ((rc = run_gemm(h, sb.stream(!gemm_is_big(m2, m1, 0, B)), Li22, A21, Li21, ld, ld, ld, sM, sM, sM, m2, m1, m2, -1.0, 0, KM_LE_I, 0, B, 1))) return rc;
     return 0;
 }
-int gpe_potrf_inv(gpe_handle* h, const SubBatch& sb, int want_L) { return potrf_inv_rec(h, sb, 0, h->npad, want_L); }
+int gpe_potrf_inv(gpe_handle* h, const FactorWs& ws, const SubBatch& sb, int want_L) { return potrf_inv_rec(h, ws, sb, 0, ws.npad, want_L); }
+
+static FactorWs handle_ws(gpe_handle* h) { return FactorWs{h->A, h->S, h->Li, h->npad, h->nleaf, h->logdet_part, h->status}; }
+
+// Fused LAUUM + gradient (128x128 tiles) when the launch fills the machine; GPE_FUSED_GRAD=0 keeps the two-kernel
+// route for A/B measurements.  The choice depends on the sub-batch size only through "does it fill the machine", and
+// both routes sum the same terms, so results agree to rounding.
+static bool llh_grad_fused(gpe_handle* h, int B) {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("GPE_FUSED_GRAD");
+        on = (e && e[0] == '0') ? 0 : 1;
+    }
+    return on && lauum_grad_supported(h->d) && gemm_is_big(h->npad, h->npad, 1, B);
+}
 
 // Everything after the covariance build for the items of `sb`, already described by h->par / h->winv.
 // with_grad = 0 stops after the GLS/likelihood scalars (fit_state path).
@@ -242,7 +265,7 @@ int gpe_factor_and_reduce(gpe_handle* h, const SubBatch& sb, int mode, int with_
     double *Wy = h->Wy + (size_t)b0 * sP, *Z = h->Z + (size_t)b0 * sP, *U = h->U + (size_t)b0 * sP;
     double* GP = h->GP + (size_t)b0 * nslab * NR * NR;
     int rc;
-    if ((rc = potrf_inv_rec(h, sb, 0, np, 0))) return rc;
+    if ((rc = potrf_inv_rec(h, handle_ws(h), sb, 0, np, 0))) return rc;
     // Wy = Linv [H | y]
     st = sb.stream(true);
     if ((rc = run_gemm(h, st, Lb, h->HY, Wy, ld, NR, NR, sM, 0, sP, np, NR, np, 1.0, 0, KM_LE_I, 0, B, 1))) return rc;
@@ -256,8 +279,19 @@ int gpe_factor_and_reduce(gpe_handle* h, const SubBatch& sb, int mode, int with_
     // U = Linv^T Z = [A^-1 H K^-T | sqrt(f) A^-1 (y - H beta)]
     if ((rc = run_gemm(h, st, Lb, Z, U, ld, NR, NR, sM, sP, sP, np, NR, np, 1.0, 0, KM_GE_I, 0, B, 2))) return rc;
     if (!with_grad) return 0;
-    // LAUUM: A^-1 = Linv^T Linv (lower tiles) into the dead A buffer
     st = sb.stream(false);
+    if (h->grad_fused) {
+        // LAUUM with the gradient reduction in its epilogue: W = A^-1 - U U^T never leaves the CTA that computed it
+        // (gpe_lauum_grad.cu).  Wy and Z are dead by now and hold U^T and -U^T.
+        ProfScope ps(h, gpe_handle::CAT_LAUUM, st);
+        cudaError_t e = launch_lauum_grad(Lb, sM, np, h->n, h->d, h->q + 1, U, Wy, Z, h->X, h->r, h->winv + (size_t)b0 * h->d,
+                                          h->gpart + (size_t)b0 * lauum_grad_ntiles(np) * grad_nvals(h->d), B, st);
+        h->launches += 2;
+        if (e != cudaSuccess) return h->fail("launch_lauum_grad", e);
+        return 0;
+    }
+    // small launches (64x64 tiles) and very wide inputs: A^-1 = Linv^T Linv (lower tiles) into the dead A buffer, then
+    // the stand-alone reduction kernel
     if ((rc = run_gemm(h, st, Lb, Lb, Ab, ld, ld, ld, sM, sM, sM, np, np, np, 1.0, 0, KM_GE_I, 1, B, 2, EPI_STORE,
                        gpe_handle::CAT_LAUUM))) return rc;
     {
@@ -401,26 +435,40 @@ int gpe_set_training(gpe_handle* h, const double* X, const double* y, const doub
                      int n, int d, int q) {
     if (!h || !X || !y || !H || n < 1 || d < 1 || q < 1) return h ? h->fail_msg("bad argument") : -2;
     if (q + 1 > NR) return h->fail_msg("q + 1 exceeds the skinny panel width (32)");
+    // the covariance / gradient kernels keep two k-major 64-row tiles of the scaled inputs (plus the skinny U tiles)
+    // in shared memory: d is bounded by the 227 KB a CTA can opt in to
+    if ((size_t)(d + NR) * (64 + 66) * sizeof(double) + 8 * (size_t)(d + 3) * sizeof(double) > 227 * 1024)
+        return h->fail_msg("d is too large for the shared-memory tiles of the covariance kernels");
+    NvtxRange nvtx("gpe_set_training");
     CK(cudaSetDevice(h->device));
     CK(cudaStreamSynchronize(h->st));
     h->free_training();
+    auto upload = [&]() -> int {
+        CK(dev_alloc(&h->X, (size_t)n * d));
+        CK(dev_alloc(&h->y, (size_t)n));
+        CK(dev_alloc(&h->H, (size_t)n * q));
+        CK(cudaMemcpyAsync(h->X, X, sizeof(double) * n * d, cudaMemcpyDefault, h->st));
+        CK(cudaMemcpyAsync(h->y, y, sizeof(double) * n, cudaMemcpyDefault, h->st));
+        CK(cudaMemcpyAsync(h->H, H, sizeof(double) * n * q, cudaMemcpyDefault, h->st));
+        if (r) {
+            CK(dev_alloc(&h->r, (size_t)n));
+            CK(cudaMemcpyAsync(h->r, r, sizeof(double) * n, cudaMemcpyDefault, h->st));
+        }
+        const int npad = ((n + NB - 1) / NB) * NB;
+        CK(dev_alloc(&h->HY, (size_t)npad * NR));
+        launch_build_hy(h->H, h->y, n, q, npad, h->HY, h->st);
+        h->launches++;
+        CK(cudaStreamSynchronize(h->st));
+        CK(cudaGetLastError());
+        return 0;
+    };
+    if (int rc = upload()) {        // a half-built training set must not look usable
+        h->free_training();
+        return rc;
+    }
     h->n = n; h->d = d; h->q = q;
     h->npad = ((n + NB - 1) / NB) * NB;
     h->nleaf = h->npad / NB;
-    CK(dev_alloc(&h->X, (size_t)n * d));
-    CK(dev_alloc(&h->y, (size_t)n));
-    CK(dev_alloc(&h->H, (size_t)n * q));
-    CK(cudaMemcpyAsync(h->X, X, sizeof(double) * n * d, cudaMemcpyDefault, h->st));
-    CK(cudaMemcpyAsync(h->y, y, sizeof(double) * n, cudaMemcpyDefault, h->st));
-    CK(cudaMemcpyAsync(h->H, H, sizeof(double) * n * q, cudaMemcpyDefault, h->st));
-    if (r) {
-        CK(dev_alloc(&h->r, (size_t)n));
-        CK(cudaMemcpyAsync(h->r, r, sizeof(double) * n, cudaMemcpyDefault, h->st));
-    }
-    CK(dev_alloc(&h->HY, (size_t)h->npad * NR));
-    launch_build_hy(h->H, h->y, n, q, h->npad, h->HY, h->st);
-    h->launches++;
-    CK(cudaStreamSynchronize(h->st));
     h->has_basis = false;
     return 0;
 }
@@ -439,13 +487,14 @@ int gpe_set_basis(gpe_handle* h, const int* idx, const int* pw, int q) {
 
 int gpe_cov_build(gpe_handle* h, const double* delta, double nugget, int kind, int predict, double s2, double* A_out) {
     if (!h || !h->n || !delta || !A_out) return h ? h->fail_msg("bad argument / no training set") : -2;
+    NvtxRange nvtx("gpe_cov_build");
     CK(cudaSetDevice(h->device));
     int rc;
     if ((rc = gpe_ensure_batch_ws(h, 1))) return rc;
     std::vector<double> dl(h->d);
     CK(cudaMemcpy(dl.data(), delta, sizeof(double) * h->d, cudaMemcpyDefault));
     if ((rc = gpe_upload_single_par(h, dl.data(), nugget, kind, predict, s2))) return rc;
-    launch_cov_build(h->X, h->r, h->n, h->d, h->npad, h->par, h->winv, h->A, 0, 1, 1, h->st);
+    CK(launch_cov_build(h->X, h->r, h->n, h->d, h->npad, h->par, h->winv, h->A, 0, 1, 1, h->st));
     h->launches++;
     size_t nn = (size_t)h->n * h->n;
     double* dst = A_out;
@@ -455,12 +504,14 @@ int gpe_cov_build(gpe_handle* h, const double* delta, double nugget, int kind, i
     h->launches++;
     if (!dev) CK(cudaMemcpyAsync(A_out, dst, nn * sizeof(double), cudaMemcpyDeviceToHost, h->st));
     CK(cudaStreamSynchronize(h->st));
+    CK(cudaGetLastError());
     return 0;
 }
 
 int gpe_cov_grad(gpe_handle* h, const double* delta, double nugget, int kind, int which, double s2, double* G_out) {
     if (!h || !h->n || !delta || !G_out) return h ? h->fail_msg("bad argument / no training set") : -2;
     if (which < -1 || which >= h->d) return h->fail_msg("which must be a delta index or -1 (nugget)");
+    NvtxRange nvtx("gpe_cov_grad");
     CK(cudaSetDevice(h->device));
     int rc;
     if ((rc = gpe_ensure_batch_ws(h, 1))) return rc;
@@ -485,7 +536,7 @@ int gpe_cov_grad(gpe_handle* h, const double* delta, double nugget, int kind, in
         CK(cudaMemcpy(G_out, host.data(), nn * sizeof(double), cudaMemcpyDefault));
         return 0;
     }
-    launch_cov_build(h->X, h->r, h->n, h->d, h->npad, h->par, h->winv, h->A, 0, 1, 1, h->st, which >= 0 ? 1 : 2, which);
+    CK(launch_cov_build(h->X, h->r, h->n, h->d, h->npad, h->par, h->winv, h->A, 0, 1, 1, h->st, which >= 0 ? 1 : 2, which));
     launch_unpad_sym(h->A, h->npad, h->n, dst, 0, h->st);
     h->launches += 2;
     if (!dev) CK(cudaMemcpyAsync(G_out, dst, nn * sizeof(double), cudaMemcpyDeviceToHost, h->st));
@@ -517,6 +568,9 @@ static int enqueue_llh_chunk(gpe_handle* h, int Bs, int p, int mode, double fixe
         group_npad_graph = e ? atoi(e) : 512;
     }
     const int ns = h->npad < (capturing ? group_npad_graph : group_npad) ? 1 : std::max(1, std::min(h->nsub, Bs / 2));
+    // one decision for the whole chunk (every group writes the same partial layout): the smallest group must still
+    // fill the machine with 128x128 tiles
+    h->grad_fused = llh_grad_fused(h, Bs / ns);
     if (ns > 1) CK(cudaEventRecord(h->ev_fork, h->st));
     for (int g = 0; g < ns; g++) {
         SubBatch sb;
@@ -531,8 +585,8 @@ static int enqueue_llh_chunk(gpe_handle* h, int Bs, int p, int mode, double fixe
         if (ns > 1) CK(cudaStreamWaitEvent(sb.st, h->ev_fork, 0));
         {
             ProfScope ps(h, gpe_handle::CAT_COV, sb.st);
-            launch_cov_build(h->X, h->r, h->n, h->d, h->npad, h->par + sb.b0, h->winv + (size_t)sb.b0 * h->d,
-                             h->A + (size_t)sb.b0 * sM, sM, sb.B, 0, sb.st);
+            CK(launch_cov_build(h->X, h->r, h->n, h->d, h->npad, h->par + sb.b0, h->winv + (size_t)sb.b0 * h->d,
+                                h->A + (size_t)sb.b0 * sM, sM, sb.B, 0, sb.st));
         }
         h->launches++;
         if ((rc = gpe_factor_and_reduce(h, sb, mode, 1, nullptr, nullptr))) return rc;
@@ -543,7 +597,8 @@ static int enqueue_llh_chunk(gpe_handle* h, int Bs, int p, int mode, double fixe
     }
     {
         ProfScope ps(h, gpe_handle::CAT_OTHER);
-        launch_grad_finalize(h->gpart, h->n, h->d, h->npad, p, mode, h->par, h->out, h->status, h->llh_d, h->grad_d,
+        launch_grad_finalize(h->gpart, h->grad_fused ? lauum_grad_ntiles(h->npad) : grad_ntiles(h->npad), h->n, h->d, h->npad, p, mode,
+                             h->par, h->out, h->status, h->llh_d, h->grad_d,
                              h->sig_d, Bs, h->st);
     }
     h->launches++;
@@ -556,6 +611,7 @@ int gpe_llh_grad_batch(gpe_handle* h, const double* theta, int B, int p, int mod
     if (!h || !h->n || !theta || B < 1 || !llh || !grad) return h ? h->fail_msg("bad argument / no training set") : -2;
     int p_expect = h->d + ((mode & GPE_MODE_NUGGET_FREE) ? 1 : 0) + ((mode & GPE_MODE_MUCM) ? 0 : 1);
     if (p != p_expect) return h->fail_msg("p does not match d and mode");
+    NvtxRange nvtx("gpe_llh_grad_batch");
     CK(cudaSetDevice(h->device));
     int rc;
     if ((rc = gpe_ensure_batch_ws(h, B))) return rc;
@@ -617,60 +673,72 @@ int gpe_dbg_gemm(gpe_handle* h, const double* A, const double* B, double* C, int
 
 int gpe_potrf(gpe_handle* h, const double* A, int n, int batch, double* L_out, double* Linv_out, double* logdet, int* status) {
     if (!h || !A || n < 1 || batch < 1) return h ? h->fail_msg("bad argument") : -2;
+    NvtxRange nvtx("gpe_potrf");
     CK(cudaSetDevice(h->device));
-    // temporary "training set" of the right size so the workspace exists
-    int npad = ((n + NB - 1) / NB) * NB;
-    if (h->npad != npad || h->n != n) {
-        std::vector<double> z((size_t)n * 2, 0.0);
-        int rc = gpe_set_training(h, z.data(), z.data(), z.data(), nullptr, n, 1, 1);
-        if (rc) return rc;
-    }
+    // Self-contained: the padded matrices, the scratch and the inverse factor live in stream-ordered temporaries
+    // (cached by the device's memory pool between calls), so the handle's training set, batch workspace and fit
+    // state are left alone.  Host inputs/outputs are staged once; padding and un-padding run on the device.
+    const int npad = ((n + NB - 1) / NB) * NB, nleaf = npad / NB;
+    const size_t nn = (size_t)npad * npad, per = (size_t)n * n;
+    size_t free_b = 0, total_b = 0;
+    CK(cudaMemGetInfo(&free_b, &total_b));
+    const size_t per_item = (3 * nn + 2 * per) * sizeof(double);
+    const long long fit = (long long)((double)free_b * 0.6 / (double)per_item);
+    if (fit < 1) return h->fail_msg("not enough device memory for one n x n factorisation");
+    const int bcap = (int)std::min<long long>({(long long)batch, 64ll, fit});
+    const bool a_dev = gpe_is_device_ptr(A), l_dev = L_out && gpe_is_device_ptr(L_out), i_dev = Linv_out && gpe_is_device_ptr(Linv_out);
+    double *Ap = nullptr, *Sp = nullptr, *Lp = nullptr, *ldp = nullptr, *src = nullptr, *dst = nullptr;
+    int* stp = nullptr;
+    TmpDev t_A(h), t_S(h), t_L(h), t_ld(h), t_st(h), t_src(h), t_dst(h);
+    CK(t_A.get(&Ap, bcap * nn));
+    CK(t_S.get(&Sp, bcap * nn));
+    CK(t_L.get(&Lp, bcap * nn));
+    CK(t_ld.get(&ldp, (size_t)bcap * nleaf));
+    CK(t_st.get(&stp, (size_t)bcap));
+    if (!a_dev) CK(t_src.get(&src, bcap * per));
+    if ((L_out && !l_dev) || (Linv_out && !i_dev)) CK(t_dst.get(&dst, bcap * per));
+    FactorWs ws{Ap, Sp, Lp, npad, nleaf, ldp, stp};
+    std::vector<double> ldh((size_t)bcap * nleaf), ldv(bcap);
     int rc;
-    if ((rc = gpe_ensure_batch_ws(h, batch))) return rc;
-    if (batch > h->Bcap) {      // more matrices than the resident workspace holds: sub-batches, one after the other
-        const size_t per = (size_t)n * n;
-        for (int b0 = 0; b0 < batch; b0 += h->Bcap) {
-            const int bs = std::min(h->Bcap, batch - b0);
-            if ((rc = gpe_potrf(h, A + b0 * per, n, bs, L_out ? L_out + b0 * per : nullptr, Linv_out ? Linv_out + b0 * per : nullptr,
-                                logdet ? logdet + b0 : nullptr, status ? status + b0 : nullptr)))
-                return rc;
+    for (int b0 = 0; b0 < batch; b0 += bcap) {
+        const int bs = std::min(bcap, batch - b0);
+        const double* Asrc = A + b0 * per;
+        if (!a_dev) {
+            CK(cudaMemcpyAsync(src, Asrc, sizeof(double) * bs * per, cudaMemcpyHostToDevice, h->st));
+            Asrc = src;
         }
-        return 0;
+        launch_pad_sym(Asrc, n, npad, Ap, bs, h->st);
+        CK(cudaMemsetAsync(Lp, 0, sizeof(double) * bs * nn, h->st));
+        CK(cudaMemsetAsync(stp, 0, sizeof(int) * bs, h->st));
+        h->launches++;
+        SubBatch sb{0, bs, h->st};
+        if ((rc = potrf_inv_rec(h, ws, sb, 0, npad, L_out != nullptr))) return rc;
+        CK(cudaGetLastError());
+        auto emit = [&](const double* padded, double* user, bool user_dev) -> int {
+            double* to = user_dev ? user + b0 * per : dst;
+            launch_unpad_lower(padded, npad, n, to, bs, h->st);
+            h->launches++;
+            if (!user_dev) {
+                CK(cudaMemcpyAsync(user + b0 * per, dst, sizeof(double) * bs * per, cudaMemcpyDeviceToHost, h->st));
+                CK(cudaStreamSynchronize(h->st));       // dst is reused by the next output
+            }
+            return 0;
+        };
+        if (Linv_out && (rc = emit(Lp, Linv_out, i_dev))) return rc;
+        if (L_out && (rc = emit(Sp, L_out, l_dev))) return rc;
+        if (logdet) {
+            CK(cudaMemcpyAsync(ldh.data(), ldp, sizeof(double) * bs * nleaf, cudaMemcpyDeviceToHost, h->st));
+            CK(cudaStreamSynchronize(h->st));
+            for (int b = 0; b < bs; b++) {
+                ldv[b] = 0.0;
+                for (int l = 0; l < nleaf; l++) ldv[b] += ldh[(size_t)b * nleaf + l];
+            }
+            CK(cudaMemcpy(logdet + b0, ldv.data(), sizeof(double) * bs, cudaMemcpyDefault));
+        }
+        if (status) CK(cudaMemcpyAsync(status + b0, stp, sizeof(int) * bs, cudaMemcpyDefault, h->st));
+        CK(cudaStreamSynchronize(h->st));
     }
-    const size_t nn = (size_t)npad * npad;
-    // identity-padded copy
-    std::vector<double> host((size_t)batch * nn, 0.0), src((size_t)batch * n * n);
-    CK(cudaMemcpy(src.data(), A, sizeof(double) * src.size(), cudaMemcpyDefault));
-    for (int b = 0; b < batch; b++) {
-        for (int i = 0; i < npad; i++)
-            for (int j = 0; j < npad; j++)
-                host[b * nn + (size_t)i * npad + j] = (i < n && j < n) ? src[((size_t)b * n + i) * n + j] : (i == j ? 1.0 : 0.0);
-    }
-    CK(cudaMemcpyAsync(h->A, host.data(), sizeof(double) * host.size(), cudaMemcpyHostToDevice, h->st));
-    CK(cudaMemsetAsync(h->status, 0, sizeof(int) * batch, h->st));
-    SubBatch sb{0, batch, h->st};
-    if ((rc = potrf_inv_rec(h, sb, 0, npad, L_out != nullptr))) return rc;
-    CK(cudaStreamSynchronize(h->st));
     CK(cudaGetLastError());
-    std::vector<double> outv((size_t)batch * n * n), ldp((size_t)batch * h->nleaf);
-    auto unpad = [&](const double* devbuf, double* dst) -> int {
-        CK(cudaMemcpy(host.data(), devbuf, sizeof(double) * host.size(), cudaMemcpyDeviceToHost));
-        for (int b = 0; b < batch; b++)
-            for (int i = 0; i < n; i++)
-                for (int j = 0; j < n; j++) outv[((size_t)b * n + i) * n + j] = (j <= i) ? host[b * nn + (size_t)i * npad + j] : 0.0;
-        CK(cudaMemcpy(dst, outv.data(), sizeof(double) * outv.size(), cudaMemcpyDefault));
-        return 0;
-    };
-    if (Linv_out && (rc = unpad(h->Li, Linv_out))) return rc;
-    if (L_out && (rc = unpad(h->S, L_out))) return rc;
-    CK(cudaMemcpy(ldp.data(), h->logdet_part, sizeof(double) * ldp.size(), cudaMemcpyDeviceToHost));
-    if (logdet) {
-        std::vector<double> ldv(batch, 0.0);
-        for (int b = 0; b < batch; b++)
-            for (int l = 0; l < h->nleaf; l++) ldv[b] += ldp[(size_t)b * h->nleaf + l];
-        CK(cudaMemcpy(logdet, ldv.data(), sizeof(double) * batch, cudaMemcpyDefault));
-    }
-    if (status) CK(cudaMemcpy(status, h->status, sizeof(int) * batch, cudaMemcpyDefault));
     return 0;
 }
 

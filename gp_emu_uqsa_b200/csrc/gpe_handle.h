@@ -57,6 +57,8 @@ struct gpe_handle {
 
     // batched likelihood workspace
     int Bcap = 0;
+    bool Bcap_final = false;
+    bool grad_fused = false;     // this chunk's LAUUM carries the gradient reduction in its epilogue (gpe_lauum_grad.cu)     // the workspace already has the largest size obtainable (env cap or device memory)
     double *A = nullptr, *S = nullptr, *Li = nullptr;        // [Bcap][npad][npad]
     double *Wy = nullptr, *Z = nullptr, *U = nullptr;        // [Bcap][npad][NR]
     double *GP = nullptr, *logdet_part = nullptr, *winv = nullptr, *beta = nullptr, *gpart = nullptr;
@@ -140,9 +142,25 @@ struct TmpDev {
     }
 };
 
+// The buffers one batched recursive factorisation works on (items are addressed through SubBatch::b0):
+// A [B][npad][npad] in (identity padded), overwritten; S scratch (ends up holding the Cholesky factor when asked
+// for); Li <- L^-1 (upper blocks must be zero on entry); logdet_part [B][nleaf]; status [B].
+struct FactorWs {
+    double *A, *S, *Li;
+    int npad, nleaf;
+    double* logdet_part;
+    int* status;
+};
+
+// NVTX range over a C-ABI entry point (makes nsys traces of g.train readable)
+struct NvtxRange {
+    explicit NvtxRange(const char* name);
+    ~NvtxRange();
+};
+
 bool gpe_is_device_ptr(const void* p);
 int gpe_ensure_batch_ws(gpe_handle* h, int B);
-int gpe_potrf_inv(gpe_handle* h, const SubBatch& sb, int want_L);
+int gpe_potrf_inv(gpe_handle* h, const FactorWs& ws, const SubBatch& sb, int want_L);
 int gpe_factor_and_reduce(gpe_handle* h, const SubBatch& sb, int mode, int with_grad, const double* beta_override, double* Kout);
 int gpe_upload_single_par(gpe_handle* h, const double* delta, double nugget, int kind, int predict, double s2_for_r);
 int gpe_run_gemm_on(gpe_handle* h, cudaStream_t st, const double* A, const double* B, double* C, int lda, int ldb, int ldc,

@@ -4,6 +4,7 @@
 #include "gpe_kernels.cuh"
 #include "gpe_b200.h"
 
+#include <algorithm>
 #include <cstdlib>
 
 namespace gpe {
@@ -138,18 +139,24 @@ __global__ void __launch_bounds__(256, 3) cov_build_kernel(const double* __restr
     }
 }
 
-void launch_cov_build(const double* X, const double* r, int n, int d, int npad, const ItemPar* par,
-                      const double* winv, double* A, long long sA, int B, int full, cudaStream_t st, int gmode, int gdim) {
+cudaError_t launch_cov_build(const double* X, const double* r, int n, int d, int npad, const ItemPar* par,
+                             const double* winv, double* A, long long sA, int B, int full, cudaStream_t st, int gmode, int gdim) {
     const int nt = npad / CT;
     dim3 grid = full ? dim3(nt, nt, B) : dim3(nt * (nt + 1) / 2, 1, B);
     size_t smem = (size_t)d * (CT + CT + 2) * sizeof(double);
     static SmemOptIn opt0, opt1, opt2;
-    opt0.ensure(cov_build_kernel<0>, smem);
-    opt1.ensure(cov_build_kernel<1>, smem);
-    opt2.ensure(cov_build_kernel<2>, smem);
-    if (gmode == 0) cov_build_kernel<0><<<grid, 256, smem, st>>>(X, r, n, d, npad, par, winv, A, sA, full, gdim);
-    else if (gmode == 1) cov_build_kernel<1><<<grid, 256, smem, st>>>(X, r, n, d, npad, par, winv, A, sA, full, gdim);
-    else cov_build_kernel<2><<<grid, 256, smem, st>>>(X, r, n, d, npad, par, winv, A, sA, full, gdim);
+    cudaError_t e;
+    if (gmode == 0) {
+        if ((e = opt0.ensure(cov_build_kernel<0>, smem)) != cudaSuccess) return e;
+        cov_build_kernel<0><<<grid, 256, smem, st>>>(X, r, n, d, npad, par, winv, A, sA, full, gdim);
+    } else if (gmode == 1) {
+        if ((e = opt1.ensure(cov_build_kernel<1>, smem)) != cudaSuccess) return e;
+        cov_build_kernel<1><<<grid, 256, smem, st>>>(X, r, n, d, npad, par, winv, A, sA, full, gdim);
+    } else {
+        if ((e = opt2.ensure(cov_build_kernel<2>, smem)) != cudaSuccess) return e;
+        cov_build_kernel<2><<<grid, 256, smem, st>>>(X, r, n, d, npad, par, winv, A, sA, full, gdim);
+    }
+    return cudaGetLastError();
 }
 
 __global__ void unpad_sym_kernel(const double* __restrict__ A, int npad, int n, double* __restrict__ out, int mirror) {
@@ -164,6 +171,38 @@ __global__ void unpad_sym_kernel(const double* __restrict__ A, int npad, int n, 
 void launch_unpad_sym(const double* A, int npad, int n, double* out, int mirror, cudaStream_t st) {
     size_t tot = (size_t)n * n;
     unpad_sym_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(A, npad, n, out, mirror);
+}
+
+__global__ void pad_sym_kernel(const double* __restrict__ src, int n, int npad, double* __restrict__ dst) {
+    const size_t nn = (size_t)npad * npad;
+    const double* sb = src + (size_t)blockIdx.y * n * n;
+    double* db = dst + (size_t)blockIdx.y * nn;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < nn; idx += (size_t)gridDim.x * blockDim.x) {
+        const int i = (int)(idx / npad), j = (int)(idx % npad);
+        db[idx] = (i < n && j < n) ? sb[(size_t)i * n + j] : (i == j ? 1.0 : 0.0);
+    }
+}
+
+void launch_pad_sym(const double* src, int n, int npad, double* dst, int batch, cudaStream_t st) {
+    const size_t nn = (size_t)npad * npad;
+    const unsigned gx = (unsigned)std::min<size_t>((nn + 255) / 256, 4096);
+    pad_sym_kernel<<<dim3(gx, batch), 256, 0, st>>>(src, n, npad, dst);
+}
+
+__global__ void unpad_lower_kernel(const double* __restrict__ src, int npad, int n, double* __restrict__ dst) {
+    const size_t tot = (size_t)n * n;
+    const double* sb = src + (size_t)blockIdx.y * npad * npad;
+    double* db = dst + (size_t)blockIdx.y * tot;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < tot; idx += (size_t)gridDim.x * blockDim.x) {
+        const int i = (int)(idx / n), j = (int)(idx % n);
+        db[idx] = (j <= i) ? sb[(size_t)i * npad + j] : 0.0;
+    }
+}
+
+void launch_unpad_lower(const double* src, int npad, int n, double* dst, int batch, cudaStream_t st) {
+    const size_t tot = (size_t)n * n;
+    const unsigned gx = (unsigned)std::min<size_t>((tot + 255) / 256, 4096);
+    unpad_lower_kernel<<<dim3(gx, batch), 256, 0, st>>>(src, npad, n, dst);
 }
 
 // =========================================================================== K2 leaf
@@ -1019,10 +1058,10 @@ __global__ void __launch_bounds__(256) grad_finalize_kernel(const double* __rest
     }
 }
 
-void launch_grad_finalize(const double* part, int n, int d, int npad, int p, int mode, const ItemPar* par,
+void launch_grad_finalize(const double* part, int ntile, int n, int d, int npad, int p, int mode, const ItemPar* par,
                           const ItemOut* out, const int* status, double* llh, double* grad,
                           double* sigma_hat, int B, cudaStream_t st) {
-    grad_finalize_kernel<<<B, 256, (d + 3) * sizeof(double), st>>>(part, grad_ntiles(npad), n, d, p, mode, par, out, status,
+    grad_finalize_kernel<<<B, 256, (d + 3) * sizeof(double), st>>>(part, ntile, n, d, p, mode, par, out, status,
                                                                   llh, grad, sigma_hat);
 }
 

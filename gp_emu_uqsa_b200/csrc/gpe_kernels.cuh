@@ -31,12 +31,17 @@ void launch_prep_theta(const double* theta, int B, int p, int d, int mode, doubl
                        ItemPar* par, double* winv, cudaStream_t st);
 
 // K1: A[b] (ld = npad, batch stride sA) from X [n,d]; lower 64x64 tiles only unless full.
-void launch_cov_build(const double* X, const double* r, int n, int d, int npad, const ItemPar* par,
-                      const double* winv, double* A, long long sA, int B, int full, cudaStream_t st,
-                      int gmode = 0, int gdim = 0);
+cudaError_t launch_cov_build(const double* X, const double* r, int n, int d, int npad, const ItemPar* par,
+                             const double* winv, double* A, long long sA, int B, int full, cudaStream_t st,
+                             int gmode = 0, int gdim = 0);
 
 // copy the n x n top-left of a padded matrix into a dense [n,n] output, mirroring the lower triangle
 void launch_unpad_sym(const double* A, int npad, int n, double* out, int mirror, cudaStream_t st);
+
+// identity-padded copies of `batch` dense [n,n] matrices -> [npad,npad], and the lower triangle (zeros above the
+// diagonal) of padded matrices back to dense [n,n]  (gpe_potrf: np.linalg.cholesky call sites)
+void launch_pad_sym(const double* src, int n, int npad, double* dst, int batch, cudaStream_t st);
+void launch_unpad_lower(const double* src, int npad, int n, double* dst, int batch, cudaStream_t st);
 
 // K2 leaf: Cholesky + triangular inverse of the 128x128 diagonal block at `off`.
 void launch_leaf(const double* A, double* Linv, int ld, long long sA, long long sL, int off,
@@ -57,9 +62,17 @@ void launch_llh_finalize(const double* Wy, const double* GP, const double* logde
 void launch_grad_partial(const double* X, const double* r, int n, int d, int npad, const double* winv,
                          const double* Ainv, long long sAinv, const double* U, int nu, double* part,
                          int B, cudaStream_t st);
-void launch_grad_finalize(const double* part, int n, int d, int npad, int p, int mode, const ItemPar* par,
+void launch_grad_finalize(const double* part, int ntile, int n, int d, int npad, int p, int mode, const ItemPar* par,
                           const ItemOut* out, const int* status, double* llh, double* grad,
                           double* sigma_hat, int B, cudaStream_t st);
+
+// K3 + K1g fused: LAUUM (A^-1 = L^-T L^-1) whose 128x128 tiles of W = A^-1 - U U^T stay in registers and are reduced to
+// the gradient partials in the epilogue (gpe_lauum_grad.cu).  U [B][np][NR] in; Ut / nUt [B][NR][np] scratch (U^T, -U^T);
+// part [B][lauum_grad_ntiles(np)][d + 3] out.  A^-1 is not stored.
+bool lauum_grad_supported(int d);
+int lauum_grad_ntiles(int npad);
+cudaError_t launch_lauum_grad(const double* Li, long long sL, int np, int n, int d, int nu, const double* U, double* Ut, double* nUt,
+                              const double* X, const double* r, const double* winv, double* part, int B, cudaStream_t st);
 
 inline int grad_ntiles(int npad) { int t = npad / 64; return t * (t + 1) / 2; }
 inline int grad_nvals(int d) { return d + 3; }

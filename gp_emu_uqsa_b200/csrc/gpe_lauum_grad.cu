@@ -1,0 +1,284 @@
+// LAUUM with the gradient reduction in its epilogue (K3 + K1g fused).
+//
+// Reference arithmetic replaced: the per-hyper-parameter solve / trace expressions of
+// _emulatoroptimise.py:345-372 and :450-487, which collapse to
+//     grad_k = 1/2 sum_ij T^k_ij W_ij,   W = A^-1 - U U^T,   U = [A^-1 H K^-T | sqrt(f) A^-1 (y - H beta)],
+// with T^k built from E_ij = exp(-sum_k ((x_ik - x_jk)/delta_k)^2)  (_emulatorkernels.py:53-71, :126-144).
+//
+// Round 1 formed A^-1 = L^-T L^-1 with the generic DMMA GEMM, stored its lower tiles (8 n^2 / 2 bytes per item) and
+// read them back in a separate reduction kernel that also recomputed E and the U.U^T dot products on the FP64 ALU
+// (3.15 ms per 32-item step, 0.32 of the FP64 roof, long-scoreboard bound on the A^-1 loads).  Here a 128x128 tile of
+// W never leaves the registers of the CTA that computed it:
+//   * the k loop runs over L^-1 (k >= i, as LAUUM) and then over the NR columns of U, whose tiles come from a
+//     pre-negated k-major copy (-U^T as the A operand, U^T as the B operand), so W = A^-1 - U U^T falls out of the
+//     tensor pipe and the 2 x 18 FMA per entry of the old dot products disappear;
+//   * the epilogue stages the scaled input tiles X_i / delta, X_j / delta in the (now free) pipeline stages,
+//     recomputes E for the 64 entries a lane holds, and reduces sum W E Delta_k^2 (k < d), sum W E, sum_diag W,
+//     sum_diag W r into one partial row per tile, which grad_finalize_kernel adds up in a fixed order.
+// A^-1 is not written at all on this path (the sensitivity code builds it on demand with the generic kernel).
+#include "gpe_gemm.cuh"
+#include "gpe_kernels.cuh"
+
+namespace gpe {
+
+struct LauumGradP {
+    const double* Li;      // [B][np][np]  L^-1 (lower; upper blocks zero)
+    long long sL;
+    int np, n, d;
+    int ku;                // k-tiles of the U part (ceil(nu / 16))
+    const double* Ut;      // [B][NR][np]   U^T
+    const double* nUt;     // [B][NR][np]  -U^T
+    long long sU;
+    const double* X;       // [n][d]
+    const double* r;       // [n] or null
+    const double* winv;    // [B][d]  1 / delta
+    double* part;          // [B][ntile][d + 3]
+    int ntile;
+};
+
+constexpr int LG_LDX = 128 + 4;     // row stride of the k-major X tiles in the epilogue
+
+__device__ __forceinline__ void tri_decode_lg(int t, int& ti, int& tj) {
+    int r = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+    while ((r + 1) * (r + 2) / 2 <= t) r++;
+    while (r * (r + 1) / 2 > t) r--;
+    ti = r;
+    tj = t - r * (r + 1) / 2;
+}
+
+__global__ void __launch_bounds__(WS_THREADS, 1) lauum_grad_kernel(LauumGradP p) {
+    constexpr int BM = 128, BN = 128, WMW = 4, WNW = WS_CONSUMERS / WMW;
+    constexpr int WTM = BM / WMW, WTN = BN / WNW, FM = WTM / 8, FN = WTN / 8;       // warp tile 32 x 64: FM = 4, FN = 8
+    constexpr int A_EL = TileShape<BM, false>::ELEMS, B_EL = TileShape<BN, false>::ELEMS;
+    constexpr int A_LD = TileShape<BM, false>::LD, B_LD = TileShape<BN, false>::LD;
+    extern __shared__ __align__(16) double smem[];
+    __shared__ __align__(8) uint64_t full_bar[GEMM_STAGES], empty_bar[GEMM_STAGES];
+
+    // lower-triangle tiles, row by row: tile t = ti (ti + 1) / 2 + tj.  Row ti has the k range [ti * 128, np):
+    // the launch starts on its longest tiles and ends on its shortest
+    int ti, tj;
+    tri_decode_lg((int)blockIdx.x, ti, tj);
+    const int b = blockIdx.z;
+    const int m0 = ti * BM, n0 = tj * BN;
+    const int kbeg = m0;
+    const int KT0 = (p.np - kbeg) / GEMM_BK, KT = KT0 + p.ku;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < GEMM_STAGES; s++) {
+            mbar_init(&full_bar[s], 32);
+            mbar_init(&empty_bar[s], WS_CONSUMERS);
+        }
+    }
+    __syncthreads();
+
+    double* As = smem;
+    double* Bs = smem + GEMM_STAGES * A_EL;
+
+    if (warp == WS_CONSUMERS) {
+        // ===== producer warp: L^-1 tiles (both operands: rows k, columns m0.. / n0..), then the U tiles =====
+        const double* Lb = p.Li + (size_t)b * p.sL;
+        const double* Ag = Lb + (size_t)kbeg * p.np + m0;
+        const double* Bg = Lb + (size_t)kbeg * p.np + n0;
+        const double* Au = p.nUt + (size_t)b * p.sU + m0;
+        const double* Bu = p.Ut + (size_t)b * p.sU + n0;
+        const size_t kstep = (size_t)GEMM_BK * p.np;
+        for (int kt = 0; kt < KT; kt++) {
+            const int s = kt % GEMM_STAGES;
+            if (kt >= GEMM_STAGES) mbar_wait(&empty_bar[s], ((kt / GEMM_STAGES) - 1) & 1);
+            if (kt < KT0) {
+                load_tile_warp<BM, false>(As + s * A_EL, Ag + kt * kstep, p.np, lane);
+                load_tile_warp<BN, false>(Bs + s * B_EL, Bg + kt * kstep, p.np, lane);
+            } else {
+                load_tile_warp<BM, false>(As + s * A_EL, Au + (kt - KT0) * kstep, p.np, lane);
+                load_tile_warp<BN, false>(Bs + s * B_EL, Bu + (kt - KT0) * kstep, p.np, lane);
+            }
+            cp_async_mbar_arrive_noinc(&full_bar[s]);
+        }
+        cp_async_wait<0>();
+        return;
+    }
+
+    // ===== consumer warps: 4 x 2 grid, warps 0..3 rows 0..3 of column 0, warps 4..7 rows 3..0 of column 1 =====
+    const int wrow = (warp < 4 ? warp : 7 - warp), wcol = warp / 4;
+    const int wm0 = wrow * WTM, wn0 = wcol * WTN;
+    const int fr = lane >> 2, fc = lane & 3;
+    // inside the diagonal block of L^-1 (k in [m0, m0 + 128)) rows k < m see only zeros of the A operand
+    const int wk_lo = wm0 / GEMM_BK;
+    double acc[FM][FN][2];
+#pragma unroll
+    for (int i = 0; i < FM; i++)
+#pragma unroll
+        for (int j = 0; j < FN; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+    const int a_off = fc * A_LD + wm0 + fr;
+    const int b_off = fc * B_LD + wn0 + fr;
+    constexpr int a_kk = 4 * A_LD, b_kk = 4 * B_LD;
+
+    for (int kt = 0; kt < KT; kt++) {
+        const int s = kt % GEMM_STAGES;
+        mbar_wait(&full_bar[s], (kt / GEMM_STAGES) & 1);
+        const double* at = As + s * A_EL + a_off;
+        const double* bt = Bs + s * B_EL + b_off;
+        if (kt >= wk_lo) {
+#pragma unroll
+            for (int kk = 0; kk < GEMM_BK / 4; kk++) {
+                double af[FM], bf[FN];
+#pragma unroll
+                for (int i = 0; i < FM; i++) af[i] = at[kk * a_kk + i * 8];
+#pragma unroll
+                for (int j = 0; j < FN; j++) bf[j] = bt[kk * b_kk + j * 8];
+#pragma unroll
+                for (int i = 0; i < FM; i++)
+#pragma unroll
+                    for (int j = 0; j < FN; j++) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[s]);
+    }
+
+    // ===== epilogue: acc = W tile.  Stage the scaled input tiles in the free pipeline stages. =====
+    const int d = p.d, n = p.n;
+    named_bar_sync(2, WS_CONSUMERS * 32);           // every consumer is past its last stage read
+    double* Xi = smem;                              // [d][LG_LDX]  rows m0 .. m0 + 127, k-major, scaled by 1 / delta
+    double* Xj = smem + (size_t)d * LG_LDX;         // [d][LG_LDX]  rows n0 ..
+    double* red = Xj + (size_t)d * LG_LDX;          // [8][d + 3]
+    {
+        const double* w = p.winv + (size_t)b * d;
+        const int row = tid >> 1, gi = m0 + row, gj = n0 + row;
+        for (int k = tid & 1; k < d; k += 2) {
+            const double wk = w[k];
+            Xi[k * LG_LDX + row] = (gi < n) ? p.X[(size_t)gi * d + k] * wk : 0.0;
+            Xj[k * LG_LDX + row] = (gj < n) ? p.X[(size_t)gj * d + k] * wk : 0.0;
+        }
+    }
+    named_bar_sync(2, WS_CONSUMERS * 32);
+
+    const int row0 = wm0 + fr, col0 = wn0 + 2 * fc;          // lane's entries: rows row0 + 8 i, columns col0 + 8 j + {0, 1}
+    const bool diag_tile = (ti == tj);
+    double sE = 0.0, sD = 0.0, sDr = 0.0;
+    // pass 1: acc <- t = (2 | 0) * W * E; the diagonal sums on the way
+#pragma unroll
+    for (int j = 0; j < FN; j++) {
+        double D[FM][2];
+#pragma unroll
+        for (int i = 0; i < FM; i++) D[i][0] = D[i][1] = 0.0;
+        const double* xjp = Xj + col0 + 8 * j;
+        const double* xip = Xi + row0;
+#pragma unroll 4
+        for (int k = 0; k < d; k++) {
+            const double2 xj = *reinterpret_cast<const double2*>(xjp + k * LG_LDX);
+#pragma unroll
+            for (int i = 0; i < FM; i++) {
+                const double xi = xip[k * LG_LDX + 8 * i];
+                const double d0 = xi - xj.x, d1 = xi - xj.y;
+                D[i][0] = fma(d0, d0, D[i][0]);
+                D[i][1] = fma(d1, d1, D[i][1]);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < FM; i++) {
+            D[i][0] = gpe_exp(-D[i][0]);
+            D[i][1] = gpe_exp(-D[i][1]);
+        }
+#pragma unroll
+        for (int i = 0; i < FM; i++) {
+            const int gi = m0 + row0 + 8 * i;
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                const int gj = n0 + col0 + 8 * j + e;
+                const double wv = acc[i][j][e];
+                double wgt = 2.0;
+                if (gi >= n || gj >= n) wgt = 0.0;          // identity padding
+                else if (diag_tile && gi <= gj) {
+                    wgt = 0.0;                              // upper triangle: each pair is taken once, from below
+                    if (gi == gj) {
+                        sD += wv;
+                        if (p.r != nullptr) sDr = fma(wv, p.r[gi], sDr);
+                    }
+                }
+                const double tv = wgt * wv * D[i][e];
+                acc[i][j][e] = tv;
+                sE += tv;
+            }
+        }
+    }
+    const int nv = d + 3;
+    sE = warp_sum(sE); sD = warp_sum(sD); sDr = warp_sum(sDr);
+    if (lane == 0) { red[warp * nv + d] = sE; red[warp * nv + d + 1] = sD; red[warp * nv + d + 2] = sDr; }
+    // pass 2: per dimension, sum t * Delta_k^2 over the lane's 64 entries
+    for (int k = 0; k < d; k++) {
+        double xi[FM];
+#pragma unroll
+        for (int i = 0; i < FM; i++) xi[i] = Xi[k * LG_LDX + row0 + 8 * i];
+        double g0 = 0.0, g1 = 0.0;
+#pragma unroll
+        for (int j = 0; j < FN; j++) {
+            const double2 xj = *reinterpret_cast<const double2*>(Xj + k * LG_LDX + col0 + 8 * j);
+#pragma unroll
+            for (int i = 0; i < FM; i++) {
+                const double d0 = xi[i] - xj.x, d1 = xi[i] - xj.y;
+                g0 = fma(acc[i][j][0] * d0, d0, g0);
+                g1 = fma(acc[i][j][1] * d1, d1, g1);
+            }
+        }
+        const double g = warp_sum(g0 + g1);
+        if (lane == 0) red[warp * nv + k] = g;
+    }
+    named_bar_sync(2, WS_CONSUMERS * 32);
+    double* pout = p.part + ((size_t)b * p.ntile + blockIdx.x) * nv;
+    for (int v = tid; v < nv; v += WS_CONSUMERS * 32) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < WS_CONSUMERS; w++) s += red[w * nv + v];
+        pout[v] = s;
+    }
+}
+
+// -U^T and U^T, k-major: Ut[b][c][i] = U[b][i][c]
+__global__ void __launch_bounds__(256) ut_kernel(const double* __restrict__ U, int np, double* __restrict__ Ut, double* __restrict__ nUt) {
+    __shared__ double T[32][NR + 1];
+    const int b = blockIdx.y, i0 = blockIdx.x * 32;
+    const double* Ub = U + ((size_t)b * np + i0) * NR;
+    for (int e = threadIdx.x; e < 32 * NR; e += 256) T[e / NR][e % NR] = Ub[e];
+    __syncthreads();
+    for (int e = threadIdx.x; e < 32 * NR; e += 256) {
+        const int c = e / 32, i = e % 32;
+        const double v = T[i][c];
+        const size_t o = ((size_t)b * NR + c) * np + i0 + i;
+        Ut[o] = v;
+        nUt[o] = -v;
+    }
+}
+
+bool lauum_grad_supported(int d) {
+    // the epilogue's two k-major input tiles + the reduction rows must fit in the pipeline stages
+    const size_t need = ((size_t)2 * d * LG_LDX + 8 * (size_t)(d + 3)) * sizeof(double);
+    return need <= gemm_smem_bytes<128, 128, false, false>();
+}
+
+cudaError_t launch_lauum_grad(const double* Li, long long sL, int np, int n, int d, int nu, const double* U, double* Ut, double* nUt,
+                              const double* X, const double* r, const double* winv, double* part, int B, cudaStream_t st) {
+    if (np % 128 || !lauum_grad_supported(d)) return cudaErrorInvalidValue;
+    ut_kernel<<<dim3(np / 32, B), 256, 0, st>>>(U, np, Ut, nUt);
+    LauumGradP p;
+    p.Li = Li; p.sL = sL; p.np = np; p.n = n; p.d = d;
+    p.ku = (nu + GEMM_BK - 1) / GEMM_BK;
+    p.Ut = Ut; p.nUt = nUt; p.sU = (long long)NR * np;
+    p.X = X; p.r = r; p.winv = winv; p.part = part;
+    const int T = np / 128;
+    p.ntile = T * (T + 1) / 2;
+    constexpr size_t smem = gemm_smem_bytes<128, 128, false, false>();
+    static SmemOptIn optin;
+    if (cudaError_t e = optin.ensure(lauum_grad_kernel, smem); e != cudaSuccess) return e;
+    lauum_grad_kernel<<<dim3(p.ntile, 1, B), WS_THREADS, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+int lauum_grad_ntiles(int npad) {
+    const int T = npad / 128;
+    return T * (T + 1) / 2;
+}
+
+}  // namespace gpe

@@ -195,7 +195,7 @@ struct ImpDesc {
 };
 
 __global__ void __launch_bounds__(256) implaus_kernel(const double* __restrict__ mean, const double* __restrict__ var, long long m,
-                                                      ImpDesc ds, long long cell_pts, double* __restrict__ Imax,
+                                                      ImpDesc ds, long long cell_pts, long long first_index, double* __restrict__ Imax,
                                                       unsigned char* __restrict__ keep, unsigned long long* __restrict__ count_lt,
                                                       unsigned long long* __restrict__ cell_min_bits,
                                                       unsigned long long* __restrict__ cell_count) {
@@ -231,7 +231,8 @@ __global__ void __launch_bounds__(256) implaus_kernel(const double* __restrict__
     if (live && keep != nullptr) keep[r] = (top[0] < ds.cm) ? 1 : 0;
     // cells are contiguous runs of cell_pts points, so a warp (32 consecutive points) almost always
     // sits inside one cell: reduce in the warp first, one atomic per warp instead of one per point
-    const long long cell = (cell_pts > 0 && live) ? r / cell_pts : -1;
+    // cells are runs of cell_pts points of the GLOBAL flat index first_index + r; the outputs start at the cell of point 0
+    const long long cell = (cell_pts > 0 && live) ? (first_index + r) / cell_pts - first_index / cell_pts : -1;
     const long long cell0 = __shfl_sync(0xffffffffu, cell, 0);
     const bool uniform = cell_pts > 0 && __all_sync(0xffffffffu, cell == cell0) && cell0 >= 0;
     for (int k = 0; k < ds.maxno; k++) {
@@ -369,6 +370,7 @@ extern "C" {
 int gpe_fit_state(gpe_handle* h, const double* delta, double nugget, double sigma, int kind, double r_div,
                   const double* beta_in, double* beta_out, double* sigma_mucm_out, int* status) {
     if (!h || !h->n || !delta) return h ? h->fail_msg("bad argument / no training set") : -2;
+    NvtxRange nvtx("gpe_fit_state");
     CK(cudaSetDevice(h->device));
     int rc;
     if ((rc = gpe_ensure_batch_ws(h, 1))) return rc;
@@ -390,7 +392,7 @@ int gpe_fit_state(gpe_handle* h, const double* delta, double nugget, double sigm
         CK(cudaMemcpyAsync(h->fbeta, bin.data(), sizeof(double) * NR, cudaMemcpyHostToDevice, h->st));
         bov = h->fbeta;
     }
-    launch_cov_build(h->X, h->r, h->n, h->d, np, h->par, h->winv, h->A, 0, 1, 0, h->st);
+    CK(launch_cov_build(h->X, h->r, h->n, h->d, np, h->par, h->winv, h->A, 0, 1, 0, h->st));
     h->launches++;
     CK(cudaMemsetAsync(h->fK, 0, sizeof(double) * NR * NR, h->st));
     CK(cudaMemsetAsync(h->status, 0, sizeof(int), h->st));
@@ -426,6 +428,7 @@ static int predict_common(gpe_handle* h, const double* Xs, const double* Hs, con
                           long long m, double* mean, double* var) {
     if (!h->fitted) return h->fail_msg("gpe_fit_state has not succeeded on this handle");
     if (!Hs && !h->has_basis) return h->fail_msg("no H* given and no device basis set (gpe_set_basis)");
+    NvtxRange nvtx(grid ? "gpe_predict_grid" : "gpe_predict");
     CK(cudaSetDevice(h->device));
     long long chunk = std::min<long long>(default_chunk(h), (m + 127) / 128 * 128);
     int rc;
@@ -507,6 +510,7 @@ int gpe_predict_grid(gpe_handle* h, const int* levels, const double* lo, const d
 int gpe_cross_cov(gpe_handle* h, const double* delta, double nugget, int kind, const double* Xs, int m, double* C_out) {
     if (h && m == 0) return 0;
     if (!h || !h->n || !delta || !Xs || !C_out || m < 1) return h ? h->fail_msg("bad argument") : -2;
+    NvtxRange nvtx("gpe_cross_cov");
     CK(cudaSetDevice(h->device));
     const int np = h->npad, d = h->d;
     int mc = (m + 127) / 128 * 128;
@@ -541,6 +545,7 @@ int gpe_predict_fullcov(gpe_handle* h, const double* Xs, const double* Hs, int m
     if (!h || !Xs || !mean || !V || m < 1) return h ? h->fail_msg("bad argument") : -2;
     if (!h->fitted) return h->fail_msg("gpe_fit_state has not succeeded on this handle");
     if (!Hs && !h->has_basis) return h->fail_msg("no H* given and no device basis set (gpe_set_basis)");
+    NvtxRange nvtx("gpe_predict_fullcov");
     CK(cudaSetDevice(h->device));
     const int np = h->npad, d = h->d, q = h->q;
     const int mp = (m + 127) / 128 * 128;
@@ -585,21 +590,26 @@ int gpe_predict_fullcov(gpe_handle* h, const double* Xs, const double* Hs, int m
         fullcov_finalize_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, h->st>>>(ZtZ, mp, aux, mp, P, Hd, bd, d, h->fwinv, h->fK, s2,
                                                                                    h->fit_c, h->fit_astar, rn, m, G, Vd, 1);
         h->launches += 3;
-        cudaMemcpyAsync(mean, md, sizeof(double) * m, cudaMemcpyDefault, h->st);
-        cudaMemcpyAsync(V, Vd, sizeof(double) * (size_t)m * m, cudaMemcpyDefault, h->st);
+        CK(cudaMemcpyAsync(mean, md, sizeof(double) * m, cudaMemcpyDefault, h->st));
+        CK(cudaMemcpyAsync(V, Vd, sizeof(double) * (size_t)m * m, cudaMemcpyDefault, h->st));
     }
-    cudaStreamSynchronize(h->st);
+    CK(cudaStreamSynchronize(h->st));
     if (rc) return rc;
     CK(cudaGetLastError());
     return 0;
 }
 
 int gpe_implausibility(gpe_handle* h, const double* mean, const double* var, int n_emul, long long m, const double* z,
-                       const double* var_extra, double cm, int maxno, long long ncell, double* Imax, unsigned char* keep,
-                       unsigned long long* count_lt, double* cell_min, unsigned long long* cell_count) {
+                       const double* var_extra, double cm, int maxno, long long cell_pts, long long first_index, long long ncell,
+                       double* Imax, unsigned char* keep, unsigned long long* count_lt, double* cell_min,
+                       unsigned long long* cell_count) {
     if (!h || !z || !var_extra || n_emul < 1 || m < 0 || (m > 0 && (!mean || !var))) return h ? h->fail_msg("bad argument") : -2;
     if (n_emul > MAXEM || maxno < 1 || maxno > n_emul) return h->fail_msg("need 1 <= maxno <= n_emul <= 16");
-    if (ncell > 0 && m % ncell) return h->fail_msg("m must be a multiple of ncell");
+    if (cell_pts < 0 || first_index < 0 || ncell < 0) return h->fail_msg("cell_pts, first_index and ncell must be non-negative");
+    if (cell_pts == 0) ncell = 0;
+    if (cell_pts > 0 && m > 0 && (first_index + m - 1) / cell_pts - first_index / cell_pts + 1 > ncell)
+        return h->fail_msg("the points span more cells than ncell");
+    NvtxRange nvtx("gpe_implausibility");
     CK(cudaSetDevice(h->device));
     ImpDesc ds;
     ds.n_emul = n_emul; ds.maxno = maxno; ds.cm = cm;
@@ -632,7 +642,7 @@ int gpe_implausibility(gpe_handle* h, const double* mean, const double* var, int
         CK(cudaMemsetAsync(ccnt, 0, sizeof(unsigned long long) * ncell * maxno, h->st));
     }
     if (m > 0) {                                                 // m == 0: zero counts, +huge cell minima
-        implaus_kernel<<<(unsigned)((m + 255) / 256), 256, 0, h->st>>>(md, vd, m, ds, ncell > 0 ? m / ncell : 0, Id, kd, cnt, cmin, ccnt);
+        implaus_kernel<<<(unsigned)((m + 255) / 256), 256, 0, h->st>>>(md, vd, m, ds, ncell > 0 ? cell_pts : 0, first_index, Id, kd, cnt, cmin, ccnt);
         h->launches++;
     }
     if (Imax && !I_dev && m > 0) CK(cudaMemcpyAsync(Imax, Id, sizeof(double) * (size_t)m * maxno, cudaMemcpyDeviceToHost, h->st));

@@ -235,6 +235,7 @@ extern "C" {
 int gpe_solve(gpe_handle* h, const double* Bm, int k, double* out) {
     if (!h || !Bm || !out || k < 1) return h ? h->fail_msg("bad argument") : -2;
     if (!h->fitted) return h->fail_msg("gpe_fit_state has not succeeded on this handle");
+    NvtxRange nvtx("gpe_solve");
     CK(cudaSetDevice(h->device));
     const int np = h->npad, n = h->n;
     double *src = nullptr, *dst = nullptr, *p0 = nullptr, *p1 = nullptr, *p2 = nullptr;
@@ -273,6 +274,7 @@ int gpe_sens_contract(gpe_handle* h, const double* gamma, const double* acoef, c
                       const double* V, int nv, double* trace_out, double* M_out) {
     if (!h || !gamma || !acoef || !mvec || !V || nv < 1 || nv > NR) return h ? h->fail_msg("bad argument (nv <= 32)") : -2;
     if (!h->fitted) return h->fail_msg("gpe_fit_state has not succeeded on this handle");
+    NvtxRange nvtx("gpe_sens_contract");
     CK(cudaSetDevice(h->device));
     const int np = h->npad, n = h->n, d = h->d;
     int rc;
@@ -326,6 +328,7 @@ int gpe_sens_main_effect(gpe_handle* h, const double* t1, const double* t2, cons
                          double* out) {
     if (!h || !h->n || !t1 || !t2 || !cdiag || !mvec || !evec || !which || !xw || !out || nwhich < 1 || points < 1)
         return h ? h->fail_msg("bad argument / no training set") : -2;
+    NvtxRange nvtx("gpe_sens_main_effect");
     CK(cudaSetDevice(h->device));
     const int n = h->n, d = h->d;
     std::vector<double> hb(4 * d + n + (size_t)nwhich * points);
@@ -360,6 +363,7 @@ int gpe_pdist_argmin(gpe_handle* h, const double* designs, int N, int n, int dim
                      long long* argmin_out) {
     if (!h || !designs || !argmin_out || N < 1 || n < 1 || dim < 1 || dim > 64 || ne < 0 || (ne > 0 && !extra) || n + ne < 2)
         return h ? h->fail_msg("bad argument (1 <= dim <= 64, at least two points)") : -2;
+    NvtxRange nvtx("gpe_pdist_argmin");
     CK(cudaSetDevice(h->device));
     const int P = n + ne, nblk = (P - 1 + PD_ROWS - 1) / PD_ROWS;
     double *dd = nullptr, *de = nullptr;

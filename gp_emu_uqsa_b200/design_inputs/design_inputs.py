@@ -29,9 +29,14 @@ def device_criterion(designs, fextra):
     return _lib.scratch_device().pdist_argmin(designs, fextra)
 
 
-def optLatinHyperCube(dim=None, n=None, N=None, minmax=None, filename="inputs", fextra=None, _criterion=None):
+def optLatinHyperCube(dim=None, n=None, N=None, minmax=None, filename="inputs", fextra=None, _criterion=None, _return=False):
     """Generate N random Latin hypercubes of n points in `dim` dimensions, keep the "best", scale it
-    to `minmax` and save it to `filename` ('%.8f' text).  Returns None.
+    to `minmax` and save it to `filename` ('%.8f' text).  Returns None (with ``_return=True``, the
+    package's own callers get the design exactly as the file holds it -- the '%.8f' text parsed back -- so
+    that ranks of a multi-GPU job need not re-read a file another rank is writing).
+
+    Multi-rank: the draws start from rank 0's generator state on every rank (``_dist.sync_numpy_rng``) and
+    only rank 0 writes the file.
 
     Selection rule kept from the reference (:73-77, a known quirk): the criterion compared between
     designs is ``argmin(pdist)`` -- the *index* of the closest pair -- not the minimum distance."""
@@ -53,6 +58,8 @@ def optLatinHyperCube(dim=None, n=None, N=None, minmax=None, filename="inputs", 
               "minimum distance between design points)...")
     if N < 1 or n < 1:      # the reference dies on an unbound name here (e.g. 2-input imp_plot: dim = 0)
         raise UnboundLocalError("optLatinHyperCube: no candidate design was generated (N = 0)")
+    from .. import _dist as _d
+    _d.sync_numpy_rng()
     # all candidates first (the RNG draws do not depend on the criterion), then the criterion in one go
     designs = _np.empty((N, n, dim))
     for k in range(0, N):
@@ -77,6 +84,10 @@ def optLatinHyperCube(dim=None, n=None, N=None, minmax=None, filename="inputs", 
     inputs = _np.array(minmax)
     for i in range(0, dim):
         D[:, i] = D[:, i] * (inputs[i, 1] - inputs[i, 0]) + inputs[i, 0]
-    _np.savetxt(filename, D, delimiter=" ", fmt='%.8f')
+    if _d.is_writer():
+        _np.savetxt(filename, D, delimiter=" ", fmt='%.8f')
+    _d.barrier()
     print("DONE!")
+    if _return:       # what np.loadtxt(filename) gives: the values rounded to the file's 8 decimals
+        return _np.array([[float('%.8f' % v) for v in row] for row in D]).reshape(n, dim)
     return None

@@ -31,7 +31,7 @@ def setup(config_file, datashuffle=True, scaleinputs=True):
     (x_V, y_V) = all_data.choose_V()
     training = _emuc.Data(x_T, y_T, basis, par, beliefs, K)
     validation = _emuc.Data(x_V, y_V, basis, par, beliefs, K)
-    post = _emuc.Posterior(validation, training, par, beliefs, K)
+    post = _emuc.Posterior(validation, training, par, beliefs, K, lazy=True)
     opt_T = _emuo.Optimize(training, basis, par, beliefs, config)
     return _emuc.Emulator(config, beliefs, par, basis, tv_conf, all_data, training, validation, post, opt_T, K)
 

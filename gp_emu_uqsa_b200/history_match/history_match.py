@@ -5,8 +5,9 @@ The reference evaluates a Posterior per grid cell per emulator and then loops ov
 Python.  Here all points of an input pair (grid^2 cells x n_lhc design points) go through ONE
 device prediction per emulator (mean + diagonal variance, ``gpe_predict``; results stay in HBM) and
 ONE ``gpe_implausibility`` launch that produces the n-th-max implausibility, the keep mask and the
-per-cell min / count reductions.  With torch.distributed initialised the cells (or rows) are
-block-partitioned over the ranks and the cell statistics are combined with all-reduce(min / sum)."""
+per-cell min / count reductions.  With torch.distributed initialised the flat point index (all cells'
+points in cell order, or the rows of the flat routines) is cut into equal tile-aligned ranges, one per
+rank -- a cell may straddle two ranks -- and the cell statistics are combined with all-reduce(min / sum)."""
 import numpy as _np
 
 from .. import _dist
@@ -44,12 +45,12 @@ def _predict_all(emuls, zs, x, act_ref, active_fn):
     return mean_d, var_d
 
 
-def _implausibility(emuls, mean_d, var_d, zs, var_extra, cm, maxno, ncell=0):
+def _implausibility(emuls, mean_d, var_d, zs, var_extra, cm, maxno, cell_pts=0, first_index=0):
     dev = emuls[0].training.device()
     import torch
     keep = torch.empty(mean_d.shape[1], dtype=torch.uint8, device=mean_d.device)
-    _, _, count, cmin, ccnt = dev.implausibility(mean_d, var_d, zs, var_extra, cm, maxno=maxno, ncell=ncell,
-                                                  want_imax=False, out=(None, keep))
+    _, _, count, cmin, ccnt = dev.implausibility(mean_d, var_d, zs, var_extra, cm, maxno=maxno, cell_pts=cell_pts,
+                                                  first_index=first_index, want_imax=False, out=(None, keep))
     return keep, count, cmin, ccnt
 
 
@@ -80,26 +81,27 @@ def imp_plot(emuls, zs, cm, var_extra, maxno=1, olhcmult=100, grid=10, act=[], f
         olhc_range = [it[1] for it in sorted(minmax.items(), key=lambda x: int(x[0])) if int(it[0]) != s[0] and int(it[0]) != s[1]]
         print("olhc_range:", olhc_range)
         filename = "imp_input_" + str(s[0]) + '_' + str(s[1])
-        _gd.optLatinHyperCube(dim, n, N, olhc_range, filename, _criterion=_gd.device_criterion)   # every rank: same seeded RNG stream
-        x_other = _np.loadtxt(filename).reshape(n, dim)
+        # the reference writes the design and reads it back (:77-84); here rank 0 writes it, everyone gets it in memory
+        x_other = _gd.optLatinHyperCube(dim, n, N, olhc_range, filename, _criterion=_gd.device_criterion, _return=True)
         other_dim = [act_ref[str(key)] for key in act_ref if int(key) not in s]
         print("\nCalculating Implausibilities...")
-        # cells [c0, c1) of this rank, cell index = i*grid + j; all their points in one array
+        # flat point index = cell * n + design point, cell = i*grid + j; this rank owns the points [p0, p1)
         ncell = grid * grid
-        c0, c1 = _dist.block(ncell, rank, world)
+        p0, p1 = _dist.block_aligned(ncell * n, rank, world)
         IMP = _np.full((ncell, maxno), _np.inf)
         ODPc = _np.zeros((ncell, maxno), dtype=_np.uint64)
-        if c1 > c0:
-            cells = _np.arange(c0, c1)
-            x = _np.empty((c1 - c0, n, num_inputs))
-            x[:, :, act_ref[str(s[0])]] = X1[cells // grid][:, None]
-            x[:, :, act_ref[str(s[1])]] = X2[cells % grid][:, None]
-            x[:, :, other_dim] = x_other[None, :, :]
-            x = x.reshape(-1, num_inputs)
+        if p1 > p0:
+            pts = _np.arange(p0, p1)
+            cells, lhc = pts // n, pts % n
+            x = _np.empty((p1 - p0, num_inputs))
+            x[:, act_ref[str(s[0])]] = X1[cells // grid]
+            x[:, act_ref[str(s[1])]] = X2[cells % grid]
+            x[:, other_dim] = x_other[lhc, :]
             active = lambda E: s[0] in E.beliefs.active_index and s[1] in E.beliefs.active_index
             mean_d, var_d = _predict_all(emuls, zs, x, act_ref, active)
-            _, _, cmin, ccnt = _implausibility(emuls, mean_d, var_d, zs, var_extra, cm, maxno, ncell=c1 - c0)
-            IMP[c0:c1], ODPc[c0:c1] = cmin, ccnt
+            _, _, cmin, ccnt = _implausibility(emuls, mean_d, var_d, zs, var_extra, cm, maxno, cell_pts=n, first_index=p0)
+            c0 = p0 // n
+            IMP[c0:c0 + cmin.shape[0]], ODPc[c0:c0 + ccnt.shape[0]] = cmin, ccnt
         IMP = _dist.all_reduce(IMP, "min")
         ODPc = _dist.all_reduce(ODPc, "sum")
         nfileStr = fileStr + "_" if fileStr != "" else fileStr
@@ -108,6 +110,7 @@ def imp_plot(emuls, zs, cm, var_extra, maxno=1, olhcmult=100, grid=10, act=[], f
                 _np.savetxt(nfileStr + str(m + 1) + "_" + "IMP_" + str(s[0]) + '_' + str(s[1]), IMP[:, m].reshape(grid, grid))
                 _np.savetxt(nfileStr + str(m + 1) + "_" + "ODP_" + str(s[0]) + '_' + str(s[1]),
                             (ODPc[:, m].astype(float) / float(n)).reshape(grid, grid))
+        _dist.barrier()
     if plot is True:
         print("imp_plot: drawing requires matplotlib (outside the rebuilt hot path); the IMP/ODP files were written")
     return
@@ -136,13 +139,13 @@ def _flat_keep(emuls, zs, cm, var_extra, x, act_ref, maxno):
     implausibility over the emulators is below cm.  Rows are block-partitioned over the ranks."""
     n = x.shape[0]
     rank, world = _dist.rank_world()
-    lo, hi = _dist.block(n, rank, world)
+    lo, hi = _dist.block_aligned(n, rank, world)
     keep = _np.zeros(n)
     if hi > lo:
         mean_d, var_d = _predict_all(emuls, zs, x[lo:hi], act_ref, lambda E: True)
         kd, _, _, _ = _implausibility(emuls, mean_d, var_d, zs, var_extra, cm, maxno)
         keep[lo:hi] = kd.cpu().numpy()
-    keep = _dist.gather_blocks(keep, n)
+    keep = _dist.gather_blocks(keep, n, bounds=_dist.block_aligned)
     return keep > 0.5
 
 
@@ -158,9 +161,10 @@ def nonimp_data(emuls, zs, cm, var_extra, datafiles, maxno=1, act=[], fileStr=""
     keep = _flat_keep(emuls, zs, cm, var_extra, sim_x, act_ref, maxno)
     nimp_inputs, nimp_outputs = sim_x[keep], sim_y[keep]
     nfileStr = fileStr + "_" if fileStr != "" else fileStr
-    if _dist.rank_world()[0] == 0:
+    if _dist.is_writer():
         _np.savetxt(nfileStr + "nonimp_" + datafiles[0], nimp_inputs)
         _np.savetxt(nfileStr + "noninp_" + datafiles[1], nimp_outputs)
+    _dist.barrier()
     print(len(nimp_inputs), "data points were non-implausible")
     return len(nimp_inputs)
 
@@ -179,13 +183,13 @@ def new_wave_design(emuls, zs, cm, var_extra, datafiles, maxno=1, olhcmult=100, 
     olhc_range = [it[1] for it in sorted(minmax.items(), key=lambda x: int(x[0]))]
     print("olhc_range:", olhc_range)
     filename = "olhc_des"
-    _gd.optLatinHyperCube(dim, n, N, olhc_range, filename, fextra=sim_x, _criterion=_gd.device_criterion)
-    x = _np.loadtxt(filename).reshape(n, dim)
+    x = _gd.optLatinHyperCube(dim, n, N, olhc_range, filename, fextra=sim_x, _criterion=_gd.device_criterion, _return=True)
     print("\nCalculating Implausibilities...")
     keep = _flat_keep(emuls, zs, cm, var_extra, x, act_ref, maxno)
     nimp_inputs = x[keep]
     nfileStr = fileStr + "_" if fileStr != "" else fileStr
-    if _dist.rank_world()[0] == 0:
+    if _dist.is_writer():
         _np.savetxt(nfileStr + datafiles[0], nimp_inputs)
+    _dist.barrier()
     print("Generated", len(nimp_inputs), "new data points")
     return len(nimp_inputs)

@@ -125,14 +125,18 @@ int gpe_predict_fullcov(gpe_handle* h, const double* Xs, const double* Hs, int m
 /* History-matching arithmetic (history_match.py:121-136, :237-250, :317-329) on per-emulator
  * mean/variance arrays mean [n_emul,m], var [n_emul,m] (device or host):
  * I_o = sqrt((mean_o - z_o)^2 / (var_o + var_extra_o)); Imax [m,maxno] ascending = the maxno
- * largest over emulators; keep [m] = Imax[r,0] < cm; count_lt [maxno] = #(Imax[r,maxno-1-k] < cm);
- * if ncell > 0, points are grouped contiguously in cells of m/ncell points and
- * cell_min [ncell,maxno], cell_count [ncell,maxno] are produced.  Any output may be NULL. */
+ * largest over emulators; keep [m] = Imax[r,0] < cm; count_lt [maxno] = #(Imax[r,maxno-1-k] < cm).
+ * Cells (imp_plot's grid cells, :91-136): if cell_pts > 0, local point r is point first_index + r of a
+ * flat global index whose consecutive runs of cell_pts points form the cells; cell_min [ncell,maxno]
+ * (min over the cell's points, +huge where the shard holds none) and cell_count [ncell,maxno]
+ * (#points below cm) are produced for the ncell cells starting at the cell of point first_index --
+ * a shard may begin and end inside a cell; the caller combines shards with min / sum.
+ * Any output may be NULL. */
 int gpe_implausibility(gpe_handle* h, const double* mean, const double* var, int n_emul,
                        long long m, const double* z, const double* var_extra, double cm,
-                       int maxno, long long ncell, double* Imax, unsigned char* keep,
-                       unsigned long long* count_lt, double* cell_min,
-                       unsigned long long* cell_count);
+                       int maxno, long long cell_pts, long long first_index, long long ncell,
+                       double* Imax, unsigned char* keep, unsigned long long* count_lt,
+                       double* cell_min, unsigned long long* cell_count);
 
 /* out [n,k] = A^-1 Bm [n,k] for the training matrix factored by gpe_fit_state -- the
  * np.linalg.solve(self.A, .) call sites of the sensitivity code

@@ -265,6 +265,7 @@ def gen_hm_api(g, h, n, seed):
                 for kind in ("IMP", "ODP"):
                     name = "g_%d_%s_%d_%d" % (m, kind, s_[0], s_[1])
                     out[name] = np.loadtxt(name)
+                    out["bytes_" + name] = np.frombuffer(open(name, "rb").read(), dtype=np.uint8)
             out["lhc_%d_%d" % tuple(s_)] = np.loadtxt("imp_input_%d_%d" % tuple(s_))
         pts = rng.random((300, 3))
         np.savetxt("sim_in", pts, fmt="%.17g")
@@ -274,11 +275,15 @@ def gen_hm_api(g, h, n, seed):
         out["nonimp_count"] = cnt
         out["nonimp_in"] = np.atleast_2d(np.loadtxt("nonimp_sim_in"))
         out["nonimp_out"] = np.atleast_2d(np.loadtxt("noninp_sim_out"))
+        for fn in ("nonimp_sim_in", "noninp_sim_out"):
+            out["bytes_" + fn] = np.frombuffer(open(fn, "rb").read(), dtype=np.uint8)
         np.random.seed(78)
         cnt2 = h.new_wave_design(emuls, zs, cm, ve, ["nonimp_sim_in", "noninp_sim_out"], maxno=1, olhcmult=40, fileStr="w2")
         out["wave_count"] = cnt2
         out["wave_in"] = np.atleast_2d(np.loadtxt("w2_nonimp_sim_in"))
         out["olhc_des"] = np.loadtxt("olhc_des")
+        for fn in ("w2_nonimp_sim_in", "olhc_des"):
+            out["bytes_" + fn] = np.frombuffer(open(fn, "rb").read(), dtype=np.uint8)
     return out
 
 
@@ -340,10 +345,192 @@ def gen_noisefit(gn):
     return out
 
 
+def bench_thetas(B_total, d, y, seed=0):
+    """bench.py:draw_thetas restated (the multistart draw of _emulatoroptimise.py:206-211 from the auto bounds), so the
+    full-size goldens sit exactly where the benchmark evaluates."""
+    np.random.seed(seed)
+    bounds = [[0.001, 1.0]] * d + [[0.001, float(np.sqrt(np.amax(y) - np.amin(y)))]]
+    tb = 2.0 * np.log(np.array(bounds))
+    grid = np.zeros((d + 1, B_total))
+    for R in range(d + 1):
+        grid[R, :] = tb[R, 0] + (tb[R, 1] - tb[R, 0]) * np.random.random_sample(B_total)
+    return np.ascontiguousarray(grid.T)
+
+
+def sha16(a):
+    import hashlib
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()[:16]
+
+
+FULL_MODES = [MODES[2], MODES[3], MODES[0], MODES[5]]   # gp4ml fixed / free nugget, mucm fixed, gp4ml alt-nugget free + r
+
+
+def gen_llh_fullsize(g, n=4096, d=16, seed=0, nugget=1e-4, which="corner", save=None):
+    """Headline shape (config 3): the REAL reference's loglikelihood_* at n=4096, d=16 (about a minute of CPU
+    per evaluation).  Stores theta, llh, grad, sigma only; X, y come from synth(n, d, seed) and the reference's
+    scaling (x-min)/(max-min), whose SHA-256 is stored so the test can prove it rebuilt the same inputs.
+    which="corner": thetas [0] guess 0 of the benchmark's draw (bench.py:draw_thetas; many tiny delta's: A is close
+    to the identity), [1] the well-correlated corner of the auto bounds (delta in [0.7, 1.0]: cond(A) ~ 1e7, the
+    ill-conditioned end), [2] guess 1 of the benchmark's draw.
+    which="mid": two thetas with delta in [0.15, 0.6] (strong but not extreme correlation) for the two gp4ml modes
+    and MUCM with a free nugget.
+    `save(out)` is called after every mode so that an interrupted run keeps what it has."""
+    import time
+    X, y, _ = synth(n, d, seed)
+    out = {"n": n, "d": d, "seed": seed, "nugget_belief": nugget}
+    bt = bench_thetas(256, d, y)
+    rng = np.random.default_rng(500 + seed)
+    ill = 0.7 + 0.3 * rng.random(d)
+    mids = [0.15 + 0.45 * rng.random(d) for _ in range(2)]
+    if which == "corner":
+        modes = FULL_MODES
+        points = [(np.exp(bt[0][:d] / 2.0), float(np.exp(bt[0][d] / 2.0)), 3e-3), (ill, 0.9, 2e-4),
+                  (np.exp(bt[1][:d] / 2.0), float(np.exp(bt[1][d] / 2.0)), 8e-3)]
+    else:
+        modes = [MODES[2], MODES[1], MODES[5]]
+        points = [(mids[0], 0.7, 1e-3), (mids[1], 1.3, 5e-3)]
+    with tempfile.TemporaryDirectory() as tmp:
+        for tag, mucm, alt, fix in modes:
+            E = build(g, tmp, X, y, mucm, alt, fix, nugget, "f_" + tag)
+            out["X_sha16"] = sha16(E.training.inputs)
+            out["H_sha16"] = sha16(E.training.H)
+            if alt == "T":
+                r = 0.01 + 0.02 * np.random.default_rng(501 + seed).random(n)
+                with RL.quiet():
+                    E.training.set_r(r)
+                out[tag + "_r"] = r
+            thetas, llhs, grads, sig = [], [], [], []
+            for t, (hp_d, hp_s, hp_n) in enumerate(points):
+                hp = list(hp_d)
+                if fix == "F":
+                    hp.append(hp_n)
+                if mucm == "F":
+                    hp.append(hp_s)
+                theta = E.K.transform(np.array(hp))
+                t0 = time.time()
+                with RL.quiet():
+                    res = (E.opt_T.loglikelihood_mucm if mucm == "T" else E.opt_T.loglikelihood_gp4ml)(theta.copy())
+                print(tag, t, "%.1f s" % (time.time() - t0), None if res is None else res[0], flush=True)
+                assert res is not None
+                thetas.append(theta); llhs.append(res[0]); grads.append(res[1].copy()); sig.append(float(E.par.sigma))
+            out[tag + "_theta"] = np.array(thetas)
+            out[tag + "_llh"] = np.array(llhs)
+            out[tag + "_grad"] = np.array(grads)
+            out[tag + "_sigma"] = np.array(sig)
+            del E
+            if save is not None:
+                save(out)
+    return out
+
+
+def gen_sens_fullsize(g, s, n=2000, d=8, seed=0, points=100):
+    """Config 5's size: uncertainty / sensitivity / main_effect(points=100) / totaleffectvariance of the REAL
+    reference at n=2000, d=8 (m=0.5, v=0.02 as SURVEY 8(d) config 5; delta 0.5, sigma 1, nugget 1e-4).  Run once
+    (tens of minutes of Python loops).  Stores the scalars/curves only; X, y from synth(n, d, seed)."""
+    import time
+    X, y, _ = synth(n, d, seed)
+    out = {"n": n, "d": d, "seed": seed}
+    with tempfile.TemporaryDirectory() as tmp:
+        E = build(g, tmp, X, y, "F", "F", "T", 1e-4, "sensfull")
+        delta = np.full(d, 0.5)
+        sigma = 1.0
+        E.par.delta = delta.copy(); E.K.d = E.par.delta; E.K.n = E.par.nugget
+        E.par.sigma = sigma
+        with RL.quiet():
+            E.training.remake()
+            E.opt_T.optimalbeta()
+            m = [0.5] * d
+            v = [0.02] * d
+            S = s.setup(E, list(m), list(v))
+        for name, fn in (("uncertainty", S.uncertainty), ("sensitivity", S.sensitivity),
+                         ("main_effect", lambda: S.main_effect(plot=False, points=points)),
+                         ("totaleffectvariance", S.totaleffectvariance)):
+            t0 = time.time()
+            with RL.quiet():
+                fn()
+            out["seconds_" + name] = time.time() - t0
+            print(name, "%.1f s" % out["seconds_" + name], flush=True)
+        out.update(X_sha16=sha16(E.training.inputs), delta=delta, sigma=sigma, nugget=float(E.par.nugget),
+                   beta=np.array(E.par.beta), m=np.array(m), v=np.array(v),
+                   input_range=np.array(E.all_data.input_range), uE=S.uE, uV=S.uV, uEV=S.uEV,
+                   senseindex=S.senseindex, effect=S.effect, mean_effect=S.mean_effect, EVTw=S.EVTw)
+    return out
+
+
+class _Swallow:
+    """Drawing stub: any attribute, call, index or arithmetic on it yields the stub (or 1.0), so the reference's
+    matplotlib calls after the arithmetic of interaction_effect (:385-401) run through without a display."""
+    def __getattr__(self, name): return self
+    def __call__(self, *a, **k): return self
+    def __getitem__(self, k): return self
+    def __sub__(self, o): return 1.0
+    __rsub__ = __truediv__ = __rtruediv__ = __mul__ = __rmul__ = __sub__
+    def __abs__(self): return 1.0
+
+
+def gen_writers(g, s):
+    """Byte-level goldens of the on-disk formats and interaction_effect (f4) for a FIXED-hyper-parameter
+    emulator (no optimiser in the way): the reference's own bytes of beliefs-N[f], inputs/outputs-oK-N[f], sense_file,
+    and the interaction matrix, together with every number that went into them."""
+    import sys as _sys
+    n, d = 40, 3
+    X, y, _ = synth(n, d, 12)
+    out = {"X_raw": X, "y": y}
+    with tempfile.TemporaryDirectory() as tmp, RL.cwd(tmp):
+        with RL.quiet():
+            cfg = RL.write_emulator_files(tmp, X, y, mucm="F", fix_nugget="T", alt_nugget="F", nugget=1e-3, name="wr",
+                                          tv_config="10 0 2")
+            E = g.setup(cfg, datashuffle=False, scaleinputs=True)
+            E.par.delta = np.array([0.41, 0.73, 0.58]); E.K.d = E.par.delta; E.K.n = E.par.nugget
+            E.par.sigma = 0.9375
+            E.training.remake(); E.validation.remake()
+            E.opt_T.optimalbeta()
+            E.post.remake()
+            for final in (False, True):
+                E.beliefs.final_beliefs(E, final)
+                E.post.final_design_points(E, final)
+        for fn in sorted(os.listdir(".")):
+            if fn.startswith("wr_") and "-" in fn:
+                out["file_" + fn] = np.frombuffer(open(fn, "rb").read(), dtype=np.uint8)
+        out.update(delta=np.array(E.par.delta), sigma=float(E.par.sigma), nugget=float(E.par.nugget), beta=np.array(E.par.beta),
+                   no_of_trains=int(E.tv_conf.no_of_trains))
+        with RL.quiet():
+            m, v = [0.5, 0.45, 0.55], [0.02, 0.03, 0.025]
+            S = s.setup(E, m, v)
+            S.uncertainty(); S.sensitivity(); S.main_effect(plot=False, points=11); S.totaleffectvariance()
+            S.to_file("sense_file")
+            out["file_sense_file"] = np.frombuffer(open("sense_file", "rb").read(), dtype=np.uint8)
+            out.update(m=np.array(m), v=np.array(v), uE=S.uE, uV=S.uV, uEV=S.uEV, senseindex=np.array(S.senseindex),
+                       EVTw=np.array(S.EVTw), effect=np.array(S.effect), mean_effect=np.array(S.mean_effect))
+            # interaction_effect with the drawing swallowed
+            mod = _sys.modules[type(S).__module__]
+            old_plt = getattr(mod, "plt", None)
+            mod.plt = _Swallow()
+            try:
+                S.interaction_effect(0, 2, points=7)
+            finally:
+                mod.plt = old_plt
+            out["interaction_0_2"] = np.array(S.interaction)
+            out["interaction_mean_effect"] = np.array(S.mean_effect)
+    return out
+
+
 def main():
     assert RL.available(), "reference not present"
     g, h, s, gn = RL.load()
     save = lambda name, d: (np.savez_compressed(os.path.join(HERE, name), **d), print("wrote", name))
+    if len(sys.argv) > 1 and sys.argv[1] == "fullsize_llh":
+        gen_llh_fullsize(g, which="corner", save=lambda o: save("llh_n4096_d16.npz", o))
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "fullsize_llh_mid":
+        gen_llh_fullsize(g, which="mid", save=lambda o: save("llh_n4096_d16_mid.npz", o))
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "fullsize_sens":
+        save("sens_n2000_d8.npz", gen_sens_fullsize(g, s))
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "writers":
+        save("writers_n40_d3.npz", gen_writers(g, s))
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "sens":
         save("sens_n60_d3.npz", gen_sens(g, s, 60, 3, 7))
         save("sens_n150_d4.npz", gen_sens(g, s, 150, 4, 8))

@@ -408,3 +408,74 @@ def test_toysim_training_log_matches_reference_line_by_line(golden_dir, tmp_path
                 assert np.allclose(na[:k], nb[:k], rtol=2e-3, atol=2e-4), (a, b)
         else:
             assert np.allclose(na, nb, rtol=2e-3, atol=1e-6), (a, b)
+
+
+def test_setup_survives_initial_beliefs_that_are_not_positive_definite(tmp_path):
+    """g.setup builds Posterior(validation, training) from the INITIAL beliefs (reference emulatorfunctions.py:52);
+    the reference gets through an ill-conditioned starting point with LU solves and lets train() replace the
+    hyper-parameters.  Here the setup-time Posterior is lazy: setup() and train() must work with nugget 0 and
+    delta 1 on duplicated inputs (a singular correlation matrix up to rounding); nothing is factored before the
+    trained hyper-parameters are in place."""
+    import gp_emu_uqsa_b200 as g
+    from oracle import ref_loader as RL          # only its text-file writer
+    rng = np.random.default_rng(21)
+    X = rng.random((80, 2))
+    X[40:] = X[:40]                                # duplicated rows: singular without a nugget
+    y = np.sin(3 * X[:, 0]) + X[:, 1] + 0.01 * rng.normal(size=80)
+    with _cwd(tmp_path), _quiet():
+        cfg = RL.write_emulator_files(str(tmp_path), X, y, mucm="F", fix_nugget="F", alt_nugget="F", nugget=0.0,
+                                      delta=[1.0, 1.0], name="sing", tries=4, tv_config="10 0 2")
+        np.random.seed(3)
+        E = g.setup(cfg, datashuffle=False, scaleinputs=True)       # must not exit
+        assert E.post._stale                                        # nothing factored yet
+        g.train(E)
+        assert np.isfinite(E.post.mean).all() and E.par.nugget > 0
+
+
+def test_written_files_are_byte_identical_to_the_reference(golden_dir, tmp_path):
+    """for a fixed-hyper-parameter emulator (tests/golden/make_golden.py writers) the checkpoint
+    files this package writes -- <beliefs>-N[f], <inputs>-oK-N[f], <outputs>-oK-N[f] -- are the reference's bytes; the
+    sensitivity results agree to 1e-9 and, written through to_file, give the reference's sense_file byte for byte once
+    the same numbers are in; interaction_effect (_sensitivityclasses.py:327-383) matches the reference's matrix."""
+    import gp_emu_uqsa_b200 as g
+    import gp_emu_uqsa_b200.sensitivity as s
+    from oracle import ref_loader as RL          # only its text-file writer
+    G = np.load(os.path.join(golden_dir, "writers_n40_d3.npz"))
+    with _cwd(tmp_path), _quiet():
+        cfg = RL.write_emulator_files(str(tmp_path), G["X_raw"], G["y"], mucm="F", fix_nugget="T", alt_nugget="F", nugget=1e-3,
+                                      name="wr", tv_config="10 0 2")
+        E = g.setup(cfg, datashuffle=False, scaleinputs=True)
+        E.par.delta = G["delta"].copy(); E.K.d = E.par.delta; E.K.n = E.par.nugget
+        E.par.sigma = float(G["sigma"])
+        E.training.remake(); E.validation.remake()
+        E.opt_T.optimalbeta()
+        assert np.allclose(E.par.beta, G["beta"], rtol=1e-9, atol=1e-12)
+        E.par.beta = G["beta"].copy()          # the same numbers in -> the same bytes out
+        E.post.remake()
+        for final in (False, True):
+            E.beliefs.final_beliefs(E, final)
+            E.post.final_design_points(E, final)
+        names = [k[5:] for k in G.files if k.startswith("file_wr_")]
+        assert len(names) == 6
+        for fn in names:
+            assert open(fn, "rb").read() == bytes(G["file_" + fn]), fn
+        S = s.setup(E, list(G["m"]), list(G["v"]))
+        S.uncertainty(); S.sensitivity(); S.main_effect(plot=False, points=11); S.totaleffectvariance()
+        scale = abs(float(G["uEV"]))
+        for name in ("uE", "uV", "uEV"):
+            assert abs(getattr(S, name) - float(G[name])) <= 1e-9 * max(scale, abs(float(G[name]))), name
+        assert np.abs(np.asarray(S.senseindex) - G["senseindex"]).max() <= 1e-9 * scale
+        assert np.abs(np.asarray(S.EVTw) - G["EVTw"]).max() <= 1e-9 * scale
+        assert np.abs(np.asarray(S.effect) - G["effect"]).max() <= 1e-9
+        S.to_file("sense_mine")
+        mine, ref = open("sense_mine").read().split("\n"), bytes(G["file_sense_file"]).decode().split("\n")
+        assert [ln.split(" ")[0] for ln in mine] == [ln.split(" ")[0] for ln in ref]
+        assert [len(ln.split(" ")) for ln in mine] == [len(ln.split(" ")) for ln in ref]
+        S.uE, S.uV, S.uEV = float(G["uE"]), float(G["uV"]), float(G["uEV"])
+        S.senseindex, S.EVTw, S.effect = G["senseindex"].copy(), G["EVTw"].copy(), G["effect"].copy()
+        S.to_file("sense_same_numbers")
+        assert open("sense_same_numbers", "rb").read() == bytes(G["file_sense_file"])
+        S2 = s.setup(E, list(G["m"]), list(G["v"]))
+        S2.interaction_effect(0, 2, points=7)
+        assert np.abs(S2.interaction - G["interaction_0_2"]).max() <= 1e-9 * max(1.0, np.abs(G["interaction_0_2"]).max())
+        assert np.abs(np.asarray(S2.mean_effect) - G["interaction_mean_effect"]).max() <= 1e-9

@@ -34,7 +34,6 @@ def test_factor_times_inverse_is_identity_n4096(dev):
     Lf, Li = np.empty_like(A), np.empty_like(A)
     ld, st = np.empty(1), np.zeros(1, dtype=np.int32)
     dev._ck(dev.L.gpe_potrf(dev.h, _lib._ptr(A), n, 1, _lib._ptr(Lf), _lib._ptr(Li), _lib._ptr(ld), _lib._ptr(st)))
-    dev.n = dev.d = dev.q = 0
     assert st[0] == 0
     assert np.allclose(np.triu(Lf, 1), 0) and np.allclose(np.triu(Li, 1), 0)
     R = Li @ Lf - np.eye(n)
@@ -178,3 +177,65 @@ def test_large_ragged_n10000_gradient_matches_finite_differences(dev):
     fd = (llh[1] - llh[2]) / (2 * eps)
     assert abs(fd - grad[0] @ v) <= 5e-6 * max(1.0, np.abs(grad[0]).max()), (fd, grad[0] @ v)
     assert np.isfinite(grad).all() and np.isfinite(sig).all()
+
+
+def test_potrf_leaves_training_set_and_fit_state_alone(dev):
+    """gpe_fit_state -> gpe_potrf (host and device buffers, another size) -> gpe_predict on ONE handle returns the
+    pre-potrf prediction bit for bit: the dense Cholesky works in its own temporaries (noise_fit.py:130-150 and
+    Posterior.mahalanobis_distance call it between predictions)."""
+    from gp_emu_uqsa_b200 import _lib
+    n, d = 700, 5
+    X, y = _synth(n, d, seed=9)
+    H = np.column_stack([np.ones(n), X])
+    dev.set_training(X, y, H)
+    dev.set_basis(list(range(d)), [1] * d)
+    beta, _, st = dev.fit_state(np.full(d, 0.4), 1e-4, 1.1, 0)
+    assert st == 0
+    P = np.random.default_rng(3).random((300, d))
+    m0, v0 = dev.predict(P)
+    l0, g0, _, st0 = dev.llh_grad_batch(2 * np.log(np.r_[np.full(d, 0.4), 1.1])[None], 0, fixed_nugget=1e-4)
+    # a 300 x 300 posterior covariance, host buffers
+    _, V = dev.predict_fullcov(P)
+    Lf = dev.cholesky(V)
+    assert np.allclose(Lf @ Lf.T, V, rtol=0, atol=1e-12 * np.abs(V).max())
+    assert np.allclose(Lf, np.linalg.cholesky(V), rtol=1e-6, atol=1e-9 * np.sqrt(np.abs(V).max()))
+    # device buffers, a batch of two, size not a multiple of the tile
+    Ad = torch.tensor(np.stack([V[:200, :200], 2.0 * V[:200, :200]]), device="cuda")
+    Ld = torch.empty_like(Ad); Lid = torch.empty_like(Ad)
+    ld = torch.empty(2, dtype=torch.float64, device="cuda"); sd = torch.zeros(2, dtype=torch.int32, device="cuda")
+    dev._ck(dev.L.gpe_potrf(dev.h, Ad.data_ptr(), 200, 2, Ld.data_ptr(), Lid.data_ptr(), ld.data_ptr(), sd.data_ptr()))
+    torch.cuda.synchronize()
+    assert int(sd.abs().sum()) == 0
+    assert torch.allclose(Ld @ Ld.transpose(1, 2), Ad, rtol=0, atol=1e-12 * float(Ad.abs().max()))
+    assert torch.allclose(Lid @ Ld, torch.eye(200, dtype=torch.float64, device="cuda").expand(2, 200, 200), rtol=0, atol=1e-8)
+    assert torch.allclose(ld, 2.0 * torch.log(torch.diagonal(Ld, dim1=1, dim2=2)).sum(1), rtol=1e-11)
+    # the handle still serves the same training set and fit
+    assert dev.n == n
+    m1, v1 = dev.predict(P)
+    assert np.array_equal(m0, m1) and np.array_equal(v0, v1)
+    l1, g1, _, st1 = dev.llh_grad_batch(2 * np.log(np.r_[np.full(d, 0.4), 1.1])[None], 0, fixed_nugget=1e-4)
+    assert np.array_equal(l0, l1) and np.array_equal(g0, g1)
+
+
+def test_implausibility_cells_of_a_shard_that_starts_and_ends_inside_a_cell(dev):
+    """Point-sharded history matching: cell statistics of arbitrary index ranges combine (min / sum) to the
+    statistics of the whole set, cells straddling shard boundaries included."""
+    rng = np.random.default_rng(12)
+    m, cell_pts, cm = 10000, 700, 1.2
+    mean = rng.normal(size=(2, m)); var = 0.1 + rng.random((2, m))
+    zs, ve = [0.1, -0.2], [0.05, 0.02]
+    ncell = (m + cell_pts - 1) // cell_pts
+    I = np.sqrt((mean - np.array(zs)[:, None]) ** 2 / (var + np.array(ve)[:, None])).max(0)
+    ref_min = np.array([I[c * cell_pts:(c + 1) * cell_pts].min() for c in range(ncell)])
+    ref_cnt = np.array([(I[c * cell_pts:(c + 1) * cell_pts] < cm).sum() for c in range(ncell)])
+    tot_min, tot_cnt, kept = np.full(ncell, np.inf), np.zeros(ncell, dtype=np.uint64), 0
+    for lo, hi in ((0, 1234), (1234, 1234), (1234, 6001), (6001, m)):          # one empty shard
+        _, keep, cnt, cmin, ccnt = dev.implausibility(mean[:, lo:hi], var[:, lo:hi], zs, ve, cm, maxno=1, cell_pts=cell_pts,
+                                                      first_index=lo, want_imax=False)
+        kept += int(cnt[0])
+        if hi > lo:
+            c0 = lo // cell_pts
+            tot_min[c0:c0 + cmin.shape[0]] = np.minimum(tot_min[c0:c0 + cmin.shape[0]], cmin[:, 0])
+            tot_cnt[c0:c0 + ccnt.shape[0]] += ccnt[:, 0]
+            assert np.array_equal(keep.astype(bool), I[lo:hi] < cm)
+    assert np.array_equal(tot_min, ref_min) and np.array_equal(tot_cnt, ref_cnt.astype(np.uint64)) and kept == int((I < cm).sum())

@@ -1,0 +1,120 @@
+"""Parity at the headline shapes against numbers produced by the REAL reference (tests/golden/make_golden.py
+fullsize_llh / fullsize_sens, run once in the build container: about a minute of CPU per likelihood evaluation,
+tens of minutes for the sensitivity routines):
+
+  * config 3: loglikelihood_gp4ml / loglikelihood_mucm at n = 4096, d = 16 -- fixed and free nugget, MUCM, and the
+    alt-nugget kernel with an r vector -- at theta's taken from the benchmark's own draw and from the
+    ill-conditioned corner of the auto bounds (delta in [0.7, 1], cond(A) ~ 1e7).  Tolerances are north_star's:
+    llh rel 1e-10, gradient 1e-9 of its largest component (not loosened for the ill-conditioned point);
+  * config 5: Sensitivity.uncertainty / sensitivity / main_effect / totaleffectvariance at n = 2000, d = 8,
+    1e-7 of E*[var f] (they are differences of O(1) integrals), main effects 1e-8.
+
+Only theta and the results are stored; X, y are regenerated from the seed and the reference's input scaling is
+re-applied -- a SHA-256 of the scaled inputs proves the test evaluates the same data the reference did."""
+import contextlib
+import hashlib
+import io
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _synth(n, d, seed):
+    rng = np.random.default_rng(seed)
+    X = rng.random((n, d))
+    w = rng.normal(size=d)
+    return X, np.sin(X @ w) + 0.1 * (X ** 2).sum(1)
+
+
+def _scaled(X):
+    """All_Data.map_inputs_0to1 (_emulatorclasses.py:448-477): (x - min) / (max - min) per column."""
+    Xs = X.copy()
+    for i in range(X.shape[1]):
+        lo, hi = np.amin(Xs[:, i]), np.amax(Xs[:, i])
+        Xs[:, i] = (Xs[:, i] - lo) / (hi - lo)
+    return Xs
+
+
+def _sha16(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()[:16]
+
+
+MODES = {"gp4ml_k_fixT": 0, "gp4ml_k_fixF": 4, "mucm_k_fixT": 1, "gp4ml_alt_fixF": 2 | 4}
+
+
+@pytest.mark.parametrize("gfile", ["llh_n4096_d16.npz", "llh_n4096_d16_mid.npz"])
+def test_llh_grad_matches_real_reference_at_n4096_d16(gfile):
+    from gp_emu_uqsa_b200 import _lib
+    path = os.path.join(GOLDEN, gfile)
+    if not os.path.exists(path):
+        pytest.skip(gfile + " not generated")
+    G = np.load(path)
+    n, d, seed = int(G["n"]), int(G["d"]), int(G["seed"])
+    Xraw, y = _synth(n, d, seed)
+    X = _scaled(Xraw)
+    H = np.column_stack([np.ones(n), X])
+    assert _sha16(X) == str(G["X_sha16"]) and _sha16(H) == str(G["H_sha16"])
+    dev = _lib.Device(0)
+    worst = {}
+    try:
+        for tag, mode in MODES.items():
+            if tag + "_theta" not in G.files:
+                continue
+            r = G[tag + "_r"] if tag + "_r" in G.files else None
+            dev.set_training(X, y, H, r)
+            theta = G[tag + "_theta"]
+            llh, grad, sig, st = dev.llh_grad_batch(theta, mode, fixed_nugget=float(G["nugget_belief"]))
+            assert (st == 0).all(), (tag, st)
+            el = np.abs(llh - G[tag + "_llh"]) / np.abs(G[tag + "_llh"])
+            eg = np.abs(grad - G[tag + "_grad"]).max(1) / np.abs(G[tag + "_grad"]).max(1)
+            worst[tag] = (el.max(), eg.max())
+            assert (el <= 1e-10).all(), (tag, "llh", el)
+            assert (eg <= 1e-9).all(), (tag, "grad", eg)
+            if mode & 1:
+                assert np.allclose(sig, G[tag + "_sigma"], rtol=1e-10, atol=0), (tag, "sigma")
+    finally:
+        dev.close()
+    print("n=4096 d=16 worst (llh rel, grad rel-to-max) per mode:", worst)
+
+
+def test_sensitivity_matches_real_reference_at_n2000_d8(tmp_path):
+    import gp_emu_uqsa_b200 as g
+    import gp_emu_uqsa_b200.sensitivity as s
+    from oracle import ref_loader as RL          # only its text-file writer
+    path = os.path.join(GOLDEN, "sens_n2000_d8.npz")
+    if not os.path.exists(path):
+        pytest.skip("sens_n2000_d8.npz not generated")
+    G = np.load(path)
+    n, d, seed = int(G["n"]), int(G["d"]), int(G["seed"])
+    X, y = _synth(n, d, seed)
+    old = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):
+            cfg = RL.write_emulator_files(str(tmp_path), X, y, mucm="F", fix_nugget="T", alt_nugget="F", nugget=1e-4, name="sensfull")
+            E = g.setup(cfg, datashuffle=False, scaleinputs=True)
+            assert _sha16(E.training.inputs) == str(G["X_sha16"])
+            E.par.delta = G["delta"].copy(); E.K.d = E.par.delta; E.K.n = E.par.nugget
+            E.par.sigma = float(G["sigma"])
+            E.training.remake()
+            E.opt_T.optimalbeta()
+            S = s.setup(E, list(G["m"]), list(G["v"]))
+            S.uncertainty()
+            S.sensitivity()
+            S.main_effect(plot=False, points=int(G["mean_effect"].shape[1]) if G["mean_effect"].ndim == 2 else 100)
+            S.totaleffectvariance()
+    finally:
+        os.chdir(old)
+    assert np.allclose(E.par.beta, G["beta"], rtol=1e-8, atol=1e-10)
+    scale = abs(float(G["uEV"]))
+    for name in ("uE", "uV", "uEV"):
+        assert abs(getattr(S, name) - float(G[name])) <= 1e-7 * max(scale, abs(float(G[name]))), name
+    assert np.abs(np.asarray(S.senseindex) - G["senseindex"]).max() <= 1e-7 * scale
+    assert np.abs(np.asarray(S.EVTw) - G["EVTw"]).max() <= 1e-7 * scale
+    assert np.abs(np.asarray(S.mean_effect) - G["mean_effect"]).max() <= 1e-8 * max(1.0, np.abs(G["mean_effect"]).max())

@@ -54,6 +54,12 @@ def test_history_match_functions_match_reference(golden_dir, tmp_path):
                 odp = np.loadtxt("g_%d_ODP_%d_%d" % (m, s_[0], s_[1]))
                 assert np.allclose(imp, gold["g_%d_IMP_%d_%d" % (m, s_[0], s_[1])], rtol=1e-7, atol=1e-9)
                 assert np.array_equal(odp, gold["g_%d_ODP_%d_%d" % (m, s_[0], s_[1])])
+                # byte level: the optical-depth files hold count ratios -> the reference's bytes exactly;
+                # the implausibility files hold minima that agree to rounding -> same layout, every number parsed equal to 1e-7
+                assert open("g_%d_ODP_%d_%d" % (m, s_[0], s_[1]), "rb").read() == bytes(gold["bytes_g_%d_ODP_%d_%d" % (m, s_[0], s_[1])])
+                mine_txt = open("g_%d_IMP_%d_%d" % (m, s_[0], s_[1])).read().split("\n")
+                ref_txt = bytes(gold["bytes_g_%d_IMP_%d_%d" % (m, s_[0], s_[1])]).decode().split("\n")
+                assert len(mine_txt) == len(ref_txt) and [len(a) for a in mine_txt] == [len(b) for b in ref_txt]
         rec = h.imp_plot_recon(cm, maxno=1, act=[0, 1, 2], fileStr="g")
         assert set(rec) == {(0, 1), (0, 2), (1, 2)}
         np.savetxt("sim_in", gold["sim_in"], fmt="%.17g")
@@ -62,11 +68,15 @@ def test_history_match_functions_match_reference(golden_dir, tmp_path):
         assert cnt == int(gold["nonimp_count"])
         assert np.allclose(np.atleast_2d(np.loadtxt("nonimp_sim_in")), gold["nonimp_in"], rtol=0, atol=1e-15)
         assert np.allclose(np.atleast_2d(np.loadtxt("noninp_sim_out")), gold["nonimp_out"], rtol=0, atol=1e-15)
+        for fn in ("nonimp_sim_in", "noninp_sim_out"):          # identical keep set -> identical bytes
+            assert open(fn, "rb").read() == bytes(gold["bytes_" + fn]), fn
         np.random.seed(78)
         cnt2 = h.new_wave_design(emuls, zs, cm, ve, ["nonimp_sim_in", "noninp_sim_out"], maxno=1, olhcmult=40, fileStr="w2")
         assert np.array_equal(np.loadtxt("olhc_des"), gold["olhc_des"])
         assert cnt2 == int(gold["wave_count"])
         assert np.allclose(np.atleast_2d(np.loadtxt("w2_nonimp_sim_in")), gold["wave_in"], rtol=0, atol=1e-15)
+        for fn in ("olhc_des", "w2_nonimp_sim_in"):
+            assert open(fn, "rb").read() == bytes(gold["bytes_" + fn]), fn
 
 
 def _beliefs(text):
