@@ -77,7 +77,7 @@ void gpe_handle::drop_graphs() {
 
 void gpe_handle::free_batch_ws() {
     drop_graphs();
-    dev_free(A); dev_free(S); dev_free(Li); dev_free(Wy); dev_free(Z); dev_free(U); dev_free(GP);
+    dev_free(A); dev_free(S); dev_free(Li); dev_free(Ex); dev_free(Wy); dev_free(Z); dev_free(U); dev_free(GP);
     dev_free(logdet_part); dev_free(par); dev_free(out); dev_free(winv); dev_free(beta);
     dev_free(status); dev_free(gpart); dev_free(theta_d); dev_free(llh_d); dev_free(grad_d); dev_free(sig_d);
     Bcap = 0;
@@ -98,7 +98,7 @@ int gpe_ensure_batch_ws(gpe_handle* h, int B) {
     // A workspace that already has the largest obtainable size is kept: batches beyond it run as sub-batches
     // (re-allocating here on every call would also destroy the CUDA graphs before they are ever replayed).
     if (B <= h->Bcap || (h->Bcap > 0 && h->Bcap_final)) return 0;
-    size_t per_item = 3ull * h->npad * h->npad * sizeof(double) + 3ull * h->npad * NR * sizeof(double);
+    size_t per_item = 4ull * h->npad * h->npad * sizeof(double) + 3ull * h->npad * NR * sizeof(double);
     size_t free_b = 0, total_b = 0;
     h->free_batch_ws();
     CK(cudaMemGetInfo(&free_b, &total_b));
@@ -111,6 +111,7 @@ int gpe_ensure_batch_ws(gpe_handle* h, int B) {
     CK(dev_alloc(&h->A, want * nn));
     CK(dev_alloc(&h->S, want * nn));
     CK(dev_alloc(&h->Li, want * nn));
+    CK(dev_alloc(&h->Ex, want * nn));
     CK(cudaMemsetAsync(h->Li, 0, want * nn * sizeof(double), h->st));
     size_t pn = (size_t)h->npad * NR;
     CK(dev_alloc(&h->Wy, want * pn));
@@ -285,6 +286,7 @@ int gpe_factor_and_reduce(gpe_handle* h, const SubBatch& sb, int mode, int with_
         // (gpe_lauum_grad.cu).  Wy and Z are dead by now and hold U^T and -U^T.
         ProfScope ps(h, gpe_handle::CAT_LAUUM, st);
         cudaError_t e = launch_lauum_grad(Lb, sM, np, h->n, h->d, h->q + 1, U, Wy, Z, h->X, h->r, h->winv + (size_t)b0 * h->d,
+                                          h->Ex + (size_t)b0 * sM, sM,
                                           h->gpart + (size_t)b0 * lauum_grad_ntiles(np) * grad_nvals(h->d), B, st);
         h->launches += 2;
         if (e != cudaSuccess) return h->fail("launch_lauum_grad", e);
@@ -586,7 +588,8 @@ static int enqueue_llh_chunk(gpe_handle* h, int Bs, int p, int mode, double fixe
         {
             ProfScope ps(h, gpe_handle::CAT_COV, sb.st);
             CK(launch_cov_build(h->X, h->r, h->n, h->d, h->npad, h->par + sb.b0, h->winv + (size_t)sb.b0 * h->d,
-                                h->A + (size_t)sb.b0 * sM, sM, sb.B, 0, sb.st));
+                                h->A + (size_t)sb.b0 * sM, sM, sb.B, 0, sb.st, 0, 0,
+                                h->grad_fused ? h->Ex + (size_t)sb.b0 * sM : nullptr));
         }
         h->launches++;
         if ((rc = gpe_factor_and_reduce(h, sb, mode, 1, nullptr, nullptr))) return rc;

@@ -17,8 +17,9 @@ static bool use_ws() {
 
 template <bool A_KC, bool B_KC>
 static cudaError_t dispatch_tiles(const GemmP& p, int epi, cudaStream_t st) {
-    if (p.M == 32) {   // skinny-M panel product (prediction: [e | Gm K^-T]^T C)
+    if (p.M == 32 || p.M == 16) {   // skinny-M panel product (prediction: [e | Gm K^-T]^T C; 16 rows when q + 1 <= 16)
         if (epi != EPI_STORE || p.N % 128) return cudaErrorInvalidValue;
+        if (p.M == 16) return launch_gemm_cfg<16, 128, 1, 8, A_KC, B_KC, EPI_STORE>(p, st);
         return launch_gemm_cfg<32, 128, 1, 8, A_KC, B_KC, EPI_STORE>(p, st);
     }
     if (p.N == 32) {

@@ -60,6 +60,7 @@ struct gpe_handle {
     bool Bcap_final = false;
     bool grad_fused = false;     // this chunk's LAUUM carries the gradient reduction in its epilogue (gpe_lauum_grad.cu)     // the workspace already has the largest size obtainable (env cap or device memory)
     double *A = nullptr, *S = nullptr, *Li = nullptr;        // [Bcap][npad][npad]
+    double* Ex = nullptr;                                    // [Bcap][npad][npad] exp(-D) kept by the covariance build for the fused gradient epilogue
     double *Wy = nullptr, *Z = nullptr, *U = nullptr;        // [Bcap][npad][NR]
     double *GP = nullptr, *logdet_part = nullptr, *winv = nullptr, *beta = nullptr, *gpart = nullptr;
     gpe::ItemPar* par = nullptr;

@@ -65,7 +65,7 @@ template <int GMODE>
 __global__ void __launch_bounds__(256, 3) cov_build_kernel(const double* __restrict__ X, const double* __restrict__ r,
                                                         int n, int d, int npad, const ItemPar* __restrict__ par,
                                                         const double* __restrict__ winv, double* __restrict__ A,
-                                                        long long sA, int full, int gdim) {
+                                                        long long sA, int full, int gdim, double* __restrict__ Eout) {
     constexpr int gmode = GMODE;
     int tj = blockIdx.x, ti = blockIdx.y;
     const int b = blockIdx.z;
@@ -135,12 +135,17 @@ __global__ void __launch_bounds__(256, 3) cov_build_kernel(const double* __restr
                 v[e] = val;
             }
             *reinterpret_cast<double2*>(&Ab[(size_t)gi * npad + gj0]) = make_double2(v[0], v[1]);
+            if constexpr (GMODE == 0) {
+                if (Eout != nullptr)
+                    *reinterpret_cast<double2*>(&Eout[(size_t)b * sA + (size_t)gi * npad + gj0]) = make_double2(D[a][2 * h], D[a][2 * h + 1]);
+            }
         }
     }
 }
 
 cudaError_t launch_cov_build(const double* X, const double* r, int n, int d, int npad, const ItemPar* par,
-                             const double* winv, double* A, long long sA, int B, int full, cudaStream_t st, int gmode, int gdim) {
+                             const double* winv, double* A, long long sA, int B, int full, cudaStream_t st, int gmode, int gdim,
+                             double* Eout) {
     const int nt = npad / CT;
     dim3 grid = full ? dim3(nt, nt, B) : dim3(nt * (nt + 1) / 2, 1, B);
     size_t smem = (size_t)d * (CT + CT + 2) * sizeof(double);
@@ -148,13 +153,13 @@ cudaError_t launch_cov_build(const double* X, const double* r, int n, int d, int
     cudaError_t e;
     if (gmode == 0) {
         if ((e = opt0.ensure(cov_build_kernel<0>, smem)) != cudaSuccess) return e;
-        cov_build_kernel<0><<<grid, 256, smem, st>>>(X, r, n, d, npad, par, winv, A, sA, full, gdim);
+        cov_build_kernel<0><<<grid, 256, smem, st>>>(X, r, n, d, npad, par, winv, A, sA, full, gdim, Eout);
     } else if (gmode == 1) {
         if ((e = opt1.ensure(cov_build_kernel<1>, smem)) != cudaSuccess) return e;
-        cov_build_kernel<1><<<grid, 256, smem, st>>>(X, r, n, d, npad, par, winv, A, sA, full, gdim);
+        cov_build_kernel<1><<<grid, 256, smem, st>>>(X, r, n, d, npad, par, winv, A, sA, full, gdim, nullptr);
     } else {
         if ((e = opt2.ensure(cov_build_kernel<2>, smem)) != cudaSuccess) return e;
-        cov_build_kernel<2><<<grid, 256, smem, st>>>(X, r, n, d, npad, par, winv, A, sA, full, gdim);
+        cov_build_kernel<2><<<grid, 256, smem, st>>>(X, r, n, d, npad, par, winv, A, sA, full, gdim, nullptr);
     }
     return cudaGetLastError();
 }

@@ -31,9 +31,11 @@ void launch_prep_theta(const double* theta, int B, int p, int d, int mode, doubl
                        ItemPar* par, double* winv, cudaStream_t st);
 
 // K1: A[b] (ld = npad, batch stride sA) from X [n,d]; lower 64x64 tiles only unless full.
+// Eout (optional, gmode 0 only): a second matrix per item that receives exp(-D_ij) itself, same tiles and strides as A --
+// the factorisation overwrites A, the fused gradient epilogue reads this copy instead of recomputing the exponentials.
 cudaError_t launch_cov_build(const double* X, const double* r, int n, int d, int npad, const ItemPar* par,
                              const double* winv, double* A, long long sA, int B, int full, cudaStream_t st,
-                             int gmode = 0, int gdim = 0);
+                             int gmode = 0, int gdim = 0, double* Eout = nullptr);
 
 // copy the n x n top-left of a padded matrix into a dense [n,n] output, mirroring the lower triangle
 void launch_unpad_sym(const double* A, int npad, int n, double* out, int mirror, cudaStream_t st);
@@ -72,7 +74,8 @@ void launch_grad_finalize(const double* part, int ntile, int n, int d, int npad,
 bool lauum_grad_supported(int d);
 int lauum_grad_ntiles(int npad);
 cudaError_t launch_lauum_grad(const double* Li, long long sL, int np, int n, int d, int nu, const double* U, double* Ut, double* nUt,
-                              const double* X, const double* r, const double* winv, double* part, int B, cudaStream_t st);
+                              const double* X, const double* r, const double* winv, const double* E, long long sE, double* part,
+                              int B, cudaStream_t st);
 
 inline int grad_ntiles(int npad) { int t = npad / 64; return t * (t + 1) / 2; }
 inline int grad_nvals(int d) { return d + 3; }

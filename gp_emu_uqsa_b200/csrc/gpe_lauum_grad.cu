@@ -12,12 +12,16 @@
 //   * the k loop runs over L^-1 (k >= i, as LAUUM) and then over the NR columns of U, whose tiles come from a
 //     pre-negated k-major copy (-U^T as the A operand, U^T as the B operand), so W = A^-1 - U U^T falls out of the
 //     tensor pipe and the 2 x 18 FMA per entry of the old dot products disappear;
-//   * the epilogue stages the scaled input tiles X_i / delta, X_j / delta in the (now free) pipeline stages,
-//     recomputes E for the 64 entries a lane holds, and reduces sum W E Delta_k^2 (k < d), sum W E, sum_diag W,
-//     sum_diag W r into one partial row per tile, which grad_finalize_kernel adds up in a fixed order.
+//   * the epilogue stages the scaled input tiles X_i / delta, X_j / delta in the (now free) pipeline stages, reads
+//     E_ij = exp(-D_ij) for the 64 entries a lane holds from the copy the covariance build kept (the FP64 pipe is the
+//     bottleneck of this path and HBM is idle: 8 bytes per entry are cheaper than 2d + 22 FP64 instructions), and
+//     reduces sum W E Delta_k^2 (k < d), sum W E, sum_diag W, sum_diag W r into one partial row per tile, which
+//     grad_finalize_kernel adds up in a fixed order.
 // A^-1 is not written at all on this path (the sensitivity code builds it on demand with the generic kernel).
 #include "gpe_gemm.cuh"
 #include "gpe_kernels.cuh"
+
+#include <algorithm>
 
 namespace gpe {
 
@@ -32,6 +36,8 @@ struct LauumGradP {
     const double* X;       // [n][d]
     const double* r;       // [n] or null
     const double* winv;    // [B][d]  1 / delta
+    const double* E;       // [B][np][np]  exp(-D) as written by the covariance build (lower 64x64 tiles)
+    long long sE;
     double* part;          // [B][ntile][d + 3]
     int ntile;
 };
@@ -95,6 +101,16 @@ __global__ void __launch_bounds__(WS_THREADS, 1) lauum_grad_kernel(LauumGradP p)
                 load_tile_warp<BN, false>(Bs + s * B_EL, Bu + (kt - KT0) * kstep, p.np, lane);
             }
             cp_async_mbar_arrive_noinc(&full_bar[s]);
+            // the epilogue reads this tile's 128 x 128 block of E (written by the covariance build a whole factorisation
+            // ago: it comes from HBM).  Ask L2 for it while the consumers still have a few k-tiles to go.
+            if (kt == KT - GEMM_STAGES - 4 || (KT < GEMM_STAGES + 5 && kt == 0)) {
+                const double* Eg = p.E + (size_t)b * p.sE + (size_t)m0 * p.np + n0;
+#pragma unroll 4
+                for (int q = 0; q < 32; q++) {                 // 128 rows x 8 lines of 128 bytes
+                    const int li = q * 32 + lane;
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(Eg + (size_t)(li >> 3) * p.np + (li & 7) * 16));
+                }
+            }
         }
         cp_async_wait<0>();
         return;
@@ -138,101 +154,125 @@ __global__ void __launch_bounds__(WS_THREADS, 1) lauum_grad_kernel(LauumGradP p)
         if (lane == 0) mbar_arrive(&empty_bar[s]);
     }
 
-    // ===== epilogue: acc = W tile.  Stage the scaled input tiles in the free pipeline stages. =====
+    // ===== epilogue: acc = W tile.  The pipeline stages are free: stage the E tile and the scaled input tiles there. =====
     const int d = p.d, n = p.n;
     named_bar_sync(2, WS_CONSUMERS * 32);           // every consumer is past its last stage read
-    double* Xi = smem;                              // [d][LG_LDX]  rows m0 .. m0 + 127, k-major, scaled by 1 / delta
-    double* Xj = smem + (size_t)d * LG_LDX;         // [d][LG_LDX]  rows n0 ..
-    double* red = Xj + (size_t)d * LG_LDX;          // [8][d + 3]
+    double* Es = smem;                              // [128][LG_LDX]  exp(-D) of this tile (from the covariance build's copy);
+                                                    //                later the per-lane partial sums [d][256]
+    double* Xi = Es + 128 * LG_LDX;                 // [d][LG_LDX]  rows m0 .. m0 + 127, k-major, scaled by 1 / delta
+    double* Xj = Xi + (size_t)d * LG_LDX;           // [d][LG_LDX]  rows n0 ..
+    double* red = Xj + (size_t)d * LG_LDX;          // [8][3]
     {
-        const double* w = p.winv + (size_t)b * d;
+        // thread -> 16-byte chunk (tid & 63) of rows (tid >> 6) + 4 it
+        const double* src = p.E + (size_t)b * p.sE + (size_t)(m0 + (tid >> 6)) * p.np + n0 + 2 * (tid & 63);
+        double* dst = Es + (tid >> 6) * LG_LDX + 2 * (tid & 63);
+        const size_t sstep = (size_t)4 * p.np;
+#pragma unroll 4
+        for (int it = 0; it < 32; it++) {
+            cp_async16(dst, src);
+            src += sstep;
+            dst += 4 * LG_LDX;
+        }
+        cp_async_commit();
+        const double* __restrict__ w = p.winv + (size_t)b * d;
+        const double* __restrict__ Xg = p.X;
         const int row = tid >> 1, gi = m0 + row, gj = n0 + row;
         for (int k = tid & 1; k < d; k += 2) {
-            const double wk = w[k];
-            Xi[k * LG_LDX + row] = (gi < n) ? p.X[(size_t)gi * d + k] * wk : 0.0;
-            Xj[k * LG_LDX + row] = (gj < n) ? p.X[(size_t)gj * d + k] * wk : 0.0;
+            const double wk = __ldg(w + k);
+            const double vi = (gi < n) ? __ldg(Xg + (size_t)gi * d + k) : 0.0;
+            const double vj = (gj < n) ? __ldg(Xg + (size_t)gj * d + k) : 0.0;
+            Xi[k * LG_LDX + row] = vi * wk;
+            Xj[k * LG_LDX + row] = vj * wk;
         }
+        cp_async_wait<0>();
     }
     named_bar_sync(2, WS_CONSUMERS * 32);
 
     const int row0 = wm0 + fr, col0 = wn0 + 2 * fc;          // lane's entries: rows row0 + 8 i, columns col0 + 8 j + {0, 1}
-    const bool diag_tile = (ti == tj);
     double sE = 0.0, sD = 0.0, sDr = 0.0;
-    // pass 1: acc <- t = (2 | 0) * W * E; the diagonal sums on the way
+    // pass 1: acc <- t = 2 W E for the pairs below the diagonal inside the n x n matrix, 0 elsewhere; the diagonal sums
+    // on the way.  Tiles strictly below the diagonal and inside the matrix -- all but a few -- need no case analysis.
+    if (ti > tj && m0 + BM <= n) {
 #pragma unroll
-    for (int j = 0; j < FN; j++) {
-        double D[FM][2];
-#pragma unroll
-        for (int i = 0; i < FM; i++) D[i][0] = D[i][1] = 0.0;
-        const double* xjp = Xj + col0 + 8 * j;
-        const double* xip = Xi + row0;
-#pragma unroll 4
-        for (int k = 0; k < d; k++) {
-            const double2 xj = *reinterpret_cast<const double2*>(xjp + k * LG_LDX);
+        for (int j = 0; j < FN; j++)
 #pragma unroll
             for (int i = 0; i < FM; i++) {
-                const double xi = xip[k * LG_LDX + 8 * i];
-                const double d0 = xi - xj.x, d1 = xi - xj.y;
-                D[i][0] = fma(d0, d0, D[i][0]);
-                D[i][1] = fma(d1, d1, D[i][1]);
+                const double2 ev = *reinterpret_cast<const double2*>(Es + (row0 + 8 * i) * LG_LDX + col0 + 8 * j);
+                const double t0 = 2.0 * acc[i][j][0] * ev.x, t1 = 2.0 * acc[i][j][1] * ev.y;
+                acc[i][j][0] = t0;
+                acc[i][j][1] = t1;
+                sE += t0 + t1;
             }
-        }
+    } else {
+        const bool diag_tile = (ti == tj);
 #pragma unroll
-        for (int i = 0; i < FM; i++) {
-            D[i][0] = gpe_exp(-D[i][0]);
-            D[i][1] = gpe_exp(-D[i][1]);
-        }
+        for (int j = 0; j < FN; j++)
 #pragma unroll
-        for (int i = 0; i < FM; i++) {
-            const int gi = m0 + row0 + 8 * i;
+            for (int i = 0; i < FM; i++) {
+                const int gi = m0 + row0 + 8 * i;
+                const double2 ev = *reinterpret_cast<const double2*>(Es + (row0 + 8 * i) * LG_LDX + col0 + 8 * j);
 #pragma unroll
-            for (int e = 0; e < 2; e++) {
-                const int gj = n0 + col0 + 8 * j + e;
-                const double wv = acc[i][j][e];
-                double wgt = 2.0;
-                if (gi >= n || gj >= n) wgt = 0.0;          // identity padding
-                else if (diag_tile && gi <= gj) {
-                    wgt = 0.0;                              // upper triangle: each pair is taken once, from below
-                    if (gi == gj) {
-                        sD += wv;
-                        if (p.r != nullptr) sDr = fma(wv, p.r[gi], sDr);
+                for (int e = 0; e < 2; e++) {
+                    const int gj = n0 + col0 + 8 * j + e;
+                    const double wv = acc[i][j][e];
+                    double tv = 2.0 * wv * (e ? ev.y : ev.x);
+                    bool below = gi < n;                        // gj < gi < n off the diagonal tiles
+                    if (diag_tile) {
+                        below = below && gj < gi;               // each pair once, from below; selected, not multiplied by 0:
+                        if (gi == gj && gi < n) {               // the copy of E holds the lower 64x64 tiles only
+                            sD += wv;
+                            if (p.r != nullptr) sDr = fma(wv, p.r[gi], sDr);
+                        }
                     }
+                    tv = below ? tv : 0.0;
+                    acc[i][j][e] = tv;
+                    sE += tv;
                 }
-                const double tv = wgt * wv * D[i][e];
-                acc[i][j][e] = tv;
-                sE += tv;
             }
-        }
     }
-    const int nv = d + 3;
     sE = warp_sum(sE); sD = warp_sum(sD); sDr = warp_sum(sDr);
-    if (lane == 0) { red[warp * nv + d] = sE; red[warp * nv + d + 1] = sD; red[warp * nv + d + 2] = sDr; }
-    // pass 2: per dimension, sum t * Delta_k^2 over the lane's 64 entries
+    if (lane == 0) { red[warp * 3] = sE; red[warp * 3 + 1] = sD; red[warp * 3 + 2] = sDr; }
+    named_bar_sync(2, WS_CONSUMERS * 32);           // the E tile is consumed: its memory now takes the partial sums
+    // pass 2: per dimension, sum t * Delta_k^2 over the lane's 64 entries (four independent accumulator chains); the
+    // lane's partial goes to shared memory, the cross-lane sums happen once at the end
+    double* gpart = Es;                             // [d][256]
     for (int k = 0; k < d; k++) {
         double xi[FM];
 #pragma unroll
         for (int i = 0; i < FM; i++) xi[i] = Xi[k * LG_LDX + row0 + 8 * i];
-        double g0 = 0.0, g1 = 0.0;
+        double g[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
 #pragma unroll
         for (int j = 0; j < FN; j++) {
             const double2 xj = *reinterpret_cast<const double2*>(Xj + k * LG_LDX + col0 + 8 * j);
 #pragma unroll
             for (int i = 0; i < FM; i++) {
                 const double d0 = xi[i] - xj.x, d1 = xi[i] - xj.y;
-                g0 = fma(acc[i][j][0] * d0, d0, g0);
-                g1 = fma(acc[i][j][1] * d1, d1, g1);
+                g[i & 1][0] = fma(acc[i][j][0] * d0, d0, g[i & 1][0]);
+                g[i & 1][1] = fma(acc[i][j][1] * d1, d1, g[i & 1][1]);
             }
         }
-        const double g = warp_sum(g0 + g1);
-        if (lane == 0) red[warp * nv + k] = g;
+        gpart[k * 256 + tid] = (g[0][0] + g[0][1]) + (g[1][0] + g[1][1]);
     }
     named_bar_sync(2, WS_CONSUMERS * 32);
+    const int nv = d + 3;
     double* pout = p.part + ((size_t)b * p.ntile + blockIdx.x) * nv;
-    for (int v = tid; v < nv; v += WS_CONSUMERS * 32) {
-        double s = 0.0;
+    // dimension k: 16 threads add 16 lane partials each, then a 16-lane butterfly -- a fixed order
+    for (int k0 = 0; k0 < d; k0 += 16) {
+        const int k = k0 + (tid >> 4), part = tid & 15;
+        double sacc = 0.0;
+        if (k < d) {
 #pragma unroll
-        for (int w = 0; w < WS_CONSUMERS; w++) s += red[w * nv + v];
-        pout[v] = s;
+            for (int q = 0; q < 16; q++) sacc += gpart[k * 256 + part * 16 + q];
+        }
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
+        if (k < d && part == 0) pout[k] = sacc;
+    }
+    if (tid < 3) {
+        double sacc = 0.0;
+#pragma unroll
+        for (int w = 0; w < WS_CONSUMERS; w++) sacc += red[w * 3 + tid];
+        pout[d + tid] = sacc;
     }
 }
 
@@ -252,24 +292,27 @@ __global__ void __launch_bounds__(256) ut_kernel(const double* __restrict__ U, i
     }
 }
 
-bool lauum_grad_supported(int d) {
-    // the epilogue's two k-major input tiles + the reduction rows must fit in the pipeline stages
-    const size_t need = ((size_t)2 * d * LG_LDX + 8 * (size_t)(d + 3)) * sizeof(double);
-    return need <= gemm_smem_bytes<128, 128, false, false>();
+static size_t lauum_grad_smem(int d) {
+    // the epilogue's E tile, two k-major input tiles and the reduction rows reuse the pipeline stages
+    const size_t epi = (std::max((size_t)128 * LG_LDX, (size_t)256 * d) + (size_t)2 * d * LG_LDX + 8 * 3) * sizeof(double);
+    return std::max(epi, gemm_smem_bytes<128, 128, false, false>());
 }
 
+bool lauum_grad_supported(int d) { return lauum_grad_smem(d) <= 227 * 1024; }
+
 cudaError_t launch_lauum_grad(const double* Li, long long sL, int np, int n, int d, int nu, const double* U, double* Ut, double* nUt,
-                              const double* X, const double* r, const double* winv, double* part, int B, cudaStream_t st) {
+                              const double* X, const double* r, const double* winv, const double* E, long long sE, double* part,
+                              int B, cudaStream_t st) {
     if (np % 128 || !lauum_grad_supported(d)) return cudaErrorInvalidValue;
     ut_kernel<<<dim3(np / 32, B), 256, 0, st>>>(U, np, Ut, nUt);
     LauumGradP p;
     p.Li = Li; p.sL = sL; p.np = np; p.n = n; p.d = d;
     p.ku = (nu + GEMM_BK - 1) / GEMM_BK;
     p.Ut = Ut; p.nUt = nUt; p.sU = (long long)NR * np;
-    p.X = X; p.r = r; p.winv = winv; p.part = part;
+    p.X = X; p.r = r; p.winv = winv; p.E = E; p.sE = sE; p.part = part;
     const int T = np / 128;
     p.ntile = T * (T + 1) / 2;
-    constexpr size_t smem = gemm_smem_bytes<128, 128, false, false>();
+    const size_t smem = lauum_grad_smem(d);
     static SmemOptIn optin;
     if (cudaError_t e = optin.ensure(lauum_grad_kernel, smem); e != cudaSuccess) return e;
     lauum_grad_kernel<<<dim3(p.ntile, 1, B), WS_THREADS, smem, st>>>(p);

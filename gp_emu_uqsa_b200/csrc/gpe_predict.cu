@@ -124,6 +124,174 @@ __global__ void __launch_bounds__(256, 3) xcov_kernel(const double* __restrict__
     }
 }
 
+
+// ---- K1x for tensor-grid points: the Gaussian kernel factorises over the input dimensions,
+//     exp(-sum_k ((x_ik - g_k)/delta_k)^2) = prod_k exp(-((x_ik - g_k)/delta_k)^2),
+// and a grid point's coordinate in dimension k takes only levels[k] values.  The d * levels one-dimensional factors
+// per training point are tabulated once per call (grid_table_kernel: sum(levels) * npad exponentials instead of
+// m * npad); an entry of the cross-covariance is then a product of table entries.  Points are consecutive flat
+// indices, so inside a CTA's run of points the digits of the leading ("slow") dimensions take at most two
+// combinations: their product is formed once per training row, and only the trailing ("fast") dimensions -- the
+// shortest suffix whose levels multiply to >= 128 -- cost one multiplication per entry each.
+// (n = 2000, d = 8, 10 levels: 2048 x 80 exponentials per call and 3 multiplications per entry, against 8 subtractions,
+// 8 FMAs and a 22-instruction exp per entry in xcov_kernel; the cross-covariance was 4.4 % of a chunk on the FP64 pipe
+// the TRMM needs.)  Each factor carries its own rounding, so an entry differs from exp(-sum) in the last few ulps --
+// the same size as the rounding of the summed exponent in the direct form; parity with the reference is checked on the
+// grid path itself (tests/test_gpu_fullsize.py).
+constexpr int GS_MAXNF = 7;      // fast dimensions (levels >= 2 => at most 7 for a product >= 128)
+struct GridSep {
+    int d, ks, nf;               // slow dimensions [0, ks), fast dimensions [ks, d)
+    int levels[MAXD], toff[MAXD];      // table rows of dimension k start at toff[k]
+    int foff[GS_MAXNF];          // offset (doubles) of fast dimension kf's block in shared memory
+    long long pfast;             // product of the fast levels
+    int ptiles;                  // 128-point tiles per CTA (<= pfast / 128: at most two slow combinations per CTA)
+};
+
+__global__ void grid_table_kernel(const double* __restrict__ Xs, const double* __restrict__ winv, GridDesc g, GridSep sp, int npad,
+                                  int ltot, double* __restrict__ T) {
+    const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (idx >= (long long)ltot * npad) return;
+    const int trow = (int)(idx / npad), i = (int)(idx % npad);
+    int k = 0;
+    while (k + 1 < sp.d && sp.toff[k + 1] <= trow) k++;
+    const int l = trow - sp.toff[k];
+    const double pt = (g.lo[k] + ((double)l + 0.5) * g.step[k]) * winv[k];      // the coordinate grid_points_kernel gives, scaled
+    const double df = Xs[(size_t)k * npad + i] - pt;
+    T[idx] = gpe_exp(-(df * df));
+}
+
+template <int NF>
+__global__ void __launch_bounds__(256) xcov_grid_kernel(const double* __restrict__ T, GridSep sp, int n, int npad, int mc,
+                                                        long long start, long long count, double cscale,
+                                                        double* __restrict__ Cm, int ldc) {
+    constexpr int ROWS = 128;
+    extern __shared__ __align__(16) double sm[];
+    double* Ps = sm;                    // [2][ROWS]  cscale * product of the slow factors, per slow combination
+    double* Tf = sm + 2 * ROWS;         // fast factors: block kf holds [ROWS][levels + 1]
+    __shared__ int sdig[2][MAXD];
+    const int tid = threadIdx.x, k0 = blockIdx.y * ROWS;
+    const long long jbase = (long long)blockIdx.x * sp.ptiles * 128;
+    const long long s0 = (start + jbase) / sp.pfast;
+    if (tid < 2) {
+        long long sidx = s0 + tid;
+        for (int k = sp.ks - 1; k >= 0; k--) {
+            sdig[tid][k] = (int)(sidx % sp.levels[k]);
+            sidx /= sp.levels[k];
+        }
+    }
+    __syncthreads();
+    {
+        const int c = tid >> 7, row = tid & (ROWS - 1);
+        double prod = cscale;
+        for (int k = 0; k < sp.ks; k++) prod *= T[(size_t)(sp.toff[k] + sdig[c][k]) * npad + k0 + row];
+        Ps[c * ROWS + row] = prod;
+    }
+#pragma unroll
+    for (int kf = 0; kf < NF; kf++) {
+        const int L = sp.levels[sp.ks + kf];
+        double* blk = Tf + sp.foff[kf];
+        for (int e = tid; e < L * ROWS; e += 256) {
+            const int l = e >> 7, row = e & (ROWS - 1);
+            blk[row * (L + 1) + l] = T[(size_t)(sp.toff[sp.ks + kf] + l) * npad + k0 + row];
+        }
+    }
+    __syncthreads();
+    const int ty = tid >> 5, tx = tid & 31;
+    for (int pt = 0; pt < sp.ptiles; pt++) {
+        const long long j0 = jbase + (long long)pt * 128;
+        if (j0 >= mc) break;
+        int off[4][NF], combo[4];
+        bool livep[4];
+#pragma unroll
+        for (int q4 = 0; q4 < 4; q4++) {
+            const long long j = j0 + 64 * (q4 >> 1) + 2 * tx + (q4 & 1);
+            livep[q4] = j < count;
+            const long long idx = start + (livep[q4] ? j : 0);
+            long long f = idx % sp.pfast;
+            combo[q4] = (int)(idx / sp.pfast - s0) & 1;
+#pragma unroll
+            for (int kf = NF - 1; kf >= 0; kf--) {
+                const int L = sp.levels[sp.ks + kf];
+                off[q4][kf] = sp.foff[kf] + (int)(f % L);
+                f /= L;
+            }
+        }
+#pragma unroll 4
+        for (int a = 0; a < ROWS / 8; a++) {
+            const int row = ty + 8 * a;
+            const bool live = k0 + row < n;
+            double v[4];
+#pragma unroll
+            for (int q4 = 0; q4 < 4; q4++) {
+                double x = Ps[combo[q4] * ROWS + row];
+#pragma unroll
+                for (int kf = 0; kf < NF; kf++) x *= Tf[off[q4][kf] + row * (sp.levels[sp.ks + kf] + 1)];
+                v[q4] = (live && livep[q4]) ? x : 0.0;
+            }
+            double* cp = Cm + (size_t)(k0 + row) * ldc + j0 + 2 * tx;
+            *reinterpret_cast<double2*>(cp) = make_double2(v[0], v[1]);
+            *reinterpret_cast<double2*>(cp + 64) = make_double2(v[2], v[3]);
+        }
+    }
+}
+
+// Plan the slow / fast split for a grid; false when the tables would not fit (fall back to xcov_kernel).
+static bool plan_grid_sep(const GridDesc& g, GridSep& sp, size_t& smem, int& ltot) {
+    sp.d = g.d;
+    ltot = 0;
+    for (int k = 0; k < g.d; k++) {
+        if (g.levels[k] < 1) return false;
+        sp.levels[k] = g.levels[k];
+        sp.toff[k] = ltot;
+        ltot += g.levels[k];
+    }
+    long long pf = 1;
+    int ks = g.d;
+    while (ks > 0 && pf < 128) pf *= g.levels[--ks];
+    sp.ks = ks; sp.nf = g.d - ks; sp.pfast = pf;
+    if (sp.nf < 1 || sp.nf > GS_MAXNF) return false;
+    sp.ptiles = (int)std::max<long long>(1, std::min<long long>(8, pf / 128));
+    if (pf < 128 && ks == 0) sp.ptiles = 1;      // the whole grid is shorter than a tile: no slow part, combinations are moot
+    size_t off = 0;
+    for (int kf = 0; kf < sp.nf; kf++) {
+        sp.foff[kf] = (int)off;
+        off += (size_t)128 * (g.levels[ks + kf] + 1);
+    }
+    smem = (2 * 128 + off) * sizeof(double);
+    return smem <= 96 * 1024 && ltot <= 4096;
+}
+
+template <int NF>
+static cudaError_t launch_xcov_grid_nf(const double* T, const GridSep& sp, int n, int npad, int mc, long long start, long long count,
+                                       double cscale, double* Cm, size_t smem, cudaStream_t st) {
+    static SmemOptIn optin;
+    if (cudaError_t e = optin.ensure(xcov_grid_kernel<NF>, smem); e != cudaSuccess) return e;
+    const int per = sp.ptiles * 128;
+    xcov_grid_kernel<NF><<<dim3((mc + per - 1) / per, npad / 128), 256, smem, st>>>(T, sp, n, npad, mc, start, count, cscale, Cm, mc);
+    return cudaGetLastError();
+}
+
+static cudaError_t launch_xcov_grid(const double* T, const GridSep& sp, int n, int npad, int mc, long long start, long long count,
+                                    double cscale, double* Cm, size_t smem, cudaStream_t st) {
+    switch (sp.nf) {
+        case 1: return launch_xcov_grid_nf<1>(T, sp, n, npad, mc, start, count, cscale, Cm, smem, st);
+        case 2: return launch_xcov_grid_nf<2>(T, sp, n, npad, mc, start, count, cscale, Cm, smem, st);
+        case 3: return launch_xcov_grid_nf<3>(T, sp, n, npad, mc, start, count, cscale, Cm, smem, st);
+        case 4: return launch_xcov_grid_nf<4>(T, sp, n, npad, mc, start, count, cscale, Cm, smem, st);
+        case 5: return launch_xcov_grid_nf<5>(T, sp, n, npad, mc, start, count, cscale, Cm, smem, st);
+        case 6: return launch_xcov_grid_nf<6>(T, sp, n, npad, mc, start, count, cscale, Cm, smem, st);
+        case 7: return launch_xcov_grid_nf<7>(T, sp, n, npad, mc, start, count, cscale, Cm, smem, st);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+struct GridXcov {        // what predict_chunk needs to build a chunk's cross-covariance from the tables
+    const double* T;
+    GridSep sp;
+    size_t smem;
+    long long start;     // flat index of the chunk's first point
+};
+
 // d >= 32 needs more than 48 KB for the two k-major tiles
 static SmemOptIn& xcov_optin() {
     static SmemOptIn o;
@@ -335,18 +503,23 @@ long long default_chunk(gpe_handle* h) {
 // One chunk on stream `st` with the buffers of `sl`: points already in P_dev [mc, d] (rows >= count
 // arbitrary but finite).
 int predict_chunk(gpe_handle* h, gpe_handle::PredSlot& sl, cudaStream_t st, const double* P_dev, const double* Hs_dev,
-                  long long count, int mc, double* mean_dev, double* var_dev) {
+                  long long count, int mc, double* mean_dev, double* var_dev, const GridXcov* gx = nullptr) {
     const int np = h->npad;
     size_t smem = (size_t)h->d * (64 + 130) * sizeof(double);
     {
         ProfScope ps(h, gpe_handle::CAT_COV, st);
-        xcov_optin().ensure(xcov_kernel, smem);
-        xcov_kernel<<<dim3(mc / 128, np / 64), 256, smem, st>>>(h->fXs, P_dev, h->fwinv, h->n, h->d, np, mc, count, h->fit_c, sl.C, mc);
+        if (gx != nullptr) {
+            CK(launch_xcov_grid(gx->T, gx->sp, h->n, np, mc, gx->start, count, h->fit_c, sl.C, gx->smem, st));
+        } else {
+            CK(xcov_optin().ensure(xcov_kernel, smem));
+            xcov_kernel<<<dim3(mc / 128, np / 64), 256, smem, st>>>(h->fXs, P_dev, h->fwinv, h->n, h->d, np, mc, count, h->fit_c, sl.C, mc);
+        }
     }
     h->launches++;
     int rc;
-    // aux = [A^-1 H K^-T | e]^T C     (TN, skinny M = 32)
-    if ((rc = gpe_run_gemm_on(h, st, h->fE, sl.C, sl.Aux, NR, mc, mc, 0, 0, 0, NR, mc, np, 1.0, 0, KM_FULL, 0, 1, 2, EPI_STORE))) return rc;
+    // aux = [A^-1 H K^-T | e]^T C     (TN, skinny: the q + 1 live columns of the panel padded to 16 or 32 rows)
+    const int maux = (h->q + 1 <= 16) ? 16 : NR;
+    if ((rc = gpe_run_gemm_on(h, st, h->fE, sl.C, sl.Aux, NR, mc, mc, 0, 0, 0, maux, mc, np, 1.0, 0, KM_FULL, 0, 1, 2, EPI_STORE))) return rc;
     int ntile = 0;
     if (var_dev != nullptr) {
         // column norms of Z = Linv C    (NN, Linv lower: k <= i), reduced in the epilogue
@@ -438,6 +611,27 @@ static int predict_common(gpe_handle* h, const double* Xs, const double* Hs, con
     const bool x_dev = Xs && gpe_is_device_ptr(Xs), h_dev = Hs && gpe_is_device_ptr(Hs);
     const bool mean_dev = gpe_is_device_ptr(mean), var_dev = var && gpe_is_device_ptr(var);
     const int d = h->d, q = h->q;
+    // tensor grid: tabulate the one-dimensional kernel factors once (GPE_GRID_SEP=0 keeps the direct kernel)
+    GridXcov gx;
+    bool use_sep = false;
+    TmpDev t_tab(h);
+    if (grid) {
+        static int sep_on = -1;
+        if (sep_on < 0) {
+            const char* e = getenv("GPE_GRID_SEP");
+            sep_on = (e && e[0] == '0') ? 0 : 1;
+        }
+        int ltot = 0;
+        if (sep_on && plan_grid_sep(*grid, gx.sp, gx.smem, ltot)) {
+            double* T = nullptr;
+            CK(t_tab.get(&T, (size_t)ltot * h->npad));
+            const long long tot = (long long)ltot * h->npad;
+            grid_table_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, h->st>>>(h->fXs, h->fwinv, *grid, gx.sp, h->npad, ltot, T);
+            h->launches++;
+            gx.T = T;
+            use_sep = true;
+        }
+    }
     const bool two = m > chunk && !h->prof_on;
     if (two) {
         CK(cudaEventRecord(h->ev_fork, h->st));
@@ -471,7 +665,8 @@ static int predict_common(gpe_handle* h, const double* Xs, const double* Hs, con
         }
         double* mo = mean_dev ? mean + s : sl.Mean;
         double* vo = var ? (var_dev ? var + s : sl.Var) : nullptr;
-        if ((rc = predict_chunk(h, sl, st, P, Hc, cnt, mc, mo, vo))) return rc;
+        gx.start = start + s;
+        if ((rc = predict_chunk(h, sl, st, P, Hc, cnt, mc, mo, vo, use_sep ? &gx : nullptr))) return rc;
         if (!mean_dev) CK(cudaMemcpyAsync(mean + s, sl.Mean, cnt * sizeof(double), cudaMemcpyDeviceToHost, st));
         if (var && !var_dev) CK(cudaMemcpyAsync(var + s, sl.Var, cnt * sizeof(double), cudaMemcpyDeviceToHost, st));
     }

@@ -36,10 +36,10 @@ MODES = [  # (tag, mucm, alt_nugget, fix_nugget)
 ]
 
 
-def build(g, tmp, X, y, mucm, alt, fix, nugget, name):
+def build(g, tmp, X, y, mucm, alt, fix, nugget, name, tv_config="10 0 0"):
     with RL.cwd(tmp), RL.quiet():
         cfg = RL.write_emulator_files(tmp, X, y, mucm=mucm, fix_nugget=fix, alt_nugget=alt,
-                                      nugget=nugget, name=name)
+                                      nugget=nugget, name=name, tv_config=tv_config)
         E = g.setup(cfg, datashuffle=False, scaleinputs=True)
     return E
 
@@ -374,6 +374,10 @@ def gen_llh_fullsize(g, n=4096, d=16, seed=0, nugget=1e-4, which="corner", save=
     ill-conditioned end), [2] guess 1 of the benchmark's draw.
     which="mid": two thetas with delta in [0.15, 0.6] (strong but not extreme correlation) for the two gp4ml modes
     and MUCM with a free nugget.
+    which="exact": tv_config "8 0 0", so that the training set is all 4096 points (with "10 0 0" the reference's
+    split keeps the first 10 * (n // 10) = 4090 points when noV = 0 -- _emulatorclasses.py:507-520 -- which is what the
+    "corner" and "mid" files hold: n_train = 4090, padded to 4096 on the device); gp4ml, MUCM and the alt-nugget kernel
+    with an r vector at the ill-conditioned corner and one mid-range theta.
     `save(out)` is called after every mode so that an interrupted run keeps what it has."""
     import time
     X, y, _ = synth(n, d, seed)
@@ -386,16 +390,20 @@ def gen_llh_fullsize(g, n=4096, d=16, seed=0, nugget=1e-4, which="corner", save=
         modes = FULL_MODES
         points = [(np.exp(bt[0][:d] / 2.0), float(np.exp(bt[0][d] / 2.0)), 3e-3), (ill, 0.9, 2e-4),
                   (np.exp(bt[1][:d] / 2.0), float(np.exp(bt[1][d] / 2.0)), 8e-3)]
-    else:
+    elif which == "mid":
         modes = [MODES[2], MODES[1], MODES[5]]
         points = [(mids[0], 0.7, 1e-3), (mids[1], 1.3, 5e-3)]
+    else:
+        modes = [MODES[2], MODES[0], MODES[5]]
+        points = [(ill, 0.9, 2e-4), (mids[0], 0.7, 1e-3)]
     with tempfile.TemporaryDirectory() as tmp:
         for tag, mucm, alt, fix in modes:
-            E = build(g, tmp, X, y, mucm, alt, fix, nugget, "f_" + tag)
+            E = build(g, tmp, X, y, mucm, alt, fix, nugget, "f_" + tag, tv_config="8 0 0" if which == "exact" else "10 0 0")
+            out["n_train"] = E.training.inputs.shape[0]
             out["X_sha16"] = sha16(E.training.inputs)
             out["H_sha16"] = sha16(E.training.H)
             if alt == "T":
-                r = 0.01 + 0.02 * np.random.default_rng(501 + seed).random(n)
+                r = 0.01 + 0.02 * np.random.default_rng(501 + seed).random(E.training.inputs.shape[0])
                 with RL.quiet():
                     E.training.set_r(r)
                 out[tag + "_r"] = r
@@ -521,6 +529,9 @@ def main():
     save = lambda name, d: (np.savez_compressed(os.path.join(HERE, name), **d), print("wrote", name))
     if len(sys.argv) > 1 and sys.argv[1] == "fullsize_llh":
         gen_llh_fullsize(g, which="corner", save=lambda o: save("llh_n4096_d16.npz", o))
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "fullsize_llh_exact":
+        gen_llh_fullsize(g, which="exact", save=lambda o: save("llh_n4096_d16_exact.npz", o))
         return
     if len(sys.argv) > 1 and sys.argv[1] == "fullsize_llh_mid":
         gen_llh_fullsize(g, which="mid", save=lambda o: save("llh_n4096_d16_mid.npz", o))

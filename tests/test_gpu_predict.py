@@ -87,8 +87,10 @@ def test_grid_prediction_matches_explicit_points_and_ragged_sizes(dev, golden_di
     m_all, v_all = dev.predict(pts)
     for start, count in [(0, total), (17, 131), (400, 20), (1, 1)]:
         mg, vg = dev.predict_grid(levels, lo, hi, start, count)
-        assert np.allclose(mg, m_all[start:start + count], rtol=1e-12, atol=1e-13)
-        assert np.allclose(vg, v_all[start:start + count], rtol=1e-10, atol=1e-14)
+        # grid path: products of tabulated one-dimensional factors; explicit path: exp of the summed exponent -- equal up
+        # to the last ulps of the cross-covariance, which the variance (a small difference of O(1) terms) magnifies
+        assert np.allclose(mg, m_all[start:start + count], rtol=1e-11, atol=1e-12)
+        assert np.allclose(vg, v_all[start:start + count], rtol=1e-9, atol=1e-13)
     # device-resident in/out, chunked (chunk < m) and not a multiple of 128
     os.environ["GPE_PRED_CHUNK"] = "256"
     try:

@@ -201,6 +201,26 @@ lo, hi = _dist.block(n, rank, world)
 keep = np.zeros(n); keep[lo:hi] = (np.arange(lo, hi) %% 3 == 0)
 keep = _dist.gather_blocks(keep, n) > 0.5
 assert np.array_equal(np.nonzero(keep)[0], np.array([0, 3, 6, 9]))
+# a NaN objective travels through the gather as a NaN (it must not become 0.0, the best possible value)
+pack = np.full((B, p + 2), -1.0)
+lo, hi = _dist.block(B, rank, world)
+pack[lo:hi, 1] = np.where(np.arange(lo, hi) == 4, np.nan, np.arange(lo, hi))
+got = _dist.gather_blocks(pack, B)
+assert np.isnan(got[4, 1]) and np.array_equal(np.delete(got[:, 1], 4), np.delete(np.arange(B, dtype=float), 4))
+# point-sharded ranges: tile-aligned interior boundaries, the same rows back in flat order
+n = 1000
+lo, hi = _dist.block_aligned(n, rank, world)
+assert (lo, hi) == ((0, 512) if rank == 0 else (512, 1000))
+keep = np.zeros(n); keep[lo:hi] = (np.arange(lo, hi) %% 7 == 0)
+keep = _dist.gather_blocks(keep, n, bounds=_dist.block_aligned) > 0.5
+assert np.array_equal(np.nonzero(keep)[0], np.arange(0, n, 7))
+# an unseeded run: every rank continues from rank 0's generator state (shuffle, guesses, Latin hypercubes)
+np.random.seed(1234 + rank)
+_dist.sync_numpy_rng()
+draw = np.random.random_sample(3)
+both = _dist.gather_blocks(np.tile(draw, (2, 1)), 2)
+assert np.array_equal(both[0], both[1])
+assert _dist.is_writer() == (rank == 0)
 dist.barrier(); dist.destroy_process_group()
 print("rank", rank, "ok")
 """
@@ -225,6 +245,38 @@ def test_header_is_plain_c(tmp_path):
     r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), str(src)],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+def test_block_aligned_partition_properties():
+    """Point ranges of the prediction / implausibility shards: contiguous, exhaustive, interior boundaries on
+    128-point tiles, sizes within one tile of each other."""
+    from gp_emu_uqsa_b200 import _dist
+    rng = np.random.default_rng(0)
+    for _ in range(300):
+        n, world = int(rng.integers(0, 10 ** 9)), int(rng.integers(1, 65))
+        edges = [_dist.block_aligned(n, r, world) for r in range(world)]
+        assert edges[0][0] == 0 and edges[-1][1] == n
+        for (lo, hi), (lo2, _) in zip(edges, edges[1:]):
+            assert hi == lo2 and lo <= hi and (hi % 128 == 0 or hi == n)
+        sizes = [hi - lo for lo, hi in edges]
+        assert max(sizes) - min(sizes) <= 128 + 127
+    assert _dist.block_aligned(10 ** 8, 3, 8) == (37499904, 50000000)
+
+
+def test_data_fingerprint_sees_permutations_and_swaps():
+    """The upload key of a data set: moments are not enough -- reordered rows, swapped outputs, a swapped
+    pair of r entries must all change it."""
+    from gp_emu_uqsa_b200 import _emulatorclasses as C
+    rng = np.random.default_rng(1)
+    a = rng.random((50, 3))
+    base = C._checksum(a)
+    assert C._checksum(a.copy()) == base
+    perm = a[rng.permutation(50)]
+    assert C._checksum(perm) != base and abs(perm.sum() - a.sum()) < 1e-12
+    sw = a.copy(); sw[[0, 1]] = sw[[1, 0]]
+    assert C._checksum(sw) != base
+    neg = a.copy(); neg[3, 1] = -neg[3, 1]
+    assert C._checksum(neg) != base
 
 
 def test_block_partition_properties():
