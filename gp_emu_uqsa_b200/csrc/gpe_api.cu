@@ -242,16 +242,26 @@ int gpe_potrf_inv(gpe_handle* h, const FactorWs& ws, const SubBatch& sb, int wan
 
 static FactorWs handle_ws(gpe_handle* h) { return FactorWs{h->A, h->S, h->Li, h->npad, h->nleaf, h->logdet_part, h->status}; }
 
-// Fused LAUUM + gradient (128x128 tiles) when the launch fills the machine; GPE_FUSED_GRAD=0 keeps the two-kernel
-// route for A/B measurements.  The choice depends on the sub-batch size only through "does it fill the machine", and
-// both routes sum the same terms, so results agree to rounding.
-static bool llh_grad_fused(gpe_handle* h, int B) {
-    static int on = -1;
-    if (on < 0) {
+// How the gradient reduction of a chunk is done (GPE_FUSED_GRAD = 0 | 1 | 2; all routes sum the same terms, results agree
+// to rounding).
+//   0: A^-1 by the generic LAUUM GEMM, stored, then the stand-alone reduction kernel that recomputes E and U.U^T
+//      (round 1; still used for launches too small for 128x128 tiles).
+//   1: LAUUM with the columns of U in its k loop stores W = A^-1 - U U^T; a light kernel reduces W against the
+//      covariance build's copy of E.
+//   2 (default when 128x128 tiles fill the machine): the reduction in LAUUM's epilogue (gpe_lauum_grad.cu); nothing
+//      of size n x n is written after the factorisation.
+// Measured on one B200 in one call, n = 4096, d = 16, 32 items, 8 streams, graph replay: 75.41 / 75.79 / 75.38 ms per step
+// for routes 0 / 1 / 2, 73.9 ms with the reduction switched off altogether.  The reduction is scalar FP64 work on the pipe
+// the DMMAs use: fusing moves it, it does not remove it.
+static int llh_grad_fused(gpe_handle* h, int B) {
+    static int mode = -1;
+    if (mode < 0) {
         const char* e = getenv("GPE_FUSED_GRAD");
-        on = (e && e[0] == '0') ? 0 : 1;
+        mode = e ? atoi(e) : 2;
     }
-    return on && lauum_grad_supported(h->d) && gemm_is_big(h->npad, h->npad, 1, B);
+    if (!gemm_is_big(h->npad, h->npad, 1, B)) return 0;
+    if (mode == 2 && !lauum_grad_supported(h->d)) return 1;
+    return mode;
 }
 
 // Everything after the covariance build for the items of `sb`, already described by h->par / h->winv.
@@ -281,7 +291,7 @@ int gpe_factor_and_reduce(gpe_handle* h, const SubBatch& sb, int mode, int with_
     if ((rc = run_gemm(h, st, Lb, Z, U, ld, NR, NR, sM, sP, sP, np, NR, np, 1.0, 0, KM_GE_I, 0, B, 2))) return rc;
     if (!with_grad) return 0;
     st = sb.stream(false);
-    if (h->grad_fused) {
+    if (h->grad_fused == 2) {
         // LAUUM with the gradient reduction in its epilogue: W = A^-1 - U U^T never leaves the CTA that computed it
         // (gpe_lauum_grad.cu).  Wy and Z are dead by now and hold U^T and -U^T.
         ProfScope ps(h, gpe_handle::CAT_LAUUM, st);
@@ -290,6 +300,23 @@ int gpe_factor_and_reduce(gpe_handle* h, const SubBatch& sb, int mode, int with_
                                           h->gpart + (size_t)b0 * lauum_grad_ntiles(np) * grad_nvals(h->d), B, st);
         h->launches += 2;
         if (e != cudaSuccess) return h->fail("launch_lauum_grad", e);
+        return 0;
+    }
+    if (h->grad_fused == 1) {
+        // split route (default for machine-filling launches): the same LAUUM launch stores W = A^-1 - U U^T (the columns of
+        // U ride along in its k loop) into the dead A buffer; a light reduction kernel combines it with the E copy
+        {
+            ProfScope ps(h, gpe_handle::CAT_LAUUM, st);
+            cudaError_t e = launch_lauum_grad(Lb, sM, np, h->n, h->d, h->q + 1, U, Wy, Z, h->X, h->r, h->winv + (size_t)b0 * h->d,
+                                              nullptr, 0, nullptr, B, st, Ab);
+            h->launches += 2;
+            if (e != cudaSuccess) return h->fail("launch_lauum_grad (store W)", e);
+        }
+        ProfScope ps(h, gpe_handle::CAT_GRAD, st);
+        cudaError_t e = launch_grad_partial_we(h->X, h->r, h->n, h->d, np, h->winv + (size_t)b0 * h->d, Ab, h->Ex + (size_t)b0 * sM, sM,
+                                               h->gpart + (size_t)b0 * grad_ntiles(np) * grad_nvals(h->d), B, st);
+        h->launches++;
+        if (e != cudaSuccess) return h->fail("launch_grad_partial_we", e);
         return 0;
     }
     // small launches (64x64 tiles) and very wide inputs: A^-1 = Linv^T Linv (lower tiles) into the dead A buffer, then
@@ -600,7 +627,7 @@ static int enqueue_llh_chunk(gpe_handle* h, int Bs, int p, int mode, double fixe
     }
     {
         ProfScope ps(h, gpe_handle::CAT_OTHER);
-        launch_grad_finalize(h->gpart, h->grad_fused ? lauum_grad_ntiles(h->npad) : grad_ntiles(h->npad), h->n, h->d, h->npad, p, mode,
+        launch_grad_finalize(h->gpart, h->grad_fused == 2 ? lauum_grad_ntiles(h->npad) : grad_ntiles(h->npad), h->n, h->d, h->npad, p, mode,
                              h->par, h->out, h->status, h->llh_d, h->grad_d,
                              h->sig_d, Bs, h->st);
     }

@@ -1026,6 +1026,113 @@ void launch_grad_partial(const double* X, const double* r, int n, int d, int npa
     grad_partial_kernel<<<dim3(nt * (nt + 1) / 2, 1, B), 256, smem, st>>>(X, r, n, d, npad, winv, Ainv, sAinv, U, nu, part);
 }
 
+
+// ---- light gradient reduction: W and E are given ---------------------------------------------------------------
+// The LAUUM launch of the likelihood path (gpe_lauum_grad.cu) appends the columns of U to its k loop, so what it stores
+// is already W = A^-1 - U U^T; the covariance build keeps a copy of E = exp(-D).  What is left per entry is
+// t = 2 W E and the d weighted sums of Delta_k^2: 3 + 3d FP64 instructions instead of 2 nu + 5d + 22 (exp) + 3 --
+// 51 instead of 125 at d = 16, nu = 18 -- for 16 bytes read per entry from an otherwise idle HBM.
+__global__ void __launch_bounds__(256, 3) grad_partial_we_kernel(const double* __restrict__ X, const double* __restrict__ r,
+                                                              int n, int d, int npad, const double* __restrict__ winv,
+                                                              const double* __restrict__ W, const double* __restrict__ E,
+                                                              long long sM, double* __restrict__ part) {
+    int ti, tj;
+    tri_decode(blockIdx.x, ti, tj);
+    const int b = blockIdx.z;
+    extern __shared__ __align__(16) double sm[];
+    double* Xi = sm;                                // [d][64]
+    double* Xj = Xi + (size_t)d * CT;               // [d][66]
+    double* red = Xj + (size_t)d * (CT + 2);        // [8][d+3]
+    const int tid = threadIdx.x;
+    const int ty = tid >> 4, tx = tid & 15;
+    // the two matrix tiles first: their latency hides behind the input-tile fill
+    const double* Wb = W + (size_t)b * sM;
+    const double* Eb = E + (size_t)b * sM;
+    double2 wv[4][2], ev[4][2];
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const size_t off = (size_t)(ti * CT + ty + 16 * a) * npad + tj * CT + 32 * h + 2 * tx;
+            wv[a][h] = __ldg(reinterpret_cast<const double2*>(Wb + off));
+            ev[a][h] = __ldg(reinterpret_cast<const double2*>(Eb + off));
+        }
+    const double* w = winv + (size_t)b * d;
+    {
+        const int row = tid >> 2, gi = ti * CT + row, gj = tj * CT + row;
+        for (int k = tid & 3; k < d; k += 4) {
+            Xi[k * CT + row] = (gi < n) ? X[(size_t)gi * d + k] * w[k] : 0.0;
+            Xj[k * (CT + 2) + row] = (gj < n) ? X[(size_t)gj * d + k] * w[k] : 0.0;
+        }
+    }
+    __syncthreads();
+    double t[4][4];
+    double sE = 0.0, sD = 0.0, sDr = 0.0;
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+        const int gi = ti * CT + ty + 16 * a;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int gj0 = tj * CT + 32 * h + 2 * tx;
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                const int gj = gj0 + e;
+                const double wvv = e ? wv[a][h].y : wv[a][h].x, evv = e ? ev[a][h].y : ev[a][h].x;
+                double tv = 2.0 * wvv * evv;
+                // W and E are valid on and below the diagonal only: every off-diagonal pair is taken once, with weight 2
+                const bool below = gi < n && gj < gi;
+                if (gi == gj && gi < n) {
+                    sD += wvv;
+                    if (r != nullptr) sDr = fma(wvv, r[gi], sDr);
+                }
+                tv = below ? tv : 0.0;
+                t[a][2 * h + e] = tv;
+                sE += tv;
+            }
+        }
+    }
+    const int nv = d + 3;
+    const int warp = tid >> 5, lane = tid & 31;
+    double* pout = part + ((size_t)b * gridDim.x + blockIdx.x) * nv;
+    sE = warp_sum(sE); sD = warp_sum(sD); sDr = warp_sum(sDr);
+    if (lane == 0) { red[warp * nv + d] = sE; red[warp * nv + d + 1] = sD; red[warp * nv + d + 2] = sDr; }
+    for (int k = 0; k < d; k++) {
+        double xi[4], xj[4];
+#pragma unroll
+        for (int a = 0; a < 4; a++) xi[a] = Xi[k * CT + ty + 16 * a];
+        const double2 v0 = *reinterpret_cast<const double2*>(&Xj[k * (CT + 2) + 2 * tx]);
+        const double2 v1 = *reinterpret_cast<const double2*>(&Xj[k * (CT + 2) + 32 + 2 * tx]);
+        xj[0] = v0.x; xj[1] = v0.y; xj[2] = v1.x; xj[3] = v1.y;
+        double g[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+        for (int a = 0; a < 4; a++)
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const double df = xi[a] - xj[c];
+                g[c] = fma(t[a][c] * df, df, g[c]);
+            }
+        const double gs = warp_sum((g[0] + g[1]) + (g[2] + g[3]));
+        if (lane == 0) red[warp * nv + k] = gs;
+    }
+    __syncthreads();
+    for (int v = tid; v < nv; v += 256) {
+        double s = 0.0;
+#pragma unroll
+        for (int wv2 = 0; wv2 < 8; wv2++) s += red[wv2 * nv + v];
+        pout[v] = s;
+    }
+}
+
+cudaError_t launch_grad_partial_we(const double* X, const double* r, int n, int d, int npad, const double* winv, const double* W,
+                                   const double* E, long long sM, double* part, int B, cudaStream_t st) {
+    const int nt = npad / CT;
+    const size_t smem = ((size_t)d * (CT + CT + 2) + 8 * (size_t)(d + 3)) * sizeof(double);
+    static SmemOptIn optin;
+    if (cudaError_t e = optin.ensure(grad_partial_we_kernel, smem); e != cudaSuccess) return e;
+    grad_partial_we_kernel<<<dim3(nt * (nt + 1) / 2, 1, B), 256, smem, st>>>(X, r, n, d, npad, winv, W, E, sM, part);
+    return cudaGetLastError();
+}
+
 // Sum the tile partials in a fixed order and apply the per-parameter prefactors
 // (parameter order [delta.., nugget?, sigma?], _emulatoroptimise.py:94-103).
 __global__ void __launch_bounds__(256) grad_finalize_kernel(const double* __restrict__ part, int ntile, int n, int d, int p,

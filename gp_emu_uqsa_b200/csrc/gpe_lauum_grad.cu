@@ -22,6 +22,7 @@
 #include "gpe_kernels.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace gpe {
 
@@ -40,6 +41,8 @@ struct LauumGradP {
     long long sE;
     double* part;          // [B][ntile][d + 3]
     int ntile;
+    double* Wout;          // non-null: store the W tile (strides sL / np) and leave the reduction to another kernel
+    int order;             // tile order: 0 lower-triangle rows, 1 the generic kernel's column groups (GPE_LG_ORDER)
 };
 
 constexpr int LG_LDX = 128 + 4;     // row stride of the k-major X tiles in the epilogue
@@ -63,7 +66,20 @@ __global__ void __launch_bounds__(WS_THREADS, 1) lauum_grad_kernel(LauumGradP p)
     // lower-triangle tiles, row by row: tile t = ti (ti + 1) / 2 + tj.  Row ti has the k range [ti * 128, np):
     // the launch starts on its longest tiles and ends on its shortest
     int ti, tj;
-    tri_decode_lg((int)blockIdx.x, ti, tj);
+    if (p.order == 0) {
+        tri_decode_lg((int)blockIdx.x, ti, tj);
+    } else {
+        // the generic kernel's order for row-triangular launches: column blocks in groups of 16, rows ascending inside a group
+        const int T = p.np / BM, id = (int)blockIdx.x;
+        const int full = (T / WS_COLGROUP) * WS_COLGROUP * T;
+        int g0, gsz, r;
+        if (id < full) { g0 = (id / (WS_COLGROUP * T)) * WS_COLGROUP; gsz = WS_COLGROUP; r = id % (WS_COLGROUP * T); }
+        else { g0 = (T / WS_COLGROUP) * WS_COLGROUP; gsz = T - g0; r = id - full; }
+        ti = r / gsz;
+        tj = g0 + (r - ti * gsz);
+        if (ti < tj) return;
+    }
+    const int tile_id = ti * (ti + 1) / 2 + tj;
     const int b = blockIdx.z;
     const int m0 = ti * BM, n0 = tj * BN;
     const int kbeg = m0;
@@ -103,7 +119,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) lauum_grad_kernel(LauumGradP p)
             cp_async_mbar_arrive_noinc(&full_bar[s]);
             // the epilogue reads this tile's 128 x 128 block of E (written by the covariance build a whole factorisation
             // ago: it comes from HBM).  Ask L2 for it while the consumers still have a few k-tiles to go.
-            if (kt == KT - GEMM_STAGES - 4 || (KT < GEMM_STAGES + 5 && kt == 0)) {
+            if (p.Wout == nullptr && (kt == KT - GEMM_STAGES - 4 || (KT < GEMM_STAGES + 5 && kt == 0))) {
                 const double* Eg = p.E + (size_t)b * p.sE + (size_t)m0 * p.np + n0;
 #pragma unroll 4
                 for (int q = 0; q < 32; q++) {                 // 128 rows x 8 lines of 128 bytes
@@ -154,6 +170,15 @@ __global__ void __launch_bounds__(WS_THREADS, 1) lauum_grad_kernel(LauumGradP p)
         if (lane == 0) mbar_arrive(&empty_bar[s]);
     }
 
+    if (p.Wout != nullptr) {                         // split route: W = A^-1 - U U^T to global memory, 16-byte stores
+        double* Cg = p.Wout + (size_t)b * p.sL + (size_t)(m0 + wm0 + fr) * p.np + n0 + wn0 + 2 * fc;
+#pragma unroll
+        for (int i = 0; i < FM; i++)
+#pragma unroll
+            for (int j = 0; j < FN; j++)
+                *reinterpret_cast<double2*>(Cg + (size_t)(8 * i) * p.np + 8 * j) = make_double2(acc[i][j][0], acc[i][j][1]);
+        return;
+    }
     // ===== epilogue: acc = W tile.  The pipeline stages are free: stage the E tile and the scaled input tiles there. =====
     const int d = p.d, n = p.n;
     named_bar_sync(2, WS_CONSUMERS * 32);           // every consumer is past its last stage read
@@ -232,30 +257,62 @@ __global__ void __launch_bounds__(WS_THREADS, 1) lauum_grad_kernel(LauumGradP p)
     }
     sE = warp_sum(sE); sD = warp_sum(sD); sDr = warp_sum(sDr);
     if (lane == 0) { red[warp * 3] = sE; red[warp * 3 + 1] = sD; red[warp * 3 + 2] = sDr; }
-    named_bar_sync(2, WS_CONSUMERS * 32);           // the E tile is consumed: its memory now takes the partial sums
-    // pass 2: per dimension, sum t * Delta_k^2 over the lane's 64 entries (four independent accumulator chains); the
-    // lane's partial goes to shared memory, the cross-lane sums happen once at the end
-    double* gpart = Es;                             // [d][256]
-    for (int k = 0; k < d; k++) {
-        double xi[FM];
+    // pass 2: per dimension, sum t * Delta_k^2 over the lane's 64 entries.  With all 64 t's in registers (128 of the 168
+    // a thread of a 9-warp CTA can have) the compiler has no room to overlap the sub -> mul -> fma triples and every
+    // instruction waits for the one before (ncu: stall_wait on each of them, 44 % of the FP64 issue rate).  So the
+    // right half of the warp tile (fragment columns 4..7) is parked in shared memory -- each lane overwrites the E
+    // entries it has just consumed, no other lane touches them -- and the two halves are reduced one after the other
+    // with eight triples in flight.  The lane's partial sums go to shared memory; cross-lane sums happen once at the end.
 #pragma unroll
-        for (int i = 0; i < FM; i++) xi[i] = Xi[k * LG_LDX + row0 + 8 * i];
-        double g[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+    for (int j = FN / 2; j < FN; j++)
 #pragma unroll
-        for (int j = 0; j < FN; j++) {
-            const double2 xj = *reinterpret_cast<const double2*>(Xj + k * LG_LDX + col0 + 8 * j);
+        for (int i = 0; i < FM; i++)
+            *reinterpret_cast<double2*>(Es + (row0 + 8 * i) * LG_LDX + col0 + 8 * j) = make_double2(acc[i][j][0], acc[i][j][1]);
+    double* gpart = Xj + (size_t)d * LG_LDX + 8 * 3;      // [d][256], behind the reduction rows
+    auto half_pass = [&](const double (&t)[FM][FN / 2][2], int jbase, bool add) {
+        for (int k = 0; k < d; k++) {
+            double xi[FM];
 #pragma unroll
-            for (int i = 0; i < FM; i++) {
-                const double d0 = xi[i] - xj.x, d1 = xi[i] - xj.y;
-                g[i & 1][0] = fma(acc[i][j][0] * d0, d0, g[i & 1][0]);
-                g[i & 1][1] = fma(acc[i][j][1] * d1, d1, g[i & 1][1]);
+            for (int i = 0; i < FM; i++) xi[i] = Xi[k * LG_LDX + row0 + 8 * i];
+            double g[FM][2];
+#pragma unroll
+            for (int i = 0; i < FM; i++) g[i][0] = g[i][1] = 0.0;
+#pragma unroll
+            for (int j = 0; j < FN / 2; j++) {
+                const double2 xj = *reinterpret_cast<const double2*>(Xj + k * LG_LDX + col0 + 8 * (jbase + j));
+                double d0[FM], d1[FM], m0[FM], m1[FM];
+#pragma unroll
+                for (int i = 0; i < FM; i++) { d0[i] = xi[i] - xj.x; d1[i] = xi[i] - xj.y; }
+#pragma unroll
+                for (int i = 0; i < FM; i++) { m0[i] = t[i][j][0] * d0[i]; m1[i] = t[i][j][1] * d1[i]; }
+#pragma unroll
+                for (int i = 0; i < FM; i++) { g[i][0] = fma(m0[i], d0[i], g[i][0]); g[i][1] = fma(m1[i], d1[i], g[i][1]); }
             }
+            const double gs = ((g[0][0] + g[0][1]) + (g[1][0] + g[1][1])) + ((g[2][0] + g[2][1]) + (g[3][0] + g[3][1]));
+            if (add) gpart[k * 256 + tid] += gs;
+            else gpart[k * 256 + tid] = gs;
         }
-        gpart[k * 256 + tid] = (g[0][0] + g[0][1]) + (g[1][0] + g[1][1]);
+    };
+    {
+        double t[FM][FN / 2][2];
+#pragma unroll
+        for (int i = 0; i < FM; i++)
+#pragma unroll
+            for (int j = 0; j < FN / 2; j++) { t[i][j][0] = acc[i][j][0]; t[i][j][1] = acc[i][j][1]; }
+        half_pass(t, 0, false);
+#pragma unroll
+        for (int i = 0; i < FM; i++)
+#pragma unroll
+            for (int j = 0; j < FN / 2; j++) {
+                const double2 v = *reinterpret_cast<const double2*>(Es + (row0 + 8 * i) * LG_LDX + col0 + 8 * (j + FN / 2));
+                t[i][j][0] = v.x;
+                t[i][j][1] = v.y;
+            }
+        half_pass(t, FN / 2, true);
     }
     named_bar_sync(2, WS_CONSUMERS * 32);
     const int nv = d + 3;
-    double* pout = p.part + ((size_t)b * p.ntile + blockIdx.x) * nv;
+    double* pout = p.part + ((size_t)b * p.ntile + tile_id) * nv;
     // dimension k: 16 threads add 16 lane partials each, then a 16-lane butterfly -- a fixed order
     for (int k0 = 0; k0 < d; k0 += 16) {
         const int k = k0 + (tid >> 4), part = tid & 15;
@@ -294,7 +351,7 @@ __global__ void __launch_bounds__(256) ut_kernel(const double* __restrict__ U, i
 
 static size_t lauum_grad_smem(int d) {
     // the epilogue's E tile, two k-major input tiles and the reduction rows reuse the pipeline stages
-    const size_t epi = (std::max((size_t)128 * LG_LDX, (size_t)256 * d) + (size_t)2 * d * LG_LDX + 8 * 3) * sizeof(double);
+    const size_t epi = ((size_t)128 * LG_LDX + (size_t)2 * d * LG_LDX + 8 * 3 + (size_t)256 * d) * sizeof(double);
     return std::max(epi, gemm_smem_bytes<128, 128, false, false>());
 }
 
@@ -302,20 +359,26 @@ bool lauum_grad_supported(int d) { return lauum_grad_smem(d) <= 227 * 1024; }
 
 cudaError_t launch_lauum_grad(const double* Li, long long sL, int np, int n, int d, int nu, const double* U, double* Ut, double* nUt,
                               const double* X, const double* r, const double* winv, const double* E, long long sE, double* part,
-                              int B, cudaStream_t st) {
-    if (np % 128 || !lauum_grad_supported(d)) return cudaErrorInvalidValue;
+                              int B, cudaStream_t st, double* Wout) {
+    if (np % 128 || (Wout == nullptr && !lauum_grad_supported(d))) return cudaErrorInvalidValue;
     ut_kernel<<<dim3(np / 32, B), 256, 0, st>>>(U, np, Ut, nUt);
     LauumGradP p;
     p.Li = Li; p.sL = sL; p.np = np; p.n = n; p.d = d;
     p.ku = (nu + GEMM_BK - 1) / GEMM_BK;
     p.Ut = Ut; p.nUt = nUt; p.sU = (long long)NR * np;
-    p.X = X; p.r = r; p.winv = winv; p.E = E; p.sE = sE; p.part = part;
+    p.X = X; p.r = r; p.winv = winv; p.E = E; p.sE = sE; p.part = part; p.Wout = Wout;
     const int T = np / 128;
     p.ntile = T * (T + 1) / 2;
-    const size_t smem = lauum_grad_smem(d);
+    const size_t smem = Wout ? gemm_smem_bytes<128, 128, false, false>() : lauum_grad_smem(d);
     static SmemOptIn optin;
     if (cudaError_t e = optin.ensure(lauum_grad_kernel, smem); e != cudaSuccess) return e;
-    lauum_grad_kernel<<<dim3(p.ntile, 1, B), WS_THREADS, smem, st>>>(p);
+    static int order = -1;
+    if (order < 0) {
+        const char* e = getenv("GPE_LG_ORDER");
+        order = e ? atoi(e) : 0;
+    }
+    p.order = order;
+    lauum_grad_kernel<<<dim3(order ? T * T : p.ntile, 1, B), WS_THREADS, smem, st>>>(p);
     return cudaGetLastError();
 }
 
