@@ -40,6 +40,8 @@ def load():
         "gpe_launch_count": (ll, [p]),
         "gpe_get_stream": (p, [p]),
         "gpe_set_streams": (i, [p, i]),
+        "gpe_set_async": (i, [p, i]),
+        "gpe_synchronize": (i, [p]),
         "gpe_profile_enable": (i, [p, i]),
         "gpe_profile_read": (i, [p, p, p, i]),
         "gpe_set_training": (i, [p, p, p, p, p, i, i, i]),
@@ -69,7 +71,7 @@ def load():
 
 
 EXPORTS = ["gpe_version", "gpe_create", "gpe_destroy", "gpe_last_error", "gpe_launch_count",
-           "gpe_get_stream", "gpe_set_streams", "gpe_profile_enable", "gpe_profile_read",
+           "gpe_get_stream", "gpe_set_streams", "gpe_set_async", "gpe_synchronize", "gpe_profile_enable", "gpe_profile_read",
            "gpe_set_training", "gpe_set_basis", "gpe_cov_build", "gpe_cov_grad", "gpe_cross_cov", "gpe_llh_grad_batch",
            "gpe_fit_state", "gpe_predict", "gpe_predict_grid", "gpe_predict_fullcov", "gpe_implausibility",
            "gpe_solve", "gpe_sens_contract", "gpe_sens_main_effect", "gpe_potrf", "gpe_pdist_argmin",
@@ -149,6 +151,13 @@ class Device:
     def set_streams(self, nstreams):
         """Number of concurrent sub-batch streams of llh_grad_batch (1 = serial launches)."""
         self._ck(self.L.gpe_set_streams(self.h, int(nstreams)))
+
+    def set_async(self, on=True):
+        """Calls whose inputs and outputs are all device tensors return once enqueued; ``synchronize()`` waits."""
+        self._ck(self.L.gpe_set_async(self.h, int(bool(on))))
+
+    def synchronize(self):
+        self._ck(self.L.gpe_synchronize(self.h))
 
     def profile_enable(self, on=True):
         self._ck(self.L.gpe_profile_enable(self.h, int(bool(on))))

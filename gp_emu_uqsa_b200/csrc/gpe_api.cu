@@ -430,6 +430,20 @@ int gpe_set_streams(gpe_handle* h, int nstreams) {
     return 0;
 }
 
+int gpe_set_async(gpe_handle* h, int on) {
+    if (!h) return -2;
+    h->async = on != 0;
+    return 0;
+}
+
+int gpe_synchronize(gpe_handle* h) {
+    if (!h) return -2;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->st));
+    CK(cudaGetLastError());
+    return 0;
+}
+
 int gpe_profile_enable(gpe_handle* h, int on) {
     if (!h) return -2;
     h->prof_on = on != 0;
@@ -686,7 +700,11 @@ int gpe_llh_grad_batch(gpe_handle* h, const double* theta, int B, int p, int mod
         if (sigma_hat) CK(cudaMemcpyAsync(sigma_hat + b0, h->sig_d, sizeof(double) * Bs, cudaMemcpyDefault, h->st));
         if (status) CK(cudaMemcpyAsync(status + b0, h->status, sizeof(int) * Bs, cudaMemcpyDefault, h->st));
     }
-    CK(cudaStreamSynchronize(h->st));
+    // asynchronous mode: everything is ordered on the handle's stream; with device-resident inputs and outputs the caller
+    // may enqueue more work (another handle's, or its own kernels on gpe_get_stream) before waiting
+    const bool all_dev = gpe_is_device_ptr(theta) && gpe_is_device_ptr(llh) && gpe_is_device_ptr(grad) &&
+                         (!sigma_hat || gpe_is_device_ptr(sigma_hat)) && (!status || gpe_is_device_ptr(status));
+    if (!(h->async && all_dev)) CK(cudaStreamSynchronize(h->st));
     return 0;
 }
 

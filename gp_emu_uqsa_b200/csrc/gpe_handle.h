@@ -12,6 +12,7 @@ struct gpe_handle {
     cudaStream_t st = nullptr;
     std::string err;
     long long launches = 0;
+    bool async = false;          // gpe_set_async: calls whose outputs are all device memory return without the final synchronize
 
     // optional per-category CUDA-event timing of every launch (gpe_profile_*)
     enum { CAT_GEMM_BIG = 0, CAT_GEMM_SMALL = 1, CAT_LEAF = 2, CAT_COV = 3, CAT_GRAD = 4, CAT_OTHER = 5, CAT_LAUUM = 6, NCAT = 7 };

@@ -147,23 +147,44 @@ __global__ void __launch_bounds__(WS_THREADS, 1) lauum_grad_kernel(LauumGradP p)
     const int b_off = fc * B_LD + wn0 + fr;
     constexpr int a_kk = 4 * A_LD, b_kk = 4 * B_LD;
 
+    // Diagonal tiles (ti == tj): only entries on or below the diagonal are used.  With the 4 x 2 warp grid the warps of
+    // rows 0, 1 in column 1 have nothing to do and the warps (row 0, column 0), (row 2, column 1) need only their left four
+    // fragment columns: per SM sub-partition that is 48 / 48 / 32 / 32 DMMAs per k4 step instead of 64 -- the tile costs
+    // 3/4 (diagonal tiles are 8.8 % of a LAUUM launch at n = 4096).  Warp-uniform, decided outside the k loop.
+    int jn = FN;
+    if (ti == tj) jn = (wcol == 0) ? (wrow == 0 ? FN / 2 : FN) : (wrow == 3 ? FN : (wrow == 2 ? FN / 2 : 0));
     for (int kt = 0; kt < KT; kt++) {
         const int s = kt % GEMM_STAGES;
         mbar_wait(&full_bar[s], (kt / GEMM_STAGES) & 1);
         const double* at = As + s * A_EL + a_off;
         const double* bt = Bs + s * B_EL + b_off;
         if (kt >= wk_lo) {
+            if (jn == FN) {
 #pragma unroll
-            for (int kk = 0; kk < GEMM_BK / 4; kk++) {
-                double af[FM], bf[FN];
+                for (int kk = 0; kk < GEMM_BK / 4; kk++) {
+                    double af[FM], bf[FN];
 #pragma unroll
-                for (int i = 0; i < FM; i++) af[i] = at[kk * a_kk + i * 8];
+                    for (int i = 0; i < FM; i++) af[i] = at[kk * a_kk + i * 8];
 #pragma unroll
-                for (int j = 0; j < FN; j++) bf[j] = bt[kk * b_kk + j * 8];
+                    for (int j = 0; j < FN; j++) bf[j] = bt[kk * b_kk + j * 8];
 #pragma unroll
-                for (int i = 0; i < FM; i++)
+                    for (int i = 0; i < FM; i++)
 #pragma unroll
-                    for (int j = 0; j < FN; j++) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+                        for (int j = 0; j < FN; j++) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+                }
+            } else if (jn == FN / 2) {
+#pragma unroll
+                for (int kk = 0; kk < GEMM_BK / 4; kk++) {
+                    double af[FM], bf[FN / 2];
+#pragma unroll
+                    for (int i = 0; i < FM; i++) af[i] = at[kk * a_kk + i * 8];
+#pragma unroll
+                    for (int j = 0; j < FN / 2; j++) bf[j] = bt[kk * b_kk + j * 8];
+#pragma unroll
+                    for (int i = 0; i < FM; i++)
+#pragma unroll
+                        for (int j = 0; j < FN / 2; j++) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+                }
             }
         }
         __syncwarp();

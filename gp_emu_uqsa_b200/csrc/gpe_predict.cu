@@ -676,7 +676,9 @@ static int predict_common(gpe_handle* h, const double* Xs, const double* Hs, con
             CK(cudaStreamWaitEvent(h->st, h->ev_join[k], 0));
         }
     }
-    CK(cudaStreamSynchronize(h->st));
+    // asynchronous mode (gpe_set_async): with device-resident points and outputs nothing on the host waits for this call
+    const bool all_dev = mean_dev && (!var || var_dev) && (!Xs || x_dev) && (!Hs || h_dev);
+    if (!(h->async && all_dev)) CK(cudaStreamSynchronize(h->st));
     CK(cudaGetLastError());
     return 0;
 }

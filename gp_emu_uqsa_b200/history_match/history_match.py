@@ -28,8 +28,10 @@ def _predict_all(emuls, zs, x, act_ref, active_fn):
     """mean/var [n_emul, m] on device for the points x [m, num_inputs] (scaled, combined columns).
     Emulators for which active_fn(E) is False contribute I = 0 (reference :93, :99-100): their slots
     are filled with mean = z, var = 1."""
+    import torch
     m = x.shape[0]
     mean_d, var_d = _device_buffers(len(emuls), m)
+    busy = []
     for o, E in enumerate(emuls):
         if not active_fn(E):
             mean_d[o].fill_(float(zs[o]))
@@ -40,8 +42,18 @@ def _predict_all(emuls, zs, x, act_ref, active_fn):
         if st != 0:
             raise _lib.GpeError("training covariance matrix of emulator %d is not positive definite" % o)
         xe = _np.ascontiguousarray(x[:, cols])
-        Hs = None if E.basis.poly is not None else E.basis.design_matrix(xe)
-        dev.predict(xe, Hs, out=(mean_d[o], var_d[o]))
+        if E.basis.poly is not None:
+            # device-resident points + asynchronous handle: the emulators' predictions are enqueued back to back on
+            # their own streams and overlap; one wait per handle at the end
+            xd = torch.from_numpy(xe).to(mean_d.device)
+            dev.set_async(True)
+            dev.predict(xd, None, out=(mean_d[o], var_d[o]))
+            busy.append((dev, xd))
+        else:
+            dev.predict(xe, E.basis.design_matrix(xe), out=(mean_d[o], var_d[o]))
+    for dev, _ in busy:
+        dev.synchronize()
+        dev.set_async(False)
     return mean_d, var_d
 
 

@@ -49,6 +49,14 @@ void* gpe_get_stream(gpe_handle* h);
  * which is what per-kernel timing with gpe_profile_* should be read under). */
 int gpe_set_streams(gpe_handle* h, int nstreams);
 
+/* Asynchronous mode (off by default).  When on, gpe_llh_grad_batch, gpe_predict and gpe_predict_grid return as soon as
+ * their work is enqueued on the handle's stream PROVIDED every input and output pointer of the call is device memory;
+ * calls with a host pointer stay synchronous.  gpe_synchronize waits for the handle's stream.  This is what lets one
+ * host thread keep several handles busy (the emulators of a history-matching job, history_match.py:96-118) or order
+ * its own kernels after a call with events on gpe_get_stream. */
+int gpe_set_async(gpe_handle* h, int on);
+int gpe_synchronize(gpe_handle* h);
+
 /* Optional per-launch CUDA-event timing by kernel category (measurement only; the reference's
  * unused @timeit helper, _emulatoroptimise.py:8-17, is the nearest analogue).  ms/count: 7 entries:
  * 0 DMMA GEMM (128-wide tiles; SYRK/TRMM updates of the factorisation and the prediction TRMM),

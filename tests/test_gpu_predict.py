@@ -200,3 +200,37 @@ def test_many_inputs_d48_needs_large_shared_memory_tiles(dev):
     mo, vo = O.posterior_diag_chunked(Xs, np.ones((m, 1)), X, y, H, A, O.optimalbeta(A, H, y), sigma, delta, nugget, 0)
     np.testing.assert_allclose(mean, mo, rtol=1e-8, atol=1e-10)
     np.testing.assert_allclose(var, vo, rtol=1e-8, atol=1e-12)
+
+
+def test_async_mode_two_handles_overlap_and_match_synchronous_results(dev, golden_dir):
+    """gpe_set_async: with device-resident points and outputs a call returns once enqueued, so one host thread can keep
+    two emulators' handles busy (history_match.py:96-118); results equal the synchronous ones bit for bit, and a call
+    with a host pointer stays synchronous."""
+    from gp_emu_uqsa_b200 import _lib
+    G = np.load(os.path.join(golden_dir, "post_n200_d4.npz"))
+    X, y = G["X"], G["y"]
+    rng = np.random.default_rng(8)
+    P = rng.random((5000, 4))
+    devs, ref = [], []
+    for k in range(2):
+        dv = _lib.Device(0)
+        dv.set_training(X, y * (1.0 + k), O.make_H_linear(X)); dv.set_basis([0, 1, 2, 3], [1] * 4)
+        dv.fit_state(G["gp4ml_k_fixT_delta"], float(G["gp4ml_k_fixT_nugget"]), float(G["gp4ml_k_fixT_sigma"]), 0)
+        devs.append(dv)
+        ref.append(dv.predict(P))
+    Pd = torch.tensor(P, device="cuda")
+    outs = [(torch.empty(5000, dtype=torch.float64, device="cuda"), torch.empty(5000, dtype=torch.float64, device="cuda")) for _ in devs]
+    torch.cuda.synchronize()
+    for dv, o in zip(devs, outs):
+        dv.set_async(True)
+        dv.predict(Pd, None, out=o)            # returns once enqueued
+    for dv in devs:
+        dv.synchronize()
+        dv.set_async(False)
+    for (m, v), (mr, vr) in zip(outs, ref):
+        assert np.array_equal(m.cpu().numpy(), mr) and np.array_equal(v.cpu().numpy(), vr)
+    devs[0].set_async(True)
+    mh, vh = devs[0].predict(P)                    # host buffers: complete on return even in asynchronous mode
+    assert np.array_equal(mh, ref[0][0]) and np.array_equal(vh, ref[0][1])
+    for dv in devs:
+        dv.close()
