@@ -15,6 +15,16 @@ static bool use_ws() {
     return v == 1;
 }
 
+// GPE_WS2=1: the two-CTAs-per-SM 128x64 kernel for the machine-filling launches (A/B knob; see gpe_gemm.cuh)
+static bool use_ws2() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("GPE_WS2");
+        v = e ? atoi(e) : 0;
+    }
+    return v == 1;
+}
+
 template <bool A_KC, bool B_KC>
 static cudaError_t dispatch_tiles(const GemmP& p, int epi, cudaStream_t st) {
     if (p.M == 32 || p.M == 16) {   // skinny-M panel product (prediction: [e | Gm K^-T]^T C; 16 rows when q + 1 <= 16)
@@ -36,9 +46,11 @@ static cudaError_t dispatch_tiles(const GemmP& p, int epi, cudaStream_t st) {
     bool big = (p.M % 128 == 0) && (p.N % 128 == 0) && (t128 >= 120);
     if (epi == EPI_SUMSQ) {
         // column norms are accumulated per 128-row tile: the partial buffer is sized for BM = 128
+        if (use_ws2()) return launch_gemm_ws2<A_KC, B_KC, EPI_SUMSQ>(p, st);
         return use_ws() ? launch_gemm_ws<A_KC, B_KC, EPI_SUMSQ>(p, st)
                         : launch_gemm_cfg<128, 128, 2, 4, A_KC, B_KC, EPI_SUMSQ>(p, st);
     }
+    if (big && use_ws2()) return launch_gemm_ws2<A_KC, B_KC, EPI_STORE>(p, st);
     if (big) return use_ws() ? launch_gemm_ws<A_KC, B_KC, EPI_STORE>(p, st)
                              : launch_gemm_cfg<128, 128, 2, 4, A_KC, B_KC, EPI_STORE>(p, st);
     // latency regime (one or two guesses at n <= 2000): 64x64 tiles would occupy under half of the SMs

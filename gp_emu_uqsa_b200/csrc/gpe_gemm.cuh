@@ -487,6 +487,208 @@ inline cudaError_t launch_gemm_ws(const GemmP& p, cudaStream_t st) {
     return launch_gemm_ws_shape<A_KC, B_KC, EPI, 2>(p, st);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Two-CTAs-per-SM flavour of the warp-specialised kernel: 128x64 tile, 4 consumer warps + 1 producer warp (160 threads),
+// 3 stages (<= 92 KB), so that two CTAs are resident on an SM.  With one CTA per SM the tensor pipe idles while a new
+// CTA fills its pipeline (barrier init, first loads from L2/HBM) and while the old one stores its tile: a few
+// microseconds per CTA, 2-3 % of a 190 us LAUUM tile but 8-15 % of the 30-70 us tiles of the h = 512 recursion level
+// (round 1: 86.5 / 77 / 56 % of the algorithmic roof at h = 2048 / 1024 / 512).  Two independent CTAs hide each other's
+// ramps; the warp tiles (64x32 / 32x64), fragment loads and the k loop are those of the one-CTA kernel, 8 math warps
+// per SM as before.
+constexpr int WS2_CONSUMERS = 4;
+constexpr int WS2_THREADS = (WS2_CONSUMERS + 1) * 32;
+constexpr int WS2_STAGES = 3;
+constexpr int WS2_COLGROUP = 32;     // 64-column blocks per L2-resident group of a row-triangular launch (2048 columns, as WS_COLGROUP)
+
+template <bool A_KC, bool B_KC, int EPI, int WMW>
+__global__ void __launch_bounds__(WS2_THREADS, 2) gemm_dmma_ws2_kernel(GemmP p) {
+    constexpr int BM = 128, BN = 64, WNW = WS2_CONSUMERS / WMW;
+    constexpr int WTM = BM / WMW, WTN = BN / WNW, FM = WTM / 8, FN = WTN / 8;      // 2x2 warps of 64x32, or 4x1 of 32x64
+    constexpr int A_EL = TileShape<BM, A_KC>::ELEMS, B_EL = TileShape<BN, B_KC>::ELEMS;
+    constexpr int A_LD = TileShape<BM, A_KC>::LD, B_LD = TileShape<BN, B_KC>::LD;
+    extern __shared__ __align__(16) double smem[];
+    __shared__ __align__(8) uint64_t full_bar[WS2_STAGES], empty_bar[WS2_STAGES];
+
+    const bool rowtri = (p.kmode == KM_LE_I || p.kmode == KM_GE_I);
+    int tj, ti;
+    if (rowtri) {
+        const int ntx = p.N / BN, nty = p.M / BM, id = (int)blockIdx.x;
+        const int full = (ntx / WS2_COLGROUP) * WS2_COLGROUP * nty;
+        int g0, gsz, r;
+        if (id < full) { g0 = (id / (WS2_COLGROUP * nty)) * WS2_COLGROUP; gsz = WS2_COLGROUP; r = id % (WS2_COLGROUP * nty); }
+        else { g0 = (ntx / WS2_COLGROUP) * WS2_COLGROUP; gsz = ntx - g0; r = id - full; }
+        const int y = r / gsz;
+        tj = g0 + (r - y * gsz);
+        ti = (p.kmode == KM_LE_I) ? nty - 1 - y : y;
+    } else {
+        tj = (p.kmode == KM_LE_J) ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;
+        ti = (int)blockIdx.y;
+    }
+    const int b = blockIdx.z;
+    if (p.lower && (ti + 1) * BM <= tj * BN) return;
+    const int m0 = ti * BM, n0 = tj * BN;
+    int kbeg = 0, kend = p.K;
+    switch (p.kmode) {
+        case KM_LE_J: kend = min(p.K, (tj + 1) * BN); break;
+        case KM_GE_J: kbeg = min(p.K, (tj * BN / GEMM_BK) * GEMM_BK); break;
+        case KM_LE_I: kend = min(p.K, (ti + 1) * BM); break;
+        case KM_GE_I: kbeg = min(p.K, ti * BM); break;
+        default: break;
+    }
+    const int KT = (kend - kbeg + GEMM_BK - 1) / GEMM_BK;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < WS2_STAGES; s++) {
+            mbar_init(&full_bar[s], 32);
+            mbar_init(&empty_bar[s], WS2_CONSUMERS);
+        }
+    }
+    __syncthreads();
+
+    double* As = smem;
+    double* Bs = smem + WS2_STAGES * A_EL;
+
+    if (warp == WS2_CONSUMERS) {
+        const double* Ag = p.A + (size_t)b * p.sA + (A_KC ? ((size_t)m0 * p.lda + kbeg) : ((size_t)kbeg * p.lda + m0));
+        const double* Bg = p.B + (size_t)b * p.sB + (B_KC ? ((size_t)n0 * p.ldb + kbeg) : ((size_t)kbeg * p.ldb + n0));
+        const size_t a_kstep = A_KC ? (size_t)GEMM_BK : (size_t)GEMM_BK * p.lda;
+        const size_t b_kstep = B_KC ? (size_t)GEMM_BK : (size_t)GEMM_BK * p.ldb;
+        for (int kt = 0; kt < KT; kt++) {
+            const int s = kt % WS2_STAGES;
+            if (kt >= WS2_STAGES) mbar_wait(&empty_bar[s], ((kt / WS2_STAGES) - 1) & 1);
+            load_tile_warp<BM, A_KC>(As + s * A_EL, Ag + kt * a_kstep, p.lda, lane);
+            load_tile_warp<BN, B_KC>(Bs + s * B_EL, Bg + kt * b_kstep, p.ldb, lane);
+            cp_async_mbar_arrive_noinc(&full_bar[s]);
+        }
+        cp_async_wait<0>();
+        if (EPI != EPI_STORE) named_bar_sync(1, WS2_THREADS);
+        return;
+    }
+
+    // consumer warps.  2x2 grid: warps 0, 1 take columns 0, 1 of row 0, warps 2, 3 columns 1, 0 of row 1 (mirrored, so the light
+    // and the heavy end of a column-triangular operand share an SM sub-partition pair); 4x1 grid: warp w takes row w.
+    const int wrow = (WMW == 2) ? warp / 2 : warp;
+    const int wcol = (WMW == 2) ? (warp < 2 ? warp : 3 - warp) : 0;
+    const int wm0 = wrow * WTM, wn0 = wcol * WTN;
+    const int fr = lane >> 2, fc = lane & 3;
+    int wk_lo = 0, wk_hi = KT;
+    switch (p.kmode) {
+        case KM_LE_J: wk_hi = min(KT, (n0 + wn0 + WTN - kbeg + GEMM_BK - 1) / GEMM_BK); break;
+        case KM_GE_J: wk_lo = max(0, (n0 + wn0 - kbeg) / GEMM_BK); break;
+        case KM_LE_I: wk_hi = min(KT, (m0 + wm0 + WTM - kbeg + GEMM_BK - 1) / GEMM_BK); break;
+        case KM_GE_I: wk_lo = max(0, (m0 + wm0 - kbeg) / GEMM_BK); break;
+        default: break;
+    }
+    double acc[FM][FN][2];
+#pragma unroll
+    for (int i = 0; i < FM; i++)
+#pragma unroll
+        for (int j = 0; j < FN; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+    const int a_off = A_KC ? ((wm0 + fr) * A_LD + fc) : (fc * A_LD + wm0 + fr);
+    const int b_off = B_KC ? ((wn0 + fr) * B_LD + fc) : (fc * B_LD + wn0 + fr);
+    constexpr int a_fstep = A_KC ? 8 * A_LD : 8;
+    constexpr int b_fstep = B_KC ? 8 * B_LD : 8;
+    constexpr int a_kk = A_KC ? 4 : 4 * A_LD;
+    constexpr int b_kk = B_KC ? 4 : 4 * B_LD;
+
+    for (int kt = 0; kt < KT; kt++) {
+        const int s = kt % WS2_STAGES;
+        mbar_wait(&full_bar[s], (kt / WS2_STAGES) & 1);
+        const double* at = As + s * A_EL + a_off;
+        const double* bt = Bs + s * B_EL + b_off;
+        if (kt >= wk_lo && kt < wk_hi) {
+#pragma unroll
+            for (int kk = 0; kk < GEMM_BK / 4; kk++) {
+                double af[FM], bf[FN];
+#pragma unroll
+                for (int i = 0; i < FM; i++) af[i] = at[kk * a_kk + i * a_fstep];
+#pragma unroll
+                for (int j = 0; j < FN; j++) bf[j] = bt[kk * b_kk + j * b_fstep];
+#pragma unroll
+                for (int i = 0; i < FM; i++)
+#pragma unroll
+                    for (int j = 0; j < FN; j++) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[s]);
+    }
+
+    if (EPI == EPI_STORE) {
+        double* Cg = p.C + (size_t)b * p.sC + (size_t)(m0 + wm0 + fr) * p.ldc + n0 + wn0 + 2 * fc;
+#pragma unroll
+        for (int i = 0; i < FM; i++)
+#pragma unroll
+            for (int j = 0; j < FN; j++) {
+                double2* dst = reinterpret_cast<double2*>(Cg + (size_t)(8 * i) * p.ldc + 8 * j);
+                double2 v;
+                v.x = p.alpha * acc[i][j][0];
+                v.y = p.alpha * acc[i][j][1];
+                if (p.accumulate) {
+                    double2 o = *dst;
+                    v.x += o.x;
+                    v.y += o.y;
+                }
+                *dst = v;
+            }
+    } else {
+        named_bar_sync(1, WS2_THREADS);     // every stage consumed, producer drained: smem is free
+        double* red = smem;                 // [WMW][BN]
+#pragma unroll
+        for (int j = 0; j < FN; j++) {
+            double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+            for (int i = 0; i < FM; i++) {
+                s0 = fma(acc[i][j][0], acc[i][j][0], s0);
+                s1 = fma(acc[i][j][1], acc[i][j][1], s1);
+            }
+#pragma unroll
+            for (int o = 4; o < 32; o <<= 1) {
+                s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+                s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+            }
+            if (fr == 0) {
+                red[wrow * BN + wn0 + 8 * j + 2 * fc] = s0;
+                red[wrow * BN + wn0 + 8 * j + 2 * fc + 1] = s1;
+            }
+        }
+        named_bar_sync(2, WS2_CONSUMERS * 32);
+        for (int c = tid; c < BN; c += WS2_CONSUMERS * 32) {
+            double tot = 0.0;
+#pragma unroll
+            for (int w = 0; w < WMW; w++) tot += red[w * BN + c];
+            p.C[(size_t)b * p.sC + (size_t)ti * p.ldc + n0 + c] = tot;
+        }
+    }
+}
+
+template <bool A_KC, bool B_KC>
+constexpr size_t gemm_ws2_smem_bytes() {
+    return (size_t)WS2_STAGES * (TileShape<128, A_KC>::ELEMS + TileShape<64, B_KC>::ELEMS) * sizeof(double);
+}
+
+template <bool A_KC, bool B_KC, int EPI, int WMW>
+inline cudaError_t launch_gemm_ws2_shape(const GemmP& p, cudaStream_t st) {
+    auto kern = gemm_dmma_ws2_kernel<A_KC, B_KC, EPI, WMW>;
+    constexpr size_t smem = gemm_ws2_smem_bytes<A_KC, B_KC>();
+    static SmemOptIn optin;
+    if (cudaError_t e = optin.ensure(kern, smem); e != cudaSuccess) return e;
+    if (p.M % 128 || p.N % 64 || p.K % GEMM_BK) return cudaErrorInvalidValue;
+    const bool rowtri = (p.kmode == KM_LE_I || p.kmode == KM_GE_I);
+    dim3 grid = rowtri ? dim3((p.M / 128) * (p.N / 64), 1, p.batch) : dim3(p.N / 64, p.M / 128, p.batch);
+    kern<<<grid, WS2_THREADS, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+template <bool A_KC, bool B_KC, int EPI>
+inline cudaError_t launch_gemm_ws2(const GemmP& p, cudaStream_t st) {
+    if (p.kmode == KM_LE_I || p.kmode == KM_GE_I) return launch_gemm_ws2_shape<A_KC, B_KC, EPI, 4>(p, st);
+    return launch_gemm_ws2_shape<A_KC, B_KC, EPI, 2>(p, st);
+}
+
 // Layout ids: 0 = (A_KC,B_KC) "NT", 1 = (A_KC,!B_KC) "NN", 2 = (!A_KC,!B_KC) "TN".
 // Tile choice: 128x128 when that still fills the machine, else 64x64; N == 32 panels use 128x32.
 cudaError_t launch_gemm(const GemmP& p, int layout, int epi, cudaStream_t st);

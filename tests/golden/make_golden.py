@@ -523,6 +523,64 @@ def gen_writers(g, s):
     return out
 
 
+def gen_config4(g, h, n=2000, d=8, m=3000):
+    """Config 4's shape with the REAL reference: two n = 2000, d = 8 emulators (outputs sin(Xw)+0.1 sum x^2 and cos(X w2) as in
+    bench.py) with fixed hyper-parameters (delta 0.5, sigma 1, nugget 1e-4, beta = optimalbeta), checkpointed with the
+    reference's own writers and rebuilt from those files; g.posterior (mean, diag of the full covariance, m = 1000 per call)
+    and history_match.nonimp_data on m points of the 10-level tensor grid.  Stores the checkpoint files (bytes), the points,
+    mean / variance per emulator and the kept rows."""
+    X, y, _ = synth(n, d, 0)
+    y2 = np.cos(X @ np.random.default_rng(1).normal(size=d))
+    rng = np.random.default_rng(44)
+    out = {}
+    with tempfile.TemporaryDirectory() as tmp, RL.cwd(tmp), RL.quiet():
+        emuls = []
+        for o, yy in enumerate((y, y2)):
+            cfg = RL.write_emulator_files(tmp, X, yy, mucm="F", fix_nugget="T", alt_nugget="F", nugget=1e-4, name="c4_%d" % o)
+            E = g.setup(cfg, datashuffle=False, scaleinputs=True)
+            E.par.delta = np.full(d, 0.5); E.K.d = E.par.delta; E.K.n = E.par.nugget
+            E.par.sigma = 1.0
+            E.training.remake()
+            E.opt_T.optimalbeta()
+            E.beliefs.final_beliefs(E, True)
+            E.post.final_design_points(E, True)
+            with open("c4_%d_config_r" % o, "w") as f:
+                f.write("beliefs c4_%d_beliefs-0f\ninputs c4_%d_input-o0-0f\noutputs c4_%d_output-o0-0f\n" % (o, o, o))
+                f.write("tv_config 10 0 0\ndelta_bounds [ ]\nsigma_bounds [ ]\nnugget_bounds [ ]\ntries 1\nconstraints bounds\n")
+            for fn in ("c4_%d_config_r" % o, "c4_%d_beliefs-0f" % o, "c4_%d_input-o0-0f" % o, "c4_%d_output-o0-0f" % o):
+                out["file_" + fn] = np.frombuffer(open(fn, "rb").read(), dtype=np.uint8)
+            emuls.append(g.setup("c4_%d_config_r" % o, datashuffle=False, scaleinputs=True))
+        # points of the 10-level grid in scaled units: random flat indices + a run of consecutive ones
+        idx = np.sort(np.concatenate([rng.choice(10 ** 8, size=m - 600, replace=False), np.arange(36999700, 36999700 + 600)]))
+        P = np.empty((m, d))
+        t = idx.copy()
+        for k in range(d - 1, -1, -1):
+            P[:, k] = (t % 10 + 0.5) / 10.0
+            t = t // 10
+        out["grid_index"] = idx
+        out["P_scaled"] = P
+        for o, E2 in enumerate(emuls):
+            mu, vd = np.empty(m), np.empty(m)
+            for c in range(0, m, 1000):
+                mean, var = g.posterior(E2, P[c:c + 1000].copy())
+                mu[c:c + 1000], vd[c:c + 1000] = mean, np.diag(var)
+            out["mean%d" % o], out["var%d" % o] = mu, vd
+            out["beta%d" % o] = np.array(E2.par.beta)
+        # the same points in the data files' units for nonimp_data (it scales them with input_minmax, _hmutilfunctions.py:126-139)
+        mm = np.array(emuls[0].beliefs.input_minmax)
+        pts = P * (mm[:, 1] - mm[:, 0]) + mm[:, 0]
+        np.savetxt("sim_in", pts, fmt="%.17g")
+        np.savetxt("sim_out", np.column_stack([pts[:, 0], pts[:, 1]]), fmt="%.17g")
+        out["sim_in"] = pts
+        zs = [float(np.median(y)), float(np.median(y2))]
+        ve = [1e-2, 1e-2]
+        out.update(zs=np.array(zs), var_extra=np.array(ve), cm=3.0)
+        cnt = h.nonimp_data(emuls, zs, 3.0, ve, ["sim_in", "sim_out"], maxno=1)
+        out["nonimp_count"] = cnt
+        out["nonimp_in"] = np.atleast_2d(np.loadtxt("nonimp_sim_in"))
+    return out
+
+
 def main():
     assert RL.available(), "reference not present"
     g, h, s, gn = RL.load()
@@ -538,6 +596,9 @@ def main():
         return
     if len(sys.argv) > 1 and sys.argv[1] == "fullsize_sens":
         save("sens_n2000_d8.npz", gen_sens_fullsize(g, s))
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "config4":
+        save("config4_n2000_d8.npz", gen_config4(g, h))
         return
     if len(sys.argv) > 1 and sys.argv[1] == "writers":
         save("writers_n40_d3.npz", gen_writers(g, s))

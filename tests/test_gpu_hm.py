@@ -131,3 +131,39 @@ def test_device_maximin_criterion_is_bit_identical_to_scipy(n, dim, ne):
     want = d._host_criterion(designs, extra)
     got = d.device_criterion(designs, extra)
     assert np.array_equal(got, want)
+
+
+def test_config4_shape_matches_real_reference(golden_dir, tmp_path):
+    """Config 4's shape against the REAL reference (tests/golden/make_golden.py config4): two n = 2000, d = 8 emulators
+    rebuilt from the reference's own checkpoint files; g.posterior's mean and diagonal variance on 3000 points of the
+    10-level grid to 1e-8 -- through the explicit-point path and, for the run of consecutive flat indices, through the
+    flat-index grid path (tabulated factors) -- and history_match.nonimp_data's kept rows identical."""
+    import gp_emu_uqsa_b200 as g
+    import gp_emu_uqsa_b200.history_match as h
+    G = np.load(os.path.join(golden_dir, "config4_n2000_d8.npz"))
+    emuls = []
+    with _cwd(tmp_path), _quiet():
+        for o in (0, 1):
+            for fn in ("c4_%d_config_r" % o, "c4_%d_beliefs-0f" % o, "c4_%d_input-o0-0f" % o, "c4_%d_output-o0-0f" % o):
+                with open(fn, "wb") as f:
+                    f.write(bytes(G["file_" + fn]))
+            emuls.append(g.setup("c4_%d_config_r" % o, datashuffle=False, scaleinputs=True))
+        P, idx = G["P_scaled"], G["grid_index"]
+        run = np.nonzero((idx >= 36999700) & (idx < 36999700 + 600))[0]
+        assert run.size == 600 and np.array_equal(idx[run], np.arange(36999700, 36999700 + 600))
+        for o, E in enumerate(emuls):
+            assert np.allclose(E.par.beta, G["beta%d" % o], rtol=1e-12, atol=0)       # read back from the checkpoint
+            mean, var = g.posterior_diag(E, P)
+            assert np.allclose(mean, G["mean%d" % o], rtol=1e-8, atol=1e-10)
+            assert np.allclose(var, G["var%d" % o], rtol=1e-8, atol=1e-9 * G["var%d" % o].max())
+            dev, _, _, st = E.training.fit(beta=E.par.beta, r_div=E.training._A_args[0])
+            assert st == 0
+            gm, gv = dev.predict_grid(np.full(8, 10, dtype=np.int32), np.zeros(8), np.ones(8), 36999700, 600)
+            assert np.allclose(gm, G["mean%d" % o][run], rtol=1e-8, atol=1e-10)
+            assert np.allclose(gv, G["var%d" % o][run], rtol=1e-8, atol=1e-9 * G["var%d" % o].max())
+        np.savetxt("sim_in", G["sim_in"], fmt="%.17g")
+        np.savetxt("sim_out", np.column_stack([G["sim_in"][:, 0], G["sim_in"][:, 1]]), fmt="%.17g")
+        cnt = h.nonimp_data(emuls, list(G["zs"]), float(G["cm"]), list(G["var_extra"]), ["sim_in", "sim_out"], maxno=1)
+        kept = np.atleast_2d(np.loadtxt("nonimp_sim_in"))
+    assert cnt == int(G["nonimp_count"])
+    assert np.allclose(kept, G["nonimp_in"], rtol=0, atol=1e-15)
