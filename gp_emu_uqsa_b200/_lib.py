@@ -55,6 +55,7 @@ def load():
         "gpe_predict_grid": (i, [p, p, p, p, ll, ll, p, p]),
         "gpe_predict_fullcov": (i, [p, p, p, i, p, p, p]),
         "gpe_implausibility": (i, [p, p, p, i, ll, p, p, d, i, ll, ll, ll, p, p, p, p, p]),
+        "gpe_predict_implaus": (i, [p, p, p, p, p, p, ll, ll, d, d, i, i, i, p, d, ll, ll, ll, p, p, p, p]),
         "gpe_solve": (i, [p, p, i, p]),
         "gpe_sens_contract": (i, [p, p, p, p, d, p, i, p, p]),
         "gpe_sens_main_effect": (i, [p, p, p, p, p, p, d, p, i, p, i, p]),
@@ -73,7 +74,7 @@ def load():
 EXPORTS = ["gpe_version", "gpe_create", "gpe_destroy", "gpe_last_error", "gpe_launch_count",
            "gpe_get_stream", "gpe_set_streams", "gpe_set_async", "gpe_synchronize", "gpe_profile_enable", "gpe_profile_read",
            "gpe_set_training", "gpe_set_basis", "gpe_cov_build", "gpe_cov_grad", "gpe_cross_cov", "gpe_llh_grad_batch",
-           "gpe_fit_state", "gpe_predict", "gpe_predict_grid", "gpe_predict_fullcov", "gpe_implausibility",
+           "gpe_fit_state", "gpe_predict", "gpe_predict_grid", "gpe_predict_fullcov", "gpe_implausibility", "gpe_predict_implaus",
            "gpe_solve", "gpe_sens_contract", "gpe_sens_main_effect", "gpe_potrf", "gpe_pdist_argmin",
            "gpe_dbg_gemm", "gpe_dbg_potrf_inv"]
 
@@ -295,6 +296,32 @@ class Device:
                                            int(maxno), int(cell_pts), int(first_index), int(ncell), _ptr(Imax), _ptr(keep),
                                            _ptr(count), _ptr(cmin), _ptr(ccnt)))
         return Imax, keep, count, cmin, ccnt
+
+    def predict_implaus(self, z, var_extra, Itop, first, last, points=None, Hs=None, grid=None, maxno=1, cm=0.0, cell_pts=0,
+                        first_index=0, keep=None):
+        """Prediction of this emulator folded into the running top-``maxno`` implausibility list ``Itop`` [m, maxno]
+        (torch CUDA tensor, ascending; see gpe_predict_implaus).  ``points``: NumPy [m,d] or torch CUDA tensor; or
+        ``grid`` = (levels, lo, hi, start, m).  On the last emulator returns (count_lt, cell_min, cell_count) and fills
+        ``keep`` (torch uint8 tensor or NumPy array) if given; otherwise returns None."""
+        if points is not None:
+            if isinstance(points, np.ndarray) or not hasattr(points, "data_ptr"):
+                points = _f64(points)
+                Hs = None if Hs is None else _f64(Hs)
+            m, lv, lo, hi, start = int(points.shape[0]), None, None, None, 0
+        else:
+            lv, lo, hi, start, m = grid
+            lv = np.ascontiguousarray(lv, dtype=np.int32)
+            lo, hi, start, m = _f64(lo), _f64(hi), int(start), int(m)
+        ncell = 0
+        if last and cell_pts and m:
+            ncell = (first_index + m - 1) // cell_pts - first_index // cell_pts + 1
+        count = np.zeros(maxno, dtype=np.uint64) if last else None
+        cmin = np.empty((ncell, maxno)) if ncell else None
+        ccnt = np.zeros((ncell, maxno), dtype=np.uint64) if ncell else None
+        self._ck(self.L.gpe_predict_implaus(self.h, _ptr(points), _ptr(Hs), _ptr(lv), _ptr(lo), _ptr(hi), start, m, float(z),
+                                            float(var_extra), int(maxno), int(bool(first)), int(bool(last)), _ptr(Itop), float(cm),
+                                            int(cell_pts), int(first_index), int(ncell), _ptr(keep), _ptr(count), _ptr(cmin), _ptr(ccnt)))
+        return (count, cmin, ccnt) if last else None
 
     # ------------------------------------------------------------------ K6
     def solve(self, Bm):

@@ -298,64 +298,144 @@ static SmemOptIn& xcov_optin() {
     return o;
 }
 
+// Implausibility folded into the prediction of one emulator (history_match.py:96-132): instead of mean / variance the
+// per-point list of the maxno largest implausibilities over the emulators seen so far, Itop [m][maxno] ascending, is
+// updated; the last emulator's pass also produces the keep mask, the counts and the cell statistics, so neither the
+// means / variances nor (unless asked for) the final list ever travel through HBM.
+constexpr int MAXEM = 16;
+struct ImpFuse {
+    double z, ve, cm;
+    int maxno, first, last;
+    double* Itop;                        // chunk's first point; in/out (out may be skipped on the last pass: store_top)
+    int store_top;
+    long long cell_pts, first_index;     // global flat index of the chunk's first point (cells as in gpe_implausibility)
+    unsigned char* keep;                 // chunk's first point, or null
+    unsigned long long *count_lt, *cell_min_bits, *cell_count;      // [maxno], [ncell][maxno] (cell 0 = the cell of the call's first point)
+    long long cell_base;                 // index of that cell: (call's first_index) / cell_pts
+};
+
 // per point: mean, variance from the GEMM outputs
+template <bool IMP>
 __global__ void __launch_bounds__(128) predict_finalize_kernel(const double* __restrict__ part, int ntile, const double* __restrict__ aux,
                                                                int ld, const double* __restrict__ P, const double* __restrict__ Hs,
                                                                BasisDesc bd, int d, const double* __restrict__ Kf,
                                                                const double* __restrict__ beta, double sigma2, double astar,
-                                                               long long count, double* __restrict__ mean, double* __restrict__ var) {
+                                                               long long count, double* __restrict__ mean, double* __restrict__ var,
+                                                               ImpFuse imp) {
     __shared__ double Ks[NR][NR + 1];
     __shared__ double bs[NR];
     const int q = bd.q;
     for (int e = threadIdx.x; e < NR * NR; e += blockDim.x) Ks[e / NR][e % NR] = Kf[e];
     if (threadIdx.x < NR) bs[threadIdx.x] = beta[threadIdx.x];
     __syncthreads();
-    long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (j >= count) return;
-    double hv[NR];
+    const long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const bool live = j < count;
+    if (!IMP && !live) return;
+    double mu = 0.0, vj = 1.0;
+    if (live) {
+        double hv[NR];
 #pragma unroll
-    for (int a = 0; a < NR; a++) {
-        double v = 0.0;
-        if (a < q) {
-            if (Hs != nullptr) v = Hs[(size_t)j * q + a];
-            else if (a == 0) v = 1.0;
-            else {
-                double x = P[(size_t)j * d + bd.idx[a]];
-                int pw = bd.pw[a];
-                v = (pw == 1) ? x : pow(x, (double)pw);
+        for (int a = 0; a < NR; a++) {
+            double v = 0.0;
+            if (a < q) {
+                if (Hs != nullptr) v = Hs[(size_t)j * q + a];
+                else if (a == 0) v = 1.0;
+                else {
+                    double x = P[(size_t)j * d + bd.idx[a]];
+                    int pw = bd.pw[a];
+                    v = (pw == 1) ? x : pow(x, (double)pw);
+                }
+            }
+            hv[a] = v;
+        }
+        mu = aux[(size_t)q * ld + j];
+#pragma unroll
+        for (int a = 0; a < NR; a++)
+            if (a < q) mu = fma(hv[a], bs[a], mu);
+        if (!IMP) {
+            mean[j] = mu;
+            if (var == nullptr) return;
+        }
+        // g = K^-1 h - aux[0:q]
+        double gn = 0.0;
+        double kv[NR];
+#pragma unroll
+        for (int a = 0; a < NR; a++) {
+            if (a < q) {
+                double s = hv[a];
+                for (int k = 0; k < a; k++) s = fma(-Ks[a][k], kv[k], s);
+                kv[a] = s / Ks[a][a];
+                double g = kv[a] - aux[(size_t)a * ld + j];
+                gn = fma(g, g, gn);
+            } else {
+                kv[a] = 0.0;
             }
         }
-        hv[a] = v;
-    }
-    double mu = aux[(size_t)q * ld + j];
-#pragma unroll
-    for (int a = 0; a < NR; a++)
-        if (a < q) mu = fma(hv[a], bs[a], mu);
-    mean[j] = mu;
-    if (var == nullptr) return;
-    // g = K^-1 h - aux[0:q]
-    double gn = 0.0;
-    double kv[NR];
-#pragma unroll
-    for (int a = 0; a < NR; a++) {
-        if (a < q) {
-            double s = hv[a];
-            for (int k = 0; k < a; k++) s = fma(-Ks[a][k], kv[k], s);
-            kv[a] = s / Ks[a][a];
-            double g = kv[a] - aux[(size_t)a * ld + j];
-            gn = fma(g, g, gn);
-        } else {
-            kv[a] = 0.0;
+        double zn = 0.0;
+        for (int t = 0; t < ntile; t++) zn += part[(size_t)t * ld + j];
+        vj = sigma2 * (astar - zn + gn);
+        if (!IMP) {
+            var[j] = vj;
+            return;
         }
     }
-    double zn = 0.0;
-    for (int t = 0; t < ntile; t++) zn += part[(size_t)t * ld + j];
-    var[j] = sigma2 * (astar - zn + gn);
+    if (IMP) {
+        // this emulator's implausibility into the ascending top-maxno list (np.sort(np.partition(I, -maxno)[-maxno:]), :129)
+        double top[MAXEM];
+#pragma unroll
+        for (int k = 0; k < MAXEM; k++) top[k] = -1.0;
+        if (live) {
+            if (!imp.first)
+                for (int k = 0; k < imp.maxno; k++) top[k] = imp.Itop[(size_t)j * imp.maxno + k];
+            const double dz = mu - imp.z;
+            const double I = sqrt(dz * dz / (vj + imp.ve));
+            if (I > top[0]) {
+                top[0] = I;
+#pragma unroll
+                for (int k = 0; k < MAXEM - 1; k++) {
+                    if (k + 1 < imp.maxno && top[k] > top[k + 1]) {
+                        double t = top[k];
+                        top[k] = top[k + 1];
+                        top[k + 1] = t;
+                    }
+                }
+            }
+            if (!imp.last || imp.store_top)
+                for (int k = 0; k < imp.maxno; k++) imp.Itop[(size_t)j * imp.maxno + k] = top[k];
+        }
+        if (!imp.last) return;
+        // last emulator: the reductions of implaus_kernel on the finished list (warp-aggregated, integer atomics: deterministic)
+        if (live && imp.keep != nullptr) imp.keep[j] = (top[0] < imp.cm) ? 1 : 0;
+        const long long cell = (imp.cell_pts > 0 && live) ? (imp.first_index + j) / imp.cell_pts - imp.cell_base : -1;
+        const long long cell0 = __shfl_sync(0xffffffffu, cell, 0);
+        const bool uniform = imp.cell_pts > 0 && __all_sync(0xffffffffu, cell == cell0) && cell0 >= 0;
+        for (int k = 0; k < imp.maxno; k++) {
+            const double vk = top[imp.maxno - 1 - k];
+            const bool lt = live && (vk < imp.cm);
+            const unsigned bal = __ballot_sync(0xffffffffu, lt);
+            if ((threadIdx.x & 31) == 0 && bal && imp.count_lt != nullptr) atomicAdd(&imp.count_lt[k], (unsigned long long)__popc(bal));
+            if (imp.cell_pts <= 0) continue;
+            if (uniform) {
+                unsigned long long bits = (unsigned long long)__double_as_longlong(vk);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    unsigned long long other = __shfl_xor_sync(0xffffffffu, bits, o);
+                    bits = other < bits ? other : bits;
+                }
+                if ((threadIdx.x & 31) == 0) {
+                    if (imp.cell_min_bits != nullptr) atomicMin(&imp.cell_min_bits[(size_t)cell0 * imp.maxno + k], bits);
+                    if (bal && imp.cell_count != nullptr) atomicAdd(&imp.cell_count[(size_t)cell0 * imp.maxno + k], (unsigned long long)__popc(bal));
+                }
+            } else if (live) {
+                if (imp.cell_min_bits != nullptr) atomicMin(&imp.cell_min_bits[(size_t)cell * imp.maxno + k], (unsigned long long)__double_as_longlong(vk));
+                if (lt && imp.cell_count != nullptr) atomicAdd(&imp.cell_count[(size_t)cell * imp.maxno + k], 1ull);
+            }
+        }
+    }
 }
 
 // K5: implausibility per point + reductions.  I >= 0, so the IEEE bit pattern orders like the value
 // and min-reductions can use integer atomics (deterministic).
-constexpr int MAXEM = 16;
 struct ImpDesc {
     int n_emul, maxno;
     double z[MAXEM], ve[MAXEM];
@@ -503,7 +583,7 @@ long long default_chunk(gpe_handle* h) {
 // One chunk on stream `st` with the buffers of `sl`: points already in P_dev [mc, d] (rows >= count
 // arbitrary but finite).
 int predict_chunk(gpe_handle* h, gpe_handle::PredSlot& sl, cudaStream_t st, const double* P_dev, const double* Hs_dev,
-                  long long count, int mc, double* mean_dev, double* var_dev, const GridXcov* gx = nullptr) {
+                  long long count, int mc, double* mean_dev, double* var_dev, const GridXcov* gx = nullptr, const ImpFuse* imp = nullptr) {
     const int np = h->npad;
     size_t smem = (size_t)h->d * (64 + 130) * sizeof(double);
     {
@@ -521,16 +601,21 @@ int predict_chunk(gpe_handle* h, gpe_handle::PredSlot& sl, cudaStream_t st, cons
     const int maux = (h->q + 1 <= 16) ? 16 : NR;
     if ((rc = gpe_run_gemm_on(h, st, h->fE, sl.C, sl.Aux, NR, mc, mc, 0, 0, 0, maux, mc, np, 1.0, 0, KM_FULL, 0, 1, 2, EPI_STORE))) return rc;
     int ntile = 0;
-    if (var_dev != nullptr) {
+    if (var_dev != nullptr || imp != nullptr) {
         // column norms of Z = Linv C    (NN, Linv lower: k <= i), reduced in the epilogue
         if ((rc = gpe_run_gemm_on(h, st, h->fLi, sl.C, sl.Part, np, mc, mc, 0, 0, 0, np, mc, np, 1.0, 0, KM_LE_I, 0, 1, 1, EPI_SUMSQ))) return rc;
         ntile = np / 128;
     }
     {
         ProfScope ps(h, gpe_handle::CAT_OTHER, st);
-        predict_finalize_kernel<<<(unsigned)((count + 127) / 128), 128, 0, st>>>(
-            sl.Part, ntile, sl.Aux, mc, P_dev, Hs_dev, basis_of(h), h->d, h->fK, h->fbeta, h->fit_sigma * h->fit_sigma,
-            h->fit_astar, count, mean_dev, var_dev);
+        if (imp != nullptr)
+            predict_finalize_kernel<true><<<(unsigned)((count + 127) / 128), 128, 0, st>>>(
+                sl.Part, ntile, sl.Aux, mc, P_dev, Hs_dev, basis_of(h), h->d, h->fK, h->fbeta, h->fit_sigma * h->fit_sigma,
+                h->fit_astar, count, nullptr, nullptr, *imp);
+        else
+            predict_finalize_kernel<false><<<(unsigned)((count + 127) / 128), 128, 0, st>>>(
+                sl.Part, ntile, sl.Aux, mc, P_dev, Hs_dev, basis_of(h), h->d, h->fK, h->fbeta, h->fit_sigma * h->fit_sigma,
+                h->fit_astar, count, mean_dev, var_dev, ImpFuse{});
     }
     h->launches++;
     return 0;
@@ -598,7 +683,7 @@ int gpe_fit_state(gpe_handle* h, const double* delta, double nugget, double sigm
 }
 
 static int predict_common(gpe_handle* h, const double* Xs, const double* Hs, const GridDesc* grid, long long start,
-                          long long m, double* mean, double* var) {
+                          long long m, double* mean, double* var, const ImpFuse* imp_call = nullptr) {
     if (!h->fitted) return h->fail_msg("gpe_fit_state has not succeeded on this handle");
     if (!Hs && !h->has_basis) return h->fail_msg("no H* given and no device basis set (gpe_set_basis)");
     NvtxRange nvtx(grid ? "gpe_predict_grid" : "gpe_predict");
@@ -609,7 +694,7 @@ static int predict_common(gpe_handle* h, const double* Xs, const double* Hs, con
     // Chunks alternate between two (stream, buffer slot) pairs: a slot's staging buffers are reused only
     // by later chunks of the same stream, which orders them.
     const bool x_dev = Xs && gpe_is_device_ptr(Xs), h_dev = Hs && gpe_is_device_ptr(Hs);
-    const bool mean_dev = gpe_is_device_ptr(mean), var_dev = var && gpe_is_device_ptr(var);
+    const bool mean_dev = imp_call || gpe_is_device_ptr(mean), var_dev = var && gpe_is_device_ptr(var);
     const int d = h->d, q = h->q;
     // tensor grid: tabulate the one-dimensional kernel factors once (GPE_GRID_SEP=0 keeps the direct kernel)
     GridXcov gx;
@@ -663,10 +748,17 @@ static int predict_common(gpe_handle* h, const double* Xs, const double* Hs, con
                 Hc = sl.H;
             }
         }
-        double* mo = mean_dev ? mean + s : sl.Mean;
+        double* mo = imp_call ? nullptr : (mean_dev ? mean + s : sl.Mean);
         double* vo = var ? (var_dev ? var + s : sl.Var) : nullptr;
         gx.start = start + s;
-        if ((rc = predict_chunk(h, sl, st, P, Hc, cnt, mc, mo, vo, use_sep ? &gx : nullptr))) return rc;
+        ImpFuse ic;
+        if (imp_call) {          // this chunk's window of the per-point arrays
+            ic = *imp_call;
+            ic.Itop += (size_t)s * ic.maxno;
+            if (ic.keep) ic.keep += s;
+            ic.first_index += s;
+        }
+        if ((rc = predict_chunk(h, sl, st, P, Hc, cnt, mc, mo, vo, use_sep ? &gx : nullptr, imp_call ? &ic : nullptr))) return rc;
         if (!mean_dev) CK(cudaMemcpyAsync(mean + s, sl.Mean, cnt * sizeof(double), cudaMemcpyDeviceToHost, st));
         if (var && !var_dev) CK(cudaMemcpyAsync(var + s, sl.Var, cnt * sizeof(double), cudaMemcpyDeviceToHost, st));
     }
@@ -677,7 +769,7 @@ static int predict_common(gpe_handle* h, const double* Xs, const double* Hs, con
         }
     }
     // asynchronous mode (gpe_set_async): with device-resident points and outputs nothing on the host waits for this call
-    const bool all_dev = mean_dev && (!var || var_dev) && (!Xs || x_dev) && (!Hs || h_dev);
+    const bool all_dev = mean_dev && (!var || var_dev) && (!Xs || x_dev) && (!Hs || h_dev) && !(imp_call && imp_call->last);
     if (!(h->async && all_dev)) CK(cudaStreamSynchronize(h->st));
     CK(cudaGetLastError());
     return 0;
@@ -702,6 +794,73 @@ int gpe_predict_grid(gpe_handle* h, const int* levels, const double* lo, const d
         g.step[k] = (hi[k] - lo[k]) / (double)levels[k];
     }
     return predict_common(h, nullptr, nullptr, &g, start, count, mean, var);
+}
+
+int gpe_predict_implaus(gpe_handle* h, const double* Xs, const double* Hs, const int* levels, const double* lo, const double* hi,
+                        long long start, long long m, double z, double var_extra, int maxno, int first, int last, double* Itop,
+                        double cm, long long cell_pts, long long first_index, long long ncell, unsigned char* keep,
+                        unsigned long long* count_lt, double* cell_min, unsigned long long* cell_count) {
+    if (h && m == 0 && !last) return 0;
+    if (!h || m < 0 || (!Xs && (!levels || !lo || !hi)) || maxno < 1 || maxno > MAXEM) return h ? h->fail_msg("bad argument") : -2;
+    if (!Itop && !(first && last)) return h->fail_msg("Itop is needed to carry the list from one emulator to the next");
+    if (Itop && !gpe_is_device_ptr(Itop)) return h->fail_msg("Itop must be device memory");
+    if (cell_pts < 0 || first_index < 0 || ncell < 0) return h->fail_msg("cell_pts, first_index and ncell must be non-negative");
+    if (cell_pts == 0) ncell = 0;
+    if (last && cell_pts > 0 && m > 0 && (first_index + m - 1) / cell_pts - first_index / cell_pts + 1 > ncell)
+        return h->fail_msg("the points span more cells than ncell");
+    NvtxRange nvtx("gpe_predict_implaus");
+    CK(cudaSetDevice(h->device));
+    ImpFuse ic{};
+    ic.z = z; ic.ve = var_extra; ic.cm = cm; ic.maxno = maxno; ic.first = first != 0; ic.last = last != 0;
+    ic.store_top = Itop != nullptr;
+    ic.first_index = first_index; ic.cell_pts = last ? cell_pts : 0; ic.cell_base = cell_pts > 0 ? first_index / cell_pts : 0;
+    double* top_tmp = nullptr;
+    unsigned char* kd = nullptr;
+    unsigned long long *cnt = nullptr, *cmin = nullptr, *ccnt = nullptr;
+    TmpDev t_top(h), t_k(h), t_cnt(h), t_cmin(h), t_ccnt(h);
+    if (!Itop) CK(t_top.get(&top_tmp, (size_t)std::max<long long>(m, 1) * maxno));      // first == last: a one-emulator job
+    ic.Itop = Itop ? Itop : top_tmp;
+    const bool k_dev = keep && gpe_is_device_ptr(keep);
+    if (last) {
+        if (keep) { if (k_dev) kd = keep; else CK(t_k.get(&kd, (size_t)std::max<long long>(m, 1))); }
+        ic.keep = kd;
+        CK(t_cnt.get(&cnt, (size_t)maxno));
+        CK(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long) * maxno, h->st));
+        ic.count_lt = cnt;
+        if (ncell > 0) {
+            CK(t_cmin.get(&cmin, (size_t)ncell * maxno));
+            CK(t_ccnt.get(&ccnt, (size_t)ncell * maxno));
+            CK(cudaMemsetAsync(cmin, 0x7f, sizeof(unsigned long long) * ncell * maxno, h->st));
+            CK(cudaMemsetAsync(ccnt, 0, sizeof(unsigned long long) * ncell * maxno, h->st));
+            ic.cell_min_bits = cmin; ic.cell_count = ccnt;
+        }
+    }
+    int rc = 0;
+    if (m > 0) {
+        if (Xs) {
+            rc = predict_common(h, Xs, Hs, nullptr, 0, m, nullptr, nullptr, &ic);
+        } else {
+            if (h->d > MAXD) return h->fail_msg("grid prediction supports d <= 64");
+            GridDesc g;
+            g.d = h->d;
+            for (int k = 0; k < h->d; k++) {
+                g.levels[k] = levels[k];
+                g.lo[k] = lo[k];
+                g.step[k] = (hi[k] - lo[k]) / (double)levels[k];
+            }
+            rc = predict_common(h, nullptr, nullptr, &g, start, m, nullptr, nullptr, &ic);
+        }
+        if (rc) return rc;
+    }
+    if (last) {
+        if (keep && !k_dev && m > 0) CK(cudaMemcpyAsync(keep, kd, (size_t)m, cudaMemcpyDeviceToHost, h->st));
+        if (count_lt) CK(cudaMemcpyAsync(count_lt, cnt, sizeof(unsigned long long) * maxno, cudaMemcpyDefault, h->st));
+        if (ncell > 0 && cell_min) CK(cudaMemcpyAsync(cell_min, cmin, sizeof(double) * ncell * maxno, cudaMemcpyDefault, h->st));
+        if (ncell > 0 && cell_count) CK(cudaMemcpyAsync(cell_count, ccnt, sizeof(unsigned long long) * ncell * maxno, cudaMemcpyDefault, h->st));
+        CK(cudaStreamSynchronize(h->st));
+        CK(cudaGetLastError());
+    }
+    return 0;
 }
 
 int gpe_cross_cov(gpe_handle* h, const double* delta, double nugget, int kind, const double* Xs, int m, double* C_out) {
@@ -779,8 +938,8 @@ int gpe_predict_fullcov(gpe_handle* h, const double* Xs, const double* Hs, int m
         BasisDesc bd = basis_of(h);
         double s2 = h->fit_sigma * h->fit_sigma;
         // mean via the diagonal finalize (var == nullptr)
-        predict_finalize_kernel<<<(m + 127) / 128, 128, 0, h->st>>>(nullptr, 0, aux, mp, P, Hd, bd, d, h->fK, h->fbeta, s2,
-                                                                     h->fit_astar, m, md, nullptr);
+        predict_finalize_kernel<false><<<(m + 127) / 128, 128, 0, h->st>>>(nullptr, 0, aux, mp, P, Hd, bd, d, h->fK, h->fbeta, s2,
+                                                                            h->fit_astar, m, md, nullptr, ImpFuse{});
         fullcov_finalize_kernel<<<(m + 127) / 128, 128, 0, h->st>>>(ZtZ, mp, aux, mp, P, Hd, bd, d, h->fwinv, h->fK, s2, h->fit_c,
                                                                      h->fit_astar, rn, m, G, Vd, 0);
         size_t tot = (size_t)m * m;

@@ -3,9 +3,9 @@ imp_plot, imp_plot_recon, nonimp_data, new_wave_design.
 
 The reference evaluates a Posterior per grid cell per emulator and then loops over points in
 Python.  Here all points of an input pair (grid^2 cells x n_lhc design points) go through ONE
-device prediction per emulator (mean + diagonal variance, ``gpe_predict``; results stay in HBM) and
-ONE ``gpe_implausibility`` launch that produces the n-th-max implausibility, the keep mask and the
-per-cell min / count reductions.  With torch.distributed initialised the flat point index (all cells'
+device prediction per emulator whose epilogue folds that emulator's implausibility into a running
+top-``maxno`` list (``gpe_predict_implaus``: means and variances never leave the device kernels);
+the last emulator's pass also produces the keep mask and the per-cell min / count reductions.  With torch.distributed initialised the flat point index (all cells'
 points in cell order, or the rows of the flat routines) is cut into equal tile-aligned ranges, one per
 rank -- a cell may straddle two ranks -- and the cell statistics are combined with all-reduce(min / sum)."""
 import numpy as _np
@@ -66,6 +66,40 @@ def _implausibility(emuls, mean_d, var_d, zs, var_extra, cm, maxno, cell_pts=0, 
     return keep, count, cmin, ccnt
 
 
+def _implausibility_fused(emuls, zs, var_extra, x, act_ref, active_fn, cm, maxno, cell_pts=0, first_index=0):
+    """(keep, count, cell_min, cell_count) for the points x without the per-emulator mean / variance arrays: every active
+    emulator's prediction folds its implausibility into the running top-``maxno`` list on the device
+    (``gpe_predict_implaus``); the last one also produces the mask and the reductions.  Emulators for which
+    ``active_fn`` is False contribute I = 0 (reference :93, :99-100): they are entered as zeros in the initial list."""
+    import torch
+    active = [o for o, E in enumerate(emuls) if active_fn(E)]
+    if not active:
+        mean_d, var_d = _predict_all(emuls, zs, x, act_ref, active_fn)
+        return _implausibility(emuls, mean_d, var_d, zs, var_extra, cm, maxno, cell_pts=cell_pts, first_index=first_index)
+    m = x.shape[0]
+    tdev = torch.device("cuda", _lib.default_device_index())
+    Itop = torch.full((m, maxno), -1.0, dtype=torch.float64, device=tdev)
+    n_inactive = len(emuls) - len(active)
+    if n_inactive:
+        Itop[:, max(0, maxno - n_inactive):] = 0.0
+    keep = torch.empty(m, dtype=torch.uint8, device=tdev)
+    torch.cuda.current_stream(tdev).synchronize()          # the handles work on their own streams
+    res = None
+    for pos, o in enumerate(active):
+        E = emuls[o]
+        cols = [act_ref[str(l)] for l in E.beliefs.active_index]
+        dev, _, _, st = E.training.fit(beta=E.par.beta, r_div=E.training._A_args[0])
+        if st != 0:
+            raise _lib.GpeError("training covariance matrix of emulator %d is not positive definite" % o)
+        xe = _np.ascontiguousarray(x[:, cols])
+        last = pos == len(active) - 1
+        Hs = None if E.basis.poly is not None else E.basis.design_matrix(xe)
+        res = dev.predict_implaus(float(zs[o]), float(var_extra[o]), Itop, first=False, last=last, points=xe, Hs=Hs, maxno=maxno,
+                                  cm=cm, cell_pts=cell_pts, first_index=first_index, keep=keep if last else None)
+    count, cmin, ccnt = res
+    return keep, count, cmin, ccnt
+
+
 def imp_plot(emuls, zs, cm, var_extra, maxno=1, olhcmult=100, grid=10, act=[], fileStr="", plot=True):
     """Implausibility / optical-depth matrices for every pair of active inputs (reference :7-151);
     written to '<fileStr_><m>_IMP_<i>_<j>' and '..._ODP_...' exactly like the reference.  Drawing the
@@ -110,8 +144,7 @@ def imp_plot(emuls, zs, cm, var_extra, maxno=1, olhcmult=100, grid=10, act=[], f
             x[:, act_ref[str(s[1])]] = X2[cells % grid]
             x[:, other_dim] = x_other[lhc, :]
             active = lambda E: s[0] in E.beliefs.active_index and s[1] in E.beliefs.active_index
-            mean_d, var_d = _predict_all(emuls, zs, x, act_ref, active)
-            _, _, cmin, ccnt = _implausibility(emuls, mean_d, var_d, zs, var_extra, cm, maxno, cell_pts=n, first_index=p0)
+            _, _, cmin, ccnt = _implausibility_fused(emuls, zs, var_extra, x, act_ref, active, cm, maxno, cell_pts=n, first_index=p0)
             c0 = p0 // n
             IMP[c0:c0 + cmin.shape[0]], ODPc[c0:c0 + ccnt.shape[0]] = cmin, ccnt
         IMP = _dist.all_reduce(IMP, "min")
@@ -154,8 +187,7 @@ def _flat_keep(emuls, zs, cm, var_extra, x, act_ref, maxno):
     lo, hi = _dist.block_aligned(n, rank, world)
     keep = _np.zeros(n)
     if hi > lo:
-        mean_d, var_d = _predict_all(emuls, zs, x[lo:hi], act_ref, lambda E: True)
-        kd, _, _, _ = _implausibility(emuls, mean_d, var_d, zs, var_extra, cm, maxno)
+        kd, _, _, _ = _implausibility_fused(emuls, zs, var_extra, x[lo:hi], act_ref, lambda E: True, cm, maxno)
         keep[lo:hi] = kd.cpu().numpy()
     keep = _dist.gather_blocks(keep, n, bounds=_dist.block_aligned)
     return keep > 0.5

@@ -146,6 +146,21 @@ int gpe_implausibility(gpe_handle* h, const double* mean, const double* var, int
                        double* Imax, unsigned char* keep, unsigned long long* count_lt,
                        double* cell_min, unsigned long long* cell_count);
 
+/* The same arithmetic folded into the prediction, one emulator per call (history_match.py:96-132 without the
+ * mean / variance arrays): predict m points for THIS handle's emulator -- explicit Xs [m,d] (+ Hs [m,q] or NULL), or, with
+ * Xs == NULL, flat indices [start, start+m) of the tensor grid (levels, lo, hi) as in gpe_predict_grid -- and fold
+ * I = sqrt((mean - z)^2 / (var + var_extra)) into Itop [m,maxno] (DEVICE memory), the ascending list of the maxno largest
+ * implausibilities over the emulators processed so far (first != 0 starts the list; an emulator that must contribute
+ * I = 0, reference :99-100, is entered by the caller as a 0 in the initial list).  On the last emulator (last != 0) the
+ * keep mask, count_lt and the cell statistics of gpe_implausibility are produced in the same pass (cm, cell_pts,
+ * first_index, ncell as there; outputs may be NULL, host or device) and Itop may be NULL when first is set as well.
+ * Per point and emulator 8*maxno bytes are read and written instead of 16 written and 16 read. */
+int gpe_predict_implaus(gpe_handle* h, const double* Xs, const double* Hs, const int* levels, const double* lo,
+                        const double* hi, long long start, long long m, double z, double var_extra, int maxno,
+                        int first, int last, double* Itop, double cm, long long cell_pts, long long first_index,
+                        long long ncell, unsigned char* keep, unsigned long long* count_lt, double* cell_min,
+                        unsigned long long* cell_count);
+
 /* out [n,k] = A^-1 Bm [n,k] for the training matrix factored by gpe_fit_state -- the
  * np.linalg.solve(self.A, .) call sites of the sensitivity code
  * (sensitivity/_sensitivityclasses.py:40-44 e, G; :187 A^-1 Rt; :451, :499 A^-1 T). */

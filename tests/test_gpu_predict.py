@@ -234,3 +234,57 @@ def test_async_mode_two_handles_overlap_and_match_synchronous_results(dev, golde
     assert np.array_equal(mh, ref[0][0]) and np.array_equal(vh, ref[0][1])
     for dv in devs:
         dv.close()
+
+
+def test_fused_implausibility_equals_the_two_step_route(dev, golden_dir):
+    """gpe_predict_implaus (prediction with the implausibility folded in, one emulator per call) against gpe_predict +
+    gpe_implausibility on the same points: identical lists, masks, counts and cell statistics -- explicit points and the
+    flat-index grid, maxno 1 and 2, a shard that starts inside a cell, and an emulator entered as I = 0."""
+    from gp_emu_uqsa_b200 import _lib
+    G = np.load(os.path.join(golden_dir, "post_n200_d4.npz"))
+    X, y = G["X"], G["y"]
+    devs = []
+    for k in range(3):
+        dv = _lib.Device(0)
+        dv.set_training(X, np.cos((k + 1) * y) + 0.1 * k, O.make_H_linear(X)); dv.set_basis([0, 1, 2, 3], [1] * 4)
+        dv.fit_state(G["gp4ml_k_fixT_delta"], float(G["gp4ml_k_fixT_nugget"]), float(G["gp4ml_k_fixT_sigma"]), 0)
+        devs.append(dv)
+    zs, ve, cm = [0.3, 0.1, -0.2], [0.02, 0.05, 0.01], 1.5
+    rng = np.random.default_rng(17)
+    levels, lo, hi = np.array([6, 5, 7, 9]), np.zeros(4), np.ones(4)
+    for mode in ("points", "grid"):
+        m, first_index, cell_pts = 1337, 211, 100
+        if mode == "points":
+            P = rng.random((m, 4))
+            mv = [dv.predict(P) for dv in devs]
+        else:
+            mv = [dv.predict_grid(levels, lo, hi, first_index, m) for dv in devs]
+        means, variances = np.array([a for a, _ in mv]), np.array([b for _, b in mv])
+        for maxno in (1, 2):
+            Iref, kref, cref, minref, cntref = devs[0].implausibility(means, variances, zs, ve, cm, maxno=maxno, cell_pts=cell_pts,
+                                                                    first_index=first_index)
+            Itop = torch.full((m, maxno), -1.0, dtype=torch.float64, device="cuda")
+            keep = torch.empty(m, dtype=torch.uint8, device="cuda")
+            torch.cuda.synchronize()
+            for o, dv in enumerate(devs):
+                kw = dict(points=P) if mode == "points" else dict(grid=(levels, lo, hi, first_index, m))
+                res = dv.predict_implaus(zs[o], ve[o], Itop, first=(o == 0), last=(o == 2), maxno=maxno, cm=cm, cell_pts=cell_pts,
+                                         first_index=first_index, keep=keep if o == 2 else None, **kw)
+            cnt, cmin, ccnt = res
+            assert np.array_equal(Itop.cpu().numpy(), Iref)
+            assert np.array_equal(keep.cpu().numpy(), kref) and np.array_equal(cnt, cref)
+            assert np.array_equal(cmin, minref) and np.array_equal(ccnt, cntref)
+        # an emulator that contributes I = 0 is a zero in the initial list: same as mean = z, var = 1 in the two-step route
+        means0, vars0 = means.copy(), variances.copy()
+        means0[1], vars0[1] = zs[1], 1.0
+        Iref, kref, cref, _, _ = devs[0].implausibility(means0, vars0, zs, ve, cm, maxno=2)
+        Itop = torch.full((m, 2), -1.0, dtype=torch.float64, device="cuda")
+        Itop[:, 1] = 0.0
+        keep = np.empty(m, dtype=np.uint8)                          # host mask
+        torch.cuda.synchronize()
+        for o in (0, 2):
+            kw = dict(points=P) if mode == "points" else dict(grid=(levels, lo, hi, first_index, m))
+            res = devs[o].predict_implaus(zs[o], ve[o], Itop, first=False, last=(o == 2), maxno=2, cm=cm, keep=keep if o == 2 else None, **kw)
+        assert np.array_equal(Itop.cpu().numpy(), Iref) and np.array_equal(keep, kref) and np.array_equal(res[0], cref)
+    for dv in devs:
+        dv.close()
