@@ -390,6 +390,28 @@ def extra_configs(args, rank, world, local):
     del E
     if world > 1 or rank != 0:
         return out
+    # ---- config 1: examples/toy-sim as shipped (the reference's own example: setup + train + its two plot grids), seed 0
+    toy = os.path.join(ROOT, "tests", "golden", "toy-sim")
+    if os.path.isdir(toy):
+        import shutil
+        t1dir = tempfile.mkdtemp(prefix="gpe_bench_toy_")
+        for f in os.listdir(toy):
+            shutil.copy(os.path.join(toy, f), t1dir)
+        best = None
+        for rep in range(2):
+            with quiet_in(t1dir):
+                np.random.seed(0)
+                t0 = time.perf_counter()
+                E1 = g.setup("toy-sim_config")
+                t1 = time.perf_counter()
+                g.train(E1)
+                t2 = time.perf_counter()
+                g.plot(E1, [0], [1], [0.3], "mean")
+                g.plot(E1, [0, 1], [2], [0.3], "mean")
+                t3 = time.perf_counter()
+            best = {"setup_s": t1 - t0, "train_s": t2 - t1, "two_plot_grids_s": t3 - t2, "delta": [float(v) for v in E1.par.delta],
+                    "sigma": float(E1.par.sigma), "reference_values": "delta [0.20458, 0.13752], sigma 0.608639 (SURVEY section 4); reference run: 0.71 s"}
+        out["config1_toysim_as_shipped"] = best
     # ---- config 2: n = 1000, d = 8, full 64-start optimisation in the four modes
     X2, y2 = synth(1000, 8)
     c2 = {}

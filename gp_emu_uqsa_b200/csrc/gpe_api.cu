@@ -150,7 +150,7 @@ static int run_gemm(gpe_handle* h, cudaStream_t st, const double* A, const doubl
     GemmP p;
     p.A = A; p.B = B; p.C = C; p.lda = lda; p.ldb = ldb; p.ldc = ldc; p.sA = sA; p.sB = sB; p.sC = sC;
     p.M = M; p.N = N; p.K = K; p.alpha = alpha; p.accumulate = acc; p.kmode = kmode; p.lower = lower; p.batch = batch;
-    bool big = (M % 128 == 0) && (N % 128 == 0) && N != 32 && M != 32;
+    bool big = (M % 128 == 0 || epi == EPI_SUMSQ) && (N % 128 == 0) && N != 32 && M != 32;
     cudaError_t e;
     {
         ProfScope ps(h, cat >= 0 ? cat : (big ? gpe_handle::CAT_GEMM_BIG : gpe_handle::CAT_GEMM_SMALL), st);

@@ -46,7 +46,8 @@ static cudaError_t dispatch_tiles(const GemmP& p, int epi, cudaStream_t st) {
     bool big = (p.M % 128 == 0) && (p.N % 128 == 0) && (t128 >= 120);
     if (epi == EPI_SUMSQ) {
         // column norms are accumulated per 128-row tile: the partial buffer is sized for BM = 128
-        if (use_ws2()) return launch_gemm_ws2<A_KC, B_KC, EPI_SUMSQ>(p, st);
+        if (use_ws2() && p.M % 128 == 0) return launch_gemm_ws2<A_KC, B_KC, EPI_SUMSQ>(p, st);
+        if (p.M % 128 && !use_ws()) return cudaErrorInvalidValue;      // the ragged last row tile exists in the ws kernel only
         return use_ws() ? launch_gemm_ws<A_KC, B_KC, EPI_SUMSQ>(p, st)
                         : launch_gemm_cfg<128, 128, 2, 4, A_KC, B_KC, EPI_SUMSQ>(p, st);
     }

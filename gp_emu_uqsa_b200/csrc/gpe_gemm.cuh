@@ -300,7 +300,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_dmma_ws_kernel(GemmP p) {
     const bool rowtri = (p.kmode == KM_LE_I || p.kmode == KM_GE_I);
     int tj, ti;
     if (rowtri) {
-        const int ntx = p.N / BN, nty = p.M / BM, id = (int)blockIdx.x;
+        const int ntx = p.N / BN, nty = (p.M + BM - 1) / BM, id = (int)blockIdx.x;
         const int full = (ntx / WS_COLGROUP) * WS_COLGROUP * nty;      // CTAs in complete groups
         int g0, gsz, r;
         if (id < full) { g0 = (id / (WS_COLGROUP * nty)) * WS_COLGROUP; gsz = WS_COLGROUP; r = id % (WS_COLGROUP * nty); }
@@ -391,23 +391,47 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_dmma_ws_kernel(GemmP p) {
     constexpr int a_kk = A_KC ? 4 : 4 * A_LD;
     constexpr int b_kk = B_KC ? 4 : 4 * B_LD;
 
+    // Ragged last row tile (column-norm launches only: the prediction product Z = L^-1 C with M = K = n rounded up to 16
+    // instead of the 128-padded size -- n = 2000: 80 live rows in the last, heaviest tile).  Rows >= M of the operand are
+    // the identity padding of L^-1, whose entries at k < K are zero, so they contribute nothing either way; warps whose
+    // rows are all (or in their upper half) beyond M skip those fragment rows.  Warp-uniform, decided outside the k loop.
+    int fm_n = FM;
+    if (EPI == EPI_SUMSQ && m0 + wm0 + WTM > p.M) {
+        const int live = p.M - m0 - wm0;
+        fm_n = live <= 0 ? 0 : (live <= WTM / 2 ? FM / 2 : FM);
+    }
     for (int kt = 0; kt < KT; kt++) {
         const int s = kt % GEMM_STAGES;
         mbar_wait(&full_bar[s], (kt / GEMM_STAGES) & 1);
         const double* at = As + s * A_EL + a_off;
         const double* bt = Bs + s * B_EL + b_off;
         if (kt >= wk_lo && kt < wk_hi) {
+            if (EPI != EPI_SUMSQ || fm_n == FM) {
 #pragma unroll
-            for (int kk = 0; kk < GEMM_BK / 4; kk++) {
-                double af[FM], bf[FN];
+                for (int kk = 0; kk < GEMM_BK / 4; kk++) {
+                    double af[FM], bf[FN];
 #pragma unroll
-                for (int i = 0; i < FM; i++) af[i] = at[kk * a_kk + i * a_fstep];
+                    for (int i = 0; i < FM; i++) af[i] = at[kk * a_kk + i * a_fstep];
 #pragma unroll
-                for (int j = 0; j < FN; j++) bf[j] = bt[kk * b_kk + j * b_fstep];
+                    for (int j = 0; j < FN; j++) bf[j] = bt[kk * b_kk + j * b_fstep];
 #pragma unroll
-                for (int i = 0; i < FM; i++)
+                    for (int i = 0; i < FM; i++)
 #pragma unroll
-                    for (int j = 0; j < FN; j++) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+                        for (int j = 0; j < FN; j++) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+                }
+            } else if (fm_n == FM / 2) {
+#pragma unroll
+                for (int kk = 0; kk < GEMM_BK / 4; kk++) {
+                    double af[FM / 2], bf[FN];
+#pragma unroll
+                    for (int i = 0; i < FM / 2; i++) af[i] = at[kk * a_kk + i * a_fstep];
+#pragma unroll
+                    for (int j = 0; j < FN; j++) bf[j] = bt[kk * b_kk + j * b_fstep];
+#pragma unroll
+                    for (int i = 0; i < FM / 2; i++)
+#pragma unroll
+                        for (int j = 0; j < FN; j++) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+                }
             }
         }
         __syncwarp();
@@ -468,9 +492,10 @@ inline cudaError_t launch_gemm_ws_shape(const GemmP& p, cudaStream_t st) {
     constexpr size_t smem = gemm_smem_bytes<128, 128, A_KC, B_KC>();
     static SmemOptIn optin;
     if (cudaError_t e = optin.ensure(kern, smem); e != cudaSuccess) return e;
-    if (p.M % 128 || p.N % 128 || p.K % GEMM_BK) return cudaErrorInvalidValue;
     const bool rowtri = (p.kmode == KM_LE_I || p.kmode == KM_GE_I);
-    dim3 grid = rowtri ? dim3((p.M / 128) * (p.N / 128), 1, p.batch) : dim3(p.N / 128, p.M / 128, p.batch);
+    const bool ragged_ok = (EPI == EPI_SUMSQ) && p.kmode == KM_LE_I && p.M % GEMM_BK == 0;      // see the kernel's fm_n
+    if ((p.M % 128 && !ragged_ok) || p.N % 128 || p.K % GEMM_BK) return cudaErrorInvalidValue;
+    dim3 grid = rowtri ? dim3(((p.M + 127) / 128) * (p.N / 128), 1, p.batch) : dim3(p.N / 128, p.M / 128, p.batch);
     kern<<<grid, WS_THREADS, smem, st>>>(p);
     return cudaGetLastError();
 }

@@ -598,13 +598,23 @@ int predict_chunk(gpe_handle* h, gpe_handle::PredSlot& sl, cudaStream_t st, cons
     h->launches++;
     int rc;
     // aux = [A^-1 H K^-T | e]^T C     (TN, skinny: the q + 1 live columns of the panel padded to 16 or 32 rows)
+    // rows / columns >= n of the padded matrices are identity padding and the slab's rows >= n are zero: the products need
+    // only the first kp = n rounded up to the k-tile (n = 2000: 2000 instead of 2048 -- the last, heaviest row tile of the
+    // triangular product has 80 live rows, not 128)
+    const int kp = std::min(np, (h->n + GEMM_BK - 1) / GEMM_BK * GEMM_BK);
     const int maux = (h->q + 1 <= 16) ? 16 : NR;
-    if ((rc = gpe_run_gemm_on(h, st, h->fE, sl.C, sl.Aux, NR, mc, mc, 0, 0, 0, maux, mc, np, 1.0, 0, KM_FULL, 0, 1, 2, EPI_STORE))) return rc;
+    if ((rc = gpe_run_gemm_on(h, st, h->fE, sl.C, sl.Aux, NR, mc, mc, 0, 0, 0, maux, mc, kp, 1.0, 0, KM_FULL, 0, 1, 2, EPI_STORE))) return rc;
     int ntile = 0;
     if (var_dev != nullptr || imp != nullptr) {
         // column norms of Z = Linv C    (NN, Linv lower: k <= i), reduced in the epilogue
-        if ((rc = gpe_run_gemm_on(h, st, h->fLi, sl.C, sl.Part, np, mc, mc, 0, 0, 0, np, mc, np, 1.0, 0, KM_LE_I, 0, 1, 1, EPI_SUMSQ))) return rc;
-        ntile = np / 128;
+        static int ragged = -1;
+        if (ragged < 0) {
+            const char* e = getenv("GPE_PRED_RAGGED");
+            ragged = (e && e[0] == '0') ? 0 : 1;
+        }
+        const int mp = ragged ? kp : np;
+        if ((rc = gpe_run_gemm_on(h, st, h->fLi, sl.C, sl.Part, np, mc, mc, 0, 0, 0, mp, mc, mp, 1.0, 0, KM_LE_I, 0, 1, 1, EPI_SUMSQ))) return rc;
+        ntile = (mp + 127) / 128;
     }
     {
         ProfScope ps(h, gpe_handle::CAT_OTHER, st);
