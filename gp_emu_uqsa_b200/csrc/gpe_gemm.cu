@@ -15,12 +15,13 @@ static bool use_ws() {
     return v == 1;
 }
 
-// GPE_WS2=1: the two-CTAs-per-SM 128x64 kernel for the machine-filling launches (A/B knob; see gpe_gemm.cuh)
+// The two-CTAs-per-SM 128x64 kernel for the machine-filling launches of the factorisation (see gpe_gemm.cuh): a
+// consistent +0.6 % on the n = 4096 step in same-box A/B runs (75.01 -> 74.53 ms, 74.81 -> 74.42 ms).  GPE_WS2=0 switches it off.
 static bool use_ws2() {
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("GPE_WS2");
-        v = e ? atoi(e) : 0;
+        v = e ? atoi(e) : 1;
     }
     return v == 1;
 }

@@ -701,6 +701,11 @@ inline cudaError_t launch_gemm_ws2_shape(const GemmP& p, cudaStream_t st) {
     constexpr size_t smem = gemm_ws2_smem_bytes<A_KC, B_KC>();
     static SmemOptIn optin;
     if (cudaError_t e = optin.ensure(kern, smem); e != cudaSuccess) return e;
+    static bool carve = false;
+    if (!carve) {       // two CTAs of ~90 KB each must both find shared memory: ask for the largest carve-out
+        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        carve = true;
+    }
     if (p.M % 128 || p.N % 64 || p.K % GEMM_BK) return cudaErrorInvalidValue;
     const bool rowtri = (p.kmode == KM_LE_I || p.kmode == KM_GE_I);
     dim3 grid = rowtri ? dim3((p.M / 128) * (p.N / 64), 1, p.batch) : dim3(p.N / 64, p.M / 128, p.batch);
