@@ -60,6 +60,7 @@ def load():
         "gpe_sens_contract": (i, [p, p, p, p, d, p, i, p, p]),
         "gpe_sens_main_effect": (i, [p, p, p, p, p, p, d, p, i, p, i, p]),
         "gpe_dbg_gemm": (i, [p, p, p, p, i, i, i, ll, ll, ll, i, i, i, d, i, i, i, i, i]),
+        "gpe_dbg_gemm_oz": (i, [p, p, p, p, i, i, i, ll, ll, ll, i, i, i, d, i, i, i, i, i, i, p, p, p, p, p]),
         "gpe_potrf": (i, [p, p, i, i, p, p, p, p]),
         "gpe_pdist_argmin": (i, [p, p, i, i, i, p, i, p]),
         "gpe_dbg_potrf_inv": (i, [p, p, i, i, p, p, p]),
@@ -76,7 +77,7 @@ EXPORTS = ["gpe_version", "gpe_create", "gpe_destroy", "gpe_last_error", "gpe_la
            "gpe_set_training", "gpe_set_basis", "gpe_cov_build", "gpe_cov_grad", "gpe_cross_cov", "gpe_llh_grad_batch",
            "gpe_fit_state", "gpe_predict", "gpe_predict_grid", "gpe_predict_fullcov", "gpe_implausibility", "gpe_predict_implaus",
            "gpe_solve", "gpe_sens_contract", "gpe_sens_main_effect", "gpe_potrf", "gpe_pdist_argmin",
-           "gpe_dbg_gemm", "gpe_dbg_potrf_inv"]
+           "gpe_dbg_gemm", "gpe_dbg_gemm_oz", "gpe_dbg_potrf_inv"]
 
 
 def default_device_index():
@@ -382,6 +383,13 @@ class Device:
         Li, ld, st = np.empty_like(A), np.empty(b), np.zeros(b, dtype=np.int32)
         self._ck(self.L.gpe_dbg_potrf_inv(self.h, _ptr(A), n, b, _ptr(Li), _ptr(ld), _ptr(st)))
         return Li, ld, st
+
+    def dbg_gemm_oz(self, A, B, Cm, M, N, K, lda, ldb, ldc, sA=0, sB=0, sC=0, alpha=1.0, accumulate=0, kmode=0,
+                    lower=0, batch=1, layout=0, nmod=18, planesA=None, planesB=None, planesD=None, sexpA=None, sexpB=None):
+        """The product of dbg_gemm on the INT8 tensor-core route (device tensors; optional outputs: residue planes, exponents)."""
+        self._ck(self.L.gpe_dbg_gemm_oz(self.h, _ptr(A), _ptr(B), _ptr(Cm), lda, ldb, ldc, sA, sB, sC, M, N, K,
+                                        float(alpha), int(accumulate), int(kmode), int(lower), int(batch), int(layout), int(nmod),
+                                        _ptr(planesA), _ptr(planesB), _ptr(planesD), _ptr(sexpA), _ptr(sexpB)))
 
     def dbg_gemm(self, A, B, Cm, M, N, K, lda, ldb, ldc, sA=0, sB=0, sC=0, alpha=1.0, accumulate=0, kmode=0,
                  lower=0, batch=1, layout=0):

@@ -152,6 +152,19 @@ static int run_gemm(gpe_handle* h, cudaStream_t st, const double* A, const doubl
     p.M = M; p.N = N; p.K = K; p.alpha = alpha; p.accumulate = acc; p.kmode = kmode; p.lower = lower; p.batch = batch;
     bool big = (M % 128 == 0 || epi == EPI_SUMSQ) && (N % 128 == 0) && N != 32 && M != 32;
     cudaError_t e;
+    if (h->oz_nmod > 0 && M >= h->oz_min && N >= h->oz_min && K >= h->oz_min && oz_supported(p, epi)) {
+        // INT8 tensor-core route (gpe_ozaki.cuh): scratch is per stream; growing it is not allowed inside a capture, and
+        // every shape has been seen eagerly at least twice before its graph is captured
+        OzWs& ws = h->oz_ws[st];
+        {
+            ProfScope ps(h, cat >= 0 ? cat : gpe_handle::CAT_GEMM_BIG, st);
+            e = oz_gemm(p, layout, h->oz_nmod, ws, st);
+        }
+        h->launches += 4;
+        h->oz_calls++;
+        if (e != cudaSuccess) return h->fail("oz_gemm", e);
+        return 0;
+    }
     {
         ProfScope ps(h, cat >= 0 ? cat : (big ? gpe_handle::CAT_GEMM_BIG : gpe_handle::CAT_GEMM_SMALL), st);
         e = launch_gemm(p, layout, epi, st);
@@ -260,6 +273,7 @@ static int llh_grad_fused(gpe_handle* h, int B) {
         mode = e ? atoi(e) : 2;
     }
     if (!gemm_is_big(h->npad, h->npad, 1, B)) return 0;
+    if (h->oz_nmod > 0 && h->npad >= h->oz_min && h->npad % OZ_BN == 0) return 0;   // LAUUM on the INT8 route, A^-1 stored
     if (mode == 2 && !lauum_grad_supported(h->d)) return 1;
     return mode;
 }
@@ -393,6 +407,8 @@ int gpe_create(int device, gpe_handle** out) {
     if (const char* e = getenv("GPE_STREAMS")) h->nsub = std::max(1, std::min((int)gpe_handle::MAX_SUB, atoi(e)));
     if (const char* e = getenv("GPE_GRAPHS")) h->use_graphs = e[0] != '0';
     if (const char* e = getenv("GPE_SIDE")) h->use_side = e[0] != '0';
+    if (const char* e = getenv("GPE_OZAKI")) h->oz_nmod = std::max(0, std::min((int)OZ_MAXMOD, atoi(e)));
+    if (const char* e = getenv("GPE_OZAKI_MIN")) h->oz_min = std::max(256, atoi(e));
     *out = h;
     return 0;
 }
@@ -415,6 +431,7 @@ int gpe_destroy(gpe_handle* h) {
             if (h->ev_sj[s][k]) cudaEventDestroy(h->ev_sj[s][k]);
         }
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    for (auto& kv : h->oz_ws) kv.second.release();
     for (auto e : h->prof_pool) cudaEventDestroy(e);
     cudaStreamDestroy(h->st);
     delete h;
@@ -716,6 +733,30 @@ int gpe_dbg_gemm(gpe_handle* h, const double* A, const double* B, double* C, int
     int rc = run_gemm(h, h->st, A, B, C, lda, ldb, ldc, sA, sB, sC, M, N, K, alpha, accumulate, kmode, lower, batch, layout);
     if (rc) return rc;
     CK(cudaStreamSynchronize(h->st));
+    return 0;
+}
+
+int gpe_dbg_gemm_oz(gpe_handle* h, const double* A, const double* B, double* C, int lda, int ldb, int ldc,
+                    long long sA, long long sB, long long sC, int M, int N, int K, double alpha, int accumulate,
+                    int kmode, int lower, int batch, int layout, int nmod, unsigned char* planesA,
+                    unsigned char* planesB, unsigned char* planesD, int* sexpA, int* sexpB) {
+    if (!h) return -2;
+    CK(cudaSetDevice(h->device));
+    GemmP p;
+    p.A = A; p.B = B; p.C = C; p.lda = lda; p.ldb = ldb; p.ldc = ldc; p.sA = sA; p.sB = sB; p.sC = sC;
+    p.M = M; p.N = N; p.K = K; p.alpha = alpha; p.accumulate = accumulate; p.kmode = kmode; p.lower = lower; p.batch = batch;
+    if (!oz_supported(p, EPI_STORE)) return h->fail_msg("gpe_dbg_gemm_oz: shape not supported by the INT8 route");
+    OzWs& ws = h->oz_ws[h->st];
+    cudaError_t e = oz_gemm(p, layout, nmod, ws, h->st);
+    if (e != cudaSuccess) return h->fail("oz_gemm", e);
+    CK(cudaStreamSynchronize(h->st));
+    const bool same = (A == B && lda == ldb && sA == sB && M == N && layout != 1);
+    const size_t nA = (size_t)batch * nmod * M * K, nB = (size_t)batch * nmod * N * K, nD = (size_t)batch * nmod * M * N;
+    if (planesA) CK(cudaMemcpy(planesA, ws.PA, nA, cudaMemcpyDefault));
+    if (planesB) CK(cudaMemcpy(planesB, same ? ws.PA : ws.PB, nB, cudaMemcpyDefault));
+    if (planesD) CK(cudaMemcpy(planesD, ws.PD, nD, cudaMemcpyDefault));
+    if (sexpA) CK(cudaMemcpy(sexpA, ws.sA, sizeof(int) * (size_t)batch * M, cudaMemcpyDefault));
+    if (sexpB) CK(cudaMemcpy(sexpB, same ? ws.sA : ws.sB, sizeof(int) * (size_t)batch * N, cudaMemcpyDefault));
     return 0;
 }
 

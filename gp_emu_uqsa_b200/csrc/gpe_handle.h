@@ -6,6 +6,8 @@
 #include "gpe_b200.h"
 #include "gpe_gemm.cuh"
 #include "gpe_kernels.cuh"
+#include "gpe_ozaki.cuh"
+#include <map>
 
 struct gpe_handle {
     int device = 0, sms = 0;
@@ -87,6 +89,12 @@ struct gpe_handle {
     // skinny product / finalize overlap the other's TRMM
     struct PredSlot { double *C = nullptr, *Part = nullptr, *Aux = nullptr, *X = nullptr, *H = nullptr, *Mean = nullptr, *Var = nullptr; };
     PredSlot ps[2];
+
+    // FP64 GEMMs emulated on the INT8 tensor cores (gpe_ozaki.cuh): number of moduli (0 = off, the default; GPE_OZAKI),
+    // smallest dimension that takes the route (GPE_OZAKI_MIN), scratch per stream
+    int oz_nmod = 0, oz_min = 1024;
+    std::map<cudaStream_t, gpe::OzWs> oz_ws;
+    long long oz_calls = 0;
 
     int fail(const char* what, cudaError_t e);
     int fail_msg(const char* what);

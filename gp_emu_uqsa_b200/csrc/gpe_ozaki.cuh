@@ -1,0 +1,42 @@
+// FP64 GEMM emulated on the INT8 tensor cores (tcgen05.mma kind::i8) by integer modular arithmetic -- "Ozaki scheme II".
+//
+// sm_100a has no FP64 tcgen05 kind: DMMA.8x8x4 peaks at the DFMA rate (37.2 TFLOP/s measured), and the big products of
+// the factorisation (gpe_api.cu:potrf_inv_rec) and LAUUM already run at 0.86 of that.  This family is the way past that
+// roof: C = op(A) op(B) is evaluated as
+//   1. oz_convert_kernel: each row of op(A) / column of op(B) is scaled by a power of two, truncated to a `bits`-bit
+//      integer and reduced modulo nmod pairwise coprime moduli p <= 256 -> unsigned 8-bit residue planes, K-major;
+//   2. oz_gemm_kernel: one exact u8 x u8 -> s32 GEMM per modulus on the tensor cores -- TMA (128B-swizzled tensor maps)
+//      feeds a 4-stage shared-memory ring, one thread issues tcgen05.mma into a double-buffered TMEM accumulator, four
+//      epilogue warps read it back with tcgen05.ld, reduce mod p and store 8-bit residues;
+//   3. oz_combine_kernel: Chinese remainder theorem in 96-bit fixed point (V/P = frac(sum_i r_i y_i / p_i)), centred,
+//      scaled back, rounded once to FP64, C = alpha * V (+ C).
+// Step 2 is exact, so the only error is the truncation of step 1: relative to (row max of A) x (column max of B), about
+// K 2^(1-bits); bits = 63 (nmod = 18), 59-60 (17), 56 (16).  The reference arithmetic this replaces is NumPy's float64
+// matmul / LAPACK inside np.linalg.cholesky and solve (_emulatoroptimise.py:313-335, 425-441); the parity bar (llh 1e-10,
+// gradient 1e-9 against the real reference at n = 4096) is what decides nmod.  oracle/ozaki2_oracle.py restates the
+// arithmetic limb for limb.  Off unless GPE_OZAKI=<nmod> is set; DMMA stays the default path.
+#pragma once
+#include "gpe_gemm.cuh"
+
+namespace gpe {
+
+constexpr int OZ_MAXMOD = 20;
+constexpr int OZ_BM = 128, OZ_BN = 256, OZ_BK = 128;   // tile of the residue GEMM; BK in bytes = elements
+
+// scratch of one stream: residue planes of the operands and of the product, scale exponents
+struct OzWs {
+    uint8_t *PA = nullptr, *PB = nullptr, *PD = nullptr;
+    int *sA = nullptr, *sB = nullptr;
+    size_t capA = 0, capB = 0, capD = 0, capS = 0;
+    void release();
+};
+
+bool oz_supported(const GemmP& p, int epi);
+// largest operand width with K 2^(2 bits) < P/2
+int oz_operand_bits(int nmod, int K);
+// makes sure `ws` can hold the planes of `p` (allocates: must not be called during stream capture when it has to grow)
+cudaError_t oz_reserve(OzWs& ws, const GemmP& p, int nmod, bool& grew);
+// C = alpha op(A) op(B) (+ C), same meaning of every field of p and of `layout` as launch_gemm (EPI_STORE only)
+cudaError_t oz_gemm(const GemmP& p, int layout, int nmod, OzWs& ws, cudaStream_t st);
+
+}  // namespace gpe

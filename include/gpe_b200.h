@@ -195,6 +195,18 @@ int gpe_dbg_gemm(gpe_handle* h, const double* A, const double* B, double* C, int
                  int ldc, long long sA, long long sB, long long sC, int M, int N, int K,
                  double alpha, int accumulate, int kmode, int lower, int batch, int layout);
 
+/* Debug/test entry: the same product evaluated on the INT8 tensor cores by integer modular arithmetic
+ * (csrc/gpe_ozaki.cuh: residues modulo nmod coprime moduli <= 256, one exact tcgen05 u8 GEMM per modulus, CRT) --
+ * the route GPE_OZAKI=<nmod> switches the large products of the factorisation to (replaces NumPy's float64 matmul /
+ * LAPACK inside np.linalg.cholesky and solve, _emulatoroptimise.py:313-335, 425-441).  M % 128 = N % 256 = K % 128 = 0;
+ * device pointers only.  The optional outputs return the intermediate pieces for exact checks: residue planes of
+ * op(A) [batch,nmod,M,K] and op(B) [batch,nmod,N,K], of the product [batch,nmod,M,N], and the scale exponents. */
+int gpe_dbg_gemm_oz(gpe_handle* h, const double* A, const double* B, double* C, int lda, int ldb,
+                    int ldc, long long sA, long long sB, long long sC, int M, int N, int K,
+                    double alpha, int accumulate, int kmode, int lower, int batch, int layout, int nmod,
+                    unsigned char* planesA, unsigned char* planesB, unsigned char* planesD,
+                    int* sexpA, int* sexpB);
+
 /* np.linalg.cholesky for `batch` SPD matrices A [batch,n,n] (device or host) -- the call sites
  * outside the likelihood: posterior_sample (emulatorfunctions.py:283), noise_fit.py:131/:143,
  * and V^-1 in Posterior.mahalanobis_distance (_emulatorclasses.py:672-673).  Outputs (any may be
