@@ -147,91 +147,111 @@ __device__ __forceinline__ uint32_t oz_residue(uint32_t lo, uint32_t hi, uint32_
 }
 
 constexpr int OZ_CV = 8;      // consecutive k per thread in the conversion
+constexpr int OZ_TRI_G = 256; // granule of the k ranges of triangular operands (covers both the 128-row and the 256-row role)
 
-template <bool KC>
-__global__ void __launch_bounds__(256) oz_convert_kernel(const double* __restrict__ src, int ld, long long sS, int R, int K,
-                                                         int nmod, int bits, uint8_t* __restrict__ planes,
-                                                         int* __restrict__ sexp) {
+// k range of row r that the residue GEMM can read: tri 0 all, 1 "k <= r" (up to the end of r's granule), 2 "k >= r"
+// (from the start of r's granule).  Nothing outside it is written or read.
+__device__ __forceinline__ void oz_row_range(int tri, int r, int K, int& klo, int& khi) {
+    klo = 0;
+    khi = K;
+    if (tri == 1) khi = min(K, (r / OZ_TRI_G + 1) * OZ_TRI_G);
+    else if (tri == 2) klo = min(K, (r / OZ_TRI_G) * OZ_TRI_G);
+}
+__device__ __forceinline__ uint32_t oz_pack4(uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3) {
+    return __byte_perm(__byte_perm(r0, r1, 0x0040), __byte_perm(r2, r3, 0x0040), 0x5410);   // PRMT: the ALU pipe is idle here
+}
+// residues of eight values for modulus a, packed
+__device__ __forceinline__ uint2 oz_residues8(const uint32_t (&lo)[OZ_CV], const uint32_t (&hi)[OZ_CV], int a) {
+    const uint32_t clo = OZC.clo[a], chi = OZC.chi[a], c0 = OZC.c0[a], m32 = OZC.m32[a], p = OZC.p[a];
+    uint32_t r[OZ_CV];
+#pragma unroll
+    for (int j = 0; j < OZ_CV; j++) r[j] = oz_residue(lo[j], hi[j], clo, chi, c0, m32, p);
+    return make_uint2(oz_pack4(r[0], r[1], r[2], r[3]), oz_pack4(r[4], r[5], r[6], r[7]));
+}
+
+// K-contiguous operand: one warp per row.
+__global__ void __launch_bounds__(256) oz_convert_kc_kernel(const double* __restrict__ src, int ld, long long sS, int R, int K,
+                                                            int nmod, int bits, int tri, uint8_t* __restrict__ planes,
+                                                            int* __restrict__ sexp) {
     const int b = blockIdx.y;
-    const double* S = src + (size_t)b * sS;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r = blockIdx.x * 8 + warp;
+    if (r >= R) return;
+    const double* row = src + (size_t)b * sS + (size_t)r * ld;
     uint8_t* Pb = planes + (size_t)b * nmod * R * K;
+    int klo, khi;
+    oz_row_range(tri, r, K, klo, khi);
+    double mx = 0.0;
+    for (int k = klo + lane * 2; k < khi; k += 64) {
+        const double2 v = *reinterpret_cast<const double2*>(row + k);
+        mx = fmax(mx, fmax(fabs(v.x), fabs(v.y)));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    const int s = oz_scale_exp(mx, bits);
+    if (lane == 0) sexp[(size_t)b * R + r] = s;
+    const double p1 = oz_pow2(s / 2), p2 = oz_pow2(s - s / 2);
+    const size_t plane = (size_t)R * K;
+    for (int k0 = klo + lane * OZ_CV; k0 < khi; k0 += 32 * OZ_CV) {
+        uint32_t lo[OZ_CV], hi[OZ_CV];
+#pragma unroll
+        for (int j = 0; j < OZ_CV; j += 2) {
+            const double2 v = *reinterpret_cast<const double2*>(row + k0 + j);
+            oz_to_u64(v.x, p1, p2, lo[j], hi[j]);
+            oz_to_u64(v.y, p1, p2, lo[j + 1], hi[j + 1]);
+        }
+        uint8_t* dst = Pb + (size_t)r * K + k0;
+#pragma unroll 2
+        for (int a = 0; a < nmod; a++) *reinterpret_cast<uint2*>(dst + (size_t)a * plane) = oz_residues8(lo, hi, a);
+    }
+}
+
+// Operand stored [k][r]: a CTA takes 32 rows r (adjacent in memory); thread (tx, ty) reads eight k of row tx per 64-wide
+// slab (each load 256 contiguous bytes across the warp), the residues of all moduli are transposed through shared memory
+// and leave as 64-byte row segments.
+constexpr int OZ_TS = 72;     // bytes per staged row (64 + 8: conflict-free 8-byte stores of a half-warp)
+__global__ void __launch_bounds__(256) oz_convert_t_kernel(const double* __restrict__ src, int ld, long long sS, int R, int K,
+                                                           int nmod, int bits, int tri, uint8_t* __restrict__ planes,
+                                                           int* __restrict__ sexp) {
     __shared__ double red[8][33];
     __shared__ int s_sh[32];
-    if (KC) {
-        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-        const int r = blockIdx.x * 8 + warp;
-        if (r >= R) return;
-        const double* row = S + (size_t)r * ld;
-        double mx = 0.0;
-        for (int k = lane * 2; k < K; k += 64) {
-            const double2 v = *reinterpret_cast<const double2*>(row + k);
-            mx = fmax(mx, fmax(fabs(v.x), fabs(v.y)));
-        }
+    __shared__ __align__(16) uint8_t stage[OZ_MAXMOD * 32 * OZ_TS];
+    const int b = blockIdx.y;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int r0 = blockIdx.x * 32, r = r0 + tx;           // R is a multiple of 32; the 32 rows share one granule
+    const double* col = src + (size_t)b * sS + r;
+    uint8_t* Pb = planes + (size_t)b * nmod * R * K;
+    int klo, khi;
+    oz_row_range(tri, r0, K, klo, khi);
+    double mx = 0.0;
+    for (int k = klo + ty; k < khi; k += 8) mx = fmax(mx, fabs(col[(size_t)k * ld]));
+    red[ty][tx] = mx;
+    __syncthreads();
+    if (ty == 0) {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        for (int j = 1; j < 8; j++) mx = fmax(mx, red[j][tx]);
         const int s = oz_scale_exp(mx, bits);
-        if (lane == 0) sexp[(size_t)b * R + r] = s;
-        const double p1 = oz_pow2(s / 2), p2 = oz_pow2(s - s / 2);
-        for (int k0 = lane * OZ_CV; k0 < K; k0 += 32 * OZ_CV) {
-            uint32_t lo[OZ_CV], hi[OZ_CV];
+        s_sh[tx] = s;
+        sexp[(size_t)b * R + r] = s;
+    }
+    __syncthreads();
+    const int s = s_sh[tx];
+    const double p1 = oz_pow2(s / 2), p2 = oz_pow2(s - s / 2);
+    const size_t plane = (size_t)R * K;
+    const int orow = threadIdx.x >> 3, och = threadIdx.x & 7;      // write-out: row, 8-byte chunk
+    for (int k0 = klo; k0 < khi; k0 += 64) {
+        uint32_t lo[OZ_CV], hi[OZ_CV];
+        const double* cp = col + (size_t)(k0 + ty * OZ_CV) * ld;
 #pragma unroll
-            for (int j = 0; j < OZ_CV; j += 2) {
-                const double2 v = *reinterpret_cast<const double2*>(row + k0 + j);
-                oz_to_u64(v.x, p1, p2, lo[j], hi[j]);
-                oz_to_u64(v.y, p1, p2, lo[j + 1], hi[j + 1]);
-            }
-            uint8_t* dst = Pb + (size_t)r * K + k0;
-            for (int a = 0; a < nmod; a++) {
-                const uint32_t clo = OZC.clo[a], chi = OZC.chi[a], c0 = OZC.c0[a], m32 = OZC.m32[a], p = OZC.p[a];
-                uint32_t w[OZ_CV / 4];
-#pragma unroll
-                for (int j4 = 0; j4 < OZ_CV / 4; j4++) {
-                    const uint32_t r0 = oz_residue(lo[4 * j4], hi[4 * j4], clo, chi, c0, m32, p);
-                    const uint32_t r1 = oz_residue(lo[4 * j4 + 1], hi[4 * j4 + 1], clo, chi, c0, m32, p);
-                    const uint32_t r2 = oz_residue(lo[4 * j4 + 2], hi[4 * j4 + 2], clo, chi, c0, m32, p);
-                    const uint32_t r3 = oz_residue(lo[4 * j4 + 3], hi[4 * j4 + 3], clo, chi, c0, m32, p);
-                    w[j4] = r0 | (r1 << 8) | (r2 << 16) | (r3 << 24);
-                }
-                *reinterpret_cast<uint2*>(dst + (size_t)a * R * K) = make_uint2(w[0], w[1]);
-            }
-        }
-    } else {
-        const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-        const int r = blockIdx.x * 32 + tx;             // R is a multiple of 32
-        const double* col = S + r;
-        double mx = 0.0;
-        for (int k = ty; k < K; k += 8) mx = fmax(mx, fabs(col[(size_t)k * ld]));
-        red[ty][tx] = mx;
+        for (int j = 0; j < OZ_CV; j++) oz_to_u64(cp[(size_t)j * ld], p1, p2, lo[j], hi[j]);
+#pragma unroll 2
+        for (int a = 0; a < nmod; a++)
+            *reinterpret_cast<uint2*>(stage + (a * 32 + tx) * OZ_TS + ty * 8) = oz_residues8(lo, hi, a);
         __syncthreads();
-        if (ty == 0) {
-#pragma unroll
-            for (int j = 1; j < 8; j++) mx = fmax(mx, red[j][tx]);
-            const int s = oz_scale_exp(mx, bits);
-            s_sh[tx] = s;
-            sexp[(size_t)b * R + r] = s;
-        }
+        uint8_t* dst = Pb + (size_t)(r0 + orow) * K + k0 + och * 8;
+        for (int a = 0; a < nmod; a++)
+            *reinterpret_cast<uint2*>(dst + (size_t)a * plane) = *reinterpret_cast<const uint2*>(stage + (a * 32 + orow) * OZ_TS + och * 8);
         __syncthreads();
-        const int s = s_sh[tx];
-        const double p1 = oz_pow2(s / 2), p2 = oz_pow2(s - s / 2);
-        for (int k0 = ty * OZ_CV; k0 < K; k0 += 8 * OZ_CV) {
-            uint32_t lo[OZ_CV], hi[OZ_CV];
-#pragma unroll
-            for (int j = 0; j < OZ_CV; j++) oz_to_u64(col[(size_t)(k0 + j) * ld], p1, p2, lo[j], hi[j]);
-            uint8_t* dst = Pb + (size_t)r * K + k0;
-            for (int a = 0; a < nmod; a++) {
-                const uint32_t clo = OZC.clo[a], chi = OZC.chi[a], c0 = OZC.c0[a], m32 = OZC.m32[a], p = OZC.p[a];
-                uint32_t w[OZ_CV / 4];
-#pragma unroll
-                for (int j4 = 0; j4 < OZ_CV / 4; j4++) {
-                    const uint32_t r0 = oz_residue(lo[4 * j4], hi[4 * j4], clo, chi, c0, m32, p);
-                    const uint32_t r1 = oz_residue(lo[4 * j4 + 1], hi[4 * j4 + 1], clo, chi, c0, m32, p);
-                    const uint32_t r2 = oz_residue(lo[4 * j4 + 2], hi[4 * j4 + 2], clo, chi, c0, m32, p);
-                    const uint32_t r3 = oz_residue(lo[4 * j4 + 3], hi[4 * j4 + 3], clo, chi, c0, m32, p);
-                    w[j4] = r0 | (r1 << 8) | (r2 << 16) | (r3 << 24);
-                }
-                *reinterpret_cast<uint2*>(dst + (size_t)a * R * K) = make_uint2(w[0], w[1]);
-            }
-        }
     }
 }
 
@@ -464,52 +484,78 @@ struct OzCombArgs {
     uint32_t f2[OZ_MAXMOD], f1[OZ_MAXMOD], f0[OZ_MAXMOD];
 };
 
-// thread: one row, four consecutive columns.  V / P = frac(sum_i r_i f_i) in 96-bit fixed point: three 64-bit
-// accumulators of 8-bit x 32-bit products, carries resolved once; the top 64 bits read as a signed number centre the
-// result in (-P/2, P/2).
-__global__ void __launch_bounds__(256) oz_combine_kernel(const uint8_t* __restrict__ D, const int* __restrict__ sA,
+// thread: one row, eight consecutive columns (a warp reads 256 contiguous bytes of each residue plane).  V / P =
+// frac(sum_i r_i f_i) in 96-bit fixed point: three 64-bit accumulators of 8-bit x 32-bit products, carries resolved once;
+// the top 64 bits read as a signed number centre the result in (-P/2, P/2).  NMOD > 0: the loop over the moduli is
+// unrolled so that all plane loads are in flight together.
+template <int NMOD>
+__global__ void __launch_bounds__(256, 2) oz_combine_kernel(const uint8_t* __restrict__ D, const int* __restrict__ sA,
                                                          const int* __restrict__ sB, double* __restrict__ C, int ldc,
                                                          long long sC, const __grid_constant__ OzCombArgs g) {
     const int b = blockIdx.z;
     const int row = blockIdx.y * 8 + (threadIdx.x >> 5);
-    const int col = blockIdx.x * 128 + (threadIdx.x & 31) * 4;
-    if (g.lower && (int)blockIdx.x > (row >> 7)) return;
-    const uint8_t* d = D + ((size_t)b * g.nmod * g.M + row) * g.N + col;
+    const int col = blockIdx.x * 256 + (threadIdx.x & 31) * 8;
+    if (g.lower && (col >> 7) > (row >> 7)) return;
+    const int nmod = NMOD > 0 ? NMOD : g.nmod;
+    const uint8_t* d = D + ((size_t)b * nmod * g.M + row) * g.N + col;
     const size_t plane = (size_t)g.M * g.N;
-    unsigned long long a2[4] = {0, 0, 0, 0}, a1[4] = {0, 0, 0, 0}, a0[4] = {0, 0, 0, 0};
-    for (int a = 0; a < g.nmod; a++) {
-        const uint32_t w = *reinterpret_cast<const uint32_t*>(d + a * plane);
-        const uint32_t f2 = g.f2[a], f1 = g.f1[a], f0 = g.f0[a];
+    unsigned long long a2[8], a1[8], a0[8];
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const uint32_t r = (w >> (8 * j)) & 0xffu;
-            a2[j] += (unsigned long long)r * f2;
-            a1[j] += (unsigned long long)r * f1;
-            a0[j] += (unsigned long long)r * f0;
+    for (int j = 0; j < 8; j++) a2[j] = a1[j] = a0[j] = 0ull;
+    if (NMOD > 0) {
+        uint2 w[NMOD > 0 ? NMOD : 1];
+#pragma unroll
+        for (int a = 0; a < NMOD; a++) w[a] = __ldg(reinterpret_cast<const uint2*>(d + a * plane));
+#pragma unroll
+        for (int a = 0; a < NMOD; a++) {
+            const uint32_t f2 = g.f2[a], f1 = g.f1[a], f0 = g.f0[a];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const uint32_t r = __byte_perm(j < 4 ? w[a].x : w[a].y, 0u, 0x4440 | (j & 3));
+                a2[j] += (unsigned long long)r * f2;
+                a1[j] += (unsigned long long)r * f1;
+                a0[j] += (unsigned long long)r * f0;
+            }
+        }
+    } else {
+        for (int a = 0; a < nmod; a++) {
+            const uint2 w = __ldg(reinterpret_cast<const uint2*>(d + a * plane));
+            const uint32_t f2 = g.f2[a], f1 = g.f1[a], f0 = g.f0[a];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const uint32_t r = __byte_perm(j < 4 ? w.x : w.y, 0u, 0x4440 | (j & 3));
+                a2[j] += (unsigned long long)r * f2;
+                a1[j] += (unsigned long long)r * f1;
+                a0[j] += (unsigned long long)r * f0;
+            }
         }
     }
-    const double ra = oz_pow2(-sA[(size_t)b * g.M + row]);
-    const int4 sb = *reinterpret_cast<const int4*>(sB + (size_t)b * g.N + col);
-    const int sbv[4] = {sb.x, sb.y, sb.z, sb.w};
-    double out[4];
+    const double ra = oz_pow2(-sA[(size_t)b * g.M + row]) * g.P;      // both exact powers of two times P: one rounding below
+    const int4 sb0 = *reinterpret_cast<const int4*>(sB + (size_t)b * g.N + col);
+    const int4 sb1 = *reinterpret_cast<const int4*>(sB + (size_t)b * g.N + col + 4);
+    const int sbv[8] = {sb0.x, sb0.y, sb0.z, sb0.w, sb1.x, sb1.y, sb1.z, sb1.w};
+    double out[8];
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
+    for (int j = 0; j < 8; j++) {
         const unsigned long long mid = a1[j] + (a0[j] >> 32);
         const uint32_t top = (uint32_t)(a2[j] + (mid >> 32));
         const long long hi64 = (long long)(((unsigned long long)top << 32) | (mid & 0xffffffffull));
         const double frac = fma((double)(uint32_t)a0[j], 0x1p-96, (double)hi64 * 0x1p-64);
-        out[j] = frac * g.P * ra * oz_pow2(-sbv[j]);
+        out[j] = frac * ra * oz_pow2(-sbv[j]);
     }
     double* c = C + (size_t)b * sC + (size_t)row * ldc + col;
-    double4 v;
-    if (g.accumulate) {
-        const double4 o = *reinterpret_cast<const double4*>(c);
-        v = make_double4(fma(g.alpha, out[0], o.x), fma(g.alpha, out[1], o.y), fma(g.alpha, out[2], o.z),
-                         fma(g.alpha, out[3], o.w));
-    } else {
-        v = make_double4(g.alpha * out[0], g.alpha * out[1], g.alpha * out[2], g.alpha * out[3]);
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        double4 v;
+        if (g.accumulate) {
+            const double4 o = *reinterpret_cast<const double4*>(c + 4 * h);
+            v = make_double4(fma(g.alpha, out[4 * h], o.x), fma(g.alpha, out[4 * h + 1], o.y), fma(g.alpha, out[4 * h + 2], o.z),
+                             fma(g.alpha, out[4 * h + 3], o.w));
+        } else {
+            v = make_double4(g.alpha * out[4 * h], g.alpha * out[4 * h + 1], g.alpha * out[4 * h + 2], g.alpha * out[4 * h + 3]);
+        }
+        *reinterpret_cast<double4*>(c + 4 * h) = v;
     }
-    *reinterpret_cast<double4*>(c) = v;
 }
 
 // ---------------------------------------------------------------------------------------------- host side
@@ -534,9 +580,9 @@ static bool same_operand(const GemmP& p, int layout) {
     return p.A == p.B && p.lda == p.ldb && p.sA == p.sB && p.M == p.N && layout != 1;
 }
 
-cudaError_t oz_reserve(OzWs& ws, const GemmP& p, int nmod, bool& grew) {
+cudaError_t oz_reserve(OzWs& ws, const GemmP& p, int nmod, bool& grew, bool same) {
     grew = false;
-    const size_t needA = (size_t)p.batch * nmod * p.M * p.K, needB = (size_t)p.batch * nmod * p.N * p.K;
+    const size_t needA = (size_t)p.batch * nmod * p.M * p.K, needB = same ? 0 : (size_t)p.batch * nmod * p.N * p.K;
     const size_t needD = (size_t)p.batch * nmod * p.M * p.N, needS = (size_t)p.batch * (size_t)(p.M > p.N ? p.M : p.N);
     auto grow = [&](uint8_t*& ptr, size_t& cap, size_t need) -> cudaError_t {
         if (need <= cap) return cudaSuccess;
@@ -596,14 +642,14 @@ static cudaError_t make_map(CUtensorMap* out, const uint8_t* base, int K, int R,
     return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
 
-static cudaError_t launch_convert(bool kc, const double* src, int ld, long long sS, int R, int K, int nmod, int bits,
+static cudaError_t launch_convert(bool kc, const double* src, int ld, long long sS, int R, int K, int nmod, int bits, int tri,
                                   uint8_t* planes, int* sexp, int batch, cudaStream_t st) {
     if (kc) {
         dim3 grid((R + 7) / 8, batch);
-        oz_convert_kernel<true><<<grid, 256, 0, st>>>(src, ld, sS, R, K, nmod, bits, planes, sexp);
+        oz_convert_kc_kernel<<<grid, 256, 0, st>>>(src, ld, sS, R, K, nmod, bits, tri, planes, sexp);
     } else {
         dim3 grid(R / 32, batch);
-        oz_convert_kernel<false><<<grid, 256, 0, st>>>(src, ld, sS, R, K, nmod, bits, planes, sexp);
+        oz_convert_t_kernel<<<grid, 256, 0, st>>>(src, ld, sS, R, K, nmod, bits, tri, planes, sexp);
     }
     return cudaGetLastError();
 }
@@ -617,15 +663,18 @@ cudaError_t oz_gemm(const GemmP& p, int layout, int nmod, OzWs& ws, cudaStream_t
     static OzConst hc = make_const();
     if (!have_crt[nmod]) { crt[nmod] = make_crt(nmod); have_crt[nmod] = true; }
     bool grew;
-    if ((e = oz_reserve(ws, p, nmod, grew)) != cudaSuccess) return e;
+    const bool same = same_operand(p, layout);
+    if ((e = oz_reserve(ws, p, nmod, grew, same)) != cudaSuccess) return e;
     const int bits = oz_operand_bits(nmod, p.K);
     const bool a_kc = layout != 2, b_kc = layout == 0;
-    const bool same = same_operand(p, layout);
-    if ((e = launch_convert(a_kc, p.A, p.lda, p.sA, p.M, p.K, nmod, bits, ws.PA, ws.sA, p.batch, st)) != cudaSuccess) return e;
+    // k ranges of triangular operands (zero blocks are neither converted nor read)
+    const int triA = p.kmode == KM_LE_I ? 1 : (p.kmode == KM_GE_I ? 2 : 0);
+    const int triB = p.kmode == KM_LE_J ? 1 : (p.kmode == KM_GE_J ? 2 : 0);
+    if ((e = launch_convert(a_kc, p.A, p.lda, p.sA, p.M, p.K, nmod, bits, triA, ws.PA, ws.sA, p.batch, st)) != cudaSuccess) return e;
     const uint8_t* PBp = ws.PA;
     const int* sBp = ws.sA;
     if (!same) {
-        if ((e = launch_convert(b_kc, p.B, p.ldb, p.sB, p.N, p.K, nmod, bits, ws.PB, ws.sB, p.batch, st)) != cudaSuccess) return e;
+        if ((e = launch_convert(b_kc, p.B, p.ldb, p.sB, p.N, p.K, nmod, bits, triB, ws.PB, ws.sB, p.batch, st)) != cudaSuccess) return e;
         PBp = ws.PB;
         sBp = ws.sB;
     }
@@ -656,8 +705,13 @@ cudaError_t oz_gemm(const GemmP& p, int layout, int nmod, OzWs& ws, cudaStream_t
     OzCombArgs c;
     c.M = p.M; c.N = p.N; c.nmod = nmod; c.lower = p.lower; c.accumulate = p.accumulate; c.alpha = p.alpha; c.P = crt[nmod].P;
     for (int a = 0; a < OZ_MAXMOD; a++) { c.f2[a] = crt[nmod].f2[a]; c.f1[a] = crt[nmod].f1[a]; c.f0[a] = crt[nmod].f0[a]; }
-    dim3 cgrid(p.N / 128, p.M / 8, p.batch);
-    oz_combine_kernel<<<cgrid, 256, 0, st>>>(ws.PD, ws.sA, sBp, p.C, p.ldc, p.sC, c);
+    dim3 cgrid(p.N / 256, p.M / 8, p.batch);
+    switch (nmod) {
+        case 16: oz_combine_kernel<16><<<cgrid, 256, 0, st>>>(ws.PD, ws.sA, sBp, p.C, p.ldc, p.sC, c); break;
+        case 17: oz_combine_kernel<17><<<cgrid, 256, 0, st>>>(ws.PD, ws.sA, sBp, p.C, p.ldc, p.sC, c); break;
+        case 18: oz_combine_kernel<18><<<cgrid, 256, 0, st>>>(ws.PD, ws.sA, sBp, p.C, p.ldc, p.sC, c); break;
+        default: oz_combine_kernel<0><<<cgrid, 256, 0, st>>>(ws.PD, ws.sA, sBp, p.C, p.ldc, p.sC, c); break;
+    }
     return cudaGetLastError();
 }
 

@@ -35,7 +35,7 @@ bool oz_supported(const GemmP& p, int epi);
 // largest operand width with K 2^(2 bits) < P/2
 int oz_operand_bits(int nmod, int K);
 // makes sure `ws` can hold the planes of `p` (allocates: must not be called during stream capture when it has to grow)
-cudaError_t oz_reserve(OzWs& ws, const GemmP& p, int nmod, bool& grew);
+cudaError_t oz_reserve(OzWs& ws, const GemmP& p, int nmod, bool& grew, bool same_operand);
 // C = alpha op(A) op(B) (+ C), same meaning of every field of p and of `layout` as launch_gemm (EPI_STORE only)
 cudaError_t oz_gemm(const GemmP& p, int layout, int nmod, OzWs& ws, cudaStream_t st);
 
