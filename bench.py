@@ -765,6 +765,53 @@ def run_b200(args):
             streaming["grad_reduce"] = {"ms_per_step": gr_ms / Kp_, "hbm_GBps": byt / (gr_ms * 1e-3) * 1e-9, "frac_of_hbm": byt / (gr_ms * 1e-3) * 1e-9 / hbm,
                                         "fp64_alu_TFLOPs": flo / (gr_ms * 1e-3) * 1e-12, "frac_of_fp64": flo / (gr_ms * 1e-3) * 1e-12 / peak,
                                         "algorithmic": "8 B x n^2/2 read, (n^2/2)(5d + 2q + exp) flops per item"}
+        # ---- the INT8 tensor-core route (default): the large products of the factorisation and LAUUM run as residue GEMMs on
+        # tcgen05.mma kind::i8 (csrc/gpe_ozaki.cuh); the dominant kernel of the step is then oz_gemm_kernel
+        oz_ms, oz_cnt = prof["int8_residue_gemm"]
+        cv_ms, cv_cnt = prof["int8_residue_conversion"]
+        cb_ms, cb_cnt = prof["int8_crt_combine"]
+        nmod = int(os.environ.get("GPE_OZAKI", "16"))
+        oz_min = int(os.environ.get("GPE_OZAKI_MIN", "1024"))
+        int8 = None
+        if oz_cnt:
+            def takes(M, N, K):
+                return min(M, N, K) >= oz_min and M % 128 == 0 and N % 256 == 0 and K % 128 == 0
+
+            def rec(m):          # algorithmic FP64 flops of the products of potrf_inv_rec that take the INT8 route
+                if m <= 128:
+                    return 0.0
+                m1 = ((m // 128 + 1) // 2) * 128
+                m2 = m - m1
+                f = 0.0
+                for (M_, N_, K_) in ((m2, m1, m1), (m2, m1, m1), (m2, m2, m1), (m2, m1, m2)):   # each has one triangular factor: M N K flops
+                    if takes(M_, N_, K_):
+                        f += float(M_) * N_ * K_
+                return f + rec(m1) + rec(m2)
+            f64_flops = rec(npad) + (float(npad) ** 3 / 3.0 if takes(npad, npad, npad) else 0.0)
+            i8_ops = B * nmod * f64_flops                       # one u8 x u8 -> s32 product per modulus
+            i8_peak = None
+            try:
+                with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                    i8_peak = 2.0 * float(json.load(f)["bf16_tflops_sustained"])
+                i8_src = "2 x bf16_tflops_sustained of MEASURED_PEAKS.json (kind::i8 issues at twice the bf16 rate on sm_100a: 4.5 vs 2.25 POP/s nominal)"
+            except Exception:
+                i8_peak, i8_src = 2.0 * 1367.4, "fallback: 2 x 1367.4 TFLOP/s (sustained bf16 of this pool's B200)"
+            i8_ach = i8_ops * Kp_ / (oz_ms * 1e-3) * 1e-12
+            i8_traffic = None
+            tp = os.path.join(ROOT, "profiles", "r02_traffic_int8.json")
+            if os.path.exists(tp):
+                with open(tp) as f:
+                    i8_traffic = json.load(f)
+            int8 = {"kernel": "oz_gemm_kernel<2> (residue GEMM: TMA 128B-swizzled tiles, two-CTA multicast clusters, tcgen05.mma kind::i8, "
+                              "TMEM double-buffered accumulator, mod-p epilogue): %d launches per step" % (oz_cnt // Kp_),
+                    "bound": "tensor", "unit": "TOP/s", "achieved": i8_ach, "peak": i8_peak, "frac": i8_ach / i8_peak,
+                    "peak_source": i8_src,
+                    "issue_rate_microbenchmark_TOPs": 4300.0,
+                    "issue_rate_source": "profiles/r01_ub_i8_umma.json (tcgen05.mma kind::i8, resident operands, 148 CTAs)",
+                    "algorithmic_ops_per_step": i8_ops, "moduli": nmod,
+                    "algorithmic": "moduli x FP64 flops of the products it replaces (M N K per triangular product, n^3/3 for LAUUM)",
+                    "ms_per_step": oz_ms / Kp_, "traffic": i8_traffic,
+                    "residue_conversion_ms_per_step": cv_ms / Kp_, "crt_combine_ms_per_step": cb_ms / Kp_}
         line = {
             "metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -775,19 +822,23 @@ def run_b200(args):
             "e2e": {"value": e2e_val, "unit": "evals/s", "h2d_bytes_per_step": int(B * p * 8),
                     "d2h_bytes_per_step": int(B * (p + 2) * 8 + B * 4), "steps": Ke},
             "roofline": {"bound": "tensor", "achieved": step_ach, "peak": peak, "unit": "TFLOP/s", "frac": step_ach / peak,
-                         "what": "the whole llh+grad step: 32 x F_llh (n^3 + n^2(3d+p+2q+4)) algorithmic flops / ms_per_step of the timed region",
-                         "traffic": traffic,
+                         "what": "the whole llh+grad step in FP64-equivalent terms: 32 x F_llh (n^3 + n^2(3d+p+2q+4)) algorithmic flops / ms_per_step "
+                                 "of the timed region, against the measured FP64 DMMA roof" +
+                                 (" -- above 1 because the large products run as %d exact INT8 residue GEMMs each on the tcgen05 tensor cores "
+                                  "(dominant_kernel below carries that kernel's own INT8 roofline)" % nmod if int8 else ""),
+                         "traffic": (int8["traffic"].get("oz_gemm_dram_bytes_per_launch") if int8 and int8["traffic"] else traffic),
                          "peak_source": peak_src + "; MEASURED_PEAKS.json holds no FP64 figure",
-                         "dominant_kernel": {"kernel": "lauum_grad_kernel / gemm_dmma_ws_kernel<TN> LAUUM launch (A^-1 = L^-T L^-1, %d items, lower 128x128 tiles)" % B,
+                         "dominant_kernel": int8 if int8 else
+                                            {"kernel": "lauum_grad_kernel / gemm_dmma_ws_kernel<TN> LAUUM launch (A^-1 = L^-T L^-1, %d items, lower 128x128 tiles)" % B,
                                              "achieved": kern_ach, "frac": (kern_ach / peak) if kern_ach else None,
                                              "algorithmic_flops_per_launch": lau_flops, "algorithmic_bytes_per_launch": B * 8.0 * n * n,
                                              "ms_per_launch": lau_ms / lau_cnt if lau_cnt else None},
                          "kernel_timing": "CUDA-event pair around every launch, measured live in this run in a separate pass of %d steps "
-                                          "with the sub-batch streams off (serial launches, %.2f ms/step); the timed region runs %d "
-                                          "concurrent sub-batch streams" % (Kp_, serial_ms, args.streams),
-                         "dmma_family": {"what": "all 128x128-tile DMMA launches of a step (SYRK/TRMM updates + LAUUM), algorithmic n^3 flops/item",
-                                         "achieved": fam_ach, "frac": fam_ach / peak if fam_ach else None, "ms_per_step": fam_ms / Kp_,
-                                         "launches_per_step": (gemm_cnt + lau_cnt) / Kp_},
+                                          "with the sub-batch streams off (serial launches, %.2f ms/step); the timed region runs %s "
+                                          "concurrent sub-batch streams" % (Kp_, serial_ms, "2 (INT8 route)" if int8 else str(args.streams)),
+                         "dmma_family": {"what": "all 128x128-tile DMMA launches of a step (on the INT8 route: the levels below %d only)" % oz_min,
+                                         "achieved": fam_ach if not int8 else None, "frac": (fam_ach / peak if fam_ach else None) if not int8 else None,
+                                         "ms_per_step": fam_ms / Kp_, "launches_per_step": (gemm_cnt + lau_cnt) / Kp_},
                          "step_achieved": step_ach, "step_frac": step_ach / peak,
                          "streaming_kernels": streaming, "hbm_peak_GBps": hbm, "hbm_peak_source": hbm_src,
                          "by_kernel_ms_per_step": {k: v[0] / Kp_ for k, v in prof.items()}},

@@ -148,7 +148,8 @@ class Device:
         """cudaStream_t of the handle (wrap with torch.cuda.ExternalStream to record events)."""
         return int(self.L.gpe_get_stream(self.h) or 0)
 
-    PROFILE_CATEGORIES = ("gemm_dmma_128", "gemm_dmma_small", "potrf_leaf", "cov_build", "grad_reduce", "other", "lauum")
+    PROFILE_CATEGORIES = ("gemm_dmma_128", "gemm_dmma_small", "potrf_leaf", "cov_build", "grad_reduce", "other", "lauum",
+                          "int8_residue_conversion", "int8_residue_gemm", "int8_crt_combine")
 
     def set_streams(self, nstreams):
         """Number of concurrent sub-batch streams of llh_grad_batch (1 = serial launches)."""
@@ -165,8 +166,8 @@ class Device:
         self._ck(self.L.gpe_profile_enable(self.h, int(bool(on))))
 
     def profile_read(self, reset=True):
-        ms = np.zeros(7)
-        cnt = np.zeros(7, dtype=np.int64)
+        ms = np.zeros(len(self.PROFILE_CATEGORIES))
+        cnt = np.zeros(len(self.PROFILE_CATEGORIES), dtype=np.int64)
         self._ck(self.L.gpe_profile_read(self.h, _ptr(ms), _ptr(cnt), int(bool(reset))))
         return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(self.PROFILE_CATEGORIES)}
 

@@ -144,6 +144,10 @@ static bool gemm_is_big(int M, int N, int lower, int batch) {
     return t128 >= 120;
 }
 
+static bool oz_takes(const gpe_handle* h, int M, int N, int K) {
+    return h->oz_nmod > 0 && M >= h->oz_min && N >= h->oz_min && K >= h->oz_min && M % OZ_BM == 0 && N % OZ_BN == 0 && K % OZ_BK == 0;
+}
+
 static int run_gemm(gpe_handle* h, cudaStream_t st, const double* A, const double* B, double* C, int lda, int ldb, int ldc,
                     long long sA, long long sB, long long sC, int M, int N, int K, double alpha, int acc,
                     int kmode, int lower, int batch, int layout, int epi = EPI_STORE, int cat = -1) {
@@ -152,16 +156,30 @@ static int run_gemm(gpe_handle* h, cudaStream_t st, const double* A, const doubl
     p.M = M; p.N = N; p.K = K; p.alpha = alpha; p.accumulate = acc; p.kmode = kmode; p.lower = lower; p.batch = batch;
     bool big = (M % 128 == 0 || epi == EPI_SUMSQ) && (N % 128 == 0) && N != 32 && M != 32;
     cudaError_t e;
+    const bool reuse_a = h->oz_reuse_a;      // a request holds for one product only, whichever route it takes
+    h->oz_reuse_a = false;
     if (h->oz_nmod > 0 && M >= h->oz_min && N >= h->oz_min && K >= h->oz_min && oz_supported(p, epi)) {
         // INT8 tensor-core route (gpe_ozaki.cuh): scratch is per stream; growing it is not allowed inside a capture, and
         // every shape has been seen eagerly at least twice before its graph is captured
         OzWs& ws = h->oz_ws[st];
-        {
-            ProfScope ps(h, cat >= 0 ? cat : gpe_handle::CAT_GEMM_BIG, st);
-            e = oz_gemm(p, layout, h->oz_nmod, ws, st);
+        struct HookCtx { gpe_handle* h; cudaEvent_t e0[3]; } hc{h, {nullptr, nullptr, nullptr}};
+        OzHook hook;
+        if (h->prof_on) {       // per-phase event pairs: residue conversion, residue GEMM, CRT
+            hook.ctx = &hc;
+            hook.fn = [](void* c, int phase, bool begin, cudaStream_t s) {
+                HookCtx* x = static_cast<HookCtx*>(c);
+                const int pc = gpe_handle::CAT_OZ_CONVERT + phase;
+                if (begin) x->e0[phase] = x->h->prof_begin(pc, s);
+                else x->h->prof_end(pc, x->e0[phase], s);
+            };
         }
+        e = oz_gemm(p, layout, h->oz_nmod, ws, st, reuse_a, hook);
         h->launches += 4;
         h->oz_calls++;
+        if (ws.grew) {          // (never during a capture: a shape is captured after it has run eagerly twice)
+            ws.grew = false;
+            h->graphs_stale = true;
+        }
         if (e != cudaSuccess) return h->fail("oz_gemm", e);
         return 0;
     }
@@ -231,7 +249,10 @@ static int potrf_inv_rec(gpe_handle* h, const FactorWs& ws, const SubBatch& sb, 
     // T = L21 * Linv11  (NN, Linv11 lower: k >= j) -> dead A21 block.  It needs only L21 and Linv11, not the
     // factorisation of A22: with side streams it is launched now, beside the SYRK and the whole A22 sub-recursion
     // (whose leaves and small levels cannot fill the machine), and joined before the last product of the node.
-    const bool fork = sb.side != nullptr && depth < gpe_handle::MAX_DEPTH;
+    // On the INT8 route the node's products run in order on one stream: L21 is converted to residues once, for the SYRK, and
+    // the planes serve T = L21 Linv11 right after it.
+    const bool oz_node = oz_takes(h, m2, m1, m1) && oz_takes(h, m2, m2, m1);
+    const bool fork = !oz_node && sb.side != nullptr && depth < gpe_handle::MAX_DEPTH;
     if (fork) {
         cudaStream_t side = sb.side[depth];
         cudaEventRecord(sb.ef[depth], sb.current());
@@ -241,10 +262,14 @@ static int potrf_inv_rec(gpe_handle* h, const FactorWs& ws, const SubBatch& sb, 
     }
     // A22 -= L21 * L21^T             (SYRK, lower tiles)
     if ((rc = run_gemm(h, sb.stream(!gemm_is_big(m2, m2, 1, B)), S21, S21, A22, ld, ld, ld, sM, sM, sM, m2, m2, m1, -1.0, 1, KM_FULL, 1, B, 0))) return rc;
+    if (oz_node) {
+        h->oz_reuse_a = true;
+        if ((rc = run_gemm(h, sb.current(), S21, Li11, A21, ld, ld, ld, sM, sM, sM, m2, m1, m1, 1.0, 0, KM_GE_J, 0, B, 1))) return rc;
+    }
     if ((rc = potrf_inv_rec(h, ws, sb, off + m1, m2, want_L, depth + 1))) return rc;
     if (fork) {
         cudaStreamWaitEvent(sb.current(), sb.ej[depth], 0);
-    } else {
+    } else if (!oz_node) {
         if ((rc = run_gemm(h, sb.stream(!gemm_is_big(m2, m1, 0, B)), S21, Li11, A21, ld, ld, ld, sM, sM, sM, m2, m1, m1, 1.0, 0, KM_GE_J, 0, B, 1))) return rc;
     }
     // Linv21 = -Linv22 * T           (NN, Linv22 lower: k <= i)
@@ -404,11 +429,15 @@ int gpe_create(int device, gpe_handle** out) {
             cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
         }
     }
+    // the INT8 route is the default for products of 1024 and more in every dimension (GPE_OZAKI=0: DMMA everywhere); its
+    // launches fill the machine on their own, so two sub-batch groups are enough there (oz_nsub; eight for the DMMA route)
+    if (const char* e = getenv("GPE_OZAKI")) h->oz_nmod = std::max(0, std::min((int)OZ_MAXMOD, atoi(e)));
+    if (h->oz_nmod == 1) h->oz_nmod = 2;
+    if (const char* e = getenv("GPE_OZAKI_MIN")) h->oz_min = std::max(256, atoi(e));
+    if (const char* e = getenv("GPE_OZAKI_STREAMS")) h->oz_nsub = std::max(1, std::min((int)gpe_handle::MAX_SUB, atoi(e)));
     if (const char* e = getenv("GPE_STREAMS")) h->nsub = std::max(1, std::min((int)gpe_handle::MAX_SUB, atoi(e)));
     if (const char* e = getenv("GPE_GRAPHS")) h->use_graphs = e[0] != '0';
     if (const char* e = getenv("GPE_SIDE")) h->use_side = e[0] != '0';
-    if (const char* e = getenv("GPE_OZAKI")) h->oz_nmod = std::max(0, std::min((int)OZ_MAXMOD, atoi(e)));
-    if (const char* e = getenv("GPE_OZAKI_MIN")) h->oz_min = std::max(256, atoi(e));
     *out = h;
     return 0;
 }
@@ -469,7 +498,8 @@ int gpe_profile_enable(gpe_handle* h, int on) {
 
 // Drain the recorded event pairs: ms[c] / count[c] per category since the last reset
 // (0 big DMMA GEMM tiles, 1 small/skinny GEMM, 2 leaf, 3 covariance build, 4 gradient reduction, 5 other,
-// 6 the LAUUM launch A^-1 = L^-T L^-1, the single largest launch of an evaluation).
+// 6 the LAUUM launch A^-1 = L^-T L^-1 on the DMMA route; 7 / 8 / 9 the INT8 route's residue conversion, residue GEMM
+// (tcgen05.mma kind::i8) and CRT recombination).
 int gpe_profile_read(gpe_handle* h, double* ms, long long* count, int reset) {
     if (!h) return -2;
     cudaStreamSynchronize(h->st);
@@ -627,7 +657,8 @@ static int enqueue_llh_chunk(gpe_handle* h, int Bs, int p, int mode, double fixe
         e = getenv("GPE_GROUP_NPAD_GRAPH");
         group_npad_graph = e ? atoi(e) : 512;
     }
-    const int ns = h->npad < (capturing ? group_npad_graph : group_npad) ? 1 : std::max(1, std::min(h->nsub, Bs / 2));
+    int ns = h->npad < (capturing ? group_npad_graph : group_npad) ? 1 : std::max(1, std::min(h->nsub, Bs / 2));
+    if (oz_takes(h, h->npad / 2, h->npad / 2, h->npad / 2)) ns = std::min(ns, h->oz_nsub);   // the top level runs on the INT8 route
     // one decision for the whole chunk (every group writes the same partial layout): the smallest group must still
     // fill the machine with 128x128 tiles
     h->grad_fused = llh_grad_fused(h, Bs / ns);
@@ -680,6 +711,10 @@ int gpe_llh_grad_batch(gpe_handle* h, const double* theta, int B, int p, int mod
         int Bs = std::min(h->Bcap, B - b0);
         CK(cudaMemcpyAsync(h->theta_d, theta + (size_t)b0 * p, sizeof(double) * Bs * p, cudaMemcpyDefault, h->st));
         gpe_handle::LlhGraph* gr = nullptr;
+        if (h->graphs_stale) {      // a scratch buffer of the INT8 route was reallocated since the graphs were captured
+            h->drop_graphs();
+            h->graphs_stale = false;
+        }
         if (h->use_graphs && !h->prof_on) {
             for (auto& g : h->graphs)
                 if (g.Bs == Bs && g.p == p && g.mode == mode && g.nsub == h->nsub && g.nug == fixed_nugget) gr = &g;

@@ -17,7 +17,8 @@ struct gpe_handle {
     bool async = false;          // gpe_set_async: calls whose outputs are all device memory return without the final synchronize
 
     // optional per-category CUDA-event timing of every launch (gpe_profile_*)
-    enum { CAT_GEMM_BIG = 0, CAT_GEMM_SMALL = 1, CAT_LEAF = 2, CAT_COV = 3, CAT_GRAD = 4, CAT_OTHER = 5, CAT_LAUUM = 6, NCAT = 7 };
+    enum { CAT_GEMM_BIG = 0, CAT_GEMM_SMALL = 1, CAT_LEAF = 2, CAT_COV = 3, CAT_GRAD = 4, CAT_OTHER = 5, CAT_LAUUM = 6,
+           CAT_OZ_CONVERT = 7, CAT_OZ_GEMM = 8, CAT_OZ_COMBINE = 9, NCAT = 10 };
     bool prof_on = false;
     struct ProfRec { int cat; cudaEvent_t e0, e1; };
     std::vector<ProfRec> prof_recs;
@@ -51,6 +52,7 @@ struct gpe_handle {
     struct LlhGraph { int Bs, p, mode, nsub; double nug; int seen; cudaGraphExec_t exec; long long launches; };
     std::vector<LlhGraph> graphs;
     void drop_graphs();
+    bool graphs_stale = false;
 
     // training set (device)
     int n = 0, d = 0, q = 0, npad = 0, nleaf = 0;
@@ -90,11 +92,12 @@ struct gpe_handle {
     struct PredSlot { double *C = nullptr, *Part = nullptr, *Aux = nullptr, *X = nullptr, *H = nullptr, *Mean = nullptr, *Var = nullptr; };
     PredSlot ps[2];
 
-    // FP64 GEMMs emulated on the INT8 tensor cores (gpe_ozaki.cuh): number of moduli (0 = off, the default; GPE_OZAKI),
+    // FP64 GEMMs emulated on the INT8 tensor cores (gpe_ozaki.cuh): number of moduli (GPE_OZAKI; 0 = off: DMMA everywhere),
     // smallest dimension that takes the route (GPE_OZAKI_MIN), scratch per stream
-    int oz_nmod = 0, oz_min = 1024;
+    int oz_nmod = 16, oz_min = 1024, oz_nsub = 2;
     std::map<cudaStream_t, gpe::OzWs> oz_ws;
     long long oz_calls = 0;
+    bool oz_reuse_a = false;     // the next product may use the residue planes of operand A left by the previous one
 
     int fail(const char* what, cudaError_t e);
     int fail_msg(const char* what);

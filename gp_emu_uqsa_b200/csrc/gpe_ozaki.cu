@@ -209,13 +209,14 @@ __global__ void __launch_bounds__(256) oz_convert_kc_kernel(const double* __rest
 // Operand stored [k][r]: a CTA takes 32 rows r (adjacent in memory); thread (tx, ty) reads eight k of row tx per 64-wide
 // slab (each load 256 contiguous bytes across the warp), the residues of all moduli are transposed through shared memory
 // and leave as 64-byte row segments.
+constexpr int OZ_THALF = 10;  // moduli staged at a time
 constexpr int OZ_TS = 72;     // bytes per staged row (64 + 8: conflict-free 8-byte stores of a half-warp)
 __global__ void __launch_bounds__(256) oz_convert_t_kernel(const double* __restrict__ src, int ld, long long sS, int R, int K,
                                                            int nmod, int bits, int tri, uint8_t* __restrict__ planes,
                                                            int* __restrict__ sexp) {
     __shared__ double red[8][33];
     __shared__ int s_sh[32];
-    __shared__ __align__(16) uint8_t stage[OZ_MAXMOD * 32 * OZ_TS];
+    __shared__ __align__(16) uint8_t stage[OZ_THALF * 32 * OZ_TS];
     const int b = blockIdx.y;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int r0 = blockIdx.x * 32, r = r0 + tx;           // R is a multiple of 32; the 32 rows share one granule
@@ -244,14 +245,19 @@ __global__ void __launch_bounds__(256) oz_convert_t_kernel(const double* __restr
         const double* cp = col + (size_t)(k0 + ty * OZ_CV) * ld;
 #pragma unroll
         for (int j = 0; j < OZ_CV; j++) oz_to_u64(cp[(size_t)j * ld], p1, p2, lo[j], hi[j]);
-#pragma unroll 2
-        for (int a = 0; a < nmod; a++)
-            *reinterpret_cast<uint2*>(stage + (a * 32 + tx) * OZ_TS + ty * 8) = oz_residues8(lo, hi, a);
-        __syncthreads();
         uint8_t* dst = Pb + (size_t)(r0 + orow) * K + k0 + och * 8;
-        for (int a = 0; a < nmod; a++)
-            *reinterpret_cast<uint2*>(dst + (size_t)a * plane) = *reinterpret_cast<const uint2*>(stage + (a * 32 + orow) * OZ_TS + och * 8);
-        __syncthreads();
+        // the moduli in groups of OZ_THALF: 23 KB of staging, so that the kernel fits on an SM beside a CTA of the residue GEMM
+        for (int a0 = 0; a0 < nmod; a0 += OZ_THALF) {
+            const int na = min(OZ_THALF, nmod - a0);
+#pragma unroll 2
+            for (int a = 0; a < na; a++)
+                *reinterpret_cast<uint2*>(stage + (a * 32 + tx) * OZ_TS + ty * 8) = oz_residues8(lo, hi, a0 + a);
+            __syncthreads();
+            for (int a = 0; a < na; a++)
+                *reinterpret_cast<uint2*>(dst + (size_t)(a0 + a) * plane) =
+                    *reinterpret_cast<const uint2*>(stage + (a * 32 + orow) * OZ_TS + och * 8);
+            __syncthreads();
+        }
     }
 }
 
@@ -301,40 +307,75 @@ __device__ __forceinline__ void oz_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// tile t of a plane product -> (tm, tn), heaviest tiles first
-__device__ __forceinline__ void oz_tile(const OzGemmArgs& g, int t, int& tm, int& tn) {
-    if (g.lower) {              // rows ascending (k >= i: heaviest first), tn <= tm / 2
+// Work unit t of a plane product -> (um, tn), heaviest first.  A unit is CL vertically adjacent 128x256 tiles (rows
+// um*CL .. um*CL+CL-1 of the tile grid) computed by the CL CTAs of a cluster, which share the tile of B.
+template <int CL>
+__device__ __forceinline__ void oz_unit(const OzGemmArgs& g, int t, int& um, int& tn) {
+    const int units_m = g.tiles_m / CL;
+    if (g.lower) {              // rows ascending (k >= i: heaviest first), tn up to the diagonal of the unit's last row
         int row = 0, before = 0;
         while (true) {
-            const int cnt = min(g.tiles_n, row / 2 + 1);
+            const int cnt = min(g.tiles_n, (row * CL + CL - 1) / 2 + 1);
             if (t < before + cnt) break;
             before += cnt;
             row++;
         }
-        tm = row;
+        um = row;
         tn = t - before;
         return;
     }
     switch (g.kmode) {
-        case KM_LE_J: tn = g.tiles_n - 1 - t / g.tiles_m; tm = t % g.tiles_m; break;
-        case KM_GE_J: tn = t / g.tiles_m; tm = t % g.tiles_m; break;
-        case KM_LE_I: tm = g.tiles_m - 1 - t / g.tiles_n; tn = t % g.tiles_n; break;
-        default: tm = t / g.tiles_n; tn = t % g.tiles_n; break;
+        case KM_LE_J: tn = g.tiles_n - 1 - t / units_m; um = t % units_m; break;
+        case KM_GE_J: tn = t / units_m; um = t % units_m; break;
+        case KM_LE_I: um = units_m - 1 - t / g.tiles_n; tn = t % g.tiles_n; break;
+        default: um = t / g.tiles_n; tn = t % g.tiles_n; break;
     }
 }
-__device__ __forceinline__ void oz_krange(const OzGemmArgs& g, int tm, int tn, int& kb0, int& kb1) {
+// k blocks of a unit (the same for all CTAs of the cluster: they run their pipelines in lock step)
+template <int CL>
+__device__ __forceinline__ void oz_krange(const OzGemmArgs& g, int um, int tn, int& kb0, int& kb1) {
     const int nkb = g.K / OZ_BK;
     kb0 = 0;
     kb1 = nkb;
     switch (g.kmode) {
         case KM_LE_J: kb1 = min(nkb, (tn + 1) * (OZ_BN / OZ_BK)); break;
         case KM_GE_J: kb0 = min(nkb - 1, tn * (OZ_BN / OZ_BK)); break;
-        case KM_LE_I: kb1 = min(nkb, (tm + 1) * (OZ_BM / OZ_BK)); break;
-        case KM_GE_I: kb0 = min(nkb - 1, tm * (OZ_BM / OZ_BK)); break;
+        case KM_LE_I: kb1 = min(nkb, (um + 1) * CL * (OZ_BM / OZ_BK)); break;
+        case KM_GE_I: kb0 = min(nkb - 1, um * CL * (OZ_BM / OZ_BK)); break;
         default: break;
     }
 }
 
+__device__ __forceinline__ uint32_t oz_cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void oz_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ void oz_tma_load_mc(void* smem, const CUtensorMap* tm, int c0, int c1, int c2, uint64_t* bar,
+                                               uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %3, "
+        "%4}], [%5], %6;\n" ::"r"(smem_u32(smem)),
+        "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ void oz_commit_mc(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::"r"(
+                     smem_u32(bar)),
+                 "h"(mask)
+                 : "memory");
+}
+
+// CL = 1: every CTA loads its own 128 x 128 tile of A and 256 x 128 tile of B per k block (48 KB per 4 MMAs: the kernel is
+// bound by the L2 -> SM bandwidth, 90 B/clk/SM at the INT8 peak).  CL = 2: the two CTAs of a cluster work on vertically
+// adjacent tiles; each loads its own tile of A and one half of the shared tile of B, multicast into both CTAs' shared
+// memory (32 KB from L2 per CTA and k block).  A stage is released when the MMAs of both CTAs have read it (their
+// tcgen05.commit arrives on both CTAs' empty barriers); a CTA's full barrier counts the bytes of all three copies.
+template <int CL>
 __global__ void __launch_bounds__(OZ_THREADS, 1) oz_gemm_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                  const __grid_constant__ CUtensorMap tmB,
                                                                  const __grid_constant__ OzGemmArgs g) {
@@ -343,12 +384,15 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_gemm_kernel(const __grid_con
     __shared__ __align__(8) uint64_t full_bar[OZ_STAGES], empty_bar[OZ_STAGES], tfull_bar[2], tempty_bar[2];
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int rank = CL > 1 ? (int)oz_cluster_rank() : 0;
+    const long long cid = blockIdx.x / CL, ncl = gridDim.x / CL;
+    constexpr uint16_t MASK = (uint16_t)((1u << CL) - 1u);
 
     if (tid == 0) {
 #pragma unroll
         for (int s = 0; s < OZ_STAGES; s++) {
             mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], 1);
+            mbar_init(&empty_bar[s], CL);
         }
 #pragma unroll
         for (int s = 0; s < 2; s++) {
@@ -365,6 +409,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_gemm_kernel(const __grid_con
     }
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
     __syncthreads();
+    if (CL > 1) oz_cluster_sync();            // the peer's barriers exist before anything is multicast to them
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     const uint32_t tmem = tmem_base_s;
     const long long total = (long long)g.nbp * g.T;
@@ -373,17 +418,24 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_gemm_kernel(const __grid_con
         if (lane == 0) {                      // ---- TMA producer
             int stage = 0;
             uint32_t phase = 0;
-            for (long long w = blockIdx.x; w < total; w += gridDim.x) {
+            for (long long w = cid; w < total; w += ncl) {
                 const int bp = (int)(w / g.T), t = (int)(w - (long long)bp * g.T);
-                int tm, tn, kb0, kb1;
-                oz_tile(g, t, tm, tn);
-                oz_krange(g, tm, tn, kb0, kb1);
+                int um, tn, kb0, kb1;
+                oz_unit<CL>(g, t, um, tn);
+                oz_krange<CL>(g, um, tn, kb0, kb1);
+                const int tm = um * CL + rank;
                 for (int kb = kb0; kb < kb1; kb++) {
                     mbar_wait(&empty_bar[stage], phase ^ 1u);
                     oz_mbar_expect_tx(&full_bar[stage], OZ_STAGE_BYTES);
                     uint8_t* sa = smem + stage * OZ_STAGE_BYTES;
                     oz_tma_load(sa, &tmA, kb * OZ_BK, tm * OZ_BM, bp, &full_bar[stage]);
-                    oz_tma_load(sa + OZ_A_BYTES, &tmB, kb * OZ_BK, tn * OZ_BN, bp, &full_bar[stage]);
+                    if (CL == 1) {
+                        oz_tma_load(sa + OZ_A_BYTES, &tmB, kb * OZ_BK, tn * OZ_BN, bp, &full_bar[stage]);
+                    } else {
+                        constexpr int HB = OZ_BN / CL;          // rows of B this CTA fetches for the cluster
+                        oz_tma_load_mc(sa + OZ_A_BYTES + rank * HB * OZ_BK, &tmB, kb * OZ_BK, tn * OZ_BN + rank * HB, bp,
+                                       &full_bar[stage], MASK);
+                    }
                     if (++stage == OZ_STAGES) { stage = 0; phase ^= 1u; }
                 }
             }
@@ -392,11 +444,11 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_gemm_kernel(const __grid_con
         if (lane == 0) {                      // ---- MMA issuer
             int stage = 0, as = 0;
             uint32_t phase = 0, aphase = 0;
-            for (long long w = blockIdx.x; w < total; w += gridDim.x) {
+            for (long long w = cid; w < total; w += ncl) {
                 const int bp = (int)(w / g.T), t = (int)(w - (long long)bp * g.T);
-                int tm, tn, kb0, kb1;
-                oz_tile(g, t, tm, tn);
-                oz_krange(g, tm, tn, kb0, kb1);
+                int um, tn, kb0, kb1;
+                oz_unit<CL>(g, t, um, tn);
+                oz_krange<CL>(g, um, tn, kb0, kb1);
                 mbar_wait(&tempty_bar[as], aphase ^ 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
                 const uint32_t dcol = tmem + (uint32_t)(as * OZ_BN);
@@ -415,7 +467,8 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_gemm_kernel(const __grid_con
                             "r"(0u), "r"(0u)
                             : "memory");
                     }
-                    oz_commit(&empty_bar[stage]);
+                    if (CL == 1) oz_commit(&empty_bar[stage]);
+                    else oz_commit_mc(&empty_bar[stage], MASK);
                     if (++stage == OZ_STAGES) { stage = 0; phase ^= 1u; }
                 }
                 oz_commit(&tfull_bar[as]);
@@ -427,10 +480,11 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_gemm_kernel(const __grid_con
         const int quad = warp & 3;
         int as = 0;
         uint32_t aphase = 0;
-        for (long long w = blockIdx.x; w < total; w += gridDim.x) {
+        for (long long w = cid; w < total; w += ncl) {
             const int bp = (int)(w / g.T), t = (int)(w - (long long)bp * g.T);
-            int tm, tn;
-            oz_tile(g, t, tm, tn);
+            int um, tn;
+            oz_unit<CL>(g, t, um, tn);
+            const int tm = um * CL + rank;
             const int a = bp % g.nmod;
             const uint32_t p = g.p[a], m39 = g.m39[a];
             mbar_wait(&tfull_bar[as], aphase);
@@ -460,7 +514,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_gemm_kernel(const __grid_con
                         const uint32_t q = (uint32_t)(((unsigned long long)x * m39) >> 39);
                         r[e] = x - q * p;
                     }
-                    wv[j] = r[0] | (r[1] << 8) | (r[2] << 16) | (r[3] << 24);
+                    wv[j] = oz_pack4(r[0], r[1], r[2], r[3]);
                 }
                 uint4* d4 = reinterpret_cast<uint4*>(drow + c * 32);
                 d4[0] = make_uint4(wv[0], wv[1], wv[2], wv[3]);
@@ -474,6 +528,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_gemm_kernel(const __grid_con
     }
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
     __syncthreads();
+    if (CL > 1) oz_cluster_sync();            // no CTA leaves while its peer can still multicast into it
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "n"(512));
 }
 
@@ -654,7 +709,7 @@ static cudaError_t launch_convert(bool kc, const double* src, int ld, long long 
     return cudaGetLastError();
 }
 
-cudaError_t oz_gemm(const GemmP& p, int layout, int nmod, OzWs& ws, cudaStream_t st) {
+cudaError_t oz_gemm(const GemmP& p, int layout, int nmod, OzWs& ws, cudaStream_t st, bool reuse_a, const OzHook& hook) {
     if (nmod < 2 || nmod > OZ_MAXMOD || !oz_supported(p, EPI_STORE)) return cudaErrorInvalidValue;
     cudaError_t e;
     if ((e = upload_const()) != cudaSuccess) return e;
@@ -665,12 +720,19 @@ cudaError_t oz_gemm(const GemmP& p, int layout, int nmod, OzWs& ws, cudaStream_t
     bool grew;
     const bool same = same_operand(p, layout);
     if ((e = oz_reserve(ws, p, nmod, grew, same)) != cudaSuccess) return e;
+    if (grew) { ws.have_a = false; ws.grew = true; }
     const int bits = oz_operand_bits(nmod, p.K);
     const bool a_kc = layout != 2, b_kc = layout == 0;
     // k ranges of triangular operands (zero blocks are neither converted nor read)
     const int triA = p.kmode == KM_LE_I ? 1 : (p.kmode == KM_GE_I ? 2 : 0);
     const int triB = p.kmode == KM_LE_J ? 1 : (p.kmode == KM_GE_J ? 2 : 0);
-    if ((e = launch_convert(a_kc, p.A, p.lda, p.sA, p.M, p.K, nmod, bits, triA, ws.PA, ws.sA, p.batch, st)) != cudaSuccess) return e;
+    hook(0, true, st);
+    const OzWs::Key keyA{p.A, p.lda, p.sA, p.M, p.K, p.batch, nmod, bits, triA, a_kc ? 1 : 0};
+    if (!(reuse_a && ws.have_a && ws.key_a == keyA)) {
+        if ((e = launch_convert(a_kc, p.A, p.lda, p.sA, p.M, p.K, nmod, bits, triA, ws.PA, ws.sA, p.batch, st)) != cudaSuccess) return e;
+    }
+    ws.key_a = keyA;
+    ws.have_a = true;
     const uint8_t* PBp = ws.PA;
     const int* sBp = ws.sA;
     if (!same) {
@@ -678,30 +740,59 @@ cudaError_t oz_gemm(const GemmP& p, int layout, int nmod, OzWs& ws, cudaStream_t
         PBp = ws.PB;
         sBp = ws.sB;
     }
+    hook(0, false, st);
     // residue GEMM
+    hook(1, true, st);
     CUtensorMap tmA, tmB;
     const int nbp = p.batch * nmod;
     if ((e = make_map(&tmA, ws.PA, p.K, p.M, nbp, OZ_BM)) != cudaSuccess) return e;
-    if ((e = make_map(&tmB, PBp, p.K, p.N, nbp, OZ_BN)) != cudaSuccess) return e;
     OzGemmArgs g;
     g.M = p.M; g.N = p.N; g.K = p.K; g.nmod = nmod; g.nbp = nbp; g.kmode = p.kmode; g.lower = p.lower;
     g.tiles_m = p.M / OZ_BM; g.tiles_n = p.N / OZ_BN;
+    static const int cl_env = [] { const char* e = getenv("GPE_OZAKI_CLUSTER"); return e ? atoi(e) : 2; }();
+    const int CL = (cl_env == 2 && g.tiles_m % 2 == 0) ? 2 : 1;
+    if ((e = make_map(&tmB, PBp, p.K, p.N, nbp, OZ_BN / CL)) != cudaSuccess) return e;
+    const int units_m = g.tiles_m / CL;
     if (p.lower) {
         int T = 0;
-        for (int r = 0; r < g.tiles_m; r++) T += std::min(g.tiles_n, r / 2 + 1);
+        for (int r = 0; r < units_m; r++) T += std::min(g.tiles_n, (r * CL + CL - 1) / 2 + 1);
         g.T = T;
     } else {
-        g.T = g.tiles_m * g.tiles_n;
+        g.T = units_m * g.tiles_n;
     }
     g.D = ws.PD;
     for (int a = 0; a < OZ_MAXMOD; a++) { g.p[a] = hc.p[a]; g.m39[a] = hc.m39[a]; }
-    static SmemOptIn optin;
-    if ((e = optin.ensure(oz_gemm_kernel, OZ_SMEM)) != cudaSuccess) return e;
     const long long total = (long long)nbp * g.T;
-    const int grid = (int)std::min<long long>(NUM_SMS, total);
-    oz_gemm_kernel<<<grid, OZ_THREADS, OZ_SMEM, st>>>(tmA, tmB, g);
+    if (CL == 1) {
+        static SmemOptIn optin;
+        if ((e = optin.ensure(oz_gemm_kernel<1>, OZ_SMEM)) != cudaSuccess) return e;
+        const int grid = (int)std::min<long long>(NUM_SMS, total);
+        oz_gemm_kernel<1><<<grid, OZ_THREADS, OZ_SMEM, st>>>(tmA, tmB, g);
+    } else {
+        static SmemOptIn optin;
+        if ((e = optin.ensure(oz_gemm_kernel<2>, OZ_SMEM)) != cudaSuccess) return e;
+        cudaLaunchConfig_t cfg = {};
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.blockDim = dim3(OZ_THREADS); cfg.dynamicSmemBytes = OZ_SMEM; cfg.stream = st; cfg.attrs = attr; cfg.numAttrs = 1;
+        static int max_clusters[16] = {0};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (!max_clusters[dev & 15]) {       // clusters that are resident at once: a persistent grid must not exceed them
+            cfg.gridDim = dim3(NUM_SMS / 2 * 2);
+            int n = 0;
+            if (cudaOccupancyMaxActiveClusters(&n, oz_gemm_kernel<2>, &cfg) != cudaSuccess || n < 1) n = NUM_SMS / 2 - 4;
+            max_clusters[dev & 15] = std::min(n, NUM_SMS / 2);
+        }
+        const int ncl = (int)std::min<long long>(max_clusters[dev & 15], total);
+        cfg.gridDim = dim3(2 * ncl);
+        if ((e = cudaLaunchKernelEx(&cfg, oz_gemm_kernel<2>, tmA, tmB, g)) != cudaSuccess) return e;
+    }
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    hook(1, false, st);
     // CRT + scale + store
+    hook(2, true, st);
     OzCombArgs c;
     c.M = p.M; c.N = p.N; c.nmod = nmod; c.lower = p.lower; c.accumulate = p.accumulate; c.alpha = p.alpha; c.P = crt[nmod].P;
     for (int a = 0; a < OZ_MAXMOD; a++) { c.f2[a] = crt[nmod].f2[a]; c.f1[a] = crt[nmod].f1[a]; c.f0[a] = crt[nmod].f0[a]; }
@@ -712,6 +803,7 @@ cudaError_t oz_gemm(const GemmP& p, int layout, int nmod, OzWs& ws, cudaStream_t
         case 18: oz_combine_kernel<18><<<cgrid, 256, 0, st>>>(ws.PD, ws.sA, sBp, p.C, p.ldc, p.sC, c); break;
         default: oz_combine_kernel<0><<<cgrid, 256, 0, st>>>(ws.PD, ws.sA, sBp, p.C, p.ldc, p.sC, c); break;
     }
+    hook(2, false, st);
     return cudaGetLastError();
 }
 

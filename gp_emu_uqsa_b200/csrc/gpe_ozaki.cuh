@@ -28,15 +28,35 @@ struct OzWs {
     uint8_t *PA = nullptr, *PB = nullptr, *PD = nullptr;
     int *sA = nullptr, *sB = nullptr;
     size_t capA = 0, capB = 0, capD = 0, capS = 0;
+    // what PA / sA hold: a caller that knows the source is unchanged since the previous product on this stream may ask for
+    // the planes to be used again (the factorisation: L21 is an operand of two consecutive products)
+    struct Key {
+        const double* src; int ld; long long stride; int R, K, batch, nmod, bits, tri, kc;
+        bool operator==(const Key& o) const {
+            return src == o.src && ld == o.ld && stride == o.stride && R == o.R && K == o.K && batch == o.batch && nmod == o.nmod &&
+                   bits == o.bits && tri == o.tri && kc == o.kc;
+        }
+    };
+    Key key_a{};
+    bool have_a = false;
+    bool grew = false;           // set when a buffer was reallocated: captured graphs that used the old one are stale
     void release();
 };
 
 bool oz_supported(const GemmP& p, int epi);
 // largest operand width with K 2^(2 bits) < P/2
 int oz_operand_bits(int nmod, int K);
+// optional per-phase hook for event timing (phase 0 residue conversion, 1 residue GEMM, 2 CRT)
+struct OzHook {
+    void* ctx = nullptr;
+    void (*fn)(void* ctx, int phase, bool begin, cudaStream_t st) = nullptr;
+    void operator()(int phase, bool begin, cudaStream_t st) const { if (fn) fn(ctx, phase, begin, st); }
+};
+
 // makes sure `ws` can hold the planes of `p` (allocates: must not be called during stream capture when it has to grow)
 cudaError_t oz_reserve(OzWs& ws, const GemmP& p, int nmod, bool& grew, bool same_operand);
 // C = alpha op(A) op(B) (+ C), same meaning of every field of p and of `layout` as launch_gemm (EPI_STORE only)
-cudaError_t oz_gemm(const GemmP& p, int layout, int nmod, OzWs& ws, cudaStream_t st);
+cudaError_t oz_gemm(const GemmP& p, int layout, int nmod, OzWs& ws, cudaStream_t st, bool reuse_a = false,
+                    const OzHook& hook = OzHook());
 
 }  // namespace gpe

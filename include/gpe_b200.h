@@ -58,10 +58,11 @@ int gpe_set_async(gpe_handle* h, int on);
 int gpe_synchronize(gpe_handle* h);
 
 /* Optional per-launch CUDA-event timing by kernel category (measurement only; the reference's
- * unused @timeit helper, _emulatoroptimise.py:8-17, is the nearest analogue).  ms/count: 7 entries:
+ * unused @timeit helper, _emulatoroptimise.py:8-17, is the nearest analogue).  ms/count: 10 entries:
  * 0 DMMA GEMM (128-wide tiles; SYRK/TRMM updates of the factorisation and the prediction TRMM),
  * 1 small/skinny GEMM, 2 Cholesky leaf, 3 covariance build, 4 gradient reduction, 5 other,
- * 6 LAUUM (A^-1 = L^-T L^-1, the largest single launch of a likelihood evaluation). */
+ * 6 LAUUM (A^-1 = L^-T L^-1) on the DMMA route, 7 / 8 / 9 the INT8 tensor-core route of the large products
+ * (csrc/gpe_ozaki.cuh): residue conversion, residue GEMM (tcgen05.mma kind::i8), CRT recombination. */
 int gpe_profile_enable(gpe_handle* h, int on);
 int gpe_profile_read(gpe_handle* h, double* ms, long long* count, int reset);
 

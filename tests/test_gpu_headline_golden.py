@@ -49,9 +49,18 @@ def _sha16(a):
 MODES = {"gp4ml_k_fixT": 0, "gp4ml_k_fixF": 4, "mucm_k_fixT": 1, "gp4ml_alt_fixF": 2 | 4}
 
 
+# route: the default (the large products of the factorisation and LAUUM on the INT8 tensor cores, 16 moduli: csrc/gpe_ozaki.cuh),
+# the same with 18 moduli, and GPE_OZAKI=0 (FP64 DMMA everywhere).  The knob is read when the handle is created.
+@pytest.mark.parametrize("route", ["int8_default", "int8_18", "dmma"])
 @pytest.mark.parametrize("gfile", ["llh_n4096_d16_exact.npz", "llh_n4096_d16.npz", "llh_n4096_d16_mid.npz"])
-def test_llh_grad_matches_real_reference_at_n4096_d16(gfile):
+def test_llh_grad_matches_real_reference_at_n4096_d16(gfile, route, monkeypatch):
     from gp_emu_uqsa_b200 import _lib
+    if route == "dmma":
+        monkeypatch.setenv("GPE_OZAKI", "0")
+    elif route == "int8_18":
+        monkeypatch.setenv("GPE_OZAKI", "18")
+    else:
+        monkeypatch.delenv("GPE_OZAKI", raising=False)
     path = os.path.join(GOLDEN, gfile)
     if not os.path.exists(path):
         pytest.skip(gfile + " not generated")
@@ -83,7 +92,7 @@ def test_llh_grad_matches_real_reference_at_n4096_d16(gfile):
                 assert np.allclose(sig, G[tag + "_sigma"], rtol=1e-10, atol=0), (tag, "sigma")
     finally:
         dev.close()
-    print("n=4096 d=16 worst (llh rel, grad rel-to-max) per mode:", worst)
+    print("n=4096 d=16 route", route, "worst (llh rel, grad rel-to-max) per mode:", worst)
 
 
 def test_sensitivity_matches_real_reference_at_n2000_d8(tmp_path):

@@ -323,3 +323,30 @@ def test_int8_slice_gemm_emulation_reaches_float64_accuracy():
     L = np.linalg.cholesky(Acov)
     assert abs(ld - 2 * np.log(np.diag(L)).sum()) <= 1e-12 * abs(ld)
     assert np.abs(Li @ L - np.eye(300)).max() < 1e-9
+
+
+def test_modular_gemm_restatement_is_exact_up_to_the_operand_truncation():
+    """oracle/ozaki2_oracle.py (the CPU restatement the GPU test of csrc/gpe_ozaki.cu compares with bit for bit): the CRT in
+    96-bit fixed point returns the exact integer product of the truncated operands, rounded once; against the true product
+    the error is at float64 level relative to |A||B| for 16, 17 and 18 moduli."""
+    import math
+    from fractions import Fraction
+    from oracle import ozaki2_oracle as oz
+    assert all(math.gcd(p, q) == 1 for i, p in enumerate(oz.MODULI) for q in oz.MODULI[:i])
+    assert [oz.operand_bits(m, 4096) for m in (16, 17, 18)] == [56, 59, 63]
+    rng = np.random.default_rng(0)
+    M, N, K = 10, 9, 48
+    A = rng.standard_normal((M, K)) * np.exp(rng.uniform(-8, 8, (M, 1))) * np.exp(rng.uniform(-6, 0, (M, K)))
+    B = rng.standard_normal((N, K)) * np.exp(rng.uniform(-8, 8, (N, 1)))
+    A[3] = 0.0
+    true = np.array([[float(sum(Fraction(float(a)) * Fraction(float(b)) for a, b in zip(A[i], B[j]))) for j in range(N)]
+                     for i in range(M)])
+    sc = np.abs(A) @ np.abs(B).T + 1e-300
+    for nmod in (16, 17, 18):
+        C, aux = oz.emulated_gemm(A, B, nmod)
+        E = oz.exact_integer_product(aux["AI"], aux["BI"])
+        want = np.array([[math.ldexp(float(E[i, j]), -int(aux["sA"][i]) - int(aux["sB"][j])) if E[i, j] else 0.0
+                          for j in range(N)] for i in range(M)])
+        assert np.max(np.abs(C - want) / np.maximum(np.abs(want), 1e-300)) < 4e-16      # P is rounded to a double once
+        assert np.max(np.abs(C - true) / sc) < 3e-16
+        assert (C[3] == 0.0).all()
