@@ -26,6 +26,7 @@ struct OzConst {
     uint32_t clo[OZ_MAXMOD];    // bytes 256^0..256^3 mod p
     uint32_t chi[OZ_MAXMOD];    // bytes 256^4..256^7 mod p
     uint32_t c0[OZ_MAXMOD];     // (-2^63) mod p
+    uint32_t np[OZ_MAXMOD];     // -p mod 2^32 (a table entry, so that the compiler cannot turn q * np + t back into a negation and a multiply)
 };
 struct OzCrt {
     uint32_t f2[OZ_MAXMOD], f1[OZ_MAXMOD], f0[OZ_MAXMOD];   // floor(2^96 y_i / p_i), most significant limb first
@@ -51,6 +52,7 @@ static OzConst make_const() {
         uint32_t t = 1 % p;                 // 2^63 mod p
         for (int j = 0; j < 63; j++) t = (t * 2u) % p;
         c.c0[a] = (p - t) % p;
+        c.np[a] = 0u - p;
     }
     return c;
 }
@@ -140,12 +142,18 @@ __device__ __forceinline__ void oz_to_u64(double x, double p1, double p2, uint32
     hi = (uint32_t)(u >> 32);
 }
 __device__ __forceinline__ uint32_t oz_residue(uint32_t lo, uint32_t hi, uint32_t clo, uint32_t chi, uint32_t c0,
-                                               uint32_t m32, uint32_t p) {
+                                               uint32_t m32, uint32_t np) {
     uint32_t t = __dp4a(lo, clo, c0);
     t = __dp4a(hi, chi, t);
-    return t - __umulhi(t, m32) * p;
+    return __umulhi(t, m32) * np + t;       // np = -p (mod 2^32): one multiply-add, no separate negation on the FMA-heavy pipe
 }
 
+#ifndef OZ_COMB_MINB
+#define OZ_COMB_MINB 3
+#endif
+#ifndef OZ_CONV_MINB
+#define OZ_CONV_MINB 4
+#endif
 constexpr int OZ_CV = 8;      // consecutive k per thread in the conversion
 constexpr int OZ_TRI_G = 256; // granule of the k ranges of triangular operands (covers both the 128-row and the 256-row role)
 
@@ -162,15 +170,15 @@ __device__ __forceinline__ uint32_t oz_pack4(uint32_t r0, uint32_t r1, uint32_t 
 }
 // residues of eight values for modulus a, packed
 __device__ __forceinline__ uint2 oz_residues8(const uint32_t (&lo)[OZ_CV], const uint32_t (&hi)[OZ_CV], int a) {
-    const uint32_t clo = OZC.clo[a], chi = OZC.chi[a], c0 = OZC.c0[a], m32 = OZC.m32[a], p = OZC.p[a];
+    const uint32_t clo = OZC.clo[a], chi = OZC.chi[a], c0 = OZC.c0[a], m32 = OZC.m32[a], np = OZC.np[a];
     uint32_t r[OZ_CV];
 #pragma unroll
-    for (int j = 0; j < OZ_CV; j++) r[j] = oz_residue(lo[j], hi[j], clo, chi, c0, m32, p);
+    for (int j = 0; j < OZ_CV; j++) r[j] = oz_residue(lo[j], hi[j], clo, chi, c0, m32, np);
     return make_uint2(oz_pack4(r[0], r[1], r[2], r[3]), oz_pack4(r[4], r[5], r[6], r[7]));
 }
 
 // K-contiguous operand: one warp per row.
-__global__ void __launch_bounds__(256) oz_convert_kc_kernel(const double* __restrict__ src, int ld, long long sS, int R, int K,
+__global__ void __launch_bounds__(256, OZ_CONV_MINB) oz_convert_kc_kernel(const double* __restrict__ src, int ld, long long sS, int R, int K,
                                                             int nmod, int bits, int tri, uint8_t* __restrict__ planes,
                                                             int* __restrict__ sexp) {
     const int b = blockIdx.y;
@@ -267,7 +275,7 @@ struct OzGemmArgs {
     int kmode, lower;
     int tiles_m, tiles_n, T;     // tiles per plane product
     uint8_t* D;                  // [nbp][M][N]
-    uint32_t p[OZ_MAXMOD], m39[OZ_MAXMOD];
+    uint32_t p[OZ_MAXMOD], m39[OZ_MAXMOD], np[OZ_MAXMOD];
 };
 
 constexpr int OZ_STAGES = 4;
@@ -302,6 +310,12 @@ __device__ __forceinline__ void oz_tma_load(void* smem, const CUtensorMap* tm, i
             smem_u32(smem)),
         "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
         : "memory");
+}
+#ifndef OZ_PREFETCH
+#define OZ_PREFETCH 0
+#endif
+__device__ __forceinline__ void oz_tma_prefetch(const CUtensorMap* tm, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];\n" ::"l"(tm), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 __device__ __forceinline__ void oz_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
@@ -436,6 +450,10 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_gemm_kernel(const __grid_con
                         oz_tma_load_mc(sa + OZ_A_BYTES + rank * HB * OZ_BK, &tmB, kb * OZ_BK, tn * OZ_BN + rank * HB, bp,
                                        &full_bar[stage], MASK);
                     }
+                    if (OZ_PREFETCH > 0 && kb + OZ_PREFETCH < kb1) {      // pull the k block OZ_PREFETCH ahead into L2
+                        oz_tma_prefetch(&tmA, (kb + OZ_PREFETCH) * OZ_BK, tm * OZ_BM, bp);
+                        oz_tma_prefetch(&tmB, (kb + OZ_PREFETCH) * OZ_BK, tn * OZ_BN + (CL > 1 ? rank * (OZ_BN / CL) : 0), bp);
+                    }
                     if (++stage == OZ_STAGES) { stage = 0; phase ^= 1u; }
                 }
             }
@@ -486,7 +504,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_gemm_kernel(const __grid_con
             oz_unit<CL>(g, t, um, tn);
             const int tm = um * CL + rank;
             const int a = bp % g.nmod;
-            const uint32_t p = g.p[a], m39 = g.m39[a];
+            const uint32_t np = g.np[a], m39 = g.m39[a];
             mbar_wait(&tfull_bar[as], aphase);
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
             const int row = tm * OZ_BM + quad * 32 + lane;
@@ -512,7 +530,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_gemm_kernel(const __grid_con
                     for (int e = 0; e < 4; e++) {
                         const uint32_t x = v[4 * j + e];
                         const uint32_t q = (uint32_t)(((unsigned long long)x * m39) >> 39);
-                        r[e] = x - q * p;
+                        r[e] = q * np + x;
                     }
                     wv[j] = oz_pack4(r[0], r[1], r[2], r[3]);
                 }
@@ -544,7 +562,7 @@ struct OzCombArgs {
 // the top 64 bits read as a signed number centre the result in (-P/2, P/2).  NMOD > 0: the loop over the moduli is
 // unrolled so that all plane loads are in flight together.
 template <int NMOD>
-__global__ void __launch_bounds__(256, 2) oz_combine_kernel(const uint8_t* __restrict__ D, const int* __restrict__ sA,
+__global__ void __launch_bounds__(256, OZ_COMB_MINB) oz_combine_kernel(const uint8_t* __restrict__ D, const int* __restrict__ sA,
                                                          const int* __restrict__ sB, double* __restrict__ C, int ldc,
                                                          long long sC, const __grid_constant__ OzCombArgs g) {
     const int b = blockIdx.z;
@@ -554,9 +572,10 @@ __global__ void __launch_bounds__(256, 2) oz_combine_kernel(const uint8_t* __res
     const int nmod = NMOD > 0 ? NMOD : g.nmod;
     const uint8_t* d = D + ((size_t)b * nmod * g.M + row) * g.N + col;
     const size_t plane = (size_t)g.M * g.N;
-    unsigned long long a2[8], a1[8], a0[8];
+    unsigned long long a1[8], a0[8];
+    uint32_t a2[8];                           // only its low 32 bits reach the result: the sum is taken modulo 1
 #pragma unroll
-    for (int j = 0; j < 8; j++) a2[j] = a1[j] = a0[j] = 0ull;
+    for (int j = 0; j < 8; j++) { a2[j] = 0u; a1[j] = a0[j] = 0ull; }
     if (NMOD > 0) {
         uint2 w[NMOD > 0 ? NMOD : 1];
 #pragma unroll
@@ -567,7 +586,7 @@ __global__ void __launch_bounds__(256, 2) oz_combine_kernel(const uint8_t* __res
 #pragma unroll
             for (int j = 0; j < 8; j++) {
                 const uint32_t r = __byte_perm(j < 4 ? w[a].x : w[a].y, 0u, 0x4440 | (j & 3));
-                a2[j] += (unsigned long long)r * f2;
+                a2[j] += r * f2;
                 a1[j] += (unsigned long long)r * f1;
                 a0[j] += (unsigned long long)r * f0;
             }
@@ -579,7 +598,7 @@ __global__ void __launch_bounds__(256, 2) oz_combine_kernel(const uint8_t* __res
 #pragma unroll
             for (int j = 0; j < 8; j++) {
                 const uint32_t r = __byte_perm(j < 4 ? w.x : w.y, 0u, 0x4440 | (j & 3));
-                a2[j] += (unsigned long long)r * f2;
+                a2[j] += r * f2;
                 a1[j] += (unsigned long long)r * f1;
                 a0[j] += (unsigned long long)r * f0;
             }
@@ -749,8 +768,11 @@ cudaError_t oz_gemm(const GemmP& p, int layout, int nmod, OzWs& ws, cudaStream_t
     OzGemmArgs g;
     g.M = p.M; g.N = p.N; g.K = p.K; g.nmod = nmod; g.nbp = nbp; g.kmode = p.kmode; g.lower = p.lower;
     g.tiles_m = p.M / OZ_BM; g.tiles_n = p.N / OZ_BN;
-    static const int cl_env = [] { const char* e = getenv("GPE_OZAKI_CLUSTER"); return e ? atoi(e) : 2; }();
-    const int CL = (cl_env == 2 && g.tiles_m % 2 == 0) ? 2 : 1;
+    static const int cl_env = [] { const char* e = getenv("GPE_OZAKI_CLUSTER"); return e ? atoi(e) : 4; }();
+    // cluster size: row-triangular products (k <= i, k >= i) pay for a larger cluster with a coarser k range per unit
+    static const int cl_env_i = [] { const char* e = getenv("GPE_OZAKI_CLUSTER_I"); return e ? atoi(e) : 4; }();
+    const int cl_want = (p.kmode == KM_LE_I || p.kmode == KM_GE_I) ? std::min(cl_env, cl_env_i) : cl_env;
+    const int CL = (cl_want >= 4 && g.tiles_m % 4 == 0) ? 4 : ((cl_want >= 2 && g.tiles_m % 2 == 0) ? 2 : 1);
     if ((e = make_map(&tmB, PBp, p.K, p.N, nbp, OZ_BN / CL)) != cudaSuccess) return e;
     const int units_m = g.tiles_m / CL;
     if (p.lower) {
@@ -761,7 +783,7 @@ cudaError_t oz_gemm(const GemmP& p, int layout, int nmod, OzWs& ws, cudaStream_t
         g.T = units_m * g.tiles_n;
     }
     g.D = ws.PD;
-    for (int a = 0; a < OZ_MAXMOD; a++) { g.p[a] = hc.p[a]; g.m39[a] = hc.m39[a]; }
+    for (int a = 0; a < OZ_MAXMOD; a++) { g.p[a] = hc.p[a]; g.m39[a] = hc.m39[a]; g.np[a] = hc.np[a]; }
     const long long total = (long long)nbp * g.T;
     if (CL == 1) {
         static SmemOptIn optin;
@@ -769,25 +791,33 @@ cudaError_t oz_gemm(const GemmP& p, int layout, int nmod, OzWs& ws, cudaStream_t
         const int grid = (int)std::min<long long>(NUM_SMS, total);
         oz_gemm_kernel<1><<<grid, OZ_THREADS, OZ_SMEM, st>>>(tmA, tmB, g);
     } else {
-        static SmemOptIn optin;
-        if ((e = optin.ensure(oz_gemm_kernel<2>, OZ_SMEM)) != cudaSuccess) return e;
+        static SmemOptIn optin2, optin4;
+        if (CL == 2) e = optin2.ensure(oz_gemm_kernel<2>, OZ_SMEM);
+        else e = optin4.ensure(oz_gemm_kernel<4>, OZ_SMEM);
+        if (e != cudaSuccess) return e;
         cudaLaunchConfig_t cfg = {};
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.blockDim = dim3(OZ_THREADS); cfg.dynamicSmemBytes = OZ_SMEM; cfg.stream = st; cfg.attrs = attr; cfg.numAttrs = 1;
-        static int max_clusters[16] = {0};
+        static int max_clusters[16][5] = {{0}};
         int dev = 0;
         cudaGetDevice(&dev);
-        if (!max_clusters[dev & 15]) {       // clusters that are resident at once: a persistent grid must not exceed them
-            cfg.gridDim = dim3(NUM_SMS / 2 * 2);
+        int& mc = max_clusters[dev & 15][CL];
+        if (!mc) {       // clusters that are resident at once: a persistent grid must not exceed them
+            cfg.gridDim = dim3(NUM_SMS / CL * CL);
             int n = 0;
-            if (cudaOccupancyMaxActiveClusters(&n, oz_gemm_kernel<2>, &cfg) != cudaSuccess || n < 1) n = NUM_SMS / 2 - 4;
-            max_clusters[dev & 15] = std::min(n, NUM_SMS / 2);
+            cudaError_t qe = CL == 2 ? cudaOccupancyMaxActiveClusters(&n, oz_gemm_kernel<2>, &cfg)
+                                     : cudaOccupancyMaxActiveClusters(&n, oz_gemm_kernel<4>, &cfg);
+            if (qe != cudaSuccess || n < 1) n = NUM_SMS / CL - 4;
+            mc = std::min(n, NUM_SMS / CL);
+            if (getenv("GPE_OZAKI_VERBOSE")) fprintf(stderr, "oz_gemm: cluster %d, %d clusters resident\n", CL, mc);
         }
-        const int ncl = (int)std::min<long long>(max_clusters[dev & 15], total);
-        cfg.gridDim = dim3(2 * ncl);
-        if ((e = cudaLaunchKernelEx(&cfg, oz_gemm_kernel<2>, tmA, tmB, g)) != cudaSuccess) return e;
+        const int ncl = (int)std::min<long long>(mc, total);
+        cfg.gridDim = dim3(CL * ncl);
+        if (CL == 2) e = cudaLaunchKernelEx(&cfg, oz_gemm_kernel<2>, tmA, tmB, g);
+        else e = cudaLaunchKernelEx(&cfg, oz_gemm_kernel<4>, tmA, tmB, g);
+        if (e != cudaSuccess) return e;
     }
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     hook(1, false, st);
