@@ -38,6 +38,7 @@ def load():
         "gpe_destroy": (i, [p]),
         "gpe_last_error": (C.c_char_p, [p]),
         "gpe_launch_count": (ll, [p]),
+        "gpe_dbg_int8_products": (ll, [p]),
         "gpe_get_stream": (p, [p]),
         "gpe_set_streams": (i, [p, i]),
         "gpe_set_async": (i, [p, i]),
@@ -77,7 +78,7 @@ EXPORTS = ["gpe_version", "gpe_create", "gpe_destroy", "gpe_last_error", "gpe_la
            "gpe_set_training", "gpe_set_basis", "gpe_cov_build", "gpe_cov_grad", "gpe_cross_cov", "gpe_llh_grad_batch",
            "gpe_fit_state", "gpe_predict", "gpe_predict_grid", "gpe_predict_fullcov", "gpe_implausibility", "gpe_predict_implaus",
            "gpe_solve", "gpe_sens_contract", "gpe_sens_main_effect", "gpe_potrf", "gpe_pdist_argmin",
-           "gpe_dbg_gemm", "gpe_dbg_gemm_oz", "gpe_dbg_potrf_inv"]
+           "gpe_dbg_gemm", "gpe_dbg_gemm_oz", "gpe_dbg_potrf_inv", "gpe_dbg_int8_products"]
 
 
 def default_device_index():
@@ -142,6 +143,11 @@ class Device:
     @property
     def launches(self):
         return int(self.L.gpe_launch_count(self.h))
+
+    @property
+    def int8_products(self):
+        """Products sent down the INT8 tensor-core route so far (csrc/gpe_ozaki.cuh)."""
+        return int(self.L.gpe_dbg_int8_products(self.h))
 
     @property
     def stream_ptr(self):

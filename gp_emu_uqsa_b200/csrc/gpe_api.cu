@@ -157,7 +157,9 @@ static int run_gemm(gpe_handle* h, cudaStream_t st, const double* A, const doubl
     bool big = (M % 128 == 0 || epi == EPI_SUMSQ) && (N % 128 == 0) && N != 32 && M != 32;
     cudaError_t e;
     const bool reuse_a = h->oz_reuse_a;      // a request holds for one product only, whichever route it takes
+    const unsigned long long a_tag = h->oz_a_tag;
     h->oz_reuse_a = false;
+    h->oz_a_tag = 0;
     if (h->oz_nmod > 0 && M >= h->oz_min && N >= h->oz_min && K >= h->oz_min && oz_supported(p, epi)) {
         // INT8 tensor-core route (gpe_ozaki.cuh): scratch is per stream; growing it is not allowed inside a capture, and
         // every shape has been seen eagerly at least twice before its graph is captured
@@ -173,7 +175,7 @@ static int run_gemm(gpe_handle* h, cudaStream_t st, const double* A, const doubl
                 else x->h->prof_end(pc, x->e0[phase], s);
             };
         }
-        e = oz_gemm(p, layout, h->oz_nmod, ws, st, reuse_a, hook);
+        e = oz_gemm(p, layout, epi, h->oz_nmod, ws, st, reuse_a, a_tag, hook);
         h->launches += 4;
         h->oz_calls++;
         if (ws.grew) {          // (never during a capture: a shape is captured after it has run eagerly twice)
@@ -520,6 +522,7 @@ int gpe_profile_read(gpe_handle* h, double* ms, long long* count, int reset) {
 
 const char* gpe_last_error(gpe_handle* h) { return h ? h->err.c_str() : "null handle"; }
 long long gpe_launch_count(gpe_handle* h) { return h ? h->launches : 0; }
+long long gpe_dbg_int8_products(gpe_handle* h) { return h ? h->oz_calls : 0; }
 
 int gpe_set_training(gpe_handle* h, const double* X, const double* y, const double* H, const double* r,
                      int n, int d, int q) {
@@ -782,7 +785,7 @@ int gpe_dbg_gemm_oz(gpe_handle* h, const double* A, const double* B, double* C, 
     p.M = M; p.N = N; p.K = K; p.alpha = alpha; p.accumulate = accumulate; p.kmode = kmode; p.lower = lower; p.batch = batch;
     if (!oz_supported(p, EPI_STORE)) return h->fail_msg("gpe_dbg_gemm_oz: shape not supported by the INT8 route");
     OzWs& ws = h->oz_ws[h->st];
-    cudaError_t e = oz_gemm(p, layout, nmod, ws, h->st);
+    cudaError_t e = oz_gemm(p, layout, EPI_STORE, nmod, ws, h->st);
     if (e != cudaSuccess) return h->fail("oz_gemm", e);
     CK(cudaStreamSynchronize(h->st));
     const bool same = (A == B && lda == ldb && sA == sB && M == N && layout != 1);

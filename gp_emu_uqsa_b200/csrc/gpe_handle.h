@@ -97,6 +97,7 @@ struct gpe_handle {
     int oz_nmod = 16, oz_min = 1024, oz_nsub = 2;
     std::map<cudaStream_t, gpe::OzWs> oz_ws;
     long long oz_calls = 0;
+    unsigned long long oz_a_tag = 0, fit_gen = 0;   // tag of operand A for the next product; generation of the fit state
     bool oz_reuse_a = false;     // the next product may use the residue planes of operand A left by the previous one
 
     int fail(const char* what, cudaError_t e);

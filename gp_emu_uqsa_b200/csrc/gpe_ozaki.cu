@@ -155,15 +155,14 @@ __device__ __forceinline__ uint32_t oz_residue(uint32_t lo, uint32_t hi, uint32_
 #define OZ_CONV_MINB 4
 #endif
 constexpr int OZ_CV = 8;      // consecutive k per thread in the conversion
-constexpr int OZ_TRI_G = 256; // granule of the k ranges of triangular operands (covers both the 128-row and the 256-row role)
-
-// k range of row r that the residue GEMM can read: tri 0 all, 1 "k <= r" (up to the end of r's granule), 2 "k >= r"
-// (from the start of r's granule).  Nothing outside it is written or read.
+// k range of row r that the residue GEMM can read: tri 0 all, > 0 "k <= r" (up to the end of r's granule of `tri` rows),
+// < 0 "k >= r" (from the start of r's granule of `-tri` rows).  The granule is the row count of the GEMM's work unit for this
+// operand (128 x cluster size for the A role, 256 for the B role).  Nothing outside the range is written or read.
 __device__ __forceinline__ void oz_row_range(int tri, int r, int K, int& klo, int& khi) {
     klo = 0;
     khi = K;
-    if (tri == 1) khi = min(K, (r / OZ_TRI_G + 1) * OZ_TRI_G);
-    else if (tri == 2) klo = min(K, (r / OZ_TRI_G) * OZ_TRI_G);
+    if (tri > 0) khi = min(K, (r / tri + 1) * tri);
+    else if (tri < 0) klo = min(K, (r / -tri) * -tri);
 }
 __device__ __forceinline__ uint32_t oz_pack4(uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3) {
     return __byte_perm(__byte_perm(r0, r1, 0x0040), __byte_perm(r2, r3, 0x0040), 0x5410);   // PRMT: the ALU pipe is idle here
@@ -632,6 +631,82 @@ __global__ void __launch_bounds__(256, OZ_COMB_MINB) oz_combine_kernel(const uin
     }
 }
 
+// The same recombination for the prediction product Z = L^-1 C, of which only the column norms are wanted
+// (EPI_SUMSQ of the DMMA kernels): part[ti][col] = sum over the 128 rows of row tile ti of Z^2.  A CTA takes one row tile
+// and 256 columns; warp w walks rows 16 w .. 16 w + 15, thread = eight columns; the eight warps' sums meet in shared memory.
+template <int NMOD>
+__global__ void __launch_bounds__(256, 2) oz_combine_sumsq_kernel(const uint8_t* __restrict__ D, const int* __restrict__ sA,
+                                                                              const int* __restrict__ sB, double* __restrict__ part,
+                                                                              int ldp, const __grid_constant__ OzCombArgs g) {
+    __shared__ double red[8][256 + 8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ti = blockIdx.y;
+    const int col = blockIdx.x * 256 + lane * 8;
+    const int nmod = NMOD > 0 ? NMOD : g.nmod;
+    const size_t plane = (size_t)g.M * g.N;
+    const int4 sb0 = *reinterpret_cast<const int4*>(sB + col);
+    const int4 sb1 = *reinterpret_cast<const int4*>(sB + col + 4);
+    const int sbv[8] = {sb0.x, sb0.y, sb0.z, sb0.w, sb1.x, sb1.y, sb1.z, sb1.w};
+    double cs[8], acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) { cs[j] = oz_pow2(-sbv[j]); acc[j] = 0.0; }
+    for (int rr = 0; rr < 16; rr++) {
+        const int row = ti * 128 + warp * 16 + rr;
+        const uint8_t* d = D + (size_t)row * g.N + col;
+        unsigned long long a1[8], a0[8];
+        uint32_t a2[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) { a2[j] = 0u; a1[j] = a0[j] = 0ull; }
+        if (NMOD > 0) {
+            uint2 w[NMOD > 0 ? NMOD : 1];
+#pragma unroll
+            for (int a = 0; a < NMOD; a++) w[a] = __ldg(reinterpret_cast<const uint2*>(d + a * plane));
+#pragma unroll
+            for (int a = 0; a < NMOD; a++) {
+                const uint32_t f2 = g.f2[a], f1 = g.f1[a], f0 = g.f0[a];
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const uint32_t r = __byte_perm(j < 4 ? w[a].x : w[a].y, 0u, 0x4440 | (j & 3));
+                    a2[j] += r * f2;
+                    a1[j] += (unsigned long long)r * f1;
+                    a0[j] += (unsigned long long)r * f0;
+                }
+            }
+        } else {
+            for (int a = 0; a < nmod; a++) {
+                const uint2 w = __ldg(reinterpret_cast<const uint2*>(d + a * plane));
+                const uint32_t f2 = g.f2[a], f1 = g.f1[a], f0 = g.f0[a];
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const uint32_t r = __byte_perm(j < 4 ? w.x : w.y, 0u, 0x4440 | (j & 3));
+                    a2[j] += r * f2;
+                    a1[j] += (unsigned long long)r * f1;
+                    a0[j] += (unsigned long long)r * f0;
+                }
+            }
+        }
+        const double ra = oz_pow2(-sA[row]) * g.P;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const unsigned long long mid = a1[j] + (a0[j] >> 32);
+            const uint32_t top = (uint32_t)(a2[j] + (mid >> 32));
+            const long long hi64 = (long long)(((unsigned long long)top << 32) | (mid & 0xffffffffull));
+            const double frac = fma((double)(uint32_t)a0[j], 0x1p-96, (double)hi64 * 0x1p-64);
+            const double z = frac * ra * cs[j];
+            acc[j] = fma(z, z, acc[j]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; j++) red[warp][lane * 8 + j] = acc[j];
+    __syncthreads();
+    {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) s += red[w][threadIdx.x];
+        part[(size_t)ti * ldp + blockIdx.x * 256 + threadIdx.x] = s;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- host side
 void OzWs::release() {
     cudaFree(PA); cudaFree(PB); cudaFree(PD); cudaFree(sA); cudaFree(sB);
@@ -640,12 +715,16 @@ void OzWs::release() {
 }
 
 bool oz_supported(const GemmP& p, int epi) {
-    if (epi != EPI_STORE) return false;
+    if (epi == EPI_SUMSQ) {     // column norms of a single product (prediction): partials [M / 128][N]
+        if (p.batch != 1 || p.lower || p.accumulate) return false;
+    } else if (epi != EPI_STORE) {
+        return false;
+    }
     if (p.M % OZ_BM || p.N % OZ_BN || p.K % OZ_BK || p.K > 32768) return false;
     if ((p.kmode == KM_LE_J || p.kmode == KM_GE_J) && p.K != p.N) return false;
     if ((p.kmode == KM_LE_I || p.kmode == KM_GE_I) && p.K != p.M) return false;
     if (p.lower && p.M != p.N) return false;
-    if (p.ldc % 4 || ((uintptr_t)p.C & 31) || (p.sC % 4)) return false;
+    if (epi == EPI_STORE && (p.ldc % 4 || ((uintptr_t)p.C & 31) || (p.sC % 4))) return false;
     if (p.lda % 2 || p.ldb % 2 || ((uintptr_t)p.A & 15) || ((uintptr_t)p.B & 15) || (p.sA % 2) || (p.sB % 2)) return false;
     return true;
 }
@@ -728,8 +807,9 @@ static cudaError_t launch_convert(bool kc, const double* src, int ld, long long 
     return cudaGetLastError();
 }
 
-cudaError_t oz_gemm(const GemmP& p, int layout, int nmod, OzWs& ws, cudaStream_t st, bool reuse_a, const OzHook& hook) {
-    if (nmod < 2 || nmod > OZ_MAXMOD || !oz_supported(p, EPI_STORE)) return cudaErrorInvalidValue;
+cudaError_t oz_gemm(const GemmP& p, int layout, int epi, int nmod, OzWs& ws, cudaStream_t st, bool reuse_a, unsigned long long a_tag,
+                    const OzHook& hook) {
+    if (nmod < 2 || nmod > OZ_MAXMOD || !oz_supported(p, epi)) return cudaErrorInvalidValue;
     cudaError_t e;
     if ((e = upload_const()) != cudaSuccess) return e;
     static OzCrt crt[OZ_MAXMOD + 1];
@@ -742,15 +822,24 @@ cudaError_t oz_gemm(const GemmP& p, int layout, int nmod, OzWs& ws, cudaStream_t
     if (grew) { ws.have_a = false; ws.grew = true; }
     const int bits = oz_operand_bits(nmod, p.K);
     const bool a_kc = layout != 2, b_kc = layout == 0;
-    // k ranges of triangular operands (zero blocks are neither converted nor read)
-    const int triA = p.kmode == KM_LE_I ? 1 : (p.kmode == KM_GE_I ? 2 : 0);
-    const int triB = p.kmode == KM_LE_J ? 1 : (p.kmode == KM_GE_J ? 2 : 0);
+    // cluster size of the residue GEMM: row-triangular products (k <= i, k >= i) pay for a larger cluster with a coarser k
+    // range per unit
+    static const int cl_env = [] { const char* e = getenv("GPE_OZAKI_CLUSTER"); return e ? atoi(e) : 4; }();
+    static const int cl_env_i = [] { const char* e = getenv("GPE_OZAKI_CLUSTER_I"); return e ? atoi(e) : 4; }();
+    const int cl_want = (p.kmode == KM_LE_I || p.kmode == KM_GE_I) ? std::min(cl_env, cl_env_i) : cl_env;
+    const int tiles_m = p.M / OZ_BM;
+    const int CL = (cl_want >= 4 && tiles_m % 4 == 0) ? 4 : ((cl_want >= 2 && tiles_m % 2 == 0) ? 2 : 1);
+    // k ranges of triangular operands (zero blocks are neither converted nor read): granule = rows of the GEMM's work unit
+    const int gA = std::max(OZ_BM * CL, same ? OZ_BN : 0);
+    const int triA = p.kmode == KM_LE_I ? gA : (p.kmode == KM_GE_I ? -gA : 0);
+    const int triB = p.kmode == KM_LE_J ? OZ_BN : (p.kmode == KM_GE_J ? -OZ_BN : 0);
     hook(0, true, st);
     const OzWs::Key keyA{p.A, p.lda, p.sA, p.M, p.K, p.batch, nmod, bits, triA, a_kc ? 1 : 0};
-    if (!(reuse_a && ws.have_a && ws.key_a == keyA)) {
+    if (!(reuse_a && ws.have_a && ws.key_a == keyA && ws.tag_a == a_tag)) {
         if ((e = launch_convert(a_kc, p.A, p.lda, p.sA, p.M, p.K, nmod, bits, triA, ws.PA, ws.sA, p.batch, st)) != cudaSuccess) return e;
     }
     ws.key_a = keyA;
+    ws.tag_a = a_tag;
     ws.have_a = true;
     const uint8_t* PBp = ws.PA;
     const int* sBp = ws.sA;
@@ -768,11 +857,6 @@ cudaError_t oz_gemm(const GemmP& p, int layout, int nmod, OzWs& ws, cudaStream_t
     OzGemmArgs g;
     g.M = p.M; g.N = p.N; g.K = p.K; g.nmod = nmod; g.nbp = nbp; g.kmode = p.kmode; g.lower = p.lower;
     g.tiles_m = p.M / OZ_BM; g.tiles_n = p.N / OZ_BN;
-    static const int cl_env = [] { const char* e = getenv("GPE_OZAKI_CLUSTER"); return e ? atoi(e) : 4; }();
-    // cluster size: row-triangular products (k <= i, k >= i) pay for a larger cluster with a coarser k range per unit
-    static const int cl_env_i = [] { const char* e = getenv("GPE_OZAKI_CLUSTER_I"); return e ? atoi(e) : 4; }();
-    const int cl_want = (p.kmode == KM_LE_I || p.kmode == KM_GE_I) ? std::min(cl_env, cl_env_i) : cl_env;
-    const int CL = (cl_want >= 4 && g.tiles_m % 4 == 0) ? 4 : ((cl_want >= 2 && g.tiles_m % 2 == 0) ? 2 : 1);
     if ((e = make_map(&tmB, PBp, p.K, p.N, nbp, OZ_BN / CL)) != cudaSuccess) return e;
     const int units_m = g.tiles_m / CL;
     if (p.lower) {
@@ -826,6 +910,17 @@ cudaError_t oz_gemm(const GemmP& p, int layout, int nmod, OzWs& ws, cudaStream_t
     OzCombArgs c;
     c.M = p.M; c.N = p.N; c.nmod = nmod; c.lower = p.lower; c.accumulate = p.accumulate; c.alpha = p.alpha; c.P = crt[nmod].P;
     for (int a = 0; a < OZ_MAXMOD; a++) { c.f2[a] = crt[nmod].f2[a]; c.f1[a] = crt[nmod].f1[a]; c.f0[a] = crt[nmod].f0[a]; }
+    if (epi == EPI_SUMSQ) {
+        dim3 sgrid(p.N / 256, p.M / 128);
+        switch (nmod) {
+            case 16: oz_combine_sumsq_kernel<16><<<sgrid, 256, 0, st>>>(ws.PD, ws.sA, sBp, p.C, p.ldc, c); break;
+            case 17: oz_combine_sumsq_kernel<17><<<sgrid, 256, 0, st>>>(ws.PD, ws.sA, sBp, p.C, p.ldc, c); break;
+            case 18: oz_combine_sumsq_kernel<18><<<sgrid, 256, 0, st>>>(ws.PD, ws.sA, sBp, p.C, p.ldc, c); break;
+            default: oz_combine_sumsq_kernel<0><<<sgrid, 256, 0, st>>>(ws.PD, ws.sA, sBp, p.C, p.ldc, c); break;
+        }
+        hook(2, false, st);
+        return cudaGetLastError();
+    }
     dim3 cgrid(p.N / 256, p.M / 8, p.batch);
     switch (nmod) {
         case 16: oz_combine_kernel<16><<<cgrid, 256, 0, st>>>(ws.PD, ws.sA, sBp, p.C, p.ldc, p.sC, c); break;

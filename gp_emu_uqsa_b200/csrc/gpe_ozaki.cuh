@@ -38,6 +38,7 @@ struct OzWs {
         }
     };
     Key key_a{};
+    unsigned long long tag_a = 0; // caller's generation of the source (0: none)
     bool have_a = false;
     bool grew = false;           // set when a buffer was reallocated: captured graphs that used the old one are stale
     void release();
@@ -55,8 +56,10 @@ struct OzHook {
 
 // makes sure `ws` can hold the planes of `p` (allocates: must not be called during stream capture when it has to grow)
 cudaError_t oz_reserve(OzWs& ws, const GemmP& p, int nmod, bool& grew, bool same_operand);
-// C = alpha op(A) op(B) (+ C), same meaning of every field of p and of `layout` as launch_gemm (EPI_STORE only)
-cudaError_t oz_gemm(const GemmP& p, int layout, int nmod, OzWs& ws, cudaStream_t st, bool reuse_a = false,
-                    const OzHook& hook = OzHook());
+// C = alpha op(A) op(B) (+ C), same meaning of every field of p, of `layout` and of `epi` as launch_gemm (EPI_SUMSQ: batch 1).
+// reuse_a: the planes of operand A left on this stream by the previous call may be used again if they describe the same
+// operand and carry the same caller tag (the caller vouches that the source has not changed)
+cudaError_t oz_gemm(const GemmP& p, int layout, int epi, int nmod, OzWs& ws, cudaStream_t st, bool reuse_a = false,
+                    unsigned long long a_tag = 0, const OzHook& hook = OzHook());
 
 }  // namespace gpe

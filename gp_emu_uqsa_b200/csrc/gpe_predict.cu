@@ -612,7 +612,14 @@ int predict_chunk(gpe_handle* h, gpe_handle::PredSlot& sl, cudaStream_t st, cons
             const char* e = getenv("GPE_PRED_RAGGED");
             ragged = (e && e[0] == '0') ? 0 : 1;
         }
-        const int mp = ragged ? kp : np;
+        int mp = ragged ? kp : np;
+        // INT8 tensor-core route (gpe_ozaki.cuh) for chunks it supports: the residue planes of L^-1 are made once per fit and
+        // stream (the tag is the generation of the fit state), the padded size is used (rows >= n of Z are zero)
+        if (h->oz_nmod > 0 && np >= h->oz_min && np % 128 == 0 && mc >= h->oz_min && mc % 256 == 0) {
+            mp = np;
+            h->oz_reuse_a = true;
+            h->oz_a_tag = h->fit_gen;
+        }
         if ((rc = gpe_run_gemm_on(h, st, h->fLi, sl.C, sl.Part, np, mc, mc, 0, 0, 0, mp, mc, mp, 1.0, 0, KM_LE_I, 0, 1, 1, EPI_SUMSQ))) return rc;
         ntile = (mp + 127) / 128;
     }
@@ -684,6 +691,7 @@ int gpe_fit_state(gpe_handle* h, const double* delta, double nugget, double sigm
     h->fit_c = kind ? 1.0 : (1.0 - nugget);
     h->fit_astar = kind ? (1.0 + nugget * nugget) : 1.0;
     h->fitted = (st == 0);
+    h->fit_gen++;
     h->fAinv_valid = false;
     if (beta_out) CK(cudaMemcpy(beta_out, bopt.data(), sizeof(double) * q, cudaMemcpyDefault));
     double sm = std::sqrt(io.quad / ((double)(h->n - q) - 2.0));

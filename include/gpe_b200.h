@@ -220,6 +220,10 @@ int gpe_potrf(gpe_handle* h, const double* A, int n, int batch, double* L_out, d
 int gpe_dbg_potrf_inv(gpe_handle* h, const double* A, int n, int batch, double* Linv_out,
                       double* logdet, int* status);
 
+/* Debug/test entry: how many products this handle has sent down the INT8 tensor-core route so far (tests use it to
+ * assert which route a call took). */
+long long gpe_dbg_int8_products(gpe_handle* h);
+
 #ifdef __cplusplus
 }
 #endif

@@ -288,3 +288,58 @@ def test_fused_implausibility_equals_the_two_step_route(dev, golden_dir):
         assert np.array_equal(Itop.cpu().numpy(), Iref) and np.array_equal(keep, kref) and np.array_equal(res[0], cref)
     for dv in devs:
         dv.close()
+
+
+@pytest.mark.parametrize("n,d,m", [(1500, 6, 2300), (2000, 8, 4096), (1024, 3, 1024)])
+def test_int8_route_of_the_prediction_product_matches_dmma_and_the_oracle(n, d, m, monkeypatch):
+    """Chunks of 1024 points and more (a multiple of 256 after padding) over 1024 and more padded training points send
+    Z = L^-1 C down the INT8 tensor-core route (gpe_ozaki.cuh, column norms taken inside the CRT pass; the residue planes of
+    L^-1 are kept per fit).  Held against GPE_OZAKI=0 (FP64 DMMA) and, for the variance, against the oracle's route
+    (north_star: 1e-8), at a length-scale mix that makes L^-1 badly scaled."""
+    from gp_emu_uqsa_b200 import _lib
+    rng = np.random.default_rng(11 + n)
+    X = rng.random((n, d))
+    y = np.sin(X @ rng.normal(size=d)) + 0.1 * (X ** 2).sum(1)
+    H = O.make_H_linear(X)
+    Xs = rng.random((m, d))
+    delta = np.linspace(0.3, 1.5, d)
+    nugget, sigma = 1e-5, 1.3
+    res = {}
+    for route in ("dmma", "int8"):
+        if route == "dmma":
+            monkeypatch.setenv("GPE_OZAKI", "0")
+        else:
+            monkeypatch.delenv("GPE_OZAKI", raising=False)
+        dv = _lib.Device(0)
+        try:
+            dv.set_training(X, y, H, None)
+            dv.set_basis(list(range(d)), [1] * d)
+            _, _, st = dv.fit_state(delta, nugget, sigma, 0)
+            assert st == 0
+            before = dv.int8_products
+            mean, var = dv.predict(Xs)
+            took = dv.int8_products - before
+            # a second call re-uses the residue planes of L^-1 (same fit generation); a new fit must not
+            mean_b, var_b = dv.predict(Xs)
+            assert np.array_equal(mean_b, mean) and np.array_equal(var_b, var)
+            dv.fit_state(delta * 1.1, nugget, sigma, 0)
+            dv.predict(Xs[:1024])
+            dv.fit_state(delta, nugget, sigma, 0)
+            mean_c, var_c = dv.predict(Xs)
+            assert np.array_equal(mean_c, mean) and np.array_equal(var_c, var)
+            res[route] = (mean, var, took)
+        finally:
+            dv.close()
+    assert res["dmma"][2] == 0
+    assert res["int8"][2] >= 1, "the INT8 route was not taken"
+    # (the mean does not go through Z, but from npad = 2048 on the fit's own large products take the INT8 route too)
+    assert np.abs(res["int8"][0] - res["dmma"][0]).max() <= 1e-10 * np.abs(res["dmma"][0]).max()
+    vd, vi = res["dmma"][1], res["int8"][1]
+    scale = sigma ** 2                                                         # the prior variance the subtraction starts from
+    assert np.abs(vi - vd).max() <= 1e-10 * scale, np.abs(vi - vd).max() / scale
+    A = O.make_A(X, delta, nugget, 0)
+    beta = O.optimalbeta(A, H, y)
+    mref, Vref = O.posterior(Xs[:256], O.make_H_linear(Xs[:256]), X, y, H, A, beta, sigma, delta, nugget, 0)
+    vref = np.diag(Vref)
+    assert np.allclose(res["int8"][0][:256], mref, rtol=1e-8, atol=1e-10)
+    assert np.allclose(vi[:256], vref, rtol=1e-8, atol=1e-8 * np.abs(vref).max())
