@@ -192,6 +192,16 @@ def hbm_peak():
 
 
 # ------------------------------------------------------------------------------------------ CPU arm
+def int8_peak():
+    """INT8 tensor-pipe roof for the residue GEMM: twice the measured sustained bf16 rate."""
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return (2.0 * float(json.load(f)["bf16_tflops_sustained"]),
+                    "2 x bf16_tflops_sustained of MEASURED_PEAKS.json (kind::i8 issues at twice the bf16 rate on sm_100a: 4.5 vs 2.25 POP/s nominal)")
+    except Exception:
+        return 2.0 * 1367.4, "fallback: 2 x 1367.4 TFLOP/s (sustained bf16 of this pool's B200)"
+
+
 def _blas_info():
     info = {"host_cpus": os.cpu_count(), "usable_cores": _host_cores(), "numpy": np.__version__}
     try:
@@ -675,6 +685,18 @@ def run_b200(args):
         hbm, hbm_src = hbm_peak()
         fpp = flops_pred(N_PRED, D_PRED, D_PRED + 1)
         gms, gcnt = pprof["gemm_dmma_128"]
+        i8ms, i8cnt = pprof["int8_residue_gemm"]
+        p_int8 = None
+        if i8cnt:        # chunks of 1024 points and more over 1024 and more padded training points: the product runs on the INT8 route
+            p_nmod = int(os.environ.get("GPE_OZAKI", "16"))
+            i8_peak, i8_src = int8_peak()
+            i8_ach = p_nmod * float(mprof) * float(N_PRED) ** 2 / (i8ms * 1e-3) * 1e-12
+            p_int8 = {"kernel": "oz_gemm_kernel<4> (residue GEMM of Z = L^-1 C, k <= i: TMA, four-CTA multicast clusters, tcgen05.mma kind::i8, "
+                                "mod-p epilogue): %d launches" % i8cnt,
+                      "bound": "tensor", "unit": "TOP/s", "achieved": i8_ach, "peak": i8_peak, "frac": i8_ach / i8_peak, "peak_source": i8_src,
+                      "moduli": p_nmod, "algorithmic": "moduli x n^2 ops per point (the triangular product's FP64 flops)",
+                      "ms": i8ms, "residue_conversion_ms": pprof["int8_residue_conversion"][0],
+                      "crt_column_norms_ms": pprof["int8_crt_combine"][0]}
         ptraffic = {}
         for tp in ("r02_traffic.json", "r01_traffic.json"):
             tp = os.path.join(ROOT, "profiles", tp)
@@ -691,18 +713,24 @@ def run_b200(args):
                  "posterior_e2e_preds_per_s": me * world / pe, "posterior_d2h_bytes_per_pred": 16,
                  "posterior_roofline": {"bound": "tensor", "achieved": preds / world * fpp * 1e-12, "peak": peak,
                                         "unit": "TFLOP/s", "frac": preds / world * fpp * 1e-12 / peak,
-                                        "kernel": "gemm_dmma_ws_kernel<NN, EPI_SUMSQ> (Z = L^-1 C with fused column norms)",
-                                        "kernel_achieved": (float(mprof) * float(N_PRED) ** 2 * 1e-12) / (gms * 1e-3) if gms else None,
-                                        "kernel_launches": gcnt,
-                                        "traffic": ptraffic.get("trmm_dram_bytes_per_launch"),
+                                        "what": "FP64-equivalent: F_pred x preds/s per GPU against the measured FP64 DMMA roof" +
+                                                (" -- above 1 because Z = L^-1 C runs as exact INT8 residue GEMMs on the tcgen05 tensor cores "
+                                                 "(dominant_kernel carries that kernel's own INT8 roofline)" if p_int8 else ""),
+                                        "kernel": "oz_gemm_kernel<4> + oz_combine_sumsq_kernel (Z = L^-1 C by residues, column norms in the CRT pass)" if p_int8
+                                                  else "gemm_dmma_ws_kernel<NN, EPI_SUMSQ> (Z = L^-1 C with fused column norms)",
+                                        "kernel_achieved": ((float(mprof) * float(N_PRED) ** 2 * 1e-12) / (gms * 1e-3) if gms else None) if not p_int8 else
+                                                           (float(mprof) * float(N_PRED) ** 2 * 1e-12) / ((i8ms + pprof["int8_residue_conversion"][0] + pprof["int8_crt_combine"][0]) * 1e-3),
+                                        "kernel_launches": gcnt if not p_int8 else i8cnt,
+                                        "dominant_kernel": p_int8,
+                                        "traffic": ptraffic.get("pred_oz_gemm_dram_bytes_per_launch" if p_int8 else "trmm_dram_bytes_per_launch"),
                                         "algorithmic_bytes_per_point": 16,
                                         "by_kernel_ms": {k: v[0] for k, v in pprof.items()},
                                         "cross_covariance": {"ms": cov_ms, "launches": cov_cnt,
                                                              "tflops_alu": mprof * float(N_PRED) * (3 * D_PRED + 1) / (cov_ms * 1e-3) * 1e-12 if cov_ms else None,
                                                              "note": "FP64 ALU + exp work (n (3d + exp) flops per point), not tensor-pipe work"},
                                         "note": "achieved = F_pred (n^2 + 2n(d+q+3)) x preds/s per GPU; kernel_achieved = n^2 flops per "
-                                                "point / CUDA-event time of the TRMM launches in a separate serial-launch pass over "
-                                                "%d points" % mprof},
+                                                "point / CUDA-event time of the launches that evaluate Z and its column norms (DMMA: the TRMM; INT8: "
+                                                "conversion + residue GEMM + CRT) in a separate serial-launch pass over %d points" % mprof},
                  "history_match": {"points_per_s": float(total) / float(th.item()),
                                    "workload": "complete history-matching pass: 2 emulators predicted over the grid with the implausibility "
                                                "folded into the prediction (cm=3, maxno=1): keep mask, count and per-cell min / count over the "
@@ -789,20 +817,14 @@ def run_b200(args):
                 return f + rec(m1) + rec(m2)
             f64_flops = rec(npad) + (float(npad) ** 3 / 3.0 if takes(npad, npad, npad) else 0.0)
             i8_ops = B * nmod * f64_flops                       # one u8 x u8 -> s32 product per modulus
-            i8_peak = None
-            try:
-                with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-                    i8_peak = 2.0 * float(json.load(f)["bf16_tflops_sustained"])
-                i8_src = "2 x bf16_tflops_sustained of MEASURED_PEAKS.json (kind::i8 issues at twice the bf16 rate on sm_100a: 4.5 vs 2.25 POP/s nominal)"
-            except Exception:
-                i8_peak, i8_src = 2.0 * 1367.4, "fallback: 2 x 1367.4 TFLOP/s (sustained bf16 of this pool's B200)"
+            i8_peak, i8_src = int8_peak()
             i8_ach = i8_ops * Kp_ / (oz_ms * 1e-3) * 1e-12
             i8_traffic = None
             tp = os.path.join(ROOT, "profiles", "r02_traffic_int8.json")
             if os.path.exists(tp):
                 with open(tp) as f:
                     i8_traffic = json.load(f)
-            int8 = {"kernel": "oz_gemm_kernel<2> (residue GEMM: TMA 128B-swizzled tiles, two-CTA multicast clusters, tcgen05.mma kind::i8, "
+            int8 = {"kernel": "oz_gemm_kernel<4> (residue GEMM: TMA 128B-swizzled tiles, four-CTA multicast clusters, tcgen05.mma kind::i8, "
                               "TMEM double-buffered accumulator, mod-p epilogue): %d launches per step" % (oz_cnt // Kp_),
                     "bound": "tensor", "unit": "TOP/s", "achieved": i8_ach, "peak": i8_peak, "frac": i8_ach / i8_peak,
                     "peak_source": i8_src,

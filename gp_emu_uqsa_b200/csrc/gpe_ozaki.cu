@@ -272,6 +272,7 @@ __global__ void __launch_bounds__(256) oz_convert_t_kernel(const double* __restr
 struct OzGemmArgs {
     int M, N, K, nmod, nbp;      // nbp = items * nmod plane products
     int kmode, lower;
+    int nmajor;                  // one operand much larger than L2 (prediction): units that share a tile of it are consecutive (oz_unit)
     int tiles_m, tiles_n, T;     // tiles per plane product
     uint8_t* D;                  // [nbp][M][N]
     uint32_t p[OZ_MAXMOD], m39[OZ_MAXMOD], np[OZ_MAXMOD];
@@ -338,9 +339,29 @@ __device__ __forceinline__ void oz_unit(const OzGemmArgs& g, int t, int& um, int
         return;
     }
     switch (g.kmode) {
-        case KM_LE_J: tn = g.tiles_n - 1 - t / units_m; um = t % units_m; break;
+        case KM_LE_J:
+            if (g.nmajor) {       // the mirror image: a tall A (the prediction product with its roles swapped), tn fastest, rotated
+                um = t / g.tiles_n;
+                tn = g.tiles_n - 1 - (t % g.tiles_n + um) % g.tiles_n;
+            } else {
+                tn = g.tiles_n - 1 - t / units_m;
+                um = t % units_m;
+            }
+            break;
         case KM_GE_J: tn = t / units_m; um = t % units_m; break;
-        case KM_LE_I: um = units_m - 1 - t / g.tiles_n; tn = t % g.tiles_n; break;
+        case KM_LE_I:
+            if (g.nmajor) {
+                // a wide B (the prediction's 65 536 points: 134 MB per plane, more than L2): the units_m units of one column
+                // tile are consecutive, so the clusters that run side by side read that tile of B from L2 and DRAM sees it
+                // once; the row unit is rotated by tn so that a cluster's static sequence (stride = number of clusters) walks
+                // through all k ranges whatever the two counts' common divisor
+                tn = t / units_m;
+                um = units_m - 1 - (t % units_m + tn) % units_m;
+            } else {
+                um = units_m - 1 - t / g.tiles_n;
+                tn = t % g.tiles_n;
+            }
+            break;
         default: um = t / g.tiles_n; tn = t % g.tiles_n; break;
     }
 }
@@ -707,6 +728,78 @@ __global__ void __launch_bounds__(256, 2) oz_combine_sumsq_kernel(const uint8_t*
     }
 }
 
+// Row norms: the prediction product with its roles swapped, Z^T = C^T L^-T (rows = points, columns = training points), so
+// that the triangular factor sits on the column side, where the k range of a unit is exact to 256 whatever the cluster size.
+// out[row] = sum over all N columns of (Z^T)^2.  A warp takes one row at a time (ROWS_PER_CTA / 8 rows per warp), a lane eight
+// consecutive columns of each 256-column segment; the lanes' sums meet by shuffles.
+constexpr int OZ_RS_ROWS = 32;
+template <int NMOD>
+__global__ void __launch_bounds__(256, 2) oz_combine_rowsumsq_kernel(const uint8_t* __restrict__ D, const int* __restrict__ sA,
+                                                                     const int* __restrict__ sB, double* __restrict__ out,
+                                                                     const __grid_constant__ OzCombArgs g) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nmod = NMOD > 0 ? NMOD : g.nmod;
+    const size_t plane = (size_t)g.M * g.N;
+    for (int rr = 0; rr < OZ_RS_ROWS / 8; rr++) {
+        const int row = blockIdx.x * OZ_RS_ROWS + rr * 8 + warp;
+        double acc = 0.0;
+        for (int c0 = 0; c0 < g.N; c0 += 256) {
+            const int col = c0 + lane * 8;
+            const uint8_t* d = D + (size_t)row * g.N + col;
+            unsigned long long a1[8], a0[8];
+            uint32_t a2[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) { a2[j] = 0u; a1[j] = a0[j] = 0ull; }
+            if (NMOD > 0) {
+                uint2 w[NMOD > 0 ? NMOD : 1];
+#pragma unroll
+                for (int a = 0; a < NMOD; a++) w[a] = __ldg(reinterpret_cast<const uint2*>(d + a * plane));
+#pragma unroll
+                for (int a = 0; a < NMOD; a++) {
+                    const uint32_t f2 = g.f2[a], f1 = g.f1[a], f0 = g.f0[a];
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        const uint32_t r = __byte_perm(j < 4 ? w[a].x : w[a].y, 0u, 0x4440 | (j & 3));
+                        a2[j] += r * f2;
+                        a1[j] += (unsigned long long)r * f1;
+                        a0[j] += (unsigned long long)r * f0;
+                    }
+                }
+            } else {
+                for (int a = 0; a < nmod; a++) {
+                    const uint2 w = __ldg(reinterpret_cast<const uint2*>(d + a * plane));
+                    const uint32_t f2 = g.f2[a], f1 = g.f1[a], f0 = g.f0[a];
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        const uint32_t r = __byte_perm(j < 4 ? w.x : w.y, 0u, 0x4440 | (j & 3));
+                        a2[j] += r * f2;
+                        a1[j] += (unsigned long long)r * f1;
+                        a0[j] += (unsigned long long)r * f0;
+                    }
+                }
+            }
+            const int4 sb0 = *reinterpret_cast<const int4*>(sB + col);
+            const int4 sb1 = *reinterpret_cast<const int4*>(sB + col + 4);
+            const int sbv[8] = {sb0.x, sb0.y, sb0.z, sb0.w, sb1.x, sb1.y, sb1.z, sb1.w};
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const unsigned long long mid = a1[j] + (a0[j] >> 32);
+                const uint32_t top = (uint32_t)(a2[j] + (mid >> 32));
+                const long long hi64 = (long long)(((unsigned long long)top << 32) | (mid & 0xffffffffull));
+                const double frac = fma((double)(uint32_t)a0[j], 0x1p-96, (double)hi64 * 0x1p-64);
+                const double z = frac * g.P * oz_pow2(-sbv[j]);      // the row's own scale is applied once, to the sum
+                acc = fma(z, z, acc);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) {
+            const double ra = oz_pow2(-sA[row]);
+            out[row] = acc * ra * ra;
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- host side
 void OzWs::release() {
     cudaFree(PA); cudaFree(PB); cudaFree(PD); cudaFree(sA); cudaFree(sB);
@@ -727,6 +820,11 @@ bool oz_supported(const GemmP& p, int epi) {
     if (epi == EPI_STORE && (p.ldc % 4 || ((uintptr_t)p.C & 31) || (p.sC % 4))) return false;
     if (p.lda % 2 || p.ldb % 2 || ((uintptr_t)p.A & 15) || ((uintptr_t)p.B & 15) || (p.sA % 2) || (p.sB % 2)) return false;
     return true;
+}
+
+bool oz_sumsq_swapped(const GemmP& p, int epi) {
+    static const int swap_env = [] { const char* e = getenv("GPE_OZAKI_SUMSQ_SWAP"); return e ? atoi(e) : 1; }();
+    return swap_env && epi == EPI_SUMSQ && p.kmode == KM_LE_I && p.M % OZ_BN == 0 && p.N % OZ_BM == 0 && p.N % OZ_RS_ROWS == 0;
 }
 
 static bool same_operand(const GemmP& p, int layout) {
@@ -822,15 +920,20 @@ cudaError_t oz_gemm(const GemmP& p, int layout, int epi, int nmod, OzWs& ws, cud
     if (grew) { ws.have_a = false; ws.grew = true; }
     const int bits = oz_operand_bits(nmod, p.K);
     const bool a_kc = layout != 2, b_kc = layout == 0;
+    // column norms of Z = A B with A lower triangular (prediction): run as Z^T = B^T A^T, the triangular factor on the column side
+    const bool swap = oz_sumsq_swapped(p, epi);
     // cluster size of the residue GEMM: row-triangular products (k <= i, k >= i) pay for a larger cluster with a coarser k
     // range per unit
     static const int cl_env = [] { const char* e = getenv("GPE_OZAKI_CLUSTER"); return e ? atoi(e) : 4; }();
     static const int cl_env_i = [] { const char* e = getenv("GPE_OZAKI_CLUSTER_I"); return e ? atoi(e) : 4; }();
-    const int cl_want = (p.kmode == KM_LE_I || p.kmode == KM_GE_I) ? std::min(cl_env, cl_env_i) : cl_env;
-    const int tiles_m = p.M / OZ_BM;
+    static const int cl_env_s = [] { const char* e = getenv("GPE_OZAKI_CLUSTER_SUMSQ"); return e ? atoi(e) : 2; }();
+    // (the prediction product -- one item, 65 536 columns, k <= i -- measured 13.6 Mpred/s with pairs against 13.35 with quadruples)
+    const int cl_want = swap ? cl_env : (epi == EPI_SUMSQ ? std::min(cl_env, cl_env_s)
+                                         : ((p.kmode == KM_LE_I || p.kmode == KM_GE_I) ? std::min(cl_env, cl_env_i) : cl_env));
+    const int tiles_m = (swap ? p.N : p.M) / OZ_BM;
     const int CL = (cl_want >= 4 && tiles_m % 4 == 0) ? 4 : ((cl_want >= 2 && tiles_m % 2 == 0) ? 2 : 1);
     // k ranges of triangular operands (zero blocks are neither converted nor read): granule = rows of the GEMM's work unit
-    const int gA = std::max(OZ_BM * CL, same ? OZ_BN : 0);
+    const int gA = swap ? OZ_BN : std::max(OZ_BM * CL, same ? OZ_BN : 0);
     const int triA = p.kmode == KM_LE_I ? gA : (p.kmode == KM_GE_I ? -gA : 0);
     const int triB = p.kmode == KM_LE_J ? OZ_BN : (p.kmode == KM_GE_J ? -OZ_BN : 0);
     hook(0, true, st);
@@ -853,11 +956,21 @@ cudaError_t oz_gemm(const GemmP& p, int layout, int epi, int nmod, OzWs& ws, cud
     hook(1, true, st);
     CUtensorMap tmA, tmB;
     const int nbp = p.batch * nmod;
-    if ((e = make_map(&tmA, ws.PA, p.K, p.M, nbp, OZ_BM)) != cudaSuccess) return e;
     OzGemmArgs g;
-    g.M = p.M; g.N = p.N; g.K = p.K; g.nmod = nmod; g.nbp = nbp; g.kmode = p.kmode; g.lower = p.lower;
-    g.tiles_m = p.M / OZ_BM; g.tiles_n = p.N / OZ_BN;
-    if ((e = make_map(&tmB, PBp, p.K, p.N, nbp, OZ_BN / CL)) != cudaSuccess) return e;
+    if (swap) {
+        if ((e = make_map(&tmA, PBp, p.K, p.N, nbp, OZ_BM)) != cudaSuccess) return e;
+        g.M = p.N; g.N = p.M; g.kmode = KM_LE_J;
+        g.tiles_m = p.N / OZ_BM; g.tiles_n = p.M / OZ_BN;
+        if ((e = make_map(&tmB, ws.PA, p.K, p.M, nbp, OZ_BN / CL)) != cudaSuccess) return e;
+    } else {
+        if ((e = make_map(&tmA, ws.PA, p.K, p.M, nbp, OZ_BM)) != cudaSuccess) return e;
+        g.M = p.M; g.N = p.N; g.kmode = p.kmode;
+        g.tiles_m = p.M / OZ_BM; g.tiles_n = p.N / OZ_BN;
+        if ((e = make_map(&tmB, PBp, p.K, p.N, nbp, OZ_BN / CL)) != cudaSuccess) return e;
+    }
+    g.K = p.K; g.nmod = nmod; g.nbp = nbp; g.lower = p.lower;
+    static const int nmajor_env = [] { const char* e = getenv("GPE_OZAKI_NMAJOR"); return e ? atoi(e) : 1; }();
+    g.nmajor = (nmajor_env && !p.lower && (swap || (p.kmode == KM_LE_I && g.tiles_n > 2 * (g.tiles_m / CL)))) ? 1 : 0;
     const int units_m = g.tiles_m / CL;
     if (p.lower) {
         int T = 0;
@@ -910,9 +1023,25 @@ cudaError_t oz_gemm(const GemmP& p, int layout, int epi, int nmod, OzWs& ws, cud
     OzCombArgs c;
     c.M = p.M; c.N = p.N; c.nmod = nmod; c.lower = p.lower; c.accumulate = p.accumulate; c.alpha = p.alpha; c.P = crt[nmod].P;
     for (int a = 0; a < OZ_MAXMOD; a++) { c.f2[a] = crt[nmod].f2[a]; c.f1[a] = crt[nmod].f1[a]; c.f0[a] = crt[nmod].f0[a]; }
+    if (swap) {
+        c.M = p.N; c.N = p.M;
+        const unsigned rgrid = (unsigned)(p.N / OZ_RS_ROWS);
+        switch (nmod) {
+            case 14: oz_combine_rowsumsq_kernel<14><<<rgrid, 256, 0, st>>>(ws.PD, sBp, ws.sA, p.C, c); break;
+            case 15: oz_combine_rowsumsq_kernel<15><<<rgrid, 256, 0, st>>>(ws.PD, sBp, ws.sA, p.C, c); break;
+            case 16: oz_combine_rowsumsq_kernel<16><<<rgrid, 256, 0, st>>>(ws.PD, sBp, ws.sA, p.C, c); break;
+            case 17: oz_combine_rowsumsq_kernel<17><<<rgrid, 256, 0, st>>>(ws.PD, sBp, ws.sA, p.C, c); break;
+            case 18: oz_combine_rowsumsq_kernel<18><<<rgrid, 256, 0, st>>>(ws.PD, sBp, ws.sA, p.C, c); break;
+            default: oz_combine_rowsumsq_kernel<0><<<rgrid, 256, 0, st>>>(ws.PD, sBp, ws.sA, p.C, c); break;
+        }
+        hook(2, false, st);
+        return cudaGetLastError();
+    }
     if (epi == EPI_SUMSQ) {
         dim3 sgrid(p.N / 256, p.M / 128);
         switch (nmod) {
+            case 14: oz_combine_sumsq_kernel<14><<<sgrid, 256, 0, st>>>(ws.PD, ws.sA, sBp, p.C, p.ldc, c); break;
+            case 15: oz_combine_sumsq_kernel<15><<<sgrid, 256, 0, st>>>(ws.PD, ws.sA, sBp, p.C, p.ldc, c); break;
             case 16: oz_combine_sumsq_kernel<16><<<sgrid, 256, 0, st>>>(ws.PD, ws.sA, sBp, p.C, p.ldc, c); break;
             case 17: oz_combine_sumsq_kernel<17><<<sgrid, 256, 0, st>>>(ws.PD, ws.sA, sBp, p.C, p.ldc, c); break;
             case 18: oz_combine_sumsq_kernel<18><<<sgrid, 256, 0, st>>>(ws.PD, ws.sA, sBp, p.C, p.ldc, c); break;
@@ -923,6 +1052,8 @@ cudaError_t oz_gemm(const GemmP& p, int layout, int epi, int nmod, OzWs& ws, cud
     }
     dim3 cgrid(p.N / 256, p.M / 8, p.batch);
     switch (nmod) {
+        case 14: oz_combine_kernel<14><<<cgrid, 256, 0, st>>>(ws.PD, ws.sA, sBp, p.C, p.ldc, p.sC, c); break;
+        case 15: oz_combine_kernel<15><<<cgrid, 256, 0, st>>>(ws.PD, ws.sA, sBp, p.C, p.ldc, p.sC, c); break;
         case 16: oz_combine_kernel<16><<<cgrid, 256, 0, st>>>(ws.PD, ws.sA, sBp, p.C, p.ldc, p.sC, c); break;
         case 17: oz_combine_kernel<17><<<cgrid, 256, 0, st>>>(ws.PD, ws.sA, sBp, p.C, p.ldc, p.sC, c); break;
         case 18: oz_combine_kernel<18><<<cgrid, 256, 0, st>>>(ws.PD, ws.sA, sBp, p.C, p.ldc, p.sC, c); break;

@@ -54,6 +54,9 @@ struct OzHook {
     void operator()(int phase, bool begin, cudaStream_t st) const { if (fn) fn(ctx, phase, begin, st); }
 };
 
+// column norms (EPI_SUMSQ, k <= i) evaluated with the roles swapped -- Z^T = B^T A^T, row norms: the output is then ONE row of
+// partial sums, C[0 .. N), instead of M / 128 rows
+bool oz_sumsq_swapped(const GemmP& p, int epi);
 // makes sure `ws` can hold the planes of `p` (allocates: must not be called during stream capture when it has to grow)
 cudaError_t oz_reserve(OzWs& ws, const GemmP& p, int nmod, bool& grew, bool same_operand);
 // C = alpha op(A) op(B) (+ C), same meaning of every field of p, of `layout` and of `epi` as launch_gemm (EPI_SUMSQ: batch 1).

@@ -615,13 +615,20 @@ int predict_chunk(gpe_handle* h, gpe_handle::PredSlot& sl, cudaStream_t st, cons
         int mp = ragged ? kp : np;
         // INT8 tensor-core route (gpe_ozaki.cuh) for chunks it supports: the residue planes of L^-1 are made once per fit and
         // stream (the tag is the generation of the fit state), the padded size is used (rows >= n of Z are zero)
-        if (h->oz_nmod > 0 && np >= h->oz_min && np % 128 == 0 && mc >= h->oz_min && mc % 256 == 0) {
-            mp = np;
-            h->oz_reuse_a = true;
-            h->oz_a_tag = h->fit_gen;
+        bool one_row = false;
+        if (h->oz_nmod > 0 && np >= h->oz_min && mc >= h->oz_min) {
+            GemmP p;
+            p.A = h->fLi; p.B = sl.C; p.C = sl.Part; p.lda = np; p.ldb = mc; p.ldc = mc; p.sA = p.sB = p.sC = 0;
+            p.M = np; p.N = mc; p.K = np; p.alpha = 1.0; p.accumulate = 0; p.kmode = KM_LE_I; p.lower = 0; p.batch = 1;
+            if (oz_supported(p, EPI_SUMSQ)) {
+                mp = np;
+                h->oz_reuse_a = true;
+                h->oz_a_tag = h->fit_gen;
+                one_row = oz_sumsq_swapped(p, EPI_SUMSQ);
+            }
         }
         if ((rc = gpe_run_gemm_on(h, st, h->fLi, sl.C, sl.Part, np, mc, mc, 0, 0, 0, mp, mc, mp, 1.0, 0, KM_LE_I, 0, 1, 1, EPI_SUMSQ))) return rc;
-        ntile = (mp + 127) / 128;
+        ntile = one_row ? 1 : (mp + 127) / 128;
     }
     {
         ProfScope ps(h, gpe_handle::CAT_OTHER, st);

@@ -290,7 +290,7 @@ def test_fused_implausibility_equals_the_two_step_route(dev, golden_dir):
         dv.close()
 
 
-@pytest.mark.parametrize("n,d,m", [(1500, 6, 2300), (2000, 8, 4096), (1024, 3, 1024)])
+@pytest.mark.parametrize("n,d,m", [(1500, 6, 2300), (2000, 8, 4096), (1024, 3, 1024), (1100, 5, 2048)])
 def test_int8_route_of_the_prediction_product_matches_dmma_and_the_oracle(n, d, m, monkeypatch):
     """Chunks of 1024 points and more (a multiple of 256 after padding) over 1024 and more padded training points send
     Z = L^-1 C down the INT8 tensor-core route (gpe_ozaki.cuh, column norms taken inside the CRT pass; the residue planes of
