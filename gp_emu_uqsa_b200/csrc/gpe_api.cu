@@ -158,12 +158,15 @@ static int run_gemm(gpe_handle* h, cudaStream_t st, const double* A, const doubl
     cudaError_t e;
     const bool reuse_a = h->oz_reuse_a;      // a request holds for one product only, whichever route it takes
     const unsigned long long a_tag = h->oz_a_tag;
+    const double b_bound = h->oz_b_bound;
     h->oz_reuse_a = false;
     h->oz_a_tag = 0;
+    h->oz_b_bound = 0.0;
     if (h->oz_nmod > 0 && M >= h->oz_min && N >= h->oz_min && K >= h->oz_min && oz_supported(p, epi)) {
         // INT8 tensor-core route (gpe_ozaki.cuh): scratch is per stream; growing it is not allowed inside a capture, and
         // every shape has been seen eagerly at least twice before its graph is captured
         OzWs& ws = h->oz_ws[st];
+        ws.b_bound = b_bound;
         struct HookCtx { gpe_handle* h; cudaEvent_t e0[3]; } hc{h, {nullptr, nullptr, nullptr}};
         OzHook hook;
         if (h->prof_on) {       // per-phase event pairs: residue conversion, residue GEMM, CRT

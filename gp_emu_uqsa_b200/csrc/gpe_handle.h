@@ -98,6 +98,7 @@ struct gpe_handle {
     std::map<cudaStream_t, gpe::OzWs> oz_ws;
     long long oz_calls = 0;
     unsigned long long oz_a_tag = 0, fit_gen = 0;   // tag of operand A for the next product; generation of the fit state
+    double oz_b_bound = 0.0;     // the next product's operand B is bounded by this in magnitude (0: unknown; one product only)
     bool oz_reuse_a = false;     // the next product may use the residue planes of operand A left by the previous one
 
     int fail(const char* what, cudaError_t e);

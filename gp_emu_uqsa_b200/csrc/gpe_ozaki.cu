@@ -179,7 +179,7 @@ __device__ __forceinline__ uint2 oz_residues8(const uint32_t (&lo)[OZ_CV], const
 // K-contiguous operand: one warp per row.
 __global__ void __launch_bounds__(256, OZ_CONV_MINB) oz_convert_kc_kernel(const double* __restrict__ src, int ld, long long sS, int R, int K,
                                                             int nmod, int bits, int tri, uint8_t* __restrict__ planes,
-                                                            int* __restrict__ sexp) {
+                                                            int* __restrict__ sexp, double fixed_max) {
     const int b = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int r = blockIdx.x * 8 + warp;
@@ -188,13 +188,15 @@ __global__ void __launch_bounds__(256, OZ_CONV_MINB) oz_convert_kc_kernel(const 
     uint8_t* Pb = planes + (size_t)b * nmod * R * K;
     int klo, khi;
     oz_row_range(tri, r, K, klo, khi);
-    double mx = 0.0;
-    for (int k = klo + lane * 2; k < khi; k += 64) {
-        const double2 v = *reinterpret_cast<const double2*>(row + k);
-        mx = fmax(mx, fmax(fabs(v.x), fabs(v.y)));
-    }
+    double mx = fixed_max;          // > 0: the caller's bound on |x| replaces the pass over the row (one scale for all rows)
+    if (!(fixed_max > 0.0)) {
+        for (int k = klo + lane * 2; k < khi; k += 64) {
+            const double2 v = *reinterpret_cast<const double2*>(row + k);
+            mx = fmax(mx, fmax(fabs(v.x), fabs(v.y)));
+        }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
     const int s = oz_scale_exp(mx, bits);
     if (lane == 0) sexp[(size_t)b * R + r] = s;
     const double p1 = oz_pow2(s / 2), p2 = oz_pow2(s - s / 2);
@@ -220,7 +222,7 @@ constexpr int OZ_THALF = 10;  // moduli staged at a time
 constexpr int OZ_TS = 72;     // bytes per staged row (64 + 8: conflict-free 8-byte stores of a half-warp)
 __global__ void __launch_bounds__(256) oz_convert_t_kernel(const double* __restrict__ src, int ld, long long sS, int R, int K,
                                                            int nmod, int bits, int tri, uint8_t* __restrict__ planes,
-                                                           int* __restrict__ sexp) {
+                                                           int* __restrict__ sexp, double fixed_max) {
     __shared__ double red[8][33];
     __shared__ int s_sh[32];
     __shared__ __align__(16) uint8_t stage[OZ_THALF * 32 * OZ_TS];
@@ -231,16 +233,24 @@ __global__ void __launch_bounds__(256) oz_convert_t_kernel(const double* __restr
     uint8_t* Pb = planes + (size_t)b * nmod * R * K;
     int klo, khi;
     oz_row_range(tri, r0, K, klo, khi);
-    double mx = 0.0;
-    for (int k = klo + ty; k < khi; k += 8) mx = fmax(mx, fabs(col[(size_t)k * ld]));
-    red[ty][tx] = mx;
-    __syncthreads();
-    if (ty == 0) {
+    if (fixed_max > 0.0) {          // the caller's bound on |x| replaces the pass over the data (one scale for all rows)
+        if (ty == 0) {
+            const int s = oz_scale_exp(fixed_max, bits);
+            s_sh[tx] = s;
+            sexp[(size_t)b * R + r] = s;
+        }
+    } else {
+        double mx = 0.0;
+        for (int k = klo + ty; k < khi; k += 8) mx = fmax(mx, fabs(col[(size_t)k * ld]));
+        red[ty][tx] = mx;
+        __syncthreads();
+        if (ty == 0) {
 #pragma unroll
-        for (int j = 1; j < 8; j++) mx = fmax(mx, red[j][tx]);
-        const int s = oz_scale_exp(mx, bits);
-        s_sh[tx] = s;
-        sexp[(size_t)b * R + r] = s;
+            for (int j = 1; j < 8; j++) mx = fmax(mx, red[j][tx]);
+            const int s = oz_scale_exp(mx, bits);
+            s_sh[tx] = s;
+            sexp[(size_t)b * R + r] = s;
+        }
     }
     __syncthreads();
     const int s = s_sh[tx];
@@ -894,13 +904,13 @@ static cudaError_t make_map(CUtensorMap* out, const uint8_t* base, int K, int R,
 }
 
 static cudaError_t launch_convert(bool kc, const double* src, int ld, long long sS, int R, int K, int nmod, int bits, int tri,
-                                  uint8_t* planes, int* sexp, int batch, cudaStream_t st) {
+                                  uint8_t* planes, int* sexp, int batch, cudaStream_t st, double fixed_max = 0.0) {
     if (kc) {
         dim3 grid((R + 7) / 8, batch);
-        oz_convert_kc_kernel<<<grid, 256, 0, st>>>(src, ld, sS, R, K, nmod, bits, tri, planes, sexp);
+        oz_convert_kc_kernel<<<grid, 256, 0, st>>>(src, ld, sS, R, K, nmod, bits, tri, planes, sexp, fixed_max);
     } else {
         dim3 grid(R / 32, batch);
-        oz_convert_t_kernel<<<grid, 256, 0, st>>>(src, ld, sS, R, K, nmod, bits, tri, planes, sexp);
+        oz_convert_t_kernel<<<grid, 256, 0, st>>>(src, ld, sS, R, K, nmod, bits, tri, planes, sexp, fixed_max);
     }
     return cudaGetLastError();
 }
@@ -916,6 +926,7 @@ cudaError_t oz_gemm(const GemmP& p, int layout, int epi, int nmod, OzWs& ws, cud
     if (!have_crt[nmod]) { crt[nmod] = make_crt(nmod); have_crt[nmod] = true; }
     bool grew;
     const bool same = same_operand(p, layout);
+    struct BoundReset { OzWs& w; ~BoundReset() { w.b_bound = 0.0; } } bound_reset{ws};
     if ((e = oz_reserve(ws, p, nmod, grew, same)) != cudaSuccess) return e;
     if (grew) { ws.have_a = false; ws.grew = true; }
     const int bits = oz_operand_bits(nmod, p.K);
@@ -947,7 +958,8 @@ cudaError_t oz_gemm(const GemmP& p, int layout, int epi, int nmod, OzWs& ws, cud
     const uint8_t* PBp = ws.PA;
     const int* sBp = ws.sA;
     if (!same) {
-        if ((e = launch_convert(b_kc, p.B, p.ldb, p.sB, p.N, p.K, nmod, bits, triB, ws.PB, ws.sB, p.batch, st)) != cudaSuccess) return e;
+        const double b_bound = ws.b_bound;      // one-shot: the caller's bound on |B| (0: none)
+        if ((e = launch_convert(b_kc, p.B, p.ldb, p.sB, p.N, p.K, nmod, bits, triB, ws.PB, ws.sB, p.batch, st, b_bound)) != cudaSuccess) return e;
         PBp = ws.PB;
         sBp = ws.sB;
     }

@@ -40,6 +40,8 @@ struct OzWs {
     Key key_a{};
     unsigned long long tag_a = 0; // caller's generation of the source (0: none)
     bool have_a = false;
+    double b_bound = 0.0;        // set before a call: |B| <= b_bound everywhere, so operand B takes one scale and its maxima are not
+                                 // searched (holds for that call only)
     bool grew = false;           // set when a buffer was reallocated: captured graphs that used the old one are stale
     void release();
 };

@@ -624,6 +624,11 @@ int predict_chunk(gpe_handle* h, gpe_handle::PredSlot& sl, cudaStream_t st, cons
                 mp = np;
                 h->oz_reuse_a = true;
                 h->oz_a_tag = h->fit_gen;
+                // every entry of the slab is c exp(-D) in [0, c]: one scale for all points, no pass over the slab for its maxima.
+                // (A point far from every training input then keeps fewer significant bits of its tiny column -- its variance
+                // is the prior's to the same absolute accuracy, which is what the subtraction prior - |Z|^2 needs.)
+                static const int fixed_env = [] { const char* e = getenv("GPE_PRED_FIXED_SCALE"); return e ? atoi(e) : 1; }();
+                if (fixed_env) h->oz_b_bound = h->fit_c;
                 one_row = oz_sumsq_swapped(p, EPI_SUMSQ);
             }
         }
