@@ -691,7 +691,7 @@ def run_b200(args):
             p_nmod = int(os.environ.get("GPE_OZAKI", "16"))
             i8_peak, i8_src = int8_peak()
             i8_ach = p_nmod * float(mprof) * float(N_PRED) ** 2 / (i8ms * 1e-3) * 1e-12
-            p_int8 = {"kernel": "oz_gemm_kernel<4> (residue GEMM of Z = L^-1 C, k <= i: TMA, four-CTA multicast clusters, tcgen05.mma kind::i8, "
+            p_int8 = {"kernel": "oz_gemm_kernel<2> (residue GEMM of Z^T = C^T L^-T, k <= j: TMA, two-CTA multicast clusters, tcgen05.mma kind::i8, "
                                 "mod-p epilogue): %d launches" % i8cnt,
                       "bound": "tensor", "unit": "TOP/s", "achieved": i8_ach, "peak": i8_peak, "frac": i8_ach / i8_peak, "peak_source": i8_src,
                       "moduli": p_nmod, "algorithmic": "moduli x n^2 ops per point (the triangular product's FP64 flops)",
@@ -716,7 +716,7 @@ def run_b200(args):
                                         "what": "FP64-equivalent: F_pred x preds/s per GPU against the measured FP64 DMMA roof" +
                                                 (" -- above 1 because Z = L^-1 C runs as exact INT8 residue GEMMs on the tcgen05 tensor cores "
                                                  "(dominant_kernel carries that kernel's own INT8 roofline)" if p_int8 else ""),
-                                        "kernel": "oz_gemm_kernel<4> + oz_combine_sumsq_kernel (Z = L^-1 C by residues, column norms in the CRT pass)" if p_int8
+                                        "kernel": "oz_convert_t_kernel + oz_gemm_kernel<2> + oz_combine_rowsumsq_kernel (Z^T = C^T L^-T by residues, row norms in the CRT pass)" if p_int8
                                                   else "gemm_dmma_ws_kernel<NN, EPI_SUMSQ> (Z = L^-1 C with fused column norms)",
                                         "kernel_achieved": ((float(mprof) * float(N_PRED) ** 2 * 1e-12) / (gms * 1e-3) if gms else None) if not p_int8 else
                                                            (float(mprof) * float(N_PRED) ** 2 * 1e-12) / ((i8ms + pprof["int8_residue_conversion"][0] + pprof["int8_crt_combine"][0]) * 1e-3),
@@ -824,7 +824,7 @@ def run_b200(args):
             if os.path.exists(tp):
                 with open(tp) as f:
                     i8_traffic = json.load(f)
-            int8 = {"kernel": "oz_gemm_kernel<4> (residue GEMM: TMA 128B-swizzled tiles, four-CTA multicast clusters, tcgen05.mma kind::i8, "
+            int8 = {"kernel": "oz_gemm_kernel<2> (residue GEMM: TMA 128B-swizzled tiles, two-CTA multicast clusters, tcgen05.mma kind::i8, "
                               "TMEM double-buffered accumulator, mod-p epilogue): %d launches per step" % (oz_cnt // Kp_),
                     "bound": "tensor", "unit": "TOP/s", "achieved": i8_ach, "peak": i8_peak, "frac": i8_ach / i8_peak,
                     "peak_source": i8_src,

@@ -935,7 +935,10 @@ cudaError_t oz_gemm(const GemmP& p, int layout, int epi, int nmod, OzWs& ws, cud
     const bool swap = oz_sumsq_swapped(p, epi);
     // cluster size of the residue GEMM: row-triangular products (k <= i, k >= i) pay for a larger cluster with a coarser k
     // range per unit
-    static const int cl_env = [] { const char* e = getenv("GPE_OZAKI_CLUSTER"); return e ? atoi(e) : 4; }();
+    // pairs by default: quadruples cut the L2 -> SM traffic further (24 instead of 32 KB per k block) but only 33 of them are
+    // resident at once (132 of the 148 SMs: the GPCs' SM counts are not multiples of four) and row-triangular operands are then
+    // converted and read in 512-row granules; same-box A/B at n = 4096, 32 items: 44.4-44.9 (pairs) against 45.4-45.9 ms per step
+    static const int cl_env = [] { const char* e = getenv("GPE_OZAKI_CLUSTER"); return e ? atoi(e) : 2; }();
     static const int cl_env_i = [] { const char* e = getenv("GPE_OZAKI_CLUSTER_I"); return e ? atoi(e) : 4; }();
     static const int cl_env_s = [] { const char* e = getenv("GPE_OZAKI_CLUSTER_SUMSQ"); return e ? atoi(e) : 2; }();
     // (the prediction product -- one item, 65 536 columns, k <= i -- measured 13.6 Mpred/s with pairs against 13.35 with quadruples)
