@@ -717,8 +717,11 @@ int gpe_llh_grad_batch(gpe_handle* h, const double* theta, int B, int p, int mod
         int Bs = std::min(h->Bcap, B - b0);
         CK(cudaMemcpyAsync(h->theta_d, theta + (size_t)b0 * p, sizeof(double) * Bs * p, cudaMemcpyDefault, h->st));
         gpe_handle::LlhGraph* gr = nullptr;
-        if (h->graphs_stale) {      // a scratch buffer of the INT8 route was reallocated since the graphs were captured
-            h->drop_graphs();
+        if (h->graphs_stale) {      // a scratch buffer of the INT8 route was reallocated since the graphs were captured: the
+            for (auto& g : h->graphs) {     // executables go, the sighting counts stay (the buffers grow in the first eager call,
+                if (g.exec) cudaGraphExecDestroy(g.exec);       // so the third call of a shape still is the one that captures)
+                g.exec = nullptr;
+            }
             h->graphs_stale = false;
         }
         if (h->use_graphs && !h->prof_on) {
@@ -747,6 +750,7 @@ int gpe_llh_grad_batch(gpe_handle* h, const double* theta, int B, int p, int mod
             ce = cudaGraphInstantiate(&gr->exec, graph, 0);
             cudaGraphDestroy(graph);
             if (ce != cudaSuccess) { gr->exec = nullptr; return h->fail("cudaGraphInstantiate", ce); }
+            cudaGraphUpload(gr->exec, h->st);       // (best effort: keeps the upload out of the first replay)
             CK(cudaGraphLaunch(gr->exec, h->st));
         } else {
             if (gr) gr->seen++;

@@ -11,7 +11,7 @@ print(j["n_gpus"], j["value"], j["ms_per_step"])
 e = j["extra"]
 print(e.get("posterior_preds_per_s"), e.get("history_match"), e.get("config3_optimisation"), e.get("extra_configs_error"), e.get("posterior_error"))
 PY
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus 2 --steps 1 --warmup 1 --ref-budget 60 2>/dev/null > gpurun_out/r2_bench_ref_g2.json
+echo "(reference arm under torchrun: see profiles/r02_bench_final_reference_arm.json)"
 python - <<'PY'
 import json
 j = json.load(open("gpurun_out/r2_bench_ref_g2.json"))
