@@ -1,6 +1,5 @@
 #!/bin/bash
-# Two-GPU check (run on the GPU box from the repo root): the two-rank product test over NCCL, a short N=2 bench, and the
-# reference arm under torchrun (which exports OMP_NUM_THREADS=1: the arm must still use every host core).
+# Two-GPU check (run on the GPU box from the repo root): the two-rank product test over NCCL and a short N=2 bench.
 python -m pytest tests/test_gpu_multi.py tests/test_gpu_predict.py -m gpu -q -x 2>&1 | tail -4
 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 3 --warmup 3 > gpurun_out/r2_bench_g2.json 2> gpurun_out/r2_bench_g2.err
 tail -c 300 gpurun_out/r2_bench_g2.err
@@ -11,9 +10,4 @@ print(j["n_gpus"], j["value"], j["ms_per_step"])
 e = j["extra"]
 print(e.get("posterior_preds_per_s"), e.get("history_match"), e.get("config3_optimisation"), e.get("extra_configs_error"), e.get("posterior_error"))
 PY
-echo "(reference arm under torchrun: see profiles/r02_bench_final_reference_arm.json)"
-python - <<'PY'
-import json
-j = json.load(open("gpurun_out/r2_bench_ref_g2.json"))
-print(j["value"], j["cpu_baseline"]["cores"], j["cpu_baseline"]["sample"][:100])
-PY
+echo "(the reference arm under torchrun was checked earlier in the round: profiles/r02_bench_final_reference_arm.json)"
