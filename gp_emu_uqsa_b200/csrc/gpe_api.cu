@@ -418,8 +418,11 @@ int gpe_create(int device, gpe_handle** out) {
     int prio_least = 0, prio_greatest = 0;
     cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
     if (const char* e = getenv("GPE_PRIO")) h->use_prio = e[0] != '0';
+    // GPE_SUB_ASYM=1 (experiment): the even sub-batch streams get the highest priority, so that one group runs at full speed and
+    // the other fills the gaps its tensor-bound kernels leave, instead of both drifting through the same phases
+    const bool asym = [] { const char* e = getenv("GPE_SUB_ASYM"); return e && e[0] != '0'; }();
     for (int s = 0; s < gpe_handle::MAX_SUB; s++) {
-        cudaStreamCreateWithPriority(&h->sub_st[s], cudaStreamNonBlocking, prio_least);
+        cudaStreamCreateWithPriority(&h->sub_st[s], cudaStreamNonBlocking, (asym && s % 2 == 0) ? prio_greatest : prio_least);
         cudaEventCreateWithFlags(&h->ev_join[s], cudaEventDisableTiming);
         if (h->use_prio) {          // the optional high-priority twin streams (experiment knob)
             cudaStreamCreateWithPriority(&h->sub_hi[s], cudaStreamNonBlocking, prio_greatest);

@@ -290,20 +290,25 @@ def test_fused_implausibility_equals_the_two_step_route(dev, golden_dir):
         dv.close()
 
 
-@pytest.mark.parametrize("n,d,m", [(1500, 6, 2300), (2000, 8, 4096), (1024, 3, 1024), (1100, 5, 2048)])
-def test_int8_route_of_the_prediction_product_matches_dmma_and_the_oracle(n, d, m, monkeypatch):
+@pytest.mark.parametrize("n,d,m,kind", [(1500, 6, 2300, 0), (2000, 8, 4096, 0), (1024, 3, 1024, 0), (1100, 5, 2048, 0),
+                                        (1500, 6, 2300, 1), (4096, 16, 1024, 0)])
+def test_int8_route_of_the_prediction_product_matches_dmma_and_the_oracle(n, d, m, kind, monkeypatch):
     """Chunks of 1024 points and more (a multiple of 256 after padding) over 1024 and more padded training points send
-    Z = L^-1 C down the INT8 tensor-core route (gpe_ozaki.cuh, column norms taken inside the CRT pass; the residue planes of
-    L^-1 are kept per fit).  Held against GPE_OZAKI=0 (FP64 DMMA) and, for the variance, against the oracle's route
-    (north_star: 1e-8), at a length-scale mix that makes L^-1 badly scaled."""
+    Z = L^-1 C down the INT8 tensor-core route (gpe_ozaki.cuh: one scale for the bounded slab, the residue planes of L^-1 kept per
+    fit, the product with its roles swapped and row norms taken inside the CRT pass when the padded size is a multiple of 256 --
+    n = 1100 keeps L^-1 on the row side).  Held against GPE_OZAKI=0 (FP64 DMMA) and, for kernel 0, against the oracle's route
+    (north_star: 1e-8), at a length-scale mix that makes L^-1 badly scaled; the last 16 points lie far outside the training
+    inputs (tiny slab columns under the common scale); kind 1 = the alternative nugget with a per-point r."""
     from gp_emu_uqsa_b200 import _lib
     rng = np.random.default_rng(11 + n)
     X = rng.random((n, d))
     y = np.sin(X @ rng.normal(size=d)) + 0.1 * (X ** 2).sum(1)
     H = O.make_H_linear(X)
     Xs = rng.random((m, d))
+    Xs[-16:] += 3.0
     delta = np.linspace(0.3, 1.5, d)
-    nugget, sigma = 1e-5, 1.3
+    nugget, sigma = (1e-5, 1.3) if kind == 0 else (3e-3, 1.3)
+    r = None if kind == 0 else 1e-4 * (1.0 + rng.random(n))
     res = {}
     for route in ("dmma", "int8"):
         if route == "dmma":
@@ -312,9 +317,9 @@ def test_int8_route_of_the_prediction_product_matches_dmma_and_the_oracle(n, d, 
             monkeypatch.delenv("GPE_OZAKI", raising=False)
         dv = _lib.Device(0)
         try:
-            dv.set_training(X, y, H, None)
+            dv.set_training(X, y, H, r)
             dv.set_basis(list(range(d)), [1] * d)
-            _, _, st = dv.fit_state(delta, nugget, sigma, 0)
+            _, _, st = dv.fit_state(delta, nugget, sigma, kind)
             assert st == 0
             before = dv.int8_products
             mean, var = dv.predict(Xs)
@@ -322,9 +327,9 @@ def test_int8_route_of_the_prediction_product_matches_dmma_and_the_oracle(n, d, 
             # a second call re-uses the residue planes of L^-1 (same fit generation); a new fit must not
             mean_b, var_b = dv.predict(Xs)
             assert np.array_equal(mean_b, mean) and np.array_equal(var_b, var)
-            dv.fit_state(delta * 1.1, nugget, sigma, 0)
+            dv.fit_state(delta * 1.1, nugget, sigma, kind)
             dv.predict(Xs[:1024])
-            dv.fit_state(delta, nugget, sigma, 0)
+            dv.fit_state(delta, nugget, sigma, kind)
             mean_c, var_c = dv.predict(Xs)
             assert np.array_equal(mean_c, mean) and np.array_equal(var_c, var)
             res[route] = (mean, var, took)
@@ -337,9 +342,13 @@ def test_int8_route_of_the_prediction_product_matches_dmma_and_the_oracle(n, d, 
     vd, vi = res["dmma"][1], res["int8"][1]
     scale = sigma ** 2                                                         # the prior variance the subtraction starts from
     assert np.abs(vi - vd).max() <= 1e-10 * scale, np.abs(vi - vd).max() / scale
+    assert np.all(vi[-16:] > 0.99 * scale)                                     # far points: the prior variance (and more)
+    if kind != 0:
+        return
     A = O.make_A(X, delta, nugget, 0)
     beta = O.optimalbeta(A, H, y)
-    mref, Vref = O.posterior(Xs[:256], O.make_H_linear(Xs[:256]), X, y, H, A, beta, sigma, delta, nugget, 0)
+    sel = np.r_[0:240, m - 16:m]
+    mref, Vref = O.posterior(Xs[sel], O.make_H_linear(Xs[sel]), X, y, H, A, beta, sigma, delta, nugget, 0)
     vref = np.diag(Vref)
-    assert np.allclose(res["int8"][0][:256], mref, rtol=1e-8, atol=1e-10)
-    assert np.allclose(vi[:256], vref, rtol=1e-8, atol=1e-8 * np.abs(vref).max())
+    assert np.allclose(res["int8"][0][sel], mref, rtol=1e-8, atol=1e-10)
+    assert np.allclose(vi[sel], vref, rtol=1e-8, atol=1e-8 * np.abs(vref).max())
