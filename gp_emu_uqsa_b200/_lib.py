@@ -104,6 +104,11 @@ def _ptr(a):
         return None
     if isinstance(a, np.ndarray):
         return a.ctypes.data
+    if a.is_cuda:
+        # the handle works on its own non-blocking stream: whatever torch has queued for this tensor (a fill, a clone)
+        # must have finished before the library reads or writes it
+        import torch
+        torch.cuda.current_stream(a.device).synchronize()
     return a.data_ptr()          # torch.Tensor
 
 

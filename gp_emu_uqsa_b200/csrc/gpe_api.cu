@@ -302,8 +302,13 @@ static int llh_grad_fused(gpe_handle* h, int B) {
         const char* e = getenv("GPE_FUSED_GRAD");
         mode = e ? atoi(e) : 2;
     }
+    h->grad_use_e = false;
     if (!gemm_is_big(h->npad, h->npad, 1, B)) return 0;
-    if (h->oz_nmod > 0 && h->npad >= h->oz_min && h->npad % OZ_BN == 0) return 0;   // LAUUM on the INT8 route, A^-1 stored
+    if (h->oz_nmod > 0 && h->npad >= h->oz_min && h->npad % OZ_BN == 0) {   // LAUUM on the INT8 route, A^-1 stored: the stand-alone
+        static const int use_e = [] { const char* e = getenv("GPE_GRAD_E"); return e ? atoi(e) : 1; }();   // reduction reads the
+        h->grad_use_e = use_e != 0;                                          // covariance build's copy of exp(-D)
+        return 0;
+    }
     if (mode == 2 && !lauum_grad_supported(h->d)) return 1;
     return mode;
 }
@@ -370,7 +375,8 @@ int gpe_factor_and_reduce(gpe_handle* h, const SubBatch& sb, int mode, int with_
     {
         ProfScope ps(h, gpe_handle::CAT_GRAD, st);
         launch_grad_partial(h->X, h->r, h->n, h->d, np, h->winv + (size_t)b0 * h->d, Ab, sM, U, h->q + 1,
-                            h->gpart + (size_t)b0 * grad_ntiles(np) * grad_nvals(h->d), B, st);
+                            h->gpart + (size_t)b0 * grad_ntiles(np) * grad_nvals(h->d), B, st,
+                            h->grad_use_e ? h->Ex + (size_t)b0 * sM : nullptr);
     }
     h->launches++;
     return 0;
@@ -687,7 +693,7 @@ static int enqueue_llh_chunk(gpe_handle* h, int Bs, int p, int mode, double fixe
             ProfScope ps(h, gpe_handle::CAT_COV, sb.st);
             CK(launch_cov_build(h->X, h->r, h->n, h->d, h->npad, h->par + sb.b0, h->winv + (size_t)sb.b0 * h->d,
                                 h->A + (size_t)sb.b0 * sM, sM, sb.B, 0, sb.st, 0, 0,
-                                h->grad_fused ? h->Ex + (size_t)sb.b0 * sM : nullptr));
+                                (h->grad_fused || h->grad_use_e) ? h->Ex + (size_t)sb.b0 * sM : nullptr));
         }
         h->launches++;
         if ((rc = gpe_factor_and_reduce(h, sb, mode, 1, nullptr, nullptr))) return rc;

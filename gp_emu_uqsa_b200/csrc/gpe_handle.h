@@ -63,6 +63,7 @@ struct gpe_handle {
     // batched likelihood workspace
     int Bcap = 0;
     bool Bcap_final = false;
+    bool grad_use_e = false;     // classic route with the covariance build's copy of exp(-D) (INT8 route)
     int grad_fused = 0;          // gradient route of the current chunk (gpe_api.cu:llh_grad_fused): 0 classic, 1 split W/E, 2 epilogue     // the workspace already has the largest size obtainable (env cap or device memory)
     double *A = nullptr, *S = nullptr, *Li = nullptr;        // [Bcap][npad][npad]
     double* Ex = nullptr;                                    // [Bcap][npad][npad] exp(-D) kept by the covariance build for the fused gradient epilogue

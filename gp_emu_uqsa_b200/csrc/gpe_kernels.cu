@@ -858,10 +858,14 @@ void launch_llh_finalize(const double* Wy, const double* GP, const double* logde
 // A^-1 is read once, E_ij = exp(-D_ij) is recomputed from X, and d+3 weighted sums are reduced.
 constexpr int GD = 16;  // dims accumulated per register pass
 
+// USE_E: E = exp(-D) is read from the copy the covariance build kept (8 B per entry from an idle HBM) instead of being
+// recomputed (2d + 22 FP64 instructions per entry on the pipe this kernel is bound by).
+template <bool USE_E>
 __global__ void __launch_bounds__(256, 3) grad_partial_kernel(const double* __restrict__ X, const double* __restrict__ r,
                                                            int n, int d, int npad, const double* __restrict__ winv,
                                                            const double* __restrict__ Ainv, long long sAinv,
-                                                           const double* __restrict__ U, int nu, double* __restrict__ part) {
+                                                           const double* __restrict__ U, int nu, double* __restrict__ part,
+                                                           const double* __restrict__ E) {
     int ti, tj;
     tri_decode(blockIdx.x, ti, tj);
     const int b = blockIdx.z;
@@ -902,6 +906,15 @@ __global__ void __launch_bounds__(256, 3) grad_partial_kernel(const double* __re
 #pragma unroll
             for (int h = 0; h < 2; h++)
                 av[a][h] = __ldg(reinterpret_cast<const double2*>(&Ab[(size_t)(ti * CT + ty + 16 * a) * npad + tj * CT + 32 * h + 2 * tx]));
+        double2 ev[4][2];
+        if (USE_E) {
+            const double* Eb = E + (size_t)b * sAinv;
+#pragma unroll
+            for (int a = 0; a < 4; a++)
+#pragma unroll
+                for (int h = 0; h < 2; h++)
+                    ev[a][h] = __ldg(reinterpret_cast<const double2*>(&Eb[(size_t)(ti * CT + ty + 16 * a) * npad + tj * CT + 32 * h + 2 * tx]));
+        }
         double D[4][4], dot[4][4];
 #pragma unroll
         for (int a = 0; a < 4; a++)
@@ -927,25 +940,32 @@ __global__ void __launch_bounds__(256, 3) grad_partial_kernel(const double* __re
                 dot[a][2 * h] = av[a][h].x - dot[a][2 * h];
                 dot[a][2 * h + 1] = av[a][h].y - dot[a][2 * h + 1];
             }
-        for (int k = 0; k < d; k++) {
-            double xi[4], xj[4];
-#pragma unroll
-            for (int a = 0; a < 4; a++) xi[a] = Xi[k * CT + ty + 16 * a];
-            double2 v0 = *reinterpret_cast<const double2*>(&Xj[k * (CT + 2) + 2 * tx]);
-            double2 v1 = *reinterpret_cast<const double2*>(&Xj[k * (CT + 2) + 32 + 2 * tx]);
-            xj[0] = v0.x; xj[1] = v0.y; xj[2] = v1.x; xj[3] = v1.y;
+        if (USE_E) {
 #pragma unroll
             for (int a = 0; a < 4; a++)
 #pragma unroll
-                for (int c = 0; c < 4; c++) {
-                    double df = xi[a] - xj[c];
-                    D[a][c] = fma(df, df, D[a][c]);
-                }
+                for (int h = 0; h < 2; h++) { D[a][2 * h] = ev[a][h].x; D[a][2 * h + 1] = ev[a][h].y; }
+        } else {
+            for (int k = 0; k < d; k++) {
+                double xi[4], xj[4];
+#pragma unroll
+                for (int a = 0; a < 4; a++) xi[a] = Xi[k * CT + ty + 16 * a];
+                double2 v0 = *reinterpret_cast<const double2*>(&Xj[k * (CT + 2) + 2 * tx]);
+                double2 v1 = *reinterpret_cast<const double2*>(&Xj[k * (CT + 2) + 32 + 2 * tx]);
+                xj[0] = v0.x; xj[1] = v0.y; xj[2] = v1.x; xj[3] = v1.y;
+#pragma unroll
+                for (int a = 0; a < 4; a++)
+#pragma unroll
+                    for (int c = 0; c < 4; c++) {
+                        double df = xi[a] - xj[c];
+                        D[a][c] = fma(df, df, D[a][c]);
+                    }
+            }
+#pragma unroll
+            for (int a = 0; a < 4; a++)
+#pragma unroll
+                for (int c = 0; c < 4; c++) D[a][c] = gpe_exp(-D[a][c]);      // 16 interleaved chains, no branches
         }
-#pragma unroll
-        for (int a = 0; a < 4; a++)
-#pragma unroll
-            for (int c = 0; c < 4; c++) D[a][c] = gpe_exp(-D[a][c]);      // 16 interleaved chains, no branches
 #pragma unroll
         for (int a = 0; a < 4; a++) {
             int gi = ti * CT + ty + 16 * a;
@@ -1018,12 +1038,17 @@ __global__ void __launch_bounds__(256, 3) grad_partial_kernel(const double* __re
 
 void launch_grad_partial(const double* X, const double* r, int n, int d, int npad, const double* winv,
                          const double* Ainv, long long sAinv, const double* U, int nu, double* part,
-                         int B, cudaStream_t st) {
+                         int B, cudaStream_t st, const double* E) {
     int nt = npad / CT;
     size_t smem = ((size_t)(d + nu) * (CT + CT + 2) + 8 * (size_t)(d + 3)) * sizeof(double);
-    static SmemOptIn optin;
-    optin.ensure(grad_partial_kernel, smem);
-    grad_partial_kernel<<<dim3(nt * (nt + 1) / 2, 1, B), 256, smem, st>>>(X, r, n, d, npad, winv, Ainv, sAinv, U, nu, part);
+    static SmemOptIn optin, optin_e;
+    if (E != nullptr) {         // (same layout and item stride as A^-1)
+        optin_e.ensure(grad_partial_kernel<true>, smem);
+        grad_partial_kernel<true><<<dim3(nt * (nt + 1) / 2, 1, B), 256, smem, st>>>(X, r, n, d, npad, winv, Ainv, sAinv, U, nu, part, E);
+    } else {
+        optin.ensure(grad_partial_kernel<false>, smem);
+        grad_partial_kernel<false><<<dim3(nt * (nt + 1) / 2, 1, B), 256, smem, st>>>(X, r, n, d, npad, winv, Ainv, sAinv, U, nu, part, nullptr);
+    }
 }
 
 

@@ -63,7 +63,7 @@ void launch_llh_finalize(const double* Wy, const double* GP, const double* logde
 // K1g: per-tile partial sums of  W_ij E_ij Delta_k^2, W_ij E_ij, W_ii, W_ii r_i.
 void launch_grad_partial(const double* X, const double* r, int n, int d, int npad, const double* winv,
                          const double* Ainv, long long sAinv, const double* U, int nu, double* part,
-                         int B, cudaStream_t st);
+                         int B, cudaStream_t st, const double* E = nullptr);
 void launch_grad_finalize(const double* part, int ntile, int n, int d, int npad, int p, int mode, const ItemPar* par,
                           const ItemOut* out, const int* status, double* llh, double* grad,
                           double* sigma_hat, int B, cudaStream_t st);
