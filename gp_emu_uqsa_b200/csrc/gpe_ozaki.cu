@@ -169,6 +169,8 @@ __device__ __forceinline__ uint32_t oz_pack4(uint32_t r0, uint32_t r1, uint32_t 
 }
 // residues of eight values for modulus a, packed
 __device__ __forceinline__ uint2 oz_residues8(const uint32_t (&lo)[OZ_CV], const uint32_t (&hi)[OZ_CV], int a) {
+    // modulus 0 is 256 (and 2^63 = 0 mod 256): the residue is the low byte, no arithmetic (a is uniform across the warp)
+    if (a == 0) return make_uint2(oz_pack4(lo[0], lo[1], lo[2], lo[3]), oz_pack4(lo[4], lo[5], lo[6], lo[7]));
     const uint32_t clo = OZC.clo[a], chi = OZC.chi[a], c0 = OZC.c0[a], m32 = OZC.m32[a], np = OZC.np[a];
     uint32_t r[OZ_CV];
 #pragma unroll
