@@ -925,7 +925,11 @@ cudaError_t oz_gemm(const GemmP& p, int layout, int epi, int nmod, OzWs& ws, cud
     static OzCrt crt[OZ_MAXMOD + 1];
     static bool have_crt[OZ_MAXMOD + 1] = {false};
     static OzConst hc = make_const();
-    if (!have_crt[nmod]) { crt[nmod] = make_crt(nmod); have_crt[nmod] = true; }
+    {   // (two handles may be driven from two host threads)
+        static std::mutex crt_mu;
+        std::lock_guard<std::mutex> lk(crt_mu);
+        if (!have_crt[nmod]) { crt[nmod] = make_crt(nmod); have_crt[nmod] = true; }
+    }
     bool grew;
     const bool same = same_operand(p, layout);
     struct BoundReset { OzWs& w; ~BoundReset() { w.b_bound = 0.0; } } bound_reset{ws};
