@@ -780,19 +780,23 @@ def run_b200(args):
         npad = (n + 127) // 128 * 128
         streaming = {}
         cov_ms, cov_cnt = prof["cov_build"]
+        # the covariance build also keeps E = exp(-D) for the gradient (the LAUUM epilogue on the DMMA route, the stand-alone
+        # reduction on the INT8 route unless GPE_GRAD_E=0)
+        e_copy = npad >= 1024 and not (prof["int8_residue_gemm"][1] and os.environ.get("GPE_GRAD_E", "1") == "0")
         if cov_ms:
-            byt = B * Kp_ * 8.0 * (npad * (npad + 64) / 2.0)             # lower 64x64 tiles written once
+            byt = B * Kp_ * (16.0 if e_copy else 8.0) * (npad * (npad + 64) / 2.0)             # lower 64x64 tiles written once
             flo = B * Kp_ * (n * n / 2.0) * (3 * d + 1)
             streaming["cov_build"] = {"ms_per_step": cov_ms / Kp_, "hbm_GBps": byt / (cov_ms * 1e-3) * 1e-9, "frac_of_hbm": byt / (cov_ms * 1e-3) * 1e-9 / hbm,
                                       "fp64_alu_TFLOPs": flo / (cov_ms * 1e-3) * 1e-12, "frac_of_fp64": flo / (cov_ms * 1e-3) * 1e-12 / peak,
-                                      "algorithmic": "8 B x n^2/2 written, (n^2/2)(3d + exp) flops per item"}
+                                      "algorithmic": "%d B x n^2/2 written (A%s), (n^2/2)(3d + exp) flops per item" % (16 if e_copy else 8, " and E = exp(-D)" if e_copy else "")}
         gr_ms, gr_cnt = prof["grad_reduce"]
         if gr_ms:
-            byt = B * Kp_ * 8.0 * (n * n / 2.0)
-            flo = B * Kp_ * (n * n / 2.0) * (5 * d + 2 * q + 1)
+            byt = B * Kp_ * (16.0 if e_copy else 8.0) * (n * n / 2.0)
+            flo = B * Kp_ * (n * n / 2.0) * ((3 * d + 2 * q) if e_copy else (5 * d + 2 * q + 1))
             streaming["grad_reduce"] = {"ms_per_step": gr_ms / Kp_, "hbm_GBps": byt / (gr_ms * 1e-3) * 1e-9, "frac_of_hbm": byt / (gr_ms * 1e-3) * 1e-9 / hbm,
                                         "fp64_alu_TFLOPs": flo / (gr_ms * 1e-3) * 1e-12, "frac_of_fp64": flo / (gr_ms * 1e-3) * 1e-12 / peak,
-                                        "algorithmic": "8 B x n^2/2 read, (n^2/2)(5d + 2q + exp) flops per item"}
+                                        "algorithmic": ("16 B x n^2/2 read (A^-1 and E), (n^2/2)(3d + 2q) flops per item" if e_copy else
+                                                        "8 B x n^2/2 read, (n^2/2)(5d + 2q + exp) flops per item")}
         # ---- the INT8 tensor-core route (default): the large products of the factorisation and LAUUM run as residue GEMMs on
         # tcgen05.mma kind::i8 (csrc/gpe_ozaki.cuh); the dominant kernel of the step is then oz_gemm_kernel
         oz_ms, oz_cnt = prof["int8_residue_gemm"]

@@ -42,6 +42,10 @@ struct OzWs {
     bool have_a = false;
     double b_bound = 0.0;        // set before a call: |B| <= b_bound everywhere, so operand B takes one scale and its maxima are not
                                  // searched (holds for that call only)
+    // high-priority twin of the stream this scratch belongs to: the residue GEMM is launched there (between two events), so that
+    // its CTAs take freed SM resources ahead of the queued CTAs of another stream's conversion / CRT launches
+    cudaStream_t hi = nullptr;
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr;
     bool grew = false;           // set when a buffer was reallocated: captured graphs that used the old one are stale
     void release();
 };
