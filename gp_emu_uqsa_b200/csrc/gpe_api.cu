@@ -196,6 +196,19 @@ static int run_gemm(gpe_handle* h, cudaStream_t st, const double* A, const doubl
     if (e != cudaSuccess) return h->fail("launch_gemm", e);
     return 0;
 }
+// Can the INT8 route hold the scratch of product `p` on stream `st`?  Grows the scratch if it must; on an allocation failure the
+// error is cleared and the caller stays on the DMMA route (a prediction chunk over a very large training set).
+bool gpe_oz_reserve(gpe_handle* h, cudaStream_t st, const GemmP& p) {
+    OzWs& ws = h->oz_ws[st];
+    bool grew = false;
+    const cudaError_t e = oz_reserve(ws, p, h->oz_nmod, grew, false);
+    if (grew) { ws.have_a = false; ws.grew = true; }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return true;
+}
 int gpe_run_gemm_on(gpe_handle* h, cudaStream_t st, const double* A, const double* B, double* C, int lda, int ldb, int ldc,
                     long long sA, long long sB, long long sC, int M, int N, int K, double alpha, int acc,
                     int kmode, int lower, int batch, int layout, int epi) {

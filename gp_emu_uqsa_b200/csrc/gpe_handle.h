@@ -179,6 +179,7 @@ int gpe_ensure_batch_ws(gpe_handle* h, int B);
 int gpe_potrf_inv(gpe_handle* h, const FactorWs& ws, const SubBatch& sb, int want_L);
 int gpe_factor_and_reduce(gpe_handle* h, const SubBatch& sb, int mode, int with_grad, const double* beta_override, double* Kout);
 int gpe_upload_single_par(gpe_handle* h, const double* delta, double nugget, int kind, int predict, double s2_for_r);
+bool gpe_oz_reserve(gpe_handle* h, cudaStream_t st, const gpe::GemmP& p);
 int gpe_run_gemm_on(gpe_handle* h, cudaStream_t st, const double* A, const double* B, double* C, int lda, int ldb, int ldc,
                     long long sA, long long sB, long long sC, int M, int N, int K, double alpha, int acc,
                     int kmode, int lower, int batch, int layout, int epi);

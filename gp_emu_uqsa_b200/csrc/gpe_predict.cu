@@ -620,7 +620,7 @@ int predict_chunk(gpe_handle* h, gpe_handle::PredSlot& sl, cudaStream_t st, cons
             GemmP p;
             p.A = h->fLi; p.B = sl.C; p.C = sl.Part; p.lda = np; p.ldb = mc; p.ldc = mc; p.sA = p.sB = p.sC = 0;
             p.M = np; p.N = mc; p.K = np; p.alpha = 1.0; p.accumulate = 0; p.kmode = KM_LE_I; p.lower = 0; p.batch = 1;
-            if (oz_supported(p, EPI_SUMSQ)) {
+            if (oz_supported(p, EPI_SUMSQ) && gpe_oz_reserve(h, st, p)) {
                 mp = np;
                 h->oz_reuse_a = true;
                 h->oz_a_tag = h->fit_gen;
