@@ -861,7 +861,7 @@ constexpr int GD = 16;  // dims accumulated per register pass
 // USE_E: E = exp(-D) is read from the copy the covariance build kept (8 B per entry from an idle HBM) instead of being
 // recomputed (2d + 22 FP64 instructions per entry on the pipe this kernel is bound by).
 template <bool USE_E>
-__global__ void __launch_bounds__(256, 3) grad_partial_kernel(const double* __restrict__ X, const double* __restrict__ r,
+__global__ void __launch_bounds__(256, 2) grad_partial_kernel(const double* __restrict__ X, const double* __restrict__ r,
                                                            int n, int d, int npad, const double* __restrict__ winv,
                                                            const double* __restrict__ Ainv, long long sAinv,
                                                            const double* __restrict__ U, int nu, double* __restrict__ part,
